@@ -1,0 +1,242 @@
+// TEST INFRASTRUCTURE -- not part of the product.
+//
+// Reference driver: a small main() of OUR OWN that links the UNMODIFIED reference sources where
+// they lie under /root/reference/scOOP (everything except the reference's main.cpp) and calls the
+// reference's own classes -- Sim, Inicializer, Conf, PairE, ParticleVector::getConlist,
+// Conf::overlap -- to dump, at full precision (C99 hex floats), what the hot path computes on the
+// configuration found in the current directory (options / top.init / config.init):
+//
+//   * the derived per-particle state after Conf::partVecInit()   (particle.cpp:3-79)
+//   * the interaction table entries in use                         (topo.cpp:5-153)
+//   * every non-zero PairE(i,j,conlist(i)) in BOTH orders          (paire.h:1209-1220)
+//   * per-particle sums in TotalEFull::oneToAll order              (totalenergycalculator.h:563-583)
+//   * the total in TotalEMatrix::allToAll(matrix) order            (totalenergycalculator.h:502-521)
+//   * Conf::overlap(i,j) flags                                     (Conf.cpp:104-239)
+//
+// It is built ONLY by oracle/Makefile into oracle/_ref/ (git-ignored) and used ONLY to
+// (1) generate tests/golden/*.ref fixtures (tests/golden/make_golden.py) and
+// (2) serve as the `--impl reference` / cpu_baseline "reference" timing arm of bench.py.
+// No reference source text is copied here; this file only *calls* the reference API.
+//
+// usage:  cd <dir with options,top.init,config.init> && sc_ref_driver dump|dump0 [out]   (dump0: pairs with particle 0 only)
+//         sc_ref_driver time <nrep> [big]      -> JSON line with timings of allToAll/oneToAll
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "mc/inicializer.h"
+#include "mc/totalenergycalculator.h"
+#include "mc/randomGenerator.h"
+
+using namespace std;
+
+// globals the reference expects its main.cpp to define (main.cpp:18-30)
+MpiCout mcout(0);
+Topo topo;
+#ifdef RAN2
+Ran2 ran2;
+#else
+#ifdef DSFMT
+Dsfmt ran2;
+#else
+MersenneTwister ran2;
+#endif
+#endif
+
+static void pv(FILE* f, const Vector& v) { fprintf(f, " %a %a %a", v.x, v.y, v.z); }
+
+static void load(Conf& conf, Sim*& sim, FileNames& files, long big_counts_n, const long* big_counts) {
+    sim = new Sim(&conf, &files, 0, 1);
+    Inicializer init(sim, &conf, &files);
+    init.initTop();
+    init.testChains();
+    if (big_counts_n > 0) {
+        // Systems above the reference's MAXN: top.init lists ONE molecule of each molecule type;
+        // replicate each molecule big_counts[k] times here, then fix the group list the same way
+        // Inicializer::initGroupLists does (inicializer.cpp:330-372).
+        ParticleVector proto = conf.pvec;
+        conf.pvec.clear();
+        int ntypes = proto.molTypeCount;
+        int at = 0;
+        for (int t = 0; t < ntypes; t++) {
+            int msz = topo.moleculeParam[t].molSize();
+            conf.pvec.first[t] = (int)conf.pvec.size();
+            for (long c = 0; c < big_counts[t]; c++)
+                for (int k = 0; k < msz; k++) conf.pvec.push_back(proto[at + k]);
+            at += msz;
+        }
+        conf.pvec.first[ntypes] = (int)conf.pvec.size();
+        conf.pvec.molTypeCount = ntypes;
+        conf.pvec.calcChainCount();
+    }
+    FILE* infile = fopen(files.configurationInFile, "r");
+    if (!infile) { fprintf(stderr, "cannot open config.init\n"); exit(1); }
+    if (!init.initConfig(&infile, conf.pvec)) exit(1);
+    fclose(infile);
+    conf.partVecInit();   // Updater::simulate does this before any energy (updater.cpp:45-60)
+}
+
+static int conidx(Conf& conf, Particle* p) { return p ? (int)(p - &conf.pvec[0]) : -1; }
+
+static int do_dump(const char* outname, bool only0) {
+    FileNames files(0);
+    Conf conf;
+    Sim* sim = nullptr;
+    load(conf, sim, files, 0, nullptr);
+    FILE* f = fopen(outname, "w");
+    int n = (int)conf.pvec.size();
+    fprintf(f, "N %d\n", n);
+    fprintf(f, "BOX %a %a %a\n", conf.geo.box.x, conf.geo.box.y, conf.geo.box.z);
+    fprintf(f, "CUT %a %a\n", topo.sqmaxcut, topo.maxcut);
+    // types in use
+    bool used[MAXT] = {false};
+    for (int i = 0; i < n; i++) used[conf.pvec[i].type] = true;
+    for (int a = 0; a < MAXT; a++) for (int b = 0; b < MAXT; b++) {
+        if (!used[a] || !used[b]) continue;
+        const Ia_param& p = topo.ia_params[a][b];
+        fprintf(f, "IA %d %d %d %d %d", a, b, p.geotype[0], p.geotype[1], (int)p.exclude);
+        fprintf(f, " %a %a %a %a %a %a %a %a %a %a %a %a", p.sigma, p.epsilon, p.A, p.B, p.pdis, p.pswitch,
+                p.pswitchINV, p.rcut, p.rcutSq, p.rcutwca, p.rcutwcaSq, p.parallel);
+        fprintf(f, " %a %a %a %a", p.len[0], p.len[1], p.half_len[0], p.half_len[1]);
+        for (int k = 0; k < 4; k++) fprintf(f, " %a", p.pangl[k]);
+        for (int k = 0; k < 4; k++) fprintf(f, " %a", p.panglsw[k]);
+        for (int k = 0; k < 4; k++) fprintf(f, " %a", p.pcangl[k]);
+        for (int k = 0; k < 4; k++) fprintf(f, " %a", p.pcanglsw[k]);
+        for (int k = 0; k < 4; k++) fprintf(f, " %a", p.pcoshalfi[k]);
+        for (int k = 0; k < 4; k++) fprintf(f, " %a", p.psinhalfi[k]);
+        fprintf(f, " %a %a %a %a %a %a %a %a", p.csecpatchrot[0], p.csecpatchrot[1], p.ssecpatchrot[0], p.ssecpatchrot[1],
+                p.chiral_cos[0], p.chiral_cos[1], p.chiral_sin[0], p.chiral_sin[1]);
+        fprintf(f, "\n");
+    }
+    for (int m = 0; m < conf.pvec.molTypeCount; m++) {
+        MoleculeParams& q = topo.moleculeParam[m];
+        fprintf(f, "MOL %d %d %d %a %a %a %a %a %a %a %a %a %a %a %a\n", m, q.molSize(), conf.pvec.first[m],
+                q.bond1eq, q.bond1c, q.bond2eq, q.bond2c, q.bonddeq, q.bonddc, q.bondheq, q.bondhc,
+                q.angle1eq, q.angle1c, q.angle2eq, q.angle2c);
+    }
+    for (int i = 0; i < n; i++) {
+        Particle& p = conf.pvec[i];
+        fprintf(f, "P %d %d %d", i, p.type, p.molType);
+        pv(f, p.pos); pv(f, p.dir); pv(f, p.patchdir[0]); pv(f, p.patchdir[1]);
+        for (int k = 0; k < 4; k++) pv(f, p.patchsides[k]);
+        pv(f, p.chdir[0]); pv(f, p.chdir[1]);
+        ConList c = conf.pvec.getConlist(i);
+        fprintf(f, " %d %d %d %d %d\n", (int)c.isEmpty, conidx(conf, c.conlist[0]), conidx(conf, c.conlist[1]),
+                conidx(conf, c.conlist[2]), conidx(conf, c.conlist[3]));
+    }
+    PairE pairE(&conf.geo);
+    // pairs, both argument orders, non-zero only
+    long npair = 0;
+    for (int i = 0; i < n; i++) {
+        ConList ci = conf.pvec.getConlist(i);
+        for (int j = 0; j < n; j++) {
+            if (i == j) continue;
+            if (only0 && i != 0 && j != 0) continue;   // pose grids: pairs with particle 0 only
+            double e = pairE(&conf.pvec[i], &conf.pvec[j], &ci);
+            if (e != 0.0) { fprintf(f, "E %d %d %a\n", i, j, e); npair++; }
+        }
+    }
+    fprintf(f, "NPAIR %ld\n", npair);
+    if (only0) {   // pose grids: overlap flags of particle 0 with every pose, both argument orders
+        for (int j = 1; j < n; j++) {
+            int a = conf.overlap(&conf.pvec[0], &conf.pvec[j], topo.ia_params);
+            int b = conf.overlap(&conf.pvec[j], &conf.pvec[0], topo.ia_params);
+            if (a || b) fprintf(f, "OV0 %d %d %d\n", j, a, b);
+        }
+        fclose(f);
+        return 0;
+    }
+    // oneToAll in TotalEFull order (ascending i != target)
+    for (int t = 0; t < n; t++) {
+        ConList ct = conf.pvec.getConlist(t);
+        double energy = 0.0;
+        for (int i = 0; i < n; i++) if (i != t) energy += pairE(&conf.pvec[t], &conf.pvec[i], &ct);
+        fprintf(f, "ONE %d %a\n", t, energy);
+    }
+    // total in TotalEMatrix::allToAll(matrix) order: i from 1, j<i, conlist(i)
+    {
+        double energy = 0.0;
+        for (int i = 1; i < n; i++) {
+            ConList ci = conf.pvec.getConlist(i);
+            for (int j = 0; j < i; j++) energy += pairE(&conf.pvec[i], &conf.pvec[j], &ci);
+        }
+        fprintf(f, "TOTAL %a\n", energy);
+    }
+    // mol2othersTrial-style sums (empty conlist, partners outside the molecule) for chain molecules
+    for (int c = 0; c < conf.pvec.getChainCount(); c++) {
+        Molecule mol = conf.pvec.getChain(c);
+        ConList empty;
+        double energy = 0.0;
+        for (unsigned j = 0; j < mol.size(); j++) {
+            for (int i = 0; i < mol[0]; i++) energy += pairE(&conf.pvec[mol[j]], &conf.pvec[i], &empty);
+            for (int i = mol.back() + 1; i < n; i++) energy += pairE(&conf.pvec[mol[j]], &conf.pvec[i], &empty);
+        }
+        fprintf(f, "MOL2O %d %d %d %a\n", c, mol[0], (int)mol.size(), energy);
+    }
+    // overlap flags as written (dead code in the reference, Conf.cpp:104-239); flagged pairs only
+    long nov = 0;
+    for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) {
+        if (conf.overlap(&conf.pvec[i], &conf.pvec[j], topo.ia_params)) { fprintf(f, "OV %d %d\n", i, j); nov++; }
+    }
+    fprintf(f, "NOV %ld\n", nov);
+    fclose(f);
+    return 0;
+}
+
+// Timing arm: the reference's own TotalEFull<PairE> (the compile-time alternative calculator,
+// totalenergycalculator.h:525-619; the default TotalEMatrix needs 2 x N^2/2 doubles and cannot
+// hold 65k particles). Times nrep oneToAll() calls on evenly spaced targets and optionally one
+// allToAll(); counts gated pair evaluations exactly as PairE::operator() gates them.
+static int do_time(int argc, char** argv) {
+    long ntargets = argc > 2 ? atol(argv[2]) : 64;
+    int do_full = argc > 3 ? atoi(argv[3]) : 0;
+    vector<long> counts;
+    for (int a = 4; a < argc; a++) counts.push_back(atol(argv[a]));
+    FileNames files(0);
+    Conf conf;
+    Sim* sim = nullptr;
+    load(conf, sim, files, (long)counts.size(), counts.data());
+    TotalEFull<PairE> calc(sim, &conf);
+    long n = (long)conf.pvec.size();
+    // gated-pair count for the sampled targets
+    double sq = topo.sqmaxcut;
+    long gated = 0, cand = 0;
+    long stride = n / ntargets; if (stride < 1) stride = 1;
+    vector<int> targets;
+    for (long t = 0; t < n && (long)targets.size() < ntargets; t += stride) targets.push_back((int)t);
+    for (int t : targets) {
+        ConList ct = conf.pvec.getConlist(t);
+        for (long i = 0; i < n; i++) if (i != t) {
+            Vector r = conf.geo.image(&conf.pvec[t].pos, &conf.pvec[i].pos);
+            cand++;
+            if (!(r.dot(r) > sq && ct.isEmpty)) gated++;
+        }
+    }
+    auto t0 = chrono::steady_clock::now();
+    double acc = 0.0;
+    for (int t : targets) acc += calc.oneToAll(t);
+    auto t1 = chrono::steady_clock::now();
+    double one_s = chrono::duration<double>(t1 - t0).count();
+    double full_s = -1.0, etot = 0.0;
+    if (do_full) {
+        auto t2 = chrono::steady_clock::now();
+        etot = calc.allToAll();
+        auto t3 = chrono::steady_clock::now();
+        full_s = chrono::duration<double>(t3 - t2).count();
+    }
+    printf("{\"n\": %ld, \"targets\": %ld, \"one_to_all_s\": %.6f, \"candidates\": %ld, \"gated_pairs\": %ld, "
+           "\"sum\": %.17g, \"all_to_all_s\": %.6f, \"e_total\": %.17g}\n",
+           n, (long)targets.size(), one_s, cand, gated, acc, full_s, etot);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc >= 2 && !strcmp(argv[1], "dump")) return do_dump(argc > 2 ? argv[2] : "ref_dump.txt", false);
+    if (argc >= 2 && !strcmp(argv[1], "dump0")) return do_dump(argc > 2 ? argv[2] : "ref_dump.txt", true);
+    if (argc >= 2 && !strcmp(argv[1], "time")) return do_time(argc, argv);
+    fprintf(stderr, "usage: sc_ref_driver dump [out] | time <ntargets> <full 0/1> [count_per_moltype ...]\n");
+    return 2;
+}

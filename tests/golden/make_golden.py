@@ -1,0 +1,225 @@
+#!/usr/bin/env python
+"""Regenerate the golden fixtures in this directory from the REFERENCE ITSELF.
+
+Runs only in the build container (needs /root/reference and oracle/_ref built by
+`make -C oracle ref`); the fixtures it writes are committed so that tests never read
+/root/reference at run time.
+
+For every Tests/test_*/new and Tests/volumeChange/*/new directory of the reference:
+  <name>_init.ref.gz   reference-driver dump of the shipped initial configuration
+  <name>.config.last   trajectory end state of the unmodified reference program (-DTESTING, Ran2)
+  <name>_end.ref.gz    reference-driver dump of that end state fed back in as config.init
+  <name>.inputs.json   options / top.init / config.init text (so tests can re-parse them)
+Pose grids modelled on Tests/Interactions_tests (test.sh, main.cpp:137-197):
+  grid_<A>_<B>.npz     top text + pose-set kind + E(0,j), E(j,0) for every pose j
+  grid_config_<kind>.txt.gz   the config.init text of each pose set (shared)
+"""
+import gzip
+import json
+import math
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "sc_ref_driver")
+SC = os.path.join(ROOT, "oracle", "_ref", "SC_testing")
+sys.path.insert(0, ROOT)
+
+BIG = {"test_mempore", "test_pscthrough", "test_wallfibril"}  # init dump only (size)
+
+
+def run(cmd, cwd):
+    subprocess.run(cmd, cwd=cwd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+def gz_copy(src, dst):
+    with open(src, "rb") as f, gzip.GzipFile(dst, "wb", mtime=0) as g:
+        shutil.copyfileobj(f, g)
+
+
+def do_case(name, src):
+    tmp = tempfile.mkdtemp(prefix="gold_")
+    for fn in os.listdir(src):
+        shutil.copy(os.path.join(src, fn), tmp)
+    inputs = {}
+    for fn in ("options", "top.init", "config.init"):
+        with open(os.path.join(tmp, fn)) as f:
+            inputs[fn] = f.read()
+    if os.path.exists(os.path.join(tmp, "wl.dat")):
+        with open(os.path.join(tmp, "wl.dat")) as f:
+            inputs["wl.dat"] = f.read()
+    big = name in BIG
+    if not big:
+        with open(os.path.join(HERE, name + ".inputs.json"), "w") as f:
+            json.dump(inputs, f)
+    else:
+        with gzip.GzipFile(os.path.join(HERE, name + ".inputs.json.gz"), "wb", mtime=0) as g:
+            g.write(json.dumps(inputs).encode())
+    run([DRIVER, "dump", "ref_dump.txt"], tmp)
+    gz_copy(os.path.join(tmp, "ref_dump.txt"), os.path.join(HERE, name + "_init.ref.gz"))
+    if not big:
+        run([SC], tmp)
+        shutil.copy(os.path.join(tmp, "config.last"), os.path.join(HERE, name + ".config.last"))
+        shutil.copy(os.path.join(tmp, "config.last"), os.path.join(tmp, "config.init"))
+        run([DRIVER, "dump", "ref_dump_end.txt"], tmp)
+        gz_copy(os.path.join(tmp, "ref_dump_end.txt"), os.path.join(HERE, name + "_end.ref.gz"))
+    shutil.rmtree(tmp)
+    print("golden:", name)
+
+
+# ---- pose grids (our own generator, same construction as Tests/Interactions_tests/main.cpp:137-197)
+def fibonacci_sphere(samples):
+    offset = 2.0 / samples
+    inc = math.pi * (3.0 - math.sqrt(5.0))
+    out = []
+    for i in range(samples):
+        z = ((i * offset) - 1) + (offset / 2)
+        r = math.sqrt(1 - z * z)
+        phi = i * inc
+        out.append((math.cos(phi) * r, math.sin(phi) * r, z))
+    return out
+
+
+def rotate(v, axis, angle):
+    c, s = math.cos(angle), math.sin(angle)
+    qw, qx, qy, qz = c, axis[0] * s, axis[1] * s, axis[2] * s
+    t2, t3, t4 = qw * qx, qw * qy, qw * qz
+    t5, t6, t7 = -qx * qx, qx * qy, qx * qz
+    t8, t9, t10 = -qy * qy, qy * qz, -qz * qz
+    x, y, z = v
+    return (2.0 * ((t8 + t10) * x + (t6 - t4) * y + (t3 + t7) * z) + x,
+            2.0 * ((t4 + t6) * x + (t5 + t10) * y + (t9 - t2) * z) + y,
+            2.0 * ((t7 - t3) * x + (t2 + t9) * y + (t5 + t8) * z) + z)
+
+
+def grid_config(kind, samples=10, angle_inc=1.0):
+    """config.init text: particle 0 = A at the box centre (dir x, patch y), then B poses."""
+    lines = ["10 10 10", "5 5 5   1 0 0  0 1 0     0 0"]
+    if kind == "sc":
+        coords = [1, 4, 7]
+        beads = fibonacci_sphere(samples)
+        for x in coords:
+            for y in coords:
+                for z in coords:
+                    for d in beads:
+                        j = 0.0
+                        while j < 6.28318530718:
+                            par = (d[0], d[1], -(d[0] + d[1]) / d[2])
+                            par = rotate(par, d, j)
+                            lines.append("%d %d %d %g %g %g %g %g %g 0 0" % (x, y, z, d[0], d[1], d[2], par[0], par[1], par[2]))
+                            j += angle_inc
+    elif kind == "sphere":
+        v = 1.0
+        while v <= 9.0 + 1e-9:
+            lines.append("%.4f 5 5  1 0 0  0 1 0  0 0" % v)
+            lines.append("5 %.4f 5  1 0 0  0 1 0  0 0" % v)
+            v += 0.0333
+    else:  # sphere partner around a rod
+        v = 1.0
+        while v <= 9.0 + 1e-9:
+            w = 1.0
+            while w <= 9.0 + 1e-9:
+                z = 1.0
+                while z <= 5.0 + 1e-9:
+                    lines.append("%.2f %.2f %.2f  1 0 0  0 1 0  0 0" % (v, w, z))
+                    z += 0.77
+                w += 0.77
+            v += 0.77
+    return "\n".join(lines) + "\n"
+
+
+SPHERE = {"SPN": "SPN 1.33 0.95", "SPA": "SPA 1.33 1.2 1.346954458 1.6"}
+SC_T = {
+    "PSC": "PSC 1.33 1.2 1.346954458 0.3 30.0 0.0 3 0.0",
+    "CPSC": "CPSC 1.33 1.2 1.346954458 0.3 30.0 0.0 3 0.0",
+    "CHPSC": "CHPSC 1.333333 1.2 1.346954458 0.3 90 5.0 3 0.0 5.0",
+    "CHCPSC": "CHCPSC 1.333333 1.2 1.346954458 0.3 90 5.0 3 0.0 5.0",
+    "TPSC": "TPSC 1.333333 1.2 1.346954458 0.3 90 5.0 3 0.0 180.0 90 5.0",
+    "TCPSC": "TCPSC 1.333333 1.2 1.346954458 0.3 90 5.0 3 0.0 180.0 90 5.0",
+    "TCHPSC": "TCHPSC 1.333333 1.2 1.346954458 0.3 90 5.0 3 0.0 180.0 90 5.0 5.0",
+    "TCHCPSC": "TCHCPSC 1.333333 1.2 1.346954458 0.3 90 5.0 3 0.0 180.0 90 5.0 5.0",
+    # extra coverage beyond the reference's grid: parallel-eps term and the rarely used SCN / SCA rods
+    "PSCpar": "PSC 1.333333 1.2 1.346954458 0.3 90 5.0 3 0.7",
+    "SCN": "SCN 1.33 1.2 3",
+    "SCA": "SCA 1.33 1.2 1.346954458 0.3 3",
+}
+
+
+def top_text(defA, defB, nB):
+    return ("[Types]\nA 1 %s\nB 2 %s\n[Molecules]\nA: {\nparticles: 1\n}\nB: {\nparticles: 2\n}\n[System]\nA 1\nB %d\n"
+            % (defA, defB, nB))
+
+
+def do_grid(nameA, defA, nameB, defB, kind, options_text):
+    cfg = grid_config(kind)
+    nB = len(cfg.strip().split("\n")) - 2
+    top = top_text(defA, defB, nB)
+    tmp = tempfile.mkdtemp(prefix="grid_")
+    for fn, txt in (("top.init", top), ("config.init", cfg), ("options", options_text)):
+        with open(os.path.join(tmp, fn), "w") as f:
+            f.write(txt)
+    run([DRIVER, "dump0", "ref_dump.txt"], tmp)
+    e0j = np.zeros(nB + 1)
+    ej0 = np.zeros(nB + 1)
+    ov0j = np.zeros(nB + 1, dtype=np.int8)
+    ovj0 = np.zeros(nB + 1, dtype=np.int8)
+    with open(os.path.join(tmp, "ref_dump.txt")) as f:
+        for line in f:
+            t = line.split()
+            if t and t[0] == "OV0":
+                ov0j[int(t[1])] = int(t[2])
+                ovj0[int(t[1])] = int(t[3])
+            if t and t[0] == "E":
+                i, j, e = int(t[1]), int(t[2]), float.fromhex(t[3])
+                if i == 0:
+                    e0j[j] = e
+                else:
+                    ej0[i] = e
+    cfg_file = os.path.join(HERE, "grid_config_%s.txt.gz" % kind)   # shared by every grid of this kind
+    if not os.path.exists(cfg_file):
+        with gzip.GzipFile(cfg_file, "wb", mtime=0) as g:
+            g.write(cfg.encode())
+    np.savez_compressed(os.path.join(HERE, "grid_%s_%s.npz" % (nameA, nameB)), top=top, kind=kind, e0j=e0j, ej0=ej0, ov0j=ov0j, ovj0=ovj0)
+    shutil.rmtree(tmp)
+    print("grid:", nameA, nameB, nB, "poses; nonzero", int(np.count_nonzero(e0j)), "overlaps", int(ov0j.sum()))
+
+
+def main():
+    if not (os.path.exists(DRIVER) and os.path.exists(SC)):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    tests = sorted(d for d in os.listdir(os.path.join(REF, "Tests")) if d.startswith("test_"))
+    if "grids" in sys.argv[1:]:
+        tests = []
+    for d in tests:
+        do_case(d, os.path.join(REF, "Tests", d, "new"))
+    for d in sorted(os.listdir(os.path.join(REF, "Tests", "volumeChange"))):
+        if "grids" in sys.argv[1:]:
+            break
+        p = os.path.join(REF, "Tests", "volumeChange", d, "new")
+        if os.path.isdir(p):
+            do_case("volumeChange_" + d, p)
+    with open(os.path.join(REF, "Tests", "Interactions_tests", "options")) as f:
+        opts = f.read()
+    names = list(SC_T)
+    for a in range(len(names)):
+        for b in range(a, len(names)):
+            do_grid(names[a], SC_T[names[a]], names[b], SC_T[names[b]], "sc", opts)
+    sn = list(SPHERE)
+    for a in range(len(sn)):
+        for b in range(a, len(sn)):
+            do_grid(sn[a], SPHERE[sn[a]], sn[b], SPHERE[sn[b]], "sphere", opts)
+    for a in names:
+        for b in sn:
+            do_grid(a, SC_T[a], b, SPHERE[b], "scsp", opts)
+            do_grid(b, SPHERE[b], a, SC_T[a], "sc", opts)   # sphere first, rod second (role swap branch)
+
+
+if __name__ == "__main__":
+    main()
