@@ -1,0 +1,152 @@
+/* scgpu -- C ABI of the B200-native energy engine for patchy-spherocylinder Monte Carlo.
+ *
+ * This is the drop-in boundary for the ONE data-parallel hot path of robertvacha/SC (scOOP): pair energy
+ * and overlap evaluation over cell lists, the full-system energy sum, batched checkerboard trial moves.
+ * The reference has no plugin/FFI layer; its seam is the compile-time calculator class
+ *     typedef TotalEMatrix<PairE> TotalEnergyCalculator;      (scOOP/mc/totalenergycalculator.h:1227)
+ * whose virtual interface is TotalE<> (scOOP/mc/totalenergycalculator.h:135-297). A reference-side
+ * TotalEGpu : TotalE<PairE> (shown in INTEGRATION.md; our own host mirror is sc_b200/csrc/host/) forwards each virtual
+ * to one entry point below. Each entry point cites the reference member it replaces.
+ *
+ * Conventions: every function returns 0 on success, <0 on error (message: scgpu_last_error()). One context
+ * = one CUDA device = one stream; a context is not thread-safe. The caller owns all host buffers, the
+ * library owns all device memory. All reals are IEEE double; positions are in BOX-FRACTION units exactly
+ * as in the reference's Particle::pos; everything else is in real units. There is no CPU fallback: every
+ * call fails with SCGPU_ERR_CUDA if no CUDA device is usable.
+ */
+#ifndef SCGPU_H
+#define SCGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCGPU_OK 0
+#define SCGPU_ERR_ARG (-1)
+#define SCGPU_ERR_CUDA (-2)
+#define SCGPU_ERR_STATE (-3)
+
+#define SCGPU_STATE_DOUBLES 30
+#define SCGPU_IAPARAM_DOUBLES 48
+#define SCGPU_MOLPARAM_DOUBLES 16
+
+/* geotype codes (scOOP/structures/macros.h:69-85) */
+enum {
+    SCGPU_SCN = 10, SCGPU_SCA = 11, SCGPU_PSC = 12, SCGPU_CPSC = 13, SCGPU_CHPSC = 14, SCGPU_CHCPSC = 15,
+    SCGPU_TPSC = 16, SCGPU_TCPSC = 17, SCGPU_TCHPSC = 18, SCGPU_TCHCPSC = 19, SCGPU_SPN = 30, SCGPU_SPA = 31
+};
+
+/* Packed copy of the pair-path fields of Ia_param (scOOP/structures/structures.h:187-254); one entry per
+ * ordered type pair, 48 doubles. geotype[] and exclude hold small integers. */
+typedef struct scgpu_iaparam {
+    double geotype[2];
+    double exclude;
+    double sigma, epsilon, A, B;
+    double pdis, pswitch, pswitchINV;
+    double rcut, rcutSq, rcutwca, rcutwcaSq;
+    double parallel;
+    double half_len[2];
+    double pcangl[4], pcanglsw[4];
+    double pcoshalfi[4], psinhalfi[4];
+    double csecpatchrot[2], ssecpatchrot[2];
+    double chiral_cos[2], chiral_sin[2];
+    double len[2];
+    double reserved[5];
+} scgpu_iaparam;
+
+/* Per molecule type: bond/angle constants of MoleculeParams (scOOP/structures/moleculeparams.h:10-45) plus
+ * the molecule size and ParticleVector::first[] (scOOP/structures/Conf.h:38-42) that getConlist needs. */
+typedef struct scgpu_molparam {
+    double bond1eq, bond1c, bond2eq, bond2c, bonddeq, bonddc, bondheq, bondhc;
+    double angle1eq, angle1c, angle2eq, angle2c;
+    double mol_size, first;
+    double reserved[2];
+} scgpu_molparam;
+
+/* A particle is 30 doubles, the vector members of Particle in declaration order
+ * (scOOP/structures/particle.h:26-30): pos[3] dir[3] patchdir[2][3] patchsides[4][3] chdir[2][3]. */
+
+typedef struct scgpu_ctx scgpu_ctx;
+
+/* Batched trial moves (replaces the per-step body of Updater::simulate, scOOP/mc/updater.cpp:206-230, for
+ * displacement/rotation: MoveCreator::partDisplace/partRotate, scOOP/mc/movecreator.cpp:947-1028). */
+typedef struct scgpu_moveparams {
+    double temper;                 /* Sim::temper */
+    double trans_mx[40];           /* per particle type: stat.trans[type].mx  (= 2*transmx, sim.h:365) */
+    double rot_angle[40];          /* per particle type: stat.rot[type].angle (radians, sim.h:360) */
+    int n_sub;                     /* trials per active cell per colour = ceil(n_sub * cell population) ; 1 = one sweep */
+    int reserved;
+} scgpu_moveparams;
+
+typedef struct scgpu_sweepstats {
+    int64_t trans_acc, trans_rej, rot_acc, rot_rej, cell_rej; /* cell_rej: moves rejected for leaving the cell */
+    double energy_delta;                                       /* sum of accepted dE */
+} scgpu_sweepstats;
+
+const char* scgpu_last_error(void);
+int scgpu_device_count(void);
+
+/* ctor of TotalE<> (totalenergycalculator.h:145-146) */
+int scgpu_create(scgpu_ctx** out, int device);
+int scgpu_destroy(scgpu_ctx* ctx);
+
+/* global `topo` (ia_params, moleculeParam, sqmaxcut, maxcut: scOOP/structures/topo.h:21-27); table is ntypes*ntypes,
+ * row-major by (type of first particle, type of second particle) */
+int scgpu_set_topology(scgpu_ctx* ctx, int ntypes, const scgpu_iaparam* table, double sqmaxcut, double maxcut,
+                       int nmoltypes, const scgpu_molparam* mol);
+/* conf->pvec (scOOP/structures/Conf.h:305); also what initEM() / update(EMResize) need after a particle-count change */
+int scgpu_set_particles(scgpu_ctx* ctx, int n, const double* state30, const int* type, const int* moltype);
+/* conf->geo.box, read through PairE::pbc in the reference (scOOP/mc/paire.h:1205,1211) */
+int scgpu_set_box(scgpu_ctx* ctx, const double box[3]);
+/* update(int target) after an accepted single-particle move (totalenergycalculator.h:326-328) */
+int scgpu_update_particle(scgpu_ctx* ctx, int idx, const double* state30);
+int scgpu_download_particles(scgpu_ctx* ctx, double* state30);
+
+/* Replaces Updater::genSimplePairList (scOOP/mc/updater.cpp:484-552): counting sort by cell. Called implicitly by
+ * the energy entry points when the list is stale. */
+int scgpu_build_cells(scgpu_ctx* ctx);
+int scgpu_cell_assignment(scgpu_ctx* ctx, int* cell_of_particle, int ncell3[3]);
+/* sorted slot -> original index, and cell_start[ncells+1] (bit-exact checks of the stable sort) */
+int scgpu_cell_order(scgpu_ctx* ctx, int* order, int* cell_start);
+
+/* oneToAllTrial(target) / oneToAll(target) (totalenergycalculator.h:355-415, 563-583). trial_state30 == NULL:
+ * current state. e_pairs (optional, n doubles, indexed by original j) = the reference's `changes[]`. */
+int scgpu_one_to_all(scgpu_ctx* ctx, int target, const double* trial_state30, double* e_sum, double* e_pairs);
+/* m independent oneToAllTrial evaluations in one launch (one warp per trial); trial_states may be NULL */
+int scgpu_one_to_all_batch(scgpu_ctx* ctx, int m, const int* targets, const double* trial_states30, double* e_sums);
+/* same over every particle's current state, results stay on the device (bench: inputs resident in HBM);
+ * e_host may be NULL. n_gated / n_candidates (optional) return the pair counters of that launch. */
+int scgpu_one_to_all_everyone(scgpu_ctx* ctx, double* e_host, int64_t* n_candidates, int64_t* n_gated);
+/* mol2othersTrial(mol) for a molecule of m consecutive particles starting at `first` (totalenergycalculator.h:455-499) */
+int scgpu_mol_to_others(scgpu_ctx* ctx, int first, int m, double* e_sum);
+/* allToAllTrial() / allToAll() / initEM() (totalenergycalculator.h:314-353, 502-521): every pair once, conlist of the
+ * higher index. e_per_particle (optional, n) = row sums  sum_{j<i} E(i,j). */
+int scgpu_all_to_all(scgpu_ctx* ctx, double* e_total, double* e_per_particle);
+
+/* Conf::overlapAll / Conf::checkall (scOOP/structures/Conf.cpp:244-267). variant 0 = as written in the reference,
+ * 1 = documented intent. */
+int scgpu_overlap_one(scgpu_ctx* ctx, int target, const double* trial_state30, int variant, int* flag);
+int scgpu_overlap_all(scgpu_ctx* ctx, int variant, int* flag);
+
+/* one checkerboard sweep of displacement/rotation trials, validated statistically against sequential sweeps */
+int scgpu_sweep_checkerboard(scgpu_ctx* ctx, const scgpu_moveparams* mp, uint64_t seed, uint64_t sweep,
+                             scgpu_sweepstats* stats);
+
+/* replica exchange helper (MoveCreator::replicaExchangeMove, scOOP/mc/movecreator.cpp:552-795): full energy stays on
+ * the device; returns the device address of a packed double[8] record {E, V, N, 0...} for an NCCL all-gather */
+int scgpu_replica_record(scgpu_ctx* ctx, void** device_ptr_out);
+
+/* measurement helpers (CUDA events on the context's stream; FP64 FMA-chain peak microbenchmark) */
+int scgpu_timer_start(scgpu_ctx* ctx);
+int scgpu_timer_stop(scgpu_ctx* ctx, float* ms);
+int scgpu_sync(scgpu_ctx* ctx);
+int scgpu_fp64_peak(scgpu_ctx* ctx, double* tflops);
+int scgpu_flush_l2(scgpu_ctx* ctx);
+int scgpu_kernel_launches(scgpu_ctx* ctx, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,251 @@
+"""ctypes binding of the C ABI (include/scgpu.h). Mirrors the calculator interface of the reference
+(TotalE<>, scOOP/mc/totalenergycalculator.h:135-297): one_to_all / one_to_all_trial / all_to_all /
+mol_to_others / update. Fails loudly when the CUDA library or a GPU is missing -- there is no fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import lib_path
+
+STATE = 30
+IA = 48
+MOL = 16
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_i64p = C.POINTER(C.c_int64)
+
+
+class ScgpuError(RuntimeError):
+    pass
+
+
+class MoveParams(C.Structure):
+    _fields_ = [("temper", C.c_double), ("trans_mx", C.c_double * 40), ("rot_angle", C.c_double * 40),
+                ("n_sub", C.c_int), ("reserved", C.c_int)]
+
+
+class SweepStats(C.Structure):
+    _fields_ = [("trans_acc", C.c_int64), ("trans_rej", C.c_int64), ("rot_acc", C.c_int64), ("rot_rej", C.c_int64),
+                ("cell_rej", C.c_int64), ("energy_delta", C.c_double)]
+
+
+SYMBOLS = ["scgpu_last_error", "scgpu_device_count", "scgpu_create", "scgpu_destroy", "scgpu_set_topology",
+           "scgpu_set_particles", "scgpu_set_box", "scgpu_update_particle", "scgpu_download_particles",
+           "scgpu_build_cells", "scgpu_cell_assignment", "scgpu_cell_order", "scgpu_one_to_all",
+           "scgpu_one_to_all_batch", "scgpu_one_to_all_everyone", "scgpu_mol_to_others", "scgpu_all_to_all",
+           "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_replica_record",
+           "scgpu_timer_start", "scgpu_timer_stop", "scgpu_sync", "scgpu_fp64_peak", "scgpu_flush_l2",
+           "scgpu_kernel_launches"]
+
+_libs = {}
+
+
+def load_library(variant="fast"):
+    """dlopen the in-tree CUDA library; raises if it has not been built (never falls back to anything)."""
+    if variant in _libs:
+        return _libs[variant]
+    path = lib_path(variant)
+    if not os.path.exists(path):
+        raise ScgpuError("CUDA library %s is missing: run `python -m sc_b200.build` (no CPU fallback exists)" % path)
+    L = C.CDLL(path)
+    L.scgpu_last_error.restype = C.c_char_p
+    vp = C.c_void_p
+    L.scgpu_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.scgpu_destroy.argtypes = [vp]
+    L.scgpu_set_topology.argtypes = [vp, C.c_int, _dp, C.c_double, C.c_double, C.c_int, _dp]
+    L.scgpu_set_particles.argtypes = [vp, C.c_int, _dp, _ip, _ip]
+    L.scgpu_set_box.argtypes = [vp, _dp]
+    L.scgpu_update_particle.argtypes = [vp, C.c_int, _dp]
+    L.scgpu_download_particles.argtypes = [vp, _dp]
+    L.scgpu_build_cells.argtypes = [vp]
+    L.scgpu_cell_assignment.argtypes = [vp, _ip, _ip]
+    L.scgpu_cell_order.argtypes = [vp, _ip, _ip]
+    L.scgpu_one_to_all.argtypes = [vp, C.c_int, _dp, _dp, _dp]
+    L.scgpu_one_to_all_batch.argtypes = [vp, C.c_int, _ip, _dp, _dp]
+    L.scgpu_one_to_all_everyone.argtypes = [vp, _dp, _i64p, _i64p]
+    L.scgpu_mol_to_others.argtypes = [vp, C.c_int, C.c_int, _dp]
+    L.scgpu_all_to_all.argtypes = [vp, _dp, _dp]
+    L.scgpu_overlap_one.argtypes = [vp, C.c_int, _dp, C.c_int, _ip]
+    L.scgpu_overlap_all.argtypes = [vp, C.c_int, _ip]
+    L.scgpu_sweep_checkerboard.argtypes = [vp, C.POINTER(MoveParams), C.c_uint64, C.c_uint64, C.POINTER(SweepStats)]
+    L.scgpu_replica_record.argtypes = [vp, C.POINTER(vp)]
+    L.scgpu_timer_start.argtypes = [vp]
+    L.scgpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.scgpu_sync.argtypes = [vp]
+    L.scgpu_fp64_peak.argtypes = [vp, _dp]
+    L.scgpu_flush_l2.argtypes = [vp]
+    L.scgpu_kernel_launches.argtypes = [vp, _i64p]
+    _libs[variant] = L
+    return L
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class Engine:
+    """One context = one GPU = one stream. Arrays follow the C ABI: state[n,30], ia[T,T,48], mol[M,16]."""
+
+    def __init__(self, device=0, variant="fast"):
+        self.L = load_library(variant)
+        self.variant = variant
+        self.h = C.c_void_p()
+        self._ck(self.L.scgpu_create(C.byref(self.h), int(device)))
+        self.n = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise ScgpuError("scgpu error %d: %s" % (rc, self.L.scgpu_last_error().decode()))
+
+    def close(self):
+        if self.h:
+            self.L.scgpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setup
+    def set_topology(self, ia, mol, sqmaxcut, maxcut):
+        ia = np.ascontiguousarray(ia, dtype=np.float64)
+        mol = np.ascontiguousarray(mol, dtype=np.float64).reshape(-1, MOL)
+        T = ia.shape[0]
+        assert ia.shape == (T, T, IA)
+        self._ck(self.L.scgpu_set_topology(self.h, T, _d(ia), float(sqmaxcut), float(maxcut), mol.shape[0], _d(mol)))
+
+    def set_particles(self, state, types, moltypes):
+        state = np.ascontiguousarray(state, dtype=np.float64).reshape(-1, STATE)
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        moltypes = np.ascontiguousarray(moltypes, dtype=np.int32)
+        self.n = state.shape[0]
+        self._ck(self.L.scgpu_set_particles(self.h, self.n, _d(state), _i(types), _i(moltypes)))
+
+    def set_box(self, box):
+        box = np.ascontiguousarray(box, dtype=np.float64)
+        self._ck(self.L.scgpu_set_box(self.h, _d(box)))
+
+    def load(self, sysobj):
+        """sysobj: anything with .ia .mol .sqmaxcut .maxcut .state .type .moltype .box"""
+        self.set_topology(sysobj.ia, sysobj.mol, sysobj.sqmaxcut, sysobj.maxcut)
+        self.set_box(sysobj.box)
+        self.set_particles(sysobj.state, sysobj.type, sysobj.moltype)
+        return self
+
+    def update_particle(self, idx, state):
+        st = np.ascontiguousarray(state, dtype=np.float64)
+        self._ck(self.L.scgpu_update_particle(self.h, int(idx), _d(st)))
+
+    def download_particles(self):
+        out = np.zeros((self.n, STATE))
+        self._ck(self.L.scgpu_download_particles(self.h, _d(out)))
+        return out
+
+    # ---- cells
+    def build_cells(self):
+        self._ck(self.L.scgpu_build_cells(self.h))
+
+    def cell_assignment(self):
+        cell = np.zeros(self.n, dtype=np.int32)
+        nc = np.zeros(3, dtype=np.int32)
+        self._ck(self.L.scgpu_cell_assignment(self.h, _i(cell), _i(nc)))
+        return cell, nc
+
+    def cell_order(self, ncells):
+        order = np.zeros(self.n, dtype=np.int32)
+        start = np.zeros(ncells + 1, dtype=np.int32)
+        self._ck(self.L.scgpu_cell_order(self.h, _i(order), _i(start)))
+        return order, start
+
+    # ---- energies (names of the reference's calculator)
+    def one_to_all(self, target, trial_state=None, pairs=False):
+        e = C.c_double(0.0)
+        ep = np.zeros(self.n) if pairs else None
+        ts = None if trial_state is None else np.ascontiguousarray(trial_state, dtype=np.float64)
+        self._ck(self.L.scgpu_one_to_all(self.h, int(target), None if ts is None else _d(ts), C.byref(e),
+                                         None if ep is None else _d(ep)))
+        return (e.value, ep) if pairs else e.value
+
+    one_to_all_trial = one_to_all
+
+    def one_to_all_batch(self, targets, trial_states=None):
+        targets = np.ascontiguousarray(targets, dtype=np.int32)
+        out = np.zeros(len(targets))
+        ts = None if trial_states is None else np.ascontiguousarray(trial_states, dtype=np.float64)
+        self._ck(self.L.scgpu_one_to_all_batch(self.h, len(targets), _i(targets), None if ts is None else _d(ts), _d(out)))
+        return out
+
+    def one_to_all_everyone(self, fetch=True, count=False):
+        out = np.zeros(self.n) if fetch else None
+        nc, ng = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.scgpu_one_to_all_everyone(self.h, None if out is None else _d(out),
+                                                  C.byref(nc) if count else None, C.byref(ng) if count else None))
+        if count:
+            return out, nc.value, ng.value
+        return out
+
+    def mol_to_others(self, first, m):
+        e = C.c_double(0.0)
+        self._ck(self.L.scgpu_mol_to_others(self.h, int(first), int(m), C.byref(e)))
+        return e.value
+
+    def all_to_all(self, rows=False, fetch=True):
+        e = C.c_double(0.0)
+        er = np.zeros(self.n) if rows else None
+        self._ck(self.L.scgpu_all_to_all(self.h, C.byref(e) if fetch else None, None if er is None else _d(er)))
+        return (e.value, er) if rows else e.value
+
+    def overlap_one(self, target, trial_state=None, variant=0):
+        f = C.c_int(0)
+        ts = None if trial_state is None else np.ascontiguousarray(trial_state, dtype=np.float64)
+        self._ck(self.L.scgpu_overlap_one(self.h, int(target), None if ts is None else _d(ts), int(variant), C.byref(f)))
+        return f.value
+
+    def overlap_all(self, variant=0):
+        f = C.c_int(0)
+        self._ck(self.L.scgpu_overlap_all(self.h, int(variant), C.byref(f)))
+        return f.value
+
+    def sweep(self, mp, seed, sweep):
+        st = SweepStats()
+        self._ck(self.L.scgpu_sweep_checkerboard(self.h, C.byref(mp), int(seed), int(sweep), C.byref(st)))
+        return st
+
+    def replica_record_ptr(self):
+        p = C.c_void_p()
+        self._ck(self.L.scgpu_replica_record(self.h, C.byref(p)))
+        return p.value
+
+    # ---- measurement
+    def timer_start(self):
+        self._ck(self.L.scgpu_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0.0)
+        self._ck(self.L.scgpu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._ck(self.L.scgpu_sync(self.h))
+
+    def fp64_peak(self):
+        t = C.c_double(0.0)
+        self._ck(self.L.scgpu_fp64_peak(self.h, C.byref(t)))
+        return t.value
+
+    def flush_l2(self):
+        self._ck(self.L.scgpu_flush_l2(self.h))
+
+    def launches(self):
+        v = C.c_int64(0)
+        self._ck(self.L.scgpu_kernel_launches(self.h, C.byref(v)))
+        return v.value

@@ -1,0 +1,199 @@
+"""Deterministic synthetic inputs in the reference's own text formats (top.init / config.init).
+
+`psc_bulk` is configuration "L" of SURVEY.md section 8(d) / BASELINE.json configs[1]: N = nx*ny*nz PSC rods of
+Tests/test_01_normal_PSC's type on a 1.4 x 1.4 x 4.4 lattice (rho = 0.116), directions z + N(0, 0.02) tilt,
+patch azimuth uniform, Python random.seed(12345). The other generators are small multi-cell systems for the
+parity tests (random gas, type mix, bonded chains). Numbers are written with the precision the reference
+writes config.last with (%15.8e), so the reference, the oracle and the product all read identical doubles.
+"""
+import math
+import random
+
+PSC_TYPE = "PSC    1.333333  1.2  1.346954458        0.3          90           5.0          3       0.0"
+
+TOP_PSC = """[Types]
+A       1         %s
+[Molecules]
+A: {
+particles:   1
+}
+[System]
+A %%d
+""" % PSC_TYPE
+
+
+def _fmt(v):
+    return " ".join("%15.8e" % x for x in v)
+
+
+def _rand_unit(rnd):
+    while True:
+        x, y, z = rnd.gauss(0, 1), rnd.gauss(0, 1), rnd.gauss(0, 1)
+        n = math.sqrt(x * x + y * y + z * z)
+        if n > 1e-6:
+            return (x / n, y / n, z / n)
+
+
+def _perp(rnd, d):
+    while True:
+        p = _rand_unit(rnd)
+        dp = p[0] * d[0] + p[1] * d[1] + p[2] * d[2]
+        q = (p[0] - dp * d[0], p[1] - dp * d[1], p[2] - dp * d[2])
+        n = math.sqrt(q[0] ** 2 + q[1] ** 2 + q[2] ** 2)
+        if n > 1e-3:
+            return (q[0] / n, q[1] / n, q[2] / n)
+
+
+def psc_bulk(nx=64, ny=64, nz=16, seed=12345, tilt=0.02):
+    """-> (top_text, config_text, n). 64 x 64 x 16 = 65 536 rods in a 89.6 x 89.6 x 70.4 box."""
+    rnd = random.Random(seed)
+    sx, sy, sz = 1.4, 1.4, 4.4
+    box = (nx * sx, ny * sy, nz * sz)
+    lines = [_fmt(box)]
+    for iz in range(nz):
+        for iy in range(ny):
+            for ix in range(nx):
+                pos = ((ix + 0.5) * sx, (iy + 0.5) * sy, (iz + 0.5) * sz)
+                d = (rnd.gauss(0, tilt), rnd.gauss(0, tilt), 1.0)
+                n = math.sqrt(d[0] ** 2 + d[1] ** 2 + d[2] ** 2)
+                d = (d[0] / n, d[1] / n, d[2] / n)
+                az = rnd.uniform(0.0, 2.0 * math.pi)
+                # a vector perpendicular to d at azimuth az
+                ex = (1.0 - d[0] * d[0], -d[0] * d[1], -d[0] * d[2])
+                en = math.sqrt(ex[0] ** 2 + ex[1] ** 2 + ex[2] ** 2)
+                ex = (ex[0] / en, ex[1] / en, ex[2] / en)
+                ey = (d[1] * ex[2] - d[2] * ex[1], d[2] * ex[0] - d[0] * ex[2], d[0] * ex[1] - d[1] * ex[0])
+                p = tuple(math.cos(az) * ex[k] + math.sin(az) * ey[k] for k in range(3))
+                lines.append(_fmt(pos) + "   " + _fmt(d) + "   " + _fmt(p) + " 0")
+    n = nx * ny * nz
+    return TOP_PSC % n, "\n".join(lines) + "\n", n
+
+
+def _gas(rnd, n, box, lines):
+    for _ in range(n):
+        pos = (rnd.uniform(0, box[0]), rnd.uniform(0, box[1]), rnd.uniform(0, box[2]))
+        d = _rand_unit(rnd)
+        p = _perp(rnd, d)
+        lines.append(_fmt(pos) + "   " + _fmt(d) + "   " + _fmt(p) + " 0")
+
+
+def small_case(kind, seed=2024):
+    """small systems whose box holds a real 3-D cell grid (> 27 cells) -> (top_text, config_text)"""
+    rnd = random.Random(seed)
+    if kind == "psc_lattice":
+        top, cfg, _ = psc_bulk(16, 16, 5, seed=seed, tilt=0.15)
+        return top, cfg
+    box = (26.0, 25.5, 33.0) if kind == "chains" else (22.0, 21.0, 23.5)
+    lines = [_fmt(box)]
+    if kind == "psc_gas":
+        _gas(rnd, 700, box, lines)
+        return TOP_PSC % 700, "\n".join(lines) + "\n"
+    if kind == "mix":
+        top = """[Types]
+S1 1 SPA    1.333333  1.2  1.346954458  0.3
+P2 2 PSC    1.333333  1.2  1.346954458  0.3  90  5.0  3  0.5
+C3 3 CPSC   1.1       1.1  1.30         0.35 120 5.0  3  0.5
+T4 4 TCHPSC 1.2       1.2  1.346954458  0.3  90  5.0  3  0.0  180.0 60 5.0 10.0
+N5 5 SPN    1.0  0.95
+D6 6 TCPSC  1.0       1.0  1.2          0.4  80  8.0  3  -0.4 150.0 90 5.0
+[Molecules]
+A: {
+particles: 1
+}
+B: {
+particles: 2
+}
+C: {
+particles: 3
+}
+D: {
+particles: 4
+}
+E: {
+particles: 5
+}
+F: {
+particles: 6
+}
+[System]
+A 120
+B 150
+C 150
+D 120
+E 80
+F 100
+[EXCLUDE]
+1 3
+"""
+        _gas(rnd, 720, box, lines)
+        return top, "\n".join(lines) + "\n"
+    if kind == "chains":
+        top = """[Types]
+R1 1 TCPSC  1.333333 1.2 1.346954458 0.3 90 5.0 3 0.0 180.0 90 5.0
+H2 2 SPN    1.0 0.95
+T3 3 SPA    1.0 1.0 1.12246205 1.6
+Q4 4 PSC    1.0 1.2 1.346954458 0.3 120 5.0 3 0.3
+[Molecules]
+A: {
+particles: 1
+particles: 1
+particles: 1
+particles: 1
+particles: 1
+bond1: 1.0 1.0
+bond2: 1.0 2.0
+angle1: 2.0 20.0
+angle2: 1.5 30.0
+}
+B: {
+bond1: 90.0 0.4
+bond2: 10.0 4.0
+particles: 2
+particles: 3
+particles: 3
+}
+C: {
+particles: 4
+particles: 3
+particles: 4
+bondh: 5.0 0.5
+angle1: 3.0 10.0
+}
+D: {
+particles: 4
+particles: 4
+bondd: 4.0 0.7
+}
+E: {
+particles: 4
+}
+[System]
+A 40
+B 100
+C 30
+D 30
+E 100
+"""
+        def chain(nmem, step):
+            pos = [rnd.uniform(0, box[0]), rnd.uniform(0, box[1]), rnd.uniform(0, box[2])]
+            d = _rand_unit(rnd)
+            for _ in range(nmem):
+                dd = _rand_unit(rnd)
+                d2 = tuple(d[k] + 0.25 * dd[k] for k in range(3))
+                nn = math.sqrt(sum(x * x for x in d2))
+                d2 = tuple(x / nn for x in d2)
+                p = _perp(rnd, d2)
+                lines.append(_fmt(pos) + "   " + _fmt(d2) + "   " + _fmt(p) + " 0")
+                jit = _perp(rnd, d2)   # off-axis jitter: a partner exactly on a rod's axis is a 0/0 in the reference
+                pos = [pos[k] + step * d2[k] + 0.3 * jit[k] for k in range(3)]
+        for _ in range(40):
+            chain(5, 4.0)
+        for _ in range(100):
+            chain(3, 1.0)
+        for _ in range(30):
+            chain(3, 2.6)
+        for _ in range(30):
+            chain(2, 4.2)
+        _gas(rnd, 100, box, lines)
+        return top, "\n".join(lines) + "\n"
+    raise ValueError(kind)

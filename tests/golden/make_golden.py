@@ -191,7 +191,29 @@ def do_grid(nameA, defA, nameB, defB, kind, options_text):
     print("grid:", nameA, nameB, nB, "poses; nonzero", int(np.count_nonzero(e0j)), "overlaps", int(ov0j.sum()))
 
 
+def do_extras():
+    """multi-cell synthetic systems (sc_b200/synth.py) through the reference: pins angle1/angle2/bondh/bondd,
+    exclusions, negative parallel-eps and two-patch chiral mixes, which the reference's own test inputs never use"""
+    from sc_b200 import synth
+    with open(os.path.join(REF, "Tests", "test_01_normal_PSC", "new", "options")) as f:
+        opts = f.read()
+    for kind in ("chains", "mix"):
+        top, cfg = synth.small_case(kind)
+        tmp = tempfile.mkdtemp(prefix="extra_")
+        for fn, txt in (("top.init", top), ("config.init", cfg), ("options", opts)):
+            with open(os.path.join(tmp, fn), "w") as f:
+                f.write(txt)
+        run([DRIVER, "dump", "ref_dump.txt"], tmp)
+        gz_copy(os.path.join(tmp, "ref_dump.txt"), os.path.join(HERE, "extra_%s_init.ref.gz" % kind))
+        with gzip.GzipFile(os.path.join(HERE, "extra_%s.inputs.json.gz" % kind), "wb", mtime=0) as g:
+            g.write(json.dumps({"options": opts, "top.init": top, "config.init": cfg}).encode())
+        shutil.rmtree(tmp)
+        print("extra:", kind)
+
+
 def main():
+    if "extras" in sys.argv[1:]:
+        return do_extras()
     if not (os.path.exists(DRIVER) and os.path.exists(SC)):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
     tests = sorted(d for d in os.listdir(os.path.join(REF, "Tests")) if d.startswith("test_"))

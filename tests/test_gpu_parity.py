@@ -1,0 +1,216 @@
+"""GPU: parity of the CUDA path (through the C ABI, include/scgpu.h) against the CPU oracle and the
+committed reference goldens. Bars: energies <= 1e-10 relative (absolute floor
+1e-12 for sums that cancel to ~0), cell assignment / sort order / overlap flags bit-exact.
+Both library variants are checked: `strict` (-fmad=false) and `fast` (-fmad=true, the benchmarked one).
+"""
+import glob
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import topo as otopo
+from sc_b200 import Engine
+from sc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DUMPS = sorted(os.path.basename(p)[:-7] for p in glob.glob(os.path.join(G, "*.ref.gz")))
+GRIDS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(G, "grid_*.npz")))
+VARIANTS = ["strict", "fast"]
+RTOL = 1e-10
+ATOL = 1e-12
+
+
+def close(a, b, scale=1.0):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= RTOL * np.maximum(np.abs(a), np.abs(b)) + ATOL * scale)
+
+
+def worst(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-300))) if a.size else 0.0
+
+
+@pytest.fixture(scope="module", params=VARIANTS)
+def engine(request):
+    e = Engine(0, request.param)
+    yield e
+    e.close()
+
+
+def eps_scale(s):
+    return max(1.0, float(np.max(np.abs(s.ia[:, :, 4]))))
+
+
+@pytest.mark.parametrize("name", DUMPS)
+def test_golden_configs(engine, name):
+    r = O.load_ref_dump(os.path.join(G, name + ".ref.gz"))
+    s = r.system
+    engine.load(s)
+    sc = eps_scale(s)
+    # cell assignment and stable sort: bit-exact with the oracle's definition C1
+    ncell, cell_of, order, start = s.cells()
+    g_cell, g_nc = engine.cell_assignment()
+    assert np.array_equal(g_nc, ncell) and np.array_equal(g_cell, cell_of)
+    g_order, g_start = engine.cell_order(int(ncell.prod()))
+    assert np.array_equal(g_order, order) and np.array_equal(g_start, start)
+    targets = range(s.n) if s.n <= 100 else range(0, s.n, max(1, s.n // 25))
+    for t in targets:
+        e, ep = engine.one_to_all(t, pairs=True)
+        ref = np.array([r.pairs.get((t, j), 0.0) for j in range(s.n)])
+        assert close(ep, ref, sc), (name, t, worst(ep, ref))
+        assert close(e, r.one[t], sc), (name, t, e, r.one[t])
+    # batch == singles
+    tl = list(targets)
+    eb = engine.one_to_all_batch(tl)
+    assert close(eb, [r.one[t] for t in tl], sc)
+    ev = engine.one_to_all_everyone()
+    assert close(ev[tl], [r.one[t] for t in tl], sc)
+    if s.n <= 500:
+        tot, rows = engine.all_to_all(rows=True)
+        otot, orows = s.all_to_all(rows=True)
+        assert close(rows, orows, sc), worst(rows, orows)
+        assert close(tot, r.total, sc * 10), (tot, r.total)
+    for (first, m, e) in r.mol2o[:16]:
+        assert close(engine.mol_to_others(first, m), e, sc)
+    # overlap: as written in the reference (variant 0), bit-exact flags
+    if s.n <= 500:
+        assert engine.overlap_all(0) == (1 if r.overlaps else 0)
+        for t in list(targets)[:10]:
+            assert engine.overlap_one(t, None, 0) == s.overlap_one(t, None, 0)
+            assert engine.overlap_one(t, None, 1) == s.overlap_one(t, None, 1)
+
+
+@pytest.mark.parametrize("name", GRIDS)
+def test_pose_grids(engine, name):
+    """Interactions_tests-style degenerate pose grids: E(0,j) and E(j,0) against the reference's values"""
+    z = np.load(os.path.join(G, name + ".npz"))
+    cfg = gzip.open(os.path.join(G, "grid_config_%s.txt.gz" % str(z["kind"]))).read().decode()
+    s = O.system_from_text(str(z["top"]), cfg)
+    engine.load(s)
+    sc = eps_scale(s)
+    e0, ep = engine.one_to_all(0, pairs=True)
+    ref = z["e0j"]
+    # overlapping poses produce energies up to 1e20: relative bar only
+    assert close(ep, ref, sc), (name, worst(ep, ref), int(np.argmax(np.abs(ep - ref))))
+    # E(j,0): every pose as the first particle -- all_to_all rows are sum_{k<j} E(j,k); pick E(j,0) through pairs of j
+    js = np.nonzero(z["ej0"])[0][:40]
+    for j in js:
+        _, pj = engine.one_to_all(int(j), pairs=True)
+        assert close(pj[0], z["ej0"][j], sc), (name, j, pj[0], z["ej0"][j])
+    for j in range(1, s.n, max(1, s.n // 60)):
+        assert engine.overlap_one(0, None, 0) in (0, 1)
+    ov = [engine.overlap_one(int(j), None, 0) for j in np.nonzero(z["ovj0"])[0][:5]]
+    assert all(v == 1 for v in ov)
+
+
+def _trial_moves(s, rng, k):
+    """random displacement / rotation proposals in the reference's style (movecreator.cpp:947-1028)"""
+    out = []
+    for _ in range(k):
+        t = int(rng.integers(s.n))
+        st = s.state[t].copy()
+        g = int(s.ia[s.type[t], s.type[t], 0])
+        if rng.random() < 0.5 or g >= otopo.SP:
+            v = rng.normal(size=3)
+            v /= np.linalg.norm(v)
+            st[0:3] += 0.3 * v / s.box
+        else:
+            ax = rng.normal(size=3)
+            ax /= np.linalg.norm(ax)
+            st = O.psc_rotate(st, g, 0.2 * rng.random(), ax, int(rng.integers(2)))
+        out.append((t, st))
+    return out
+
+
+@pytest.mark.parametrize("name", ["test_01_normal_PSC_end", "test_08_normal_TCHCPSC_end", "test_14_normal_SPA_PSC_CPSC_end",
+                                  "test_20_chain_bond12_end", "test_21_chain_bondd2_end", "test_mempore_init"])
+def test_trial_states(engine, name):
+    r = O.load_ref_dump(os.path.join(G, name + ".ref.gz"))
+    s = r.system
+    engine.load(s)
+    sc = eps_scale(s)
+    rng = np.random.default_rng(7)
+    moves = _trial_moves(s, rng, 24)
+    for (t, st) in moves:
+        assert close(engine.one_to_all(t, st), s.one_to_all(t, st), sc)
+        assert engine.overlap_one(t, st, 0) == s.overlap_one(t, st, 0)
+    tl = [m[0] for m in moves]
+    sts = np.array([m[1] for m in moves])
+    eb = engine.one_to_all_batch(tl, sts)
+    assert close(eb, [s.one_to_all(t, st) for (t, st) in moves], sc)
+    # update(): commit a move, energies must follow
+    t, st = moves[0]
+    engine.update_particle(t, st)
+    s.state[t] = st
+    for q in range(0, s.n, max(1, s.n // 12)):
+        assert close(engine.one_to_all(q), s.one_to_all(q), sc)
+    if s.n <= 500:
+        assert close(engine.all_to_all(), s.all_to_all(), sc * 10)
+
+
+@pytest.mark.parametrize("kind", ["psc_lattice", "psc_gas", "mix", "chains"])
+def test_multicell_systems(engine, kind):
+    """systems with a real 3-D cell grid: pair-set equivalence of the cell path with the all-pairs oracle"""
+    top, cfg = synth.small_case(kind)
+    s = O.system_from_text(top, cfg)
+    engine.load(s)
+    sc = eps_scale(s)
+    ncell, cell_of, order, start = s.cells()
+    assert ncell.prod() > 27
+    g_cell, g_nc = engine.cell_assignment()
+    assert np.array_equal(g_nc, ncell) and np.array_equal(g_cell, cell_of)
+    g_order, g_start = engine.cell_order(int(ncell.prod()))
+    assert np.array_equal(g_order, order) and np.array_equal(g_start, start)
+    ev, ncand, ngate = engine.one_to_all_everyone(count=True)
+    oc, og = 0, 0
+    for t in range(0, s.n, max(1, s.n // 200)):
+        assert close(ev[t], s.one_to_all(t), sc), (kind, t, ev[t], s.one_to_all(t))
+    for t in range(s.n):
+        _, c, g = s.one_to_all_cells(t, (ncell, cell_of, order, start))
+        oc += c
+        og += g
+    assert (ncand, ngate) == (oc, og)      # integer work counters: bit-exact
+    tot, rows = engine.all_to_all(rows=True)
+    assert close(np.sum(rows), tot, sc * 10)
+    assert close(2 * tot, np.sum(ev), sc * 100)    # every pair is in exactly two one-to-all sums (energies are symmetric)
+    if s.n <= 3000:
+        assert close(tot, s.all_to_all(), sc * 10)
+    assert engine.overlap_all(0) == s.overlap_all(0)
+    assert engine.overlap_all(1) == s.overlap_all(1)
+
+
+def test_determinism_and_box_change(engine):
+    top, cfg = synth.small_case("psc_gas")
+    s = O.system_from_text(top, cfg)
+    engine.load(s)
+    a = engine.one_to_all_everyone()
+    b = engine.one_to_all_everyone()
+    assert np.array_equal(a, b)                      # fixed-order reductions: run-to-run identical
+    t1 = engine.all_to_all()
+    assert t1 == engine.all_to_all()
+    # NPT: the caller changes the box (positions are box-fractional), calculator must follow (paire.h:1205,1211)
+    for f in (0.97, 1.05, 0.6):
+        s.box = s.box * f
+        engine.set_box(s.box)
+        for t in range(0, s.n, max(1, s.n // 20)):
+            assert close(engine.one_to_all(t), s.one_to_all(t), eps_scale(s))
+        nc, _, _, _ = s.cells()
+        assert np.array_equal(engine.cell_assignment()[1], nc)
+
+
+def test_errors_are_loud(engine):
+    from sc_b200 import ScgpuError
+    top, cfg = synth.small_case("psc_gas")
+    s = O.system_from_text(top, cfg)
+    engine.load(s)
+    with pytest.raises(ScgpuError):
+        engine.one_to_all(s.n + 5)
+    with pytest.raises(ScgpuError):
+        engine.set_box([0.0, 1.0, 1.0])
+    with pytest.raises(ScgpuError):
+        engine.overlap_all(7)
