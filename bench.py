@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the scOOP energy hot path on B200, with its roofline and the CPU reference beside it.
+
+    python bench.py --gpus N --steps K --warmup W            our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU code on this box's host cores
+
+Workload (BASELINE.json configs[1], SURVEY.md 8(d) "L"): 65 536 PSC rods, bulk NVT lattice, box 89.6 x 89.6 x 70.4,
+synthetic (sc_b200/synth.py, seed 12345). A STEP = one pass of the pair-energy path over the whole system: the
+one-to-all trial energy of every particle against its 27-cell neighbourhood (N = 65 536 oneToAllTrial evaluations,
+one warp each, one kernel launch). Metric = gated pair-energy evaluations per second (pairs that pass the
+reference's sqmaxcut gate and reach a functor, PairE::operator(), scOOP/mc/paire.h:1209-1220).
+At N > 1 every rank holds its own replica (parallel tempering: one replica per GPU, weak scaling) and the ranks
+exchange their {E, V, N} records with one NCCL all-gather per step, as replicaExchangeMove does every nrepchange sweeps.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pair_energy_evals_per_s"
+UNIT = "gated pair-energy evals/s"
+WORKLOAD = "65536 PSC bulk NVT (configs[1]), one-to-all trial energy of every particle over cell lists"
+FLOP_WEIGHTS = {"add": 1, "mul": 1, "div": 1, "sqrt": 1, "cos": 20, "acos": 20, "pow": 3}
+
+
+def workload_texts():
+    from sc_b200 import synth
+    return synth.psc_bulk()     # (top_text, config_text, n)
+
+
+def options_text():
+    # the reference needs an `options` file; these are Tests/test_01_normal_PSC's values
+    return """ptype = 1
+press = 0
+paralpress = 0
+shave = 0
+nequil = 0
+adjust = 0
+nsweeps  = 2
+paramfrq = 0
+report   = 0
+nrepchange = 0
+nGrandCanon = 0
+nClustMove = 0
+movie    = 0
+chainprob = 0.0
+transmx = 0.0212
+rotmx = 7.5
+edge_mx = 0.0
+chainmmx = 0.0
+chainrmx = 0.0
+temper = 0.1
+paraltemper = 0.1
+wlm = 0
+wlmtype = 0
+switchprob = 0.00
+pairlist_update = 10
+seed = 145658
+write_cluster = 0
+"""
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference timing (oracle/_ref/sc_ref_fast = our driver + the unmodified reference sources, -Ofast)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(ntargets, reps, nproc):
+    """Runs `nproc` independent copies of the reference's oneToAll loop (its only parallel model is independent
+    replicas/ranks) over a bounded sample: `ntargets` evenly spaced trial particles x `reps` repetitions each."""
+    top, cfg, n = workload_texts()
+    drv = os.path.join(ROOT, "oracle", "_ref", "sc_ref_fast")
+    if not os.path.exists(drv):
+        return None
+    tmp = tempfile.mkdtemp(prefix="scref_")
+    try:
+        with open(os.path.join(tmp, "top.init"), "w") as f:
+            f.write(top.replace("A %d" % n, "A 1"))      # one molecule; the driver replicates it n times (MAXN bypass)
+        with open(os.path.join(tmp, "config.init"), "w") as f:
+            f.write(cfg)
+        with open(os.path.join(tmp, "options"), "w") as f:
+            f.write(options_text())
+        procs = [subprocess.Popen([drv, "time", str(ntargets), str(reps), str(n)], cwd=tmp, stdout=subprocess.PIPE,
+                                  stderr=subprocess.DEVNULL, text=True) for _ in range(nproc)]
+        outs = [p.communicate()[0] for p in procs]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    recs = []
+    for o in outs:
+        for line in o.splitlines():
+            if line.startswith("REFJSON "):
+                recs.append(json.loads(line[8:]))
+    if len(recs) != nproc:
+        return None
+    gated = sum(r["gated_pairs"] for r in recs)
+    tmax = max(r["one_to_all_s"] for r in recs)
+    return {"value": gated / tmax, "unit": UNIT, "cores": nproc, "kind": "reference",
+            "sample": "%d trial particles x %d reps per process, %d independent processes (reference is single-threaded); "
+                      "TotalEFull<PairE>::oneToAll over the reference's neighbour lists, -Ofast -march=x86-64-v3; "
+                      "list construction (%.2f s per process for the sample) not charged" % (ntargets, reps, nproc, recs[0]["list_build_s"]),
+            "seconds": tmax, "gated_pairs": gated}
+
+
+def cpu_port_fallback(ntargets):
+    """oracle port, 1 core -- only if oracle/_ref did not travel"""
+    from oracle import oracle as O
+    top, cfg, n = workload_texts()
+    s = O.system_from_text(top, cfg)
+    cells = s.cells()
+    t0 = time.perf_counter()
+    gated = 0
+    for t in range(0, n, max(1, n // ntargets)):
+        gated += s.one_to_all_cells(t, cells)[2]
+    dt = time.perf_counter() - t0
+    return {"value": gated / dt, "unit": UNIT, "cores": 1, "kind": "port", "sample": "%d trial particles, C oracle over cell lists" % ntargets,
+            "seconds": dt, "gated_pairs": gated}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.samples = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            t = [x.strip() for x in s.split(",")]
+            try:
+                sm.append(float(t[0])); mx.append(float(t[1]))
+            except Exception:
+                continue
+            for k, nm in enumerate(names):
+                if len(t) > 2 + k and t[2 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from sc_b200 import Engine
+    from sc_b200.host import HostSystem
+    top, cfg, n = workload_texts()
+    hs = HostSystem(top, cfg)                 # product-side parser (C++ host mirror), not the oracle
+    eng = Engine(local, "fast")
+    eng.load(hs)
+    if world > 1:
+        # parallel tempering: every replica starts from the same lattice but lives at its own temperature; for the
+        # energy pass only the configuration matters, so perturb it per rank to make the replicas distinct
+        rng = np.random.default_rng(1000 + rank)
+        st = hs.state.copy()
+        st[:, 0:3] += rng.normal(scale=2e-4, size=(n, 3))
+        eng.set_particles(st, hs.type, hs.moltype)
+    _, ncand, ngate = eng.one_to_all_everyone(fetch=True, count=True)   # also builds the cell list
+    peak = eng.fp64_peak()
+    import torch
+    rec_t = None
+    if world > 1:
+        from sc_b200.replica import record_tensor
+        gathered = torch.zeros(world * 8, dtype=torch.float64, device="cuda")
+
+    def step():
+        eng.one_to_all_everyone(fetch=False)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    eng.sync()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    clocks = Clocks(local) if rank == 0 else None
+    l0 = eng.launches()
+    kernel_ms = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.flush_l2()                        # inputs (18 MB) are smaller than L2: flush between timed iterations
+        eng.timer_start()
+        step()
+        kernel_ms.append(eng.timer_stop())
+        if world > 1:                         # replica exchange record: full energy -> NCCL all-gather (not in kernel_ms)
+            rec_t = record_tensor(eng)
+            dist.all_gather_into_tensor(gathered, rec_t)
+    eng.sync()
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = eng.launches() - l0 - args.steps            # minus the flush launches (not part of the step)
+    clk = clocks.stop() if clocks else None
+    total_ms = float(np.sum(kernel_ms))
+    pairs = float(ngate) * args.steps
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        p = torch.tensor([pairs, float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(p, op=dist.ReduceOp.SUM)
+        pairs, launches = float(p[0].item()), int(p[1].item())
+    value = pairs / (total_ms * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers: H2D of the configuration, cell build, energy pass, D2H of energies
+    state_host = hs.state.copy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        eng.set_particles(state_host, hs.type, hs.moltype)
+        eng.one_to_all_everyone(fetch=True)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.set_particles(state_host, hs.type, hs.moltype)
+        e_host = eng.one_to_all_everyone(fetch=True)
+    eng.sync()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = float(ngate) * e2e_steps * world / e2e_s
+    h2d = state_host.nbytes + hs.type.nbytes + hs.moltype.nbytes
+    d2h = e_host.nbytes
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (k_one_to_all): FP64 pipe. Algorithmic flops counted by the op-counting oracle
+    roof = {"bound": "fp64", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None, "traffic": None}
+    try:
+        from oracle import oracle as O
+        s = O.system_from_text(top, cfg)
+        sample = list(range(0, n, 64))
+        d = O.count_flops(s, sample)
+        flops_sample = sum(FLOP_WEIGHTS[k] * d[k] for k in FLOP_WEIGHTS)
+        flops_step = flops_sample * (n / len(sample))
+        ach = flops_step / (np.mean(kernel_ms) * 1e-3) / 1e12
+        roof.update({"achieved": ach, "frac": ach / peak, "flops_per_launch": flops_step,
+                     "flops_per_gated_pair": flops_sample / max(1, d["gated"]),
+                     "peak_source": "DFMA-chain microbenchmark in this process (scgpu_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                     "kernel_ms": float(np.mean(kernel_ms))})
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            roof["traffic"] = json.load(open(prof)).get("k_one_to_all_dram_bytes_per_launch")
+    except Exception as ex:      # the roofline numerator needs the oracle; never let it kill the bench line
+        roof["error"] = repr(ex)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_reference(2048, 24, os.cpu_count() or 1) or cpu_port_fallback(256)
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+           "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "particles_per_replica": n, "replicas": world, "l2": "flushed between timed steps",
+                      "gated_pairs_per_step": int(ngate), "candidates_per_step": int(ncand), "library": "libscgpu.so (-fmad=true)",
+                      "parallelism": "replica-per-GPU"},
+           "roofline": roof, "cpu_baseline": cpu,
+           "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
+           "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ntargets, reps = 2048, 8
+    vals, secs = [], []
+    r = None
+    for k in range(args.warmup + args.steps):
+        r = cpu_reference(ntargets, reps, cores)
+        if r is None:
+            r = cpu_port_fallback(256)
+        if k >= args.warmup:
+            vals.append(r["gated_pairs"])
+            secs.append(r["seconds"])
+    value = float(np.sum(vals) / np.sum(secs))
+    cb = dict(r)
+    cb["value"] = value
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": float(np.mean(secs) * 1e3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": {"workload": WORKLOAD, "particles_per_replica": 65536, "step_sample": cb["sample"]},
+           "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

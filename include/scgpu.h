@@ -119,8 +119,10 @@ int scgpu_one_to_all_batch(scgpu_ctx* ctx, int m, const int* targets, const doub
 /* same over every particle's current state, results stay on the device (bench: inputs resident in HBM);
  * e_host may be NULL. n_gated / n_candidates (optional) return the pair counters of that launch. */
 int scgpu_one_to_all_everyone(scgpu_ctx* ctx, double* e_host, int64_t* n_candidates, int64_t* n_gated);
-/* mol2othersTrial(mol) for a molecule of m consecutive particles starting at `first` (totalenergycalculator.h:455-499) */
-int scgpu_mol_to_others(scgpu_ctx* ctx, int first, int m, double* e_sum);
+/* mol2others(mol) / mol2othersTrial(mol) for a molecule of m consecutive particles starting at `first`
+ * (totalenergycalculator.h:417-499): members x non-members with an EMPTY conlist. trial_states30 (m*30, optional)
+ * = the members' states as mutated by the caller. */
+int scgpu_mol_to_others(scgpu_ctx* ctx, int first, int m, const double* trial_states30, double* e_sum);
 /* allToAllTrial() / allToAll() / initEM() (totalenergycalculator.h:314-353, 502-521): every pair once, conlist of the
  * higher index. e_per_particle (optional, n) = row sums  sum_{j<i} E(i,j). */
 int scgpu_all_to_all(scgpu_ctx* ctx, double* e_total, double* e_per_particle);

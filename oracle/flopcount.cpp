@@ -1,0 +1,73 @@
+// TEST / MEASUREMENT INFRASTRUCTURE -- not part of the product.
+// The oracle (sc_oracle.c) re-instantiated over an op-counting scalar: every `double` in it becomes CD, whose
+// arithmetic operators bump global counters. This yields the ALGORITHMIC flop count of the hot path on exactly the
+// pair set of a benchmark configuration: add/sub/mul/div/sqrt = 1 flop each, compares /
+// negation / fabs / selects = 0, libm calls counted separately (cos, acos, pow) and weighted by bench.py.
+#include <cmath>
+#include <cstring>
+#include <cstdlib>
+
+struct Counters { long long add, mul, div, sqrt_, cos_, acos_, pow_; };
+static Counters g_cnt = {0, 0, 0, 0, 0, 0, 0};
+
+struct CD {
+    double v;
+    CD() = default;
+    template <typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>
+    CD(T x) : v((double)x) {}
+    explicit operator int() const { return (int)v; }
+    explicit operator double() const { return v; }
+    explicit operator bool() const { return v != 0.0; }
+};
+#define BIN(op, ctr)                                                                                    \
+    static inline CD operator op(CD a, CD b) { g_cnt.ctr++; CD r; r.v = a.v op b.v; return r; }         \
+    template <typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>       \
+    static inline CD operator op(CD a, T b) { g_cnt.ctr++; CD r; r.v = a.v op (double)b; return r; }     \
+    template <typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>       \
+    static inline CD operator op(T a, CD b) { g_cnt.ctr++; CD r; r.v = (double)a op b.v; return r; }
+BIN(+, add) BIN(-, add) BIN(*, mul) BIN(/, div)
+#define CMP(op)                                                                                         \
+    static inline bool operator op(CD a, CD b) { return a.v op b.v; }                                   \
+    template <typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>       \
+    static inline bool operator op(CD a, T b) { return a.v op (double)b; }                              \
+    template <typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>       \
+    static inline bool operator op(T a, CD b) { return (double)a op b.v; }
+CMP(<) CMP(>) CMP(<=) CMP(>=) CMP(==) CMP(!=)
+static inline CD operator-(CD a) { CD r; r.v = -a.v; return r; }
+static inline CD& operator+=(CD& a, CD b) { a = a + b; return a; }
+static inline CD& operator-=(CD& a, CD b) { a = a - b; return a; }
+static inline CD& operator*=(CD& a, CD b) { a = a * b; return a; }
+static inline CD& operator/=(CD& a, CD b) { a = a / b; return a; }
+static inline CD sqrt(CD a) { g_cnt.sqrt_++; return CD(std::sqrt(a.v)); }
+static inline CD fabs(CD a) { return CD(std::fabs(a.v)); }
+static inline CD cos(CD a) { g_cnt.cos_++; return CD(std::cos(a.v)); }
+static inline CD acos(CD a) { g_cnt.acos_++; return CD(std::acos(a.v)); }
+static inline CD floor(CD a) { return CD(std::floor(a.v)); }
+template <typename T> static inline CD pow(CD a, T b) { g_cnt.pow_++; return CD(std::pow(a.v, (double)b)); }
+static inline CD modf(CD a, CD* ip) { double i; double f = std::modf(a.v, &i); ip->v = i; return CD(f); }
+
+#define double CD
+#define sco_image cnt_sco_image
+#define sco_min_dist_segments cnt_sco_min_dist_segments
+#define sco_get_conlist cnt_sco_get_conlist
+#define sco_particle_init cnt_sco_particle_init
+#define sco_pair_energy cnt_sco_pair_energy
+#define sco_one_to_all cnt_sco_one_to_all
+#define sco_all_to_all cnt_sco_all_to_all
+#define sco_mol_to_others cnt_sco_mol_to_others
+#define sco_overlap_pair cnt_sco_overlap_pair
+#define sco_overlap_one cnt_sco_overlap_one
+#define sco_overlap_all cnt_sco_overlap_all
+#define sco_cell_dims cnt_sco_cell_dims
+#define sco_cell_assign cnt_sco_cell_assign
+#define sco_cell_sort cnt_sco_cell_sort
+#define sco_one_to_all_cells cnt_sco_one_to_all_cells
+#define sco_psc_rotate cnt_sco_psc_rotate
+#include "sc_oracle.c"
+#undef double
+
+extern "C" void cnt_reset(void) { memset(&g_cnt, 0, sizeof g_cnt); }
+extern "C" void cnt_get(long long* out7) {
+    out7[0] = g_cnt.add; out7[1] = g_cnt.mul; out7[2] = g_cnt.div; out7[3] = g_cnt.sqrt_;
+    out7[4] = g_cnt.cos_; out7[5] = g_cnt.acos_; out7[6] = g_cnt.pow_;
+}

@@ -180,6 +180,38 @@ class System:
                 lib().sco_particle_init(_d(self.ia[t, t]), _d(self.state[i]))
 
 
+_clib = None
+
+
+def count_flops(system, targets):
+    """Algorithmic operation counts of the cell-path one-to-all over `targets` (oracle/flopcount.cpp):
+    returns dict(add, mul, div, sqrt, cos, acos, pow, candidates, gated)."""
+    global _clib
+    if _clib is None:
+        path = os.path.join(HERE, "libscoracle_count.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-s", "-C", HERE, "count"])
+        _clib = C.CDLL(path)
+        _clib.cnt_sco_one_to_all_cells.restype = C.c_double
+        _clib.cnt_sco_one_to_all_cells.argtypes = [C.POINTER(_SysC), C.c_int, _dp, _ip, _ip, _ip, _ip,
+                                                   C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    s = system.c()
+    ncell, cell_of, order, start = system.cells()
+    _clib.cnt_reset()
+    cand = gated = 0
+    for t in targets:
+        nc, ng = C.c_long(0), C.c_long(0)
+        _clib.cnt_sco_one_to_all_cells(C.byref(s), int(t), None, _i(cell_of), _i(ncell), _i(order), _i(start), C.byref(nc), C.byref(ng))
+        cand += nc.value
+        gated += ng.value
+    out = (C.c_longlong * 7)()
+    _clib.cnt_get(out)
+    names = ["add", "mul", "div", "sqrt", "cos", "acos", "pow"]
+    d = {k: int(out[i]) for i, k in enumerate(names)}
+    d["candidates"], d["gated"] = cand, gated
+    return d
+
+
 def psc_rotate(state, geotype, angle, axis, positive):
     st = np.ascontiguousarray(state, dtype=np.float64).copy()
     ax = np.ascontiguousarray(axis, dtype=np.float64)

@@ -19,7 +19,7 @@
 // No reference source text is copied here; this file only *calls* the reference API.
 //
 // usage:  cd <dir with options,top.init,config.init> && sc_ref_driver dump|dump0 [out]   (dump0: pairs with particle 0 only)
-//         sc_ref_driver time <nrep> [big]      -> JSON line with timings of allToAll/oneToAll
+//         sc_ref_driver time <ntargets> <reps> [count_per_moltype ...]  -> "REFJSON {...}" line: oneToAll timing
 #include <cstdio>
 #include <cstring>
 #include <ctime>
@@ -187,49 +187,67 @@ static int do_dump(const char* outname, bool only0) {
 }
 
 // Timing arm: the reference's own TotalEFull<PairE> (the compile-time alternative calculator,
-// totalenergycalculator.h:525-619; the default TotalEMatrix needs 2 x N^2/2 doubles and cannot
-// hold 65k particles). Times nrep oneToAll() calls on evenly spaced targets and optionally one
-// allToAll(); counts gated pair evaluations exactly as PairE::operator() gates them.
+// totalenergycalculator.h:525-619; the default TotalEMatrix needs 2 x N^2/2 doubles and cannot hold 65k particles)
+// looping over the reference's neighbour lists (conf.neighborList, filled here for the sampled targets with the
+// cut-off rule of Updater::genSimplePairList, updater.cpp:484-552, and main.cpp:117-126). Only the energy loop is
+// timed -- the reference's O(N^2) list construction is reported separately, not charged. `reps` repeats the sample.
 static int do_time(int argc, char** argv) {
     long ntargets = argc > 2 ? atol(argv[2]) : 64;
-    int do_full = argc > 3 ? atoi(argv[3]) : 0;
+    int reps = argc > 3 ? atoi(argv[3]) : 1;
     vector<long> counts;
     for (int a = 4; a < argc; a++) counts.push_back(atol(argv[a]));
     FileNames files(0);
     Conf conf;
     Sim* sim = nullptr;
     load(conf, sim, files, (long)counts.size(), counts.data());
-    TotalEFull<PairE> calc(sim, &conf);
     long n = (long)conf.pvec.size();
-    // gated-pair count for the sampled targets
-    double sq = topo.sqmaxcut;
-    long gated = 0, cand = 0;
+    for (int i = 0; i < MAXT; i++) for (int j = 0; j < MAXT; j++) {   // main.cpp:117-126
+        double m = AVER(sim->stat.trans[i].mx, sim->stat.trans[j].mx);
+        m *= (1 + sim->pairlist_update) * 2;
+        m += topo.maxcut;
+        sim->max_dist_squared[i][j] = m * m;
+    }
     long stride = n / ntargets; if (stride < 1) stride = 1;
     vector<int> targets;
     for (long t = 0; t < n && (long)targets.size() < ntargets; t += stride) targets.push_back((int)t);
+    conf.neighborList.resize(n);
+    conf.pairlist_update = true;
+    double sq = topo.sqmaxcut;
+    long gated = 0, cand = 0;
+    auto l0 = chrono::steady_clock::now();
     for (int t : targets) {
+        vector<long> nb;
         ConList ct = conf.pvec.getConlist(t);
         for (long i = 0; i < n; i++) if (i != t) {
             Vector r = conf.geo.image(&conf.pvec[t].pos, &conf.pvec[i].pos);
-            cand++;
-            if (!(r.dot(r) > sq && ct.isEmpty)) gated++;
+            double r2 = r.dot(r);
+            bool bonded = false;
+            for (int q = 0; q < 4; q++) if (ct.conlist[q] == &conf.pvec[i]) bonded = true;
+            if (r2 <= sim->max_dist_squared[conf.pvec[t].type][conf.pvec[i].type] || bonded) {
+                nb.push_back(i);
+                cand++;
+                if (!(r2 > sq && ct.isEmpty)) gated++;
+            }
         }
+        conf.neighborList[t].neighborID = (long*)malloc(sizeof(long) * (nb.size() + 1));
+        memcpy(conf.neighborList[t].neighborID, nb.data(), sizeof(long) * nb.size());
+        conf.neighborList[t].neighborCount = (long)nb.size();
     }
+    auto l1 = chrono::steady_clock::now();
+    double list_s = chrono::duration<double>(l1 - l0).count();
+    TotalEFull<PairE> calc(sim, &conf);
+    calc.pairListUpdate = true;
     auto t0 = chrono::steady_clock::now();
     double acc = 0.0;
-    for (int t : targets) acc += calc.oneToAll(t);
+    for (int r = 0; r < reps; r++)
+        for (int t : targets) acc += calc.oneToAll(t);
     auto t1 = chrono::steady_clock::now();
     double one_s = chrono::duration<double>(t1 - t0).count();
-    double full_s = -1.0, etot = 0.0;
-    if (do_full) {
-        auto t2 = chrono::steady_clock::now();
-        etot = calc.allToAll();
-        auto t3 = chrono::steady_clock::now();
-        full_s = chrono::duration<double>(t3 - t2).count();
-    }
-    printf("{\"n\": %ld, \"targets\": %ld, \"one_to_all_s\": %.6f, \"candidates\": %ld, \"gated_pairs\": %ld, "
-           "\"sum\": %.17g, \"all_to_all_s\": %.6f, \"e_total\": %.17g}\n",
-           n, (long)targets.size(), one_s, cand, gated, acc, full_s, etot);
+    for (int t : targets) { free(conf.neighborList[t].neighborID); conf.neighborList[t].neighborID = NULL; }
+    conf.neighborList.clear();
+    printf("REFJSON {\"n\": %ld, \"targets\": %ld, \"reps\": %d, \"one_to_all_s\": %.6f, \"list_candidates\": %ld, "
+           "\"gated_pairs\": %ld, \"list_build_s\": %.6f, \"sum\": %.17g}\n",
+           n, (long)targets.size(), reps, one_s, cand * reps, gated * reps, list_s, acc);
     return 0;
 }
 
@@ -237,6 +255,6 @@ int main(int argc, char** argv) {
     if (argc >= 2 && !strcmp(argv[1], "dump")) return do_dump(argc > 2 ? argv[2] : "ref_dump.txt", false);
     if (argc >= 2 && !strcmp(argv[1], "dump0")) return do_dump(argc > 2 ? argv[2] : "ref_dump.txt", true);
     if (argc >= 2 && !strcmp(argv[1], "time")) return do_time(argc, argv);
-    fprintf(stderr, "usage: sc_ref_driver dump [out] | time <ntargets> <full 0/1> [count_per_moltype ...]\n");
+    fprintf(stderr, "usage: sc_ref_driver dump|dump0 [out] | time <ntargets> <reps> [count_per_moltype ...]\n");
     return 2;
 }

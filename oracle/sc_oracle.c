@@ -1073,7 +1073,8 @@ double sco_one_to_all_cells(const sco_system* s, int target, const double* trial
     for (k = 0; k < nl; k++) {
         int j = list[k];
         vec3 r = image(s->box, ld(st), ld(s->state + (size_t)j * SCO_STATE));
-        if (!(dot(r, r) > s->sqmaxcut && cl.is_empty)) gated++;
+        /* work counter of the cell path: pairs that reach a functor there = inside sqmaxcut, or bonded */
+        if (dot(r, r) <= s->sqmaxcut || j == cl.con[0] || j == cl.con[1] || j == cl.con[2] || j == cl.con[3]) gated++;
         energy += sco_pair_energy(s, st, s->type[target], s->moltype[target], target,
                                   s->state + (size_t)j * SCO_STATE, s->type[j], j, &cl);
     }

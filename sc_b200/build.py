@@ -40,6 +40,24 @@ def build(variant=None, force=False, verbose=False):
     return [lib_path(v) for v in names]
 
 
+HOST_SRCS = [os.path.join(HERE, "csrc", "host", f) for f in ("topology.cpp", "calculator.cpp", "schost_capi.cpp")]
+HOST_DEPS = HOST_SRCS + [os.path.join(HERE, "csrc", "host", f) for f in ("topology.hpp", "calculator.hpp")]
+HOST_LIB = os.path.join(HERE, "libschost.so")
+
+
+def build_host(force=False):
+    """C++ host mirror of the reference's formats and calculator interface (sc_b200/csrc/host), linked to libscgpu.so."""
+    if not force and os.path.exists(HOST_LIB):
+        t = os.path.getmtime(HOST_LIB)
+        if not any(os.path.getmtime(d) > t for d in HOST_DEPS + [lib_path("fast")]):
+            return HOST_LIB
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-ffp-contract=off", "-o", HOST_LIB] + HOST_SRCS + \
+          ["-L" + HERE, "-lscgpu", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     import sys
     build(force="--force" in sys.argv, verbose=True)
+    build_host(force="--force" in sys.argv)

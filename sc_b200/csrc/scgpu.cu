@@ -244,11 +244,11 @@ __device__ double warp_one_to_all(const DevSys& s, const double* s1, int type1, 
             if (j < e) {
                 double4 pw = s.posw[j];
                 int orig = w_orig(pw.w);
-                if (filt(f, orig)) {
+                bool bonded = (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
+                if (filt(f, orig) && !bonded) {      // bonded partners are handled (and counted) once, below
                     n_cand++;
                     v3 r_cm = image(s.box, p1, mk(pw.x, pw.y, pw.z));
-                    bool bonded = (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
-                    pass = !bonded && (dot(r_cm, r_cm) <= s.sqmaxcut);   // PairE gate (mc/paire.h:1214); bonded partners below
+                    pass = (dot(r_cm, r_cm) <= s.sqmaxcut);   // PairE gate (mc/paire.h:1214)
                 }
             }
             unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -304,7 +304,7 @@ k_one_to_all(DevSys s, int m, int gw, const int* __restrict__ targets, const dou
     if (active) target = (MODE == 0) ? targets[t] : (MODE == 3 ? excl_lo + t : t);
     double* rec1 = sh_rec[g * gw];
     if (active && gwid == 0) {
-        if (MODE == 0 && trial_states) {
+        if ((MODE == 0 || MODE == 3) && trial_states) {
             if (lane < 30) rec1[lane] = trial_states[(size_t)t * 30 + c_api_of[lane]];
         } else {
             rec1[lane] = s.rec[(size_t)s.slot_of[target] * REC + lane];
@@ -814,13 +814,18 @@ extern "C" int scgpu_one_to_all_everyone(scgpu_ctx* c, double* e_host, int64_t* 
     return SCGPU_OK;
 }
 
-extern "C" int scgpu_mol_to_others(scgpu_ctx* c, int first, int m, double* e_sum) {
+extern "C" int scgpu_mol_to_others(scgpu_ctx* c, int first, int m, const double* trial_states30, double* e_sum) {
     ARG(c && e_sum, "scgpu_mol_to_others: NULL argument");
     ARG(first >= 0 && m > 0 && first + m <= c->n, "scgpu_mol_to_others: molecule range out of bounds");
     CK(cudaSetDevice(c->device));
     if (int r = ensure_cells(c)) return r;
+    if (trial_states30) {
+        if (ensure_trial(c, m)) return SCGPU_ERR_CUDA;
+        CK(cudaMemcpyAsync(c->d_trial, trial_states30, (size_t)m * 30 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
     DevSys s = view(c);
-    k_one_to_all<3><<<(m + OTA_WARPS - 1) / OTA_WARPS, OTA_THREADS, 0, c->stream>>>(s, m, 1, nullptr, nullptr, first, first + m, c->d_out, nullptr, nullptr);
+    k_one_to_all<3><<<(m + OTA_WARPS - 1) / OTA_WARPS, OTA_THREADS, 0, c->stream>>>(s, m, 1, nullptr, trial_states30 ? c->d_trial : nullptr, first, first + m,
+                                                                                      c->d_out, nullptr, nullptr);
     k_reduce_fixed<<<1, 256, 0, c->stream>>>(m, c->d_out, c->d_scalar);
     c->launches += 2;
     CK(cudaGetLastError());

@@ -66,7 +66,7 @@ def load_library(variant="fast"):
     L.scgpu_one_to_all.argtypes = [vp, C.c_int, _dp, _dp, _dp]
     L.scgpu_one_to_all_batch.argtypes = [vp, C.c_int, _ip, _dp, _dp]
     L.scgpu_one_to_all_everyone.argtypes = [vp, _dp, _i64p, _i64p]
-    L.scgpu_mol_to_others.argtypes = [vp, C.c_int, C.c_int, _dp]
+    L.scgpu_mol_to_others.argtypes = [vp, C.c_int, C.c_int, _dp, _dp]
     L.scgpu_all_to_all.argtypes = [vp, _dp, _dp]
     L.scgpu_overlap_one.argtypes = [vp, C.c_int, _dp, C.c_int, _ip]
     L.scgpu_overlap_all.argtypes = [vp, C.c_int, _ip]
@@ -193,9 +193,10 @@ class Engine:
             return out, nc.value, ng.value
         return out
 
-    def mol_to_others(self, first, m):
+    def mol_to_others(self, first, m, trial_states=None):
         e = C.c_double(0.0)
-        self._ck(self.L.scgpu_mol_to_others(self.h, int(first), int(m), C.byref(e)))
+        ts = None if trial_states is None else np.ascontiguousarray(trial_states, dtype=np.float64)
+        self._ck(self.L.scgpu_mol_to_others(self.h, int(first), int(m), None if ts is None else _d(ts), C.byref(e)))
         return e.value
 
     def all_to_all(self, rows=False, fetch=True):
