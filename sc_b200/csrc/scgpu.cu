@@ -10,7 +10,7 @@
 //
 // Kernels:
 //   k_cell_count / k_cell_scan / k_cell_fill / k_cell_place   counting sort by cell, stable (row C1)
-//   k_one_to_all<MODE>                                         one warp-group per trial particle (rows A1-A11, A13)
+//   k_gate_cheap<MODE> / k_patch / k_combine                    one-to-all energies in three dense phases (rows A1-A11, A13)
 //   k_reduce_fixed                                             fixed-order total for allToAll
 //   k_overlap                                                  warp-vote early exit (row A12)
 //   k_sweep_colour                                             checkerboard displacement/rotation trials (row A14)
@@ -182,9 +182,16 @@ __global__ void k_unsort(DevSys s, double* __restrict__ api) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// warp-group one-to-all: the heart of the hot path
+// one-to-all energy: the heart of the hot path, in three launches
+//   k_gate_cheap  one warp-group per trial particle: scan the 27 neighbour cells, warp-ballot-compact the candidates that
+//                 pass the sqmaxcut gate, evaluate everything EXCEPT the rod-rod patch attraction on dense 32-lane batches,
+//                 and compact the (few) pairs that owe a patch evaluation into a global work list
+//   k_patch       one thread per listed pair: the patch geometry + attraction (the expensive ~10 %), densely packed
+//   k_combine     per trial particle: partial + its patch terms, summed in list order (deterministic)
 // ------------------------------------------------------------------------------------------------
-constexpr int QCAP = 64;
+constexpr int QCAP = 64;      // per-warp gated-candidate queue (ints, shared memory)
+constexpr int PCAP = 64;      // per-warp patch-pair buffer (ints, shared memory), flushed to the global list in chunks
+// a warp that collects more than PCAP patch partners for one particle flushes several chunks; they are chained
 
 struct Filter {
     int self;        // original index never paired with itself
@@ -203,11 +210,27 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Energy of one (trial) particle against the 27-cell neighbourhood + its bonded partners.
+struct PatchList {            // global work list of pairs that owe pair_energy_patch()
+    int2* pair;               // x: slot of the first particle (>= 0) or -1-t for a trial record; y: slot of the second
+    double* e;                // result of k_patch, same index
+    int* total;               // running fill (atomicAdd); reset by k_combine
+    int cap;
+    int* warp_head;           // per warp: id of its first chunk, -1 if it has none
+    int4* chunks;             // {start in pair[]/e[], length, id of the warp's next chunk or -1, unused}
+    int* chunk_count;         // running fill of chunks[] (atomicAdd); reset by k_combine
+    int chunk_cap;
+    int* overflow;            // sticky flag: a list was too small -> results invalid, the host grows the lists and repeats
+    double* trial_rec;        // [m][REC] internal records of trial states (only when the caller passed trial states)
+};
+
+// Energy of one (trial) particle against the 27-cell neighbourhood + its bonded partners, WITHOUT rod-rod patch terms.
 // s1: this particle's internal record in shared memory. Executed by `gw` cooperating warps (group warp id `gwid`).
-// Returns this WARP's partial sum (identical in all lanes). queue: QCAP ints of shared memory private to the warp.
-__device__ double warp_one_to_all(const DevSys& s, const double* s1, int type1, int moltype1, const ConList& cl, const Filter& f,
-                                  int gw, int gwid, int* queue, double* e_pairs, unsigned long long* counters) {
+// Returns this WARP's partial sum (identical in all lanes). queue / pbuf: shared memory private to the warp.
+// first_ref: what k_patch needs to find this particle's record (slot >= 0, or -1-t for a trial record).
+template <bool RODS>
+__device__ double warp_gate_cheap(const DevSys& s, const double* s1, int type1, int moltype1, const ConList& cl, const Filter& f,
+                                  int gw, int gwid, int* queue, int* pbuf, int first_ref, int warp_global, const PatchList& pl,
+                                  double* e_pairs, unsigned long long* counters) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const v3 p1 = ld3(s1 + R_POS);
@@ -217,18 +240,49 @@ __device__ double warp_one_to_all(const DevSys& s, const double* s1, int type1, 
     const int nx = s.nc[0] == 1 ? 1 : 3, ny = s.nc[1] == 1 ? 1 : 3, nz = s.nc[2] == 1 ? 1 : 3;
     const int ncell_nb = nx * ny * nz;
     double acc = 0.0;
-    int qn = 0;
-    unsigned long long n_cand = 0, n_gate = 0;
+    int qn = 0, pn = 0, last_chunk = -1, head = -1;
+    unsigned n_cand = 0, n_gate = 0;
 
-    auto eval_slot = [&](int slot) {
-        double4 pw = s.posw[slot];
-        v3 r_cm = image(s.box, p1, mk(pw.x, pw.y, pw.z));
-        double dotrcm = dot(r_cm, r_cm);
-        int orig = w_orig(pw.w);
-        double e = pair_energy_gated(s.box, s.ia, s.ntypes, s.mol, r_cm, dotrcm, s1, type1, moltype1,
-                                     s.rec + (size_t)slot * REC, w_type(pw.w), orig, cl);
-        if (e_pairs) e_pairs[orig] = e;
-        acc += e;
+    // hand the buffered patch pairs to k_patch as one contiguous run of the global list
+    auto flush_chunk = [&]() {
+        int base = 0, cid = 0;
+        if (lane == 0) { base = atomicAdd(pl.total, pn); cid = atomicAdd(pl.chunk_count, 1); }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        cid = __shfl_sync(0xffffffffu, cid, 0);
+        bool ok = (cid < pl.chunk_cap) && (base + pn <= pl.cap);
+        if (ok) {
+            for (int k = lane; k < pn; k += 32) pl.pair[base + k] = make_int2(first_ref, pbuf[k]);
+            if (lane == 0) {
+                pl.chunks[cid] = make_int4(base, pn, -1, 0);
+                if (last_chunk >= 0) pl.chunks[last_chunk].z = cid;
+            }
+            if (head < 0) head = cid;
+            last_chunk = cid;
+        } else if (lane == 0) atomicExch(pl.overflow, 1);
+        pn = 0;
+        __syncwarp();
+    };
+    auto eval_slot = [&](int slot, bool on) {
+        bool np = false;
+        if (on) {
+            double4 pw = s.posw[slot];
+            v3 r_cm = image(s.box, p1, mk(pw.x, pw.y, pw.z));
+            double dotrcm = dot(r_cm, r_cm);
+            int orig = w_orig(pw.w);
+            double e = pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r_cm, dotrcm, s1, type1, moltype1,
+                                         s.rec + (size_t)slot * REC, w_type(pw.w), orig, cl, np);
+            if (e_pairs) e_pairs[orig] = e;
+            acc += e;
+            n_gate++;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, np);
+        if (m) {
+            int c = __popc(m);
+            if (pn + c > PCAP) flush_chunk();
+            if (np) pbuf[pn + __popc(m & lt_mask)] = slot;
+            pn += c;
+            __syncwarp();
+        }
     };
 
     for (int k = gwid; k < ncell_nb; k += gw) {
@@ -244,7 +298,7 @@ __device__ double warp_one_to_all(const DevSys& s, const double* s1, int type1, 
             if (j < e) {
                 double4 pw = s.posw[j];
                 int orig = w_orig(pw.w);
-                bool bonded = (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
+                bool bonded = !RODS && (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
                 if (filt(f, orig) && !bonded) {      // bonded partners are handled (and counted) once, below
                     n_cand++;
                     v3 r_cm = image(s.box, p1, mk(pw.x, pw.y, pw.z));
@@ -256,9 +310,7 @@ __device__ double warp_one_to_all(const DevSys& s, const double* s1, int type1, 
             qn += __popc(m);
             __syncwarp();
             if (qn >= 32) {
-                n_gate++;
-                eval_slot(queue[lane]);
-                __syncwarp();
+                eval_slot(queue[lane], true);
                 int rest = qn - 32;
                 int mv = (lane < rest) ? queue[32 + lane] : 0;
                 __syncwarp();
@@ -268,17 +320,20 @@ __device__ double warp_one_to_all(const DevSys& s, const double* s1, int type1, 
             }
         }
     }
-    if (lane < qn) { n_gate++; eval_slot(queue[lane]); }
-    __syncwarp();
+    if (qn > 0) eval_slot(lane < qn ? queue[lane] : 0, lane < qn);
     // bonded partners: never gated (conlist not empty, mc/paire.h:1214), wherever they are
-    if (gwid == 0 && !cl.is_empty && lane < 4) {
-        int orig = cl.con[lane];
-        if (orig >= 0 && filt(f, orig)) { n_cand++; n_gate++; eval_slot(s.slot_of[orig]); }
+    if (!RODS && gwid == 0 && !cl.is_empty) {
+        int orig = lane < 4 ? cl.con[lane] : -1;
+        bool on = orig >= 0 && filt(f, orig);
+        if (on) n_cand++;
+        eval_slot(on ? s.slot_of[orig] : 0, on);
     }
+    if (pn > 0) flush_chunk();
+    if (lane == 0) pl.warp_head[warp_global] = head;
     if (counters) {
-        n_cand = __reduce_add_sync(0xffffffffu, (unsigned)n_cand);
-        n_gate = __reduce_add_sync(0xffffffffu, (unsigned)n_gate);
-        if (lane == 0) { atomicAdd(&counters[0], n_cand); atomicAdd(&counters[1], n_gate); }
+        n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+        n_gate = __reduce_add_sync(0xffffffffu, n_gate);
+        if (lane == 0) { atomicAdd(&counters[0], (unsigned long long)n_cand); atomicAdd(&counters[1], (unsigned long long)n_gate); }
     }
     return warp_sum(acc);
 }
@@ -288,13 +343,14 @@ constexpr int OTA_WARPS = OTA_THREADS / 32;
 
 // MODE 0: targets[] (+ optional trial states in C-ABI layout); MODE 1: every particle, own state, all partners;
 // MODE 2: allToAll rows (partners with a smaller original index); MODE 3: molecule members vs non-members, empty conlist
-template <int MODE>
-__global__ void __launch_bounds__(OTA_THREADS)
-k_one_to_all(DevSys s, int m, int gw, const int* __restrict__ targets, const double* __restrict__ trial_states,
-             int excl_lo, int excl_hi, double* __restrict__ out, double* __restrict__ e_pairs, unsigned long long* counters) {
+template <int MODE, bool RODS>
+__global__ void __launch_bounds__(OTA_THREADS, RODS ? 5 : 3)
+k_gate_cheap(DevSys s, int m, int gw, const int* __restrict__ targets, const double* __restrict__ trial_states,
+             int excl_lo, int excl_hi, PatchList pl, double* __restrict__ warp_partial, double* __restrict__ e_pairs,
+             unsigned long long* counters) {
     __shared__ double sh_rec[OTA_WARPS][REC];
     __shared__ int sh_queue[OTA_WARPS][QCAP];
-    __shared__ double sh_part[OTA_WARPS];
+    __shared__ int sh_pbuf[OTA_WARPS][PCAP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int groups_per_block = OTA_WARPS / gw;
     const int g = wid / gw, gwid = wid % gw;
@@ -303,34 +359,71 @@ k_one_to_all(DevSys s, int m, int gw, const int* __restrict__ targets, const dou
     int target = 0;
     if (active) target = (MODE == 0) ? targets[t] : (MODE == 3 ? excl_lo + t : t);
     double* rec1 = sh_rec[g * gw];
+    const bool trial = (MODE == 0 || MODE == 3) && trial_states != nullptr;
     if (active && gwid == 0) {
-        if ((MODE == 0 || MODE == 3) && trial_states) {
-            if (lane < 30) rec1[lane] = trial_states[(size_t)t * 30 + c_api_of[lane]];
+        if (trial) {
+            double v = (lane < 30) ? trial_states[(size_t)t * 30 + c_api_of[lane]] : 0.0;
+            rec1[lane] = v;
+            pl.trial_rec[(size_t)t * REC + lane] = v;      // k_patch reads the trial record from here
         } else {
             rec1[lane] = s.rec[(size_t)s.slot_of[target] * REC + lane];
         }
     }
     __syncthreads();
-    double part = 0.0;
-    if (active) {
-        int type1 = s.type[target], moltype1 = s.moltype[target];
-        ConList cl;
-        if (MODE == 3) { cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0; }
-        else get_conlist(s.mol, moltype1, target, cl);
-        Filter f;
-        f.self = target;
-        f.excl_lo = (MODE == 3) ? excl_lo : 0;
-        f.excl_hi = (MODE == 3) ? excl_hi : 0;
-        f.max_idx = (MODE == 2) ? target : 0x7fffffff;
-        part = warp_one_to_all(s, rec1, type1, moltype1, cl, f, gw, gwid, sh_queue[wid], e_pairs, counters);
+    if (!active) return;
+    int type1 = s.type[target], moltype1 = s.moltype[target];
+    ConList cl;
+    if (MODE == 3 || RODS) { cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0; }
+    else get_conlist(s.mol, moltype1, target, cl);
+    Filter f;
+    f.self = target;
+    f.excl_lo = (MODE == 3) ? excl_lo : 0;
+    f.excl_hi = (MODE == 3) ? excl_hi : 0;
+    f.max_idx = (MODE == 2) ? target : 0x7fffffff;
+    const int first_ref = trial ? (-1 - t) : s.slot_of[target];
+    const int wg = t * gw + gwid;
+    double part = warp_gate_cheap<RODS>(s, rec1, type1, moltype1, cl, f, gw, gwid, sh_queue[wid], sh_pbuf[wid], first_ref, wg, pl, e_pairs, counters);
+    if (lane == 0) warp_partial[wg] = part;
+}
+
+// one thread per listed pair; grid-stride because the list length lives on the device
+__global__ void __launch_bounds__(128)
+k_patch(DevSys s, PatchList pl, const int* __restrict__ targets, int mode, int excl_lo, double* __restrict__ e_pairs) {
+    int total = *pl.total;
+    if (total > pl.cap) total = pl.cap;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        int2 pr = pl.pair[p];
+        const double* s1;
+        int type1;
+        if (pr.x >= 0) { s1 = s.rec + (size_t)pr.x * REC; type1 = w_type(s.posw[pr.x].w); }
+        else {
+            int t = -1 - pr.x;
+            s1 = pl.trial_rec + (size_t)t * REC;
+            type1 = s.type[mode == 0 ? targets[t] : excl_lo + t];
+        }
+        double4 pw = s.posw[pr.y];
+        v3 r_cm = image(s.box, ld3(s1 + R_POS), mk(pw.x, pw.y, pw.z));
+        double e = pair_energy_patch(s.ia[type1 * s.ntypes + w_type(pw.w)], r_cm, s1, s.rec + (size_t)pr.y * REC);
+        pl.e[p] = e;
+        if (e_pairs) e_pairs[w_orig(pw.w)] += e;     // single-target calls only: one writer per partner
     }
-    if (lane == 0) sh_part[wid] = part;
-    __syncthreads();
-    if (active && gwid == 0 && lane == 0) {
-        double e = 0.0;
-        for (int k = 0; k < gw; k++) e += sh_part[g * gw + k];   // fixed order
-        out[t] = e;
+}
+
+// per trial particle: partial sums of its warps, then its patch terms in list order
+__global__ void k_combine(int m, int gw, PatchList pl, const double* __restrict__ warp_partial, double* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) { *pl.total = 0; *pl.chunk_count = 0; }   // the lists are consumed: reset for the next launch (stream order makes this safe)
+    if (t >= m) return;
+    double e = 0.0;
+    for (int k = 0; k < gw; k++) e += warp_partial[t * gw + k];
+    for (int k = 0; k < gw; k++) {
+        for (int cid = pl.warp_head[t * gw + k]; cid >= 0;) {
+            int4 ch = pl.chunks[cid];
+            for (int r = 0; r < ch.y; r++) e += pl.e[ch.x + r];
+            cid = ch.z;
+        }
     }
+    out[t] = e;
 }
 
 // deterministic total: one block, each thread strides in a fixed pattern, fixed tree
@@ -447,6 +540,18 @@ struct scgpu_ctx {
     // scratch
     double* d_out = nullptr;         // n doubles
     double* d_pairs = nullptr;       // n doubles
+    // patch work list (k_gate_cheap -> k_patch -> k_combine)
+    int2* d_pl_pair = nullptr;
+    double* d_pl_e = nullptr;
+    int* d_pl_total = nullptr;
+    int* d_pl_overflow = nullptr;
+    int pl_cap = 0;
+    bool rods_only = false;          // every particle an un-bonded rod: the specialised kernels apply
+    int* d_warp_head = nullptr;
+    int4* d_chunks = nullptr;
+    int chunk_cap = 0;
+    double* d_warp_partial = nullptr;
+    double* d_trial_rec = nullptr;   // [trial_cap][REC]
     double* d_trial = nullptr;       // staging for trial states
     int* d_targets = nullptr;
     int trial_cap = 0;
@@ -503,6 +608,9 @@ extern "C" int scgpu_create(scgpu_ctx** out, int device) {
     c->sm_count = prop.multiProcessorCount;
     CK(cudaMalloc(&c->d_scalar, 16 * sizeof(double)));
     CK(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&c->d_pl_total, 4 * sizeof(int)));     // [0] pairs in the list, [1] overflow flag, [2] chunks in use
+    CK(cudaMemset(c->d_pl_total, 0, 4 * sizeof(int)));
+    c->d_pl_overflow = c->d_pl_total + 1;
     CK(cudaMemset(c->d_scalar, 0, 16 * sizeof(double)));
     *out = c;
     return SCGPU_OK;
@@ -512,6 +620,8 @@ static void free_particles(scgpu_ctx* c) {
     cudaFree(c->d_api); cudaFree(c->d_posw); cudaFree(c->d_rec); cudaFree(c->d_type); cudaFree(c->d_moltype);
     cudaFree(c->d_cell_of); cudaFree(c->d_order); cudaFree(c->d_slot_of); cudaFree(c->d_tmp); cudaFree(c->d_out);
     cudaFree(c->d_pairs); cudaFree(c->d_flags);
+    cudaFree(c->d_pl_pair); cudaFree(c->d_pl_e); cudaFree(c->d_warp_head); cudaFree(c->d_chunks); cudaFree(c->d_warp_partial);
+    c->d_pl_pair = nullptr; c->d_pl_e = nullptr; c->d_warp_head = nullptr; c->d_chunks = nullptr; c->d_warp_partial = nullptr;
     c->d_api = nullptr; c->d_posw = nullptr; c->d_rec = nullptr; c->d_type = c->d_moltype = c->d_cell_of = c->d_order = c->d_slot_of = c->d_tmp = nullptr;
     c->d_out = c->d_pairs = nullptr; c->d_flags = nullptr;
     c->cap = 0;
@@ -523,7 +633,7 @@ extern "C" int scgpu_destroy(scgpu_ctx* c) {
     cudaStreamSynchronize(c->stream);
     free_particles(c);
     cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_counts); cudaFree(c->d_cell_start); cudaFree(c->d_cursor);
-    cudaFree(c->d_trial); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_counters); cudaFree(c->d_flush);
+    cudaFree(c->d_trial); cudaFree(c->d_trial_rec); cudaFree(c->d_pl_total); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_counters); cudaFree(c->d_flush);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -596,6 +706,13 @@ extern "C" int scgpu_set_particles(scgpu_ctx* c, int n, const double* state30, c
         CK(cudaMalloc(&c->d_out, N * sizeof(double)));
         CK(cudaMalloc(&c->d_pairs, N * sizeof(double)));
         CK(cudaMalloc(&c->d_flags, N * sizeof(int)));
+        c->pl_cap = (int)(N * 24 < 16384 ? 16384 : N * 24);
+        CK(cudaMalloc(&c->d_pl_pair, (size_t)c->pl_cap * sizeof(int2)));
+        CK(cudaMalloc(&c->d_pl_e, (size_t)c->pl_cap * sizeof(double)));
+        c->chunk_cap = (int)(N + 64) + c->pl_cap / PCAP + 64;
+        CK(cudaMalloc(&c->d_warp_head, (N + 64) * sizeof(int)));
+        CK(cudaMalloc(&c->d_chunks, (size_t)c->chunk_cap * sizeof(int4)));
+        CK(cudaMalloc(&c->d_warp_partial, (N + 64) * sizeof(double)));
         c->cap = n;
     }
     c->n = n;
@@ -611,6 +728,19 @@ extern "C" int scgpu_set_particles(scgpu_ctx* c, int n, const double* state30, c
     CK(cudaMemcpyAsync(c->d_moltype, pin + bytes + (size_t)n * sizeof(int), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     c->h_api.assign(state30, state30 + (size_t)n * 30);
     CK(cudaStreamSynchronize(c->stream));
+    // specialisation switch: only rod-rod functors and no bonded molecule among the particles present
+    {
+        std::vector<char> tu(c->ntypes, 0), mu(c->nmol, 0);
+        for (int i = 0; i < n; i++) { tu[type[i]] = 1; mu[moltype[i]] = 1; }
+        bool rods = true;
+        for (int a = 0; a < c->ntypes && rods; a++) for (int b = 0; b < c->ntypes && rods; b++) {
+            if (!tu[a] || !tu[b]) continue;
+            int k = (int)c->h_ia[(size_t)a * c->ntypes + b].reserved[0];
+            if (!(k == K_SC_PSCCPSC || k == K_SC_CPSC || k == K_SC_PSC || k == K_SC_SCN)) rods = false;
+        }
+        for (int mm = 0; mm < c->nmol && rods; mm++) if (mu[mm] && c->h_mol[mm].mol_size != 1.0) rods = false;
+        c->rods_only = rods;
+    }
     c->cells_valid = false;
     c->api_stale = false;
     return SCGPU_OK;
@@ -738,11 +868,58 @@ extern "C" int scgpu_download_particles(scgpu_ctx* c, double* state30) {
 
 static int ensure_trial(scgpu_ctx* c, int m) {
     if (m <= c->trial_cap) return 0;
-    cudaFree(c->d_trial); cudaFree(c->d_targets);
-    c->d_trial = nullptr; c->d_targets = nullptr; c->trial_cap = 0;
+    cudaFree(c->d_trial); cudaFree(c->d_targets); cudaFree(c->d_trial_rec);
+    c->d_trial = nullptr; c->d_targets = nullptr; c->d_trial_rec = nullptr; c->trial_cap = 0;
+    CK(cudaMalloc(&c->d_trial_rec, (size_t)m * REC * sizeof(double)));
     CK(cudaMalloc(&c->d_trial, (size_t)m * 30 * sizeof(double)));
     CK(cudaMalloc(&c->d_targets, (size_t)m * sizeof(int)));
     c->trial_cap = m;
+    return 0;
+}
+
+// the three launches behind every energy entry point
+static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_targets, const double* d_trial, int excl_lo, int excl_hi,
+                         double* d_out, double* d_pairs, unsigned long long* d_counters) {
+    DevSys s = view(c);
+    PatchList pl;
+    pl.pair = c->d_pl_pair; pl.e = c->d_pl_e; pl.total = c->d_pl_total; pl.cap = c->pl_cap;
+    pl.warp_head = c->d_warp_head; pl.chunks = c->d_chunks; pl.chunk_count = c->d_pl_total + 2; pl.chunk_cap = c->chunk_cap;
+    pl.trial_rec = c->d_trial_rec; pl.overflow = c->d_pl_overflow;
+    int groups_per_block = OTA_WARPS / gw;
+    int blocks = (m + groups_per_block - 1) / groups_per_block;
+#define LAUNCH_GC(M, R) k_gate_cheap<M, R><<<blocks, OTA_THREADS, 0, c->stream>>>(s, m, gw, d_targets, d_trial, excl_lo, excl_hi, pl, c->d_warp_partial, d_pairs, d_counters)
+    if (c->rods_only) {
+        switch (mode) { case 0: LAUNCH_GC(0, true); break; case 1: LAUNCH_GC(1, true); break; case 2: LAUNCH_GC(2, true); break; default: LAUNCH_GC(3, true); break; }
+    } else {
+        switch (mode) { case 0: LAUNCH_GC(0, false); break; case 1: LAUNCH_GC(1, false); break; case 2: LAUNCH_GC(2, false); break; default: LAUNCH_GC(3, false); break; }
+    }
+#undef LAUNCH_GC
+    int pblocks = m <= 64 ? 8 : c->sm_count * 8;
+    k_patch<<<pblocks, 128, 0, c->stream>>>(s, pl, d_targets, mode, excl_lo, d_pairs);
+    k_combine<<<(m + 255) / 256, 256, 0, c->stream>>>(m, gw, pl, c->d_warp_partial, d_out);
+    c->launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// the patch work list is sized for ~24 patch partners per particle on average; if a launch overflowed it (sticky device
+// flag) the results of that launch are invalid: grow the list 4x and let the caller repeat the launch
+static int overflow_then_grow(scgpu_ctx* c, bool* repeat) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, c->d_pl_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *repeat = false;
+    if (!flag) return 0;
+    if ((long long)c->pl_cap * 4 > (1ll << 30)) { g_err = "patch work list overflow: more patch pairs than the list can ever hold"; return SCGPU_ERR_STATE; }
+    cudaFree(c->d_pl_pair); cudaFree(c->d_pl_e); cudaFree(c->d_chunks);
+    c->d_pl_pair = nullptr; c->d_pl_e = nullptr; c->d_chunks = nullptr;
+    c->pl_cap *= 4;
+    c->chunk_cap = c->cap + 64 + c->pl_cap / PCAP + 64;
+    CK(cudaMalloc(&c->d_pl_pair, (size_t)c->pl_cap * sizeof(int2)));
+    CK(cudaMalloc(&c->d_pl_e, (size_t)c->pl_cap * sizeof(double)));
+    CK(cudaMalloc(&c->d_chunks, (size_t)c->chunk_cap * sizeof(int4)));
+    CK(cudaMemsetAsync(c->d_pl_total, 0, 4 * sizeof(int), c->stream));
+    *repeat = true;
     return 0;
 }
 
@@ -754,16 +931,15 @@ extern "C" int scgpu_one_to_all(scgpu_ctx* c, int target, const double* trial_st
     if (ensure_trial(c, 1)) return SCGPU_ERR_CUDA;
     CK(cudaMemcpyAsync(c->d_targets, &target, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     if (trial_state30) CK(cudaMemcpyAsync(c->d_trial, trial_state30, 30 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if (e_pairs) CK(cudaMemsetAsync(c->d_pairs, 0, (size_t)c->n * sizeof(double), c->stream));
-    DevSys s = view(c);
-    // a single trial: all 4 warps of one block share the 27 neighbour cells
-    k_one_to_all<0><<<1, OTA_THREADS, 0, c->stream>>>(s, 1, OTA_WARPS, c->d_targets, trial_state30 ? c->d_trial : nullptr, 0, 0,
-                                                       c->d_out, e_pairs ? c->d_pairs : nullptr, nullptr);
-    c->launches++;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(e_sum, c->d_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (e_pairs) CK(cudaMemcpyAsync(e_pairs, c->d_pairs, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    for (bool repeat = true; repeat;) {
+        if (e_pairs) CK(cudaMemsetAsync(c->d_pairs, 0, (size_t)c->n * sizeof(double), c->stream));
+        // a single trial: all 4 warps of one block share the 27 neighbour cells
+        if (launch_energy(c, 0, 1, OTA_WARPS, c->d_targets, trial_state30 ? c->d_trial : nullptr, 0, 0, c->d_out,
+                          e_pairs ? c->d_pairs : nullptr, nullptr)) return SCGPU_ERR_CUDA;
+        CK(cudaMemcpyAsync(e_sum, c->d_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (e_pairs) CK(cudaMemcpyAsync(e_pairs, c->d_pairs, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (int r = overflow_then_grow(c, &repeat)) return r;
+    }
     return SCGPU_OK;
 }
 
@@ -783,13 +959,11 @@ extern "C" int scgpu_one_to_all_batch(scgpu_ctx* c, int m, const int* targets, c
     if (sb) CK(cudaMemcpyAsync(c->d_trial, pin + tb, sb, cudaMemcpyHostToDevice, c->stream));
     double* d_res = c->d_out;
     if (m > c->n) { g_err = "scgpu_one_to_all_batch: m larger than the particle count is not supported"; return SCGPU_ERR_ARG; }
-    DevSys s = view(c);
-    k_one_to_all<0><<<(m + OTA_WARPS - 1) / OTA_WARPS, OTA_THREADS, 0, c->stream>>>(s, m, 1, c->d_targets, sb ? c->d_trial : nullptr, 0, 0,
-                                                                                      d_res, nullptr, nullptr);
-    c->launches++;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(pin + tb + sb, d_res, ob, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    for (bool repeat = true; repeat;) {
+        if (launch_energy(c, 0, m, 1, c->d_targets, sb ? c->d_trial : nullptr, 0, 0, d_res, nullptr, nullptr)) return SCGPU_ERR_CUDA;
+        CK(cudaMemcpyAsync(pin + tb + sb, d_res, ob, cudaMemcpyDeviceToHost, c->stream));
+        if (int r = overflow_then_grow(c, &repeat)) return r;
+    }
     memcpy(e_sums, pin + tb + sb, ob);
     return SCGPU_OK;
 }
@@ -799,16 +973,15 @@ extern "C" int scgpu_one_to_all_everyone(scgpu_ctx* c, double* e_host, int64_t* 
     CK(cudaSetDevice(c->device));
     if (int r = ensure_cells(c)) return r;
     bool count = n_candidates || n_gated;
-    if (count) CK(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream));
-    DevSys s = view(c);
-    k_one_to_all<1><<<(c->n + OTA_WARPS - 1) / OTA_WARPS, OTA_THREADS, 0, c->stream>>>(s, c->n, 1, nullptr, nullptr, 0, 0, c->d_out, nullptr,
-                                                                                         count ? c->d_counters : nullptr);
-    c->launches++;
-    CK(cudaGetLastError());
-    if (e_host) CK(cudaMemcpyAsync(e_host, c->d_out, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     unsigned long long h[2] = {0, 0};
-    if (count) CK(cudaMemcpyAsync(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-    if (e_host || count) CK(cudaStreamSynchronize(c->stream));
+    for (bool repeat = true; repeat;) {
+        if (count) CK(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream));
+        if (launch_energy(c, 1, c->n, 1, nullptr, nullptr, 0, 0, c->d_out, nullptr, count ? c->d_counters : nullptr)) return SCGPU_ERR_CUDA;
+        if (e_host) CK(cudaMemcpyAsync(e_host, c->d_out, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (count) CK(cudaMemcpyAsync(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        repeat = false;
+        if (e_host || count) { if (int r = overflow_then_grow(c, &repeat)) return r; }   // asynchronous calls are checked by scgpu_sync
+    }
     if (n_candidates) *n_candidates = (int64_t)h[0];
     if (n_gated) *n_gated = (int64_t)h[1];
     return SCGPU_OK;
@@ -823,22 +996,21 @@ extern "C" int scgpu_mol_to_others(scgpu_ctx* c, int first, int m, const double*
         if (ensure_trial(c, m)) return SCGPU_ERR_CUDA;
         CK(cudaMemcpyAsync(c->d_trial, trial_states30, (size_t)m * 30 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     }
-    DevSys s = view(c);
-    k_one_to_all<3><<<(m + OTA_WARPS - 1) / OTA_WARPS, OTA_THREADS, 0, c->stream>>>(s, m, 1, nullptr, trial_states30 ? c->d_trial : nullptr, first, first + m,
-                                                                                      c->d_out, nullptr, nullptr);
-    k_reduce_fixed<<<1, 256, 0, c->stream>>>(m, c->d_out, c->d_scalar);
-    c->launches += 2;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(e_sum, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    for (bool repeat = true; repeat;) {
+        if (launch_energy(c, 3, m, 1, nullptr, trial_states30 ? c->d_trial : nullptr, first, first + m, c->d_out, nullptr, nullptr)) return SCGPU_ERR_CUDA;
+        k_reduce_fixed<<<1, 256, 0, c->stream>>>(m, c->d_out, c->d_scalar);
+        c->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(e_sum, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (int r = overflow_then_grow(c, &repeat)) return r;
+    }
     return SCGPU_OK;
 }
 
 static int launch_all_to_all(scgpu_ctx* c) {
-    DevSys s = view(c);
-    k_one_to_all<2><<<(c->n + OTA_WARPS - 1) / OTA_WARPS, OTA_THREADS, 0, c->stream>>>(s, c->n, 1, nullptr, nullptr, 0, 0, c->d_out, nullptr, nullptr);
+    if (launch_energy(c, 2, c->n, 1, nullptr, nullptr, 0, 0, c->d_out, nullptr, nullptr)) return SCGPU_ERR_CUDA;
     k_reduce_fixed<<<1, 1024, 0, c->stream>>>(c->n, c->d_out, c->d_scalar);
-    c->launches += 2;
+    c->launches += 1;
     CK(cudaGetLastError());
     return 0;
 }
@@ -847,10 +1019,13 @@ extern "C" int scgpu_all_to_all(scgpu_ctx* c, double* e_total, double* e_per_par
     ARG(c, "scgpu_all_to_all: NULL argument");
     CK(cudaSetDevice(c->device));
     if (int r = ensure_cells(c)) return r;
-    if (launch_all_to_all(c)) return SCGPU_ERR_CUDA;
-    if (e_total) CK(cudaMemcpyAsync(e_total, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (e_per_particle) CK(cudaMemcpyAsync(e_per_particle, c->d_out, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (e_total || e_per_particle) CK(cudaStreamSynchronize(c->stream));
+    for (bool repeat = true; repeat;) {
+        if (launch_all_to_all(c)) return SCGPU_ERR_CUDA;
+        if (e_total) CK(cudaMemcpyAsync(e_total, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (e_per_particle) CK(cudaMemcpyAsync(e_per_particle, c->d_out, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        repeat = false;
+        if (e_total || e_per_particle) { if (int r = overflow_then_grow(c, &repeat)) return r; }
+    }
     return SCGPU_OK;
 }
 
@@ -858,7 +1033,10 @@ extern "C" int scgpu_replica_record(scgpu_ctx* c, void** device_ptr_out) {
     ARG(c && device_ptr_out, "scgpu_replica_record: NULL argument");
     CK(cudaSetDevice(c->device));
     if (int r = ensure_cells(c)) return r;
-    if (launch_all_to_all(c)) return SCGPU_ERR_CUDA;
+    for (bool repeat = true; repeat;) {
+        if (launch_all_to_all(c)) return SCGPU_ERR_CUDA;
+        if (int r = overflow_then_grow(c, &repeat)) return r;
+    }
     double rec[7] = {c->box[0] * c->box[1] * c->box[2], (double)c->n, 0, 0, 0, 0, 0};
     // record = {E (written by the reduction at d_scalar[0]), V, N, ...}: lay it out at d_scalar[8..15]
     CK(cudaMemcpyAsync(c->d_scalar + 8, c->d_scalar, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -925,7 +1103,9 @@ extern "C" int scgpu_timer_stop(scgpu_ctx* c, float* ms) {
 extern "C" int scgpu_sync(scgpu_ctx* c) {
     ARG(c, "scgpu_sync: NULL context");
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
+    bool grew = false;
+    if (int r = overflow_then_grow(c, &grew)) return r;
+    if (grew) { g_err = "scgpu_sync: an asynchronous energy launch overflowed the patch work list; its results are invalid (the list has been grown: repeat the call)"; return SCGPU_ERR_STATE; }
     return SCGPU_OK;
 }
 extern "C" int scgpu_kernel_launches(scgpu_ctx* c, int64_t* launches) {

@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Small driver for ncu: loads the 65 536-PSC workload and runs a few passes of one entry point.
+usage: python scripts/profile_step.py [everyone|all_to_all|cells|sweep] [reps]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sc_b200 import Engine, synth                    # noqa: E402
+from sc_b200.host import HostSystem                  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "everyone"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+top, cfg, n = synth.psc_bulk()
+hs = HostSystem(top, cfg)
+eng = Engine(0, "fast").load(hs)
+eng.build_cells()
+for _ in range(reps):
+    if what == "everyone":
+        eng.one_to_all_everyone(fetch=False)
+    elif what == "all_to_all":
+        eng.all_to_all(fetch=False)
+    elif what == "cells":
+        eng.set_particles(hs.state, hs.type, hs.moltype)
+        eng.build_cells()
+    elif what == "sweep":
+        from sc_b200.engine import MoveParams
+        mp = MoveParams()
+        mp.temper = 0.1
+        for k in range(40):
+            mp.trans_mx[k] = 0.0424
+            mp.rot_angle[k] = 7.5 / 180.0 * 1.5707963267948966 * 0.5
+        mp.n_sub = 1
+        eng.sweep(mp, 12345, _)
+eng.sync()
+print("done", what, reps)
