@@ -189,7 +189,7 @@ __global__ void k_unsort(DevSys s, double* __restrict__ api) {
 //   k_patch       one thread per listed pair: the patch geometry + attraction (the expensive ~10 %), densely packed
 //   k_combine     per trial particle: partial + its patch terms, summed in list order (deterministic)
 // ------------------------------------------------------------------------------------------------
-constexpr int QCAP = 64;      // per-warp gated-candidate queue (ints, shared memory)
+constexpr int QCAP = 96;      // per-warp gated-candidate queue (ints, shared memory): < 32 left over + up to 64 new
 constexpr int PCAP = 64;      // per-warp patch-pair buffer (ints, shared memory), flushed to the global list in chunks
 // a warp that collects more than PCAP patch partners for one particle flushes several chunks; they are chained
 
@@ -393,13 +393,14 @@ k_gate_cheap(DevSys s, int m, int gw, const int* __restrict__ targets, const dou
 // candidate array instead of 27 partially filled cell segments (lane utilisation of the gate ~100 % instead of ~55 %).
 // Cells whose neighbourhood does not fit the tile fall back to the per-warp global-memory scan.
 // ------------------------------------------------------------------------------------------------
-constexpr int TILE = 704;     // 704 x (32 + 24 + 4) B + per-warp scratch stays under the 48 KB static shared-memory limit
+__device__ __forceinline__ double rel_frac(double u, double cen) { double d = u - cen; return d - rint(d); }
+constexpr int TILE = 960;     // 960 x (16 + 24 + 4) B + per-warp scratch stays under the 48 KB static shared-memory limit     // 704 x (32 + 24 + 4) B + per-warp scratch stays under the 48 KB static shared-memory limit
 constexpr int CB_WARPS = 4;
 
 template <int MODE, bool RODS>
 __global__ void __launch_bounds__(CB_WARPS * 32, RODS ? 4 : 3)
 k_gate_cheap_cells(DevSys s, PatchList pl, double* __restrict__ warp_partial, unsigned long long* counters) {
-    __shared__ double4 t_pw[TILE];
+    __shared__ float4 t_pf[TILE];     // FP32 fractional coordinates relative to the cell centre (conservative pre-gate); w = original index
     __shared__ double t_dir[RODS ? TILE * 3 : 3];
     __shared__ int t_slot[TILE];
     __shared__ double sh_rec[CB_WARPS][REC];
@@ -432,12 +433,18 @@ k_gate_cheap_cells(DevSys s, PatchList pl, double* __restrict__ warp_partial, un
     __syncthreads();
     const int C = sh_off[ncell_nb];
     const bool tiled = C <= TILE;
+    // centre of this cell in fractional coordinates; positions are staged relative to it so that FP32 keeps ~1e-8 of a cell
+    const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
+    const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
+    const float pre_cut = (float)(s.sqmaxcut * 1.001) ;   // conservative: the exact FP64 gate is re-applied before evaluation
     if (tiled) {
         for (int p = threadIdx.x; p < C; p += blockDim.x) {
             int k = 0;
             while (k + 1 < ncell_nb && sh_off[k + 1] <= p) k++;
             int slot = sh_b[k] + (p - sh_off[k]);
-            t_pw[p] = s.posw[slot];
+            double4 pw = s.posw[slot];
+            t_pf[p] = make_float4((float)rel_frac(pw.x + s.shift[0], ccen[0]), (float)rel_frac(pw.y + s.shift[1], ccen[1]),
+                                  (float)rel_frac(pw.z + s.shift[2], ccen[2]), __int_as_float(w_orig(pw.w)));
             t_slot[p] = slot;
             if (RODS) {
                 const double* r = s.rec + (size_t)slot * REC;
@@ -491,13 +498,15 @@ k_gate_cheap_cells(DevSys s, PatchList pl, double* __restrict__ warp_partial, un
                 bool np = false;
                 int slot = 0;
                 if (on) {
-                    double4 pw = t_pw[p];
                     slot = t_slot[p];
+                    double4 pw = s.posw[slot];
                     v3 r_cm = image(s.box, p1, mk(pw.x, pw.y, pw.z));
                     double dotrcm = dot(r_cm, r_cm);
-                    const double* s2 = RODS ? &t_dir[3 * p] : s.rec + (size_t)slot * REC;
-                    acc += pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r_cm, dotrcm, s1, type1, moltype1, s2, w_type(pw.w), w_orig(pw.w), cl, np);
-                    n_gate++;
+                    if (dotrcm <= s.sqmaxcut) {            // the exact PairE gate (mc/paire.h:1214)
+                        const double* s2 = RODS ? &t_dir[3 * p] : s.rec + (size_t)slot * REC;
+                        acc += pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r_cm, dotrcm, s1, type1, moltype1, s2, w_type(pw.w), w_orig(pw.w), cl, np);
+                        n_gate++;
+                    }
                 }
                 unsigned m = __ballot_sync(0xffffffffu, np);
                 if (m) {
@@ -508,29 +517,35 @@ k_gate_cheap_cells(DevSys s, PatchList pl, double* __restrict__ warp_partial, un
                     __syncwarp();
                 }
             };
-            for (int base = 0; base < C; base += 32) {
-                int p = base + lane;
-                bool pass = false;
-                if (p < C) {
-                    double4 pw = t_pw[p];
-                    int orig = w_orig(pw.w);
-                    bool bonded = !RODS && (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
-                    if (filt(f, orig) && !bonded) {
-                        n_cand++;
-                        v3 r_cm = image(s.box, p1, mk(pw.x, pw.y, pw.z));
-                        pass = (dot(r_cm, r_cm) <= s.sqmaxcut);   // PairE gate (mc/paire.h:1214)
-                    }
-                }
-                unsigned m = __ballot_sync(0xffffffffu, pass);
-                if (pass) queue[qn + __popc(m & lt_mask)] = p;
-                qn += __popc(m);
+            const float t1x = (float)rel_frac(tpw.x + s.shift[0], ccen[0]), t1y = (float)rel_frac(tpw.y + s.shift[1], ccen[1]),
+                        t1z = (float)rel_frac(tpw.z + s.shift[2], ccen[2]);
+            auto pre_gate = [&](int p) -> bool {
+                if (p >= C) return false;
+                float4 q = t_pf[p];
+                int orig = __float_as_int(q.w);
+                bool bonded = !RODS && (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
+                if (!filt(f, orig) || bonded) return false;
+                n_cand++;
+                float dx = t1x - q.x, dy = t1y - q.y, dz = t1z - q.z;
+                dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
+                return dx * dx + dy * dy + dz * dz <= pre_cut;
+            };
+            for (int base = 0; base < C; base += 64) {
+                bool pa = pre_gate(base + lane), pb = pre_gate(base + 32 + lane);
+                unsigned ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
+                int na = __popc(ma);
+                if (pa) queue[qn + __popc(ma & lt_mask)] = base + lane;
+                if (pb) queue[qn + na + __popc(mb & lt_mask)] = base + 32 + lane;
+                qn += na + __popc(mb);
                 __syncwarp();
-                if (qn >= 32) {
+                while (qn >= 32) {
                     eval_tile(queue[lane], true);
                     int rest = qn - 32;
-                    int mv = (lane < rest) ? queue[32 + lane] : 0;
+                    int mv0 = (lane < rest) ? queue[32 + lane] : 0;
+                    int mv1 = (lane + 32 < rest) ? queue[64 + lane] : 0;
                     __syncwarp();
-                    if (lane < rest) queue[lane] = mv;
+                    if (lane < rest) queue[lane] = mv0;
+                    if (lane + 32 < rest) queue[32 + lane] = mv1;
                     qn = rest;
                     __syncwarp();
                 }
