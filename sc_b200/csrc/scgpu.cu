@@ -586,8 +586,10 @@ k_gate_cheap_cells(DevSys s, PatchList pl, double* __restrict__ warp_partial, un
     }
 }
 
+#include "sweep.cuh"
+
 // one thread per listed pair; grid-stride because the list length lives on the device
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_patch(DevSys s, PatchList pl, const int* __restrict__ targets, int mode, int excl_lo, double* __restrict__ e_pairs) {
     int total = *pl.total;
     if (total > pl.cap) total = pl.cap;
@@ -758,6 +760,8 @@ struct scgpu_ctx {
     double* d_scalar = nullptr;      // 16 doubles: [0] total, [8..] replica record
     int* d_flags = nullptr;          // n ints
     unsigned long long* d_counters = nullptr;   // 8
+    void* d_sweep_acc = nullptr;
+    int sweep_acc_cap = 0;
     double* d_flush = nullptr;
     size_t flush_n = 0;
     void* h_pinned = nullptr;        // pinned staging, grown on demand
@@ -833,6 +837,7 @@ extern "C" int scgpu_destroy(scgpu_ctx* c) {
     cudaStreamSynchronize(c->stream);
     free_particles(c);
     cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_counts); cudaFree(c->d_cell_start); cudaFree(c->d_cursor);
+    cudaFree(c->d_sweep_acc);
     cudaFree(c->d_trial); cudaFree(c->d_trial_rec); cudaFree(c->d_pl_total); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_counters); cudaFree(c->d_flush);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -973,7 +978,8 @@ static int sync_api_from_sorted(scgpu_ctx* c) {
     return 0;
 }
 
-extern "C" int scgpu_build_cells(scgpu_ctx* c) {
+// shift: fractional grid offset; even_grid: checkerboard sweeps need an even cell count (>= 4) per axis, else one cell
+static int build_cells_impl(scgpu_ctx* c, const double shift[3], bool even_grid) {
     ARG(c, "scgpu_build_cells: NULL context");
     ARG(c->n > 0 && c->ntypes > 0 && c->box[0] > 0, "scgpu_build_cells: topology, particles and box must be set first");
     CK(cudaSetDevice(c->device));
@@ -981,7 +987,9 @@ extern "C" int scgpu_build_cells(scgpu_ctx* c) {
     for (int d = 0; d < 3; d++) {
         int nc = (int)floor(c->box[d] / c->maxcut);
         if (nc < 3) nc = 1;      // fewer than 3 cells: the +-1 neighbours would alias through the periodic image
+        if (even_grid) nc = (nc >= 4) ? (nc & ~1) : 1;
         c->nc[d] = nc;
+        c->shift[d] = shift[d];
     }
     long long ncells = (long long)c->nc[0] * c->nc[1] * c->nc[2];
     ARG(ncells < (1ll << 30), "scgpu_build_cells: too many cells");
@@ -1005,6 +1013,11 @@ extern "C" int scgpu_build_cells(scgpu_ctx* c) {
     c->cells_valid = true;
     c->h_cell_of.clear();   // host mirror fetched lazily by scgpu_update_particle
     return SCGPU_OK;
+}
+
+extern "C" int scgpu_build_cells(scgpu_ctx* c) {
+    const double zero[3] = {0.0, 0.0, 0.0};
+    return build_cells_impl(c, zero, false);
 }
 
 static int ensure_cells(scgpu_ctx* c) {
@@ -1285,10 +1298,69 @@ extern "C" int scgpu_overlap_all(scgpu_ctx* c, int variant, int* flag) {
     return SCGPU_OK;
 }
 
+static inline unsigned long long splitmix64(unsigned long long& x) {
+    unsigned long long z = (x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
 extern "C" int scgpu_sweep_checkerboard(scgpu_ctx* c, const scgpu_moveparams* mp, uint64_t seed, uint64_t sweep, scgpu_sweepstats* stats) {
-    (void)c; (void)mp; (void)seed; (void)sweep; (void)stats;
-    g_err = "scgpu_sweep_checkerboard: not built into this library yet";
-    return SCGPU_ERR_STATE;
+    ARG(c && mp, "scgpu_sweep_checkerboard: NULL argument");
+    ARG(mp->temper > 0 && mp->n_sub >= 1, "scgpu_sweep_checkerboard: temperature and n_sub must be positive");
+    ARG(c->n > 0 && c->ntypes > 0 && c->ntypes <= 40, "scgpu_sweep_checkerboard: set topology (<= 40 types) and particles first");
+    CK(cudaSetDevice(c->device));
+    // random grid shift and colour order for this sweep: a pure function of (seed, sweep)
+    unsigned long long st = seed * 0xD1342543DE82EF95ull + sweep * 0x9E3779B97F4A7C15ull + 0x2545F4914F6CDD1Dull;
+    double shift[3];
+    for (int d = 0; d < 3; d++) shift[d] = (double)(splitmix64(st) >> 11) * (1.0 / 9007199254740992.0);
+    if (int r = build_cells_impl(c, shift, true)) return r;
+    int3 ncol = make_int3(c->nc[0] >= 4 ? 2 : 1, c->nc[1] >= 4 ? 2 : 1, c->nc[2] >= 4 ? 2 : 1);
+    int ncolours = ncol.x * ncol.y * ncol.z;
+    int order[8];
+    for (int k = 0; k < ncolours; k++) order[k] = k;
+    for (int k = ncolours - 1; k > 0; k--) { int j = (int)(splitmix64(st) % (unsigned long long)(k + 1)); int t = order[k]; order[k] = order[j]; order[j] = t; }
+    SweepParams sp;
+    sp.temper = mp->temper;
+    sp.n_sub = mp->n_sub;
+    for (int t = 0; t < 40; t++) {
+        sp.trans_mx[t] = mp->trans_mx[t];
+        sp.rot_angle[t] = mp->rot_angle[t];
+        sp.geotype_of_type[t] = (t < c->ntypes) ? (int)c->h_ia[(size_t)t * c->ntypes + t].geotype[0] : 0;
+    }
+    if (c->sweep_acc_cap < c->ncells) {
+        cudaFree(c->d_sweep_acc);
+        c->d_sweep_acc = nullptr;
+        CK(cudaMalloc(&c->d_sweep_acc, (size_t)c->ncells * sizeof(SweepAcc)));
+        c->sweep_acc_cap = c->ncells;
+    }
+    CK(cudaMemsetAsync(c->d_sweep_acc, 0, (size_t)c->ncells * sizeof(SweepAcc), c->stream));
+    CK(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
+    DevSys s = view(c);
+    int nactive = (c->nc[0] / ncol.x) * (c->nc[1] / ncol.y) * (c->nc[2] / ncol.z);
+    for (int k = 0; k < ncolours; k++) {
+        k_sweep_colour<<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    c->api_stale = true;           // the cell-sorted arrays are now the newest copy of the configuration
+    c->h_cell_of.clear();
+    int fail = 0;
+    std::vector<SweepAcc> acc;
+    if (stats) acc.resize(c->ncells);
+    CK(cudaMemcpyAsync(&fail, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (stats) CK(cudaMemcpyAsync(acc.data(), c->d_sweep_acc, (size_t)c->ncells * sizeof(SweepAcc), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (fail) { g_err = "scgpu_sweep_checkerboard: a cell neighbourhood holds more particles than the staged tile (SW_TILE); configuration too dense for this build"; return SCGPU_ERR_STATE; }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int i = 0; i < c->ncells; i++) {       // fixed order
+            stats->trans_acc += acc[i].trans_acc; stats->trans_rej += acc[i].trans_rej;
+            stats->rot_acc += acc[i].rot_acc; stats->rot_rej += acc[i].rot_rej;
+            stats->cell_rej += acc[i].cell_rej; stats->energy_delta += acc[i].de;
+        }
+    }
+    return SCGPU_OK;
 }
 
 extern "C" int scgpu_timer_start(scgpu_ctx* c) {
