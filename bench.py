@@ -246,7 +246,11 @@ def run_ours(args):
     value = pairs / (total_ms * 1e-3)
 
     # ---- end to end through the C ABI with HOST buffers: H2D of the configuration, cell build, energy pass, D2H of energies
-    state_host = hs.state.copy()
+    # page-locked host buffer (the contract's "pinned host memory"): the library DMAs straight from it
+    import torch as _t
+    pinned = _t.empty((n, 30), dtype=_t.float64).pin_memory()
+    state_host = pinned.numpy()
+    state_host[:] = hs.state
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         eng.set_particles(state_host, hs.type, hs.moltype)

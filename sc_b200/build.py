@@ -40,7 +40,7 @@ def build(variant=None, force=False, verbose=False):
     return [lib_path(v) for v in names]
 
 
-HOST_SRCS = [os.path.join(HERE, "csrc", "host", f) for f in ("topology.cpp", "calculator.cpp", "schost_capi.cpp")]
+HOST_SRCS = [os.path.join(HERE, "csrc", "host", f) for f in ("topology.cpp", "calculator.cpp", "schost_capi.cpp", "mc_driver.cpp")]
 HOST_DEPS = HOST_SRCS + [os.path.join(HERE, "csrc", "host", f) for f in ("topology.hpp", "calculator.hpp")]
 HOST_LIB = os.path.join(HERE, "libschost.so")
 

@@ -37,23 +37,29 @@ double TotalEGpu::allToAll() {
 }
 double TotalEGpu::allToAllTrial() { return allToAll(); }   // box already mutated by the caller; pushBox() picks it up
 
+// The reference reads the box through a pointer (PairE::pbc), so a REJECTED volume move restores it behind the calculator's
+// back: every entry point therefore re-sends the current host box first (three doubles; re-gridding only if ncell changes).
 double TotalEGpu::oneToAll(int target) {
     double e = 0.0;
+    pushBox();
     check(scgpu_one_to_all(ctx, target, nullptr, &e, nullptr), "scgpu_one_to_all");
     return e;
 }
 double TotalEGpu::oneToAllTrial(int target) {
     double e = 0.0;
+    pushBox();
     check(scgpu_one_to_all(ctx, target, &conf->state[(size_t)target * 30], &e, nullptr), "scgpu_one_to_all");
     return e;
 }
 double TotalEGpu::mol2others(const Molecule& mol) {
     double e = 0.0;
+    pushBox();
     check(scgpu_mol_to_others(ctx, mol.front(), (int)mol.size(), nullptr, &e), "scgpu_mol_to_others");
     return e;
 }
 double TotalEGpu::mol2othersTrial(const Molecule& mol) {
     double e = 0.0;
+    pushBox();
     check(scgpu_mol_to_others(ctx, mol.front(), (int)mol.size(), &conf->state[(size_t)mol.front() * 30], &e), "scgpu_mol_to_others");
     return e;
 }

@@ -714,7 +714,8 @@ __global__ void k_flush(double* buf, size_t n) {
 struct scgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // timer
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;      // bounce-buffer hand-off in scgpu_set_particles
     int sm_count = 148;
     // topology
     int ntypes = 0, nmol = 0;
@@ -727,7 +728,7 @@ struct scgpu_ctx {
     int n = 0, cap = 0;
     double box[3] = {0, 0, 0};
     double shift[3] = {0, 0, 0};
-    std::vector<double> h_api;       // host mirror of positions only is not enough for update(): keep full mirror
+    std::vector<double> h_api;       // unused host mirror (kept for ABI stability of the struct layout in debuggers)
     std::vector<int> h_cell_of;
     double* d_api = nullptr;
     double4* d_posw = nullptr;
@@ -807,6 +808,8 @@ extern "C" int scgpu_create(scgpu_ctx** out, int device) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
+    CK(cudaEventCreateWithFlags(&c->ev2, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev3, cudaEventDisableTiming));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -840,7 +843,7 @@ extern "C" int scgpu_destroy(scgpu_ctx* c) {
     cudaFree(c->d_sweep_acc);
     cudaFree(c->d_trial); cudaFree(c->d_trial_rec); cudaFree(c->d_pl_total); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_counters); cudaFree(c->d_flush);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->stream);
     delete c;
     return SCGPU_OK;
@@ -921,17 +924,34 @@ extern "C" int scgpu_set_particles(scgpu_ctx* c, int n, const double* state30, c
         c->cap = n;
     }
     c->n = n;
-    // pinned staging so that the copy is a true async DMA inside timed regions
+    // Host -> device. If the caller's buffers are already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+    // the DMA reads them directly; otherwise they are staged through a pinned bounce buffer in 2 MB chunks so that the
+    // host memcpy of chunk k+1 overlaps the DMA of chunk k.
     size_t bytes = (size_t)n * 30 * sizeof(double);
-    if (ensure_pinned(c, bytes + 2 * (size_t)n * sizeof(int))) return SCGPU_ERR_CUDA;
-    char* pin = (char*)c->h_pinned;
-    memcpy(pin, state30, bytes);
-    memcpy(pin + bytes, type, (size_t)n * sizeof(int));
-    memcpy(pin + bytes + (size_t)n * sizeof(int), moltype, (size_t)n * sizeof(int));
-    CK(cudaMemcpyAsync(c->d_api, pin, bytes, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_type, pin + bytes, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_moltype, pin + bytes + (size_t)n * sizeof(int), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    c->h_api.assign(state30, state30 + (size_t)n * 30);
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    if (is_pinned(state30)) {
+        CK(cudaMemcpyAsync(c->d_api, state30, bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        const size_t CH = 2u << 20;
+        if (ensure_pinned(c, 2 * CH)) return SCGPU_ERR_CUDA;
+        char* pin = (char*)c->h_pinned;
+        cudaEvent_t evs[2] = {c->ev2, c->ev3};
+        int k = 0;
+        for (size_t off = 0; off < bytes; off += CH, k ^= 1) {
+            size_t len = bytes - off < CH ? bytes - off : CH;
+            if (off >= 2 * CH) CK(cudaEventSynchronize(evs[k]));          // this half of the bounce buffer is free again
+            memcpy(pin + k * CH, (const char*)state30 + off, len);
+            CK(cudaMemcpyAsync((char*)c->d_api + off, pin + k * CH, len, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaEventRecord(evs[k], c->stream));
+        }
+    }
+    CK(cudaMemcpyAsync(c->d_type, type, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_moltype, moltype, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    c->h_api.clear();            // host mirror (needed only by scgpu_update_particle) is refreshed lazily from the device
     CK(cudaStreamSynchronize(c->stream));
     // specialisation switch: only rod-rod functors and no bonded molecule among the particles present
     {
@@ -1048,8 +1068,7 @@ extern "C" int scgpu_update_particle(scgpu_ctx* c, int idx, const double* state3
     ARG(idx >= 0 && idx < c->n, "scgpu_update_particle: index out of range");
     CK(cudaSetDevice(c->device));
     if (sync_api_from_sorted(c)) return SCGPU_ERR_CUDA;
-    memcpy(&c->h_api[(size_t)idx * 30], state30, 30 * sizeof(double));
-    CK(cudaMemcpyAsync(c->d_api + (size_t)idx * 30, &c->h_api[(size_t)idx * 30], 30 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_api + (size_t)idx * 30, state30, 30 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (c->cells_valid) {
         if (c->h_cell_of.empty()) {
             c->h_cell_of.resize(c->n);
@@ -1075,7 +1094,6 @@ extern "C" int scgpu_download_particles(scgpu_ctx* c, double* state30) {
     if (sync_api_from_sorted(c)) return SCGPU_ERR_CUDA;
     CK(cudaMemcpyAsync(state30, c->d_api, (size_t)c->n * 30 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->h_api.assign(state30, state30 + (size_t)c->n * 30);
     return SCGPU_OK;
 }
 

@@ -42,6 +42,10 @@ def _load():
         L.schost_calc_update_box.argtypes = [vp]
         L.schost_calc_ctx.argtypes = [vp]
         L.schost_calc_ctx.restype = vp
+        L.schost_mc_last_error.restype = C.c_char_p
+        L.schost_run_mc.argtypes = [vp, C.c_char_p, C.c_int, C.c_long, _dp]
+        L.schost_config_last.argtypes = [vp, C.c_int, C.c_char_p, C.c_long]
+        L.schost_config_last.restype = C.c_long
         _lib = L
     return _lib
 
@@ -85,6 +89,30 @@ class HostSystem:
         b = np.ascontiguousarray(box, dtype=np.float64)
         _ck(_load().schost_set_box(self.h, b.ctypes.data_as(_dp)))
         self.box[:] = b
+
+    def refresh(self):
+        """re-read the arrays after the C++ side changed the configuration (sequential MC driver)"""
+        cut = np.zeros(2)
+        _load().schost_export(self.h, self.state.ctypes.data_as(_dp), self.type.ctypes.data_as(_ip), self.moltype.ctypes.data_as(_ip),
+                              self.ia.ctypes.data_as(_dp), self.mol.ctypes.data_as(_dp), self.box.ctypes.data_as(_dp), cut.ctypes.data_as(_dp))
+
+    def run_mc(self, options_text, device=0, nsweeps=0):
+        """production run of the reference program (Updater::simulate) through TotalEGpu; returns a stats dict"""
+        L = _load()
+        out = np.zeros(13)
+        if L.schost_run_mc(self.h, options_text.encode(), int(device), int(nsweeps), out.ctypes.data_as(_dp)) != 0:
+            raise HostError(L.schost_mc_last_error().decode())
+        self.refresh()
+        keys = ["trans_acc", "trans_rej", "rot_acc", "rot_rej", "chainm_acc", "chainm_rej", "chainr_acc", "chainr_rej", "edge_acc", "edge_rej",
+                "e_start", "e_end", "drift"]
+        return dict(zip(keys, out.tolist()))
+
+    def config_last(self, testing_format=True):
+        L = _load()
+        n = L.schost_config_last(self.h, 1 if testing_format else 0, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        L.schost_config_last(self.h, 1 if testing_format else 0, buf, n)
+        return buf.raw[:n].decode()
 
     def close(self):
         if self.h:

@@ -211,9 +211,32 @@ def do_extras():
         print("extra:", kind)
 
 
+def do_short():
+    """volumeChange cases run 20 000 sweeps; a 1 500-sweep trajectory of the unmodified reference is the golden for the
+    sequential GPU-path test (the sequential C-ABI path pays two synchronous launches per trial)"""
+    import re
+    for d in sorted(os.listdir(os.path.join(REF, "Tests", "volumeChange"))):
+        src = os.path.join(REF, "Tests", "volumeChange", d, "new")
+        if not os.path.isdir(src):
+            continue
+        tmp = tempfile.mkdtemp(prefix="short_")
+        for fn in os.listdir(src):
+            shutil.copy(os.path.join(src, fn), tmp)
+        opt = open(os.path.join(tmp, "options")).read()
+        opt = re.sub(r"(?m)^nsweeps\s*=\s*\d+", "nsweeps = 1500", opt)
+        with open(os.path.join(tmp, "options"), "w") as f:
+            f.write(opt)
+        run([SC], tmp)
+        shutil.copy(os.path.join(tmp, "config.last"), os.path.join(HERE, "volumeChange_%s.short1500.config.last" % d))
+        shutil.rmtree(tmp)
+        print("short:", d)
+
+
 def main():
     if "extras" in sys.argv[1:]:
         return do_extras()
+    if "short" in sys.argv[1:]:
+        return do_short()
     if not (os.path.exists(DRIVER) and os.path.exists(SC)):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
     tests = sorted(d for d in os.listdir(os.path.join(REF, "Tests")) if d.startswith("test_"))
