@@ -765,6 +765,8 @@ struct scgpu_ctx {
     int sweep_acc_cap = 0;
     double* d_flush = nullptr;
     size_t flush_n = 0;
+    char* h_small = nullptr;         // 1 KB pinned: single-call inputs [0..255], results [256..511], update staging [512..751]
+    char* d_single = nullptr;        // 256 B device staging of a single call: trial record [0..239], target index [240..243]
     void* h_pinned = nullptr;        // pinned staging, grown on demand
     size_t pinned_bytes = 0;
     int64_t launches = 0;
@@ -813,6 +815,8 @@ extern "C" int scgpu_create(scgpu_ctx** out, int device) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    CK(cudaMallocHost((void**)&c->h_small, 1024));
+    CK(cudaMalloc((void**)&c->d_single, 256));
     CK(cudaMalloc(&c->d_scalar, 16 * sizeof(double)));
     CK(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     CK(cudaMalloc(&c->d_pl_total, 4 * sizeof(int)));     // [0] pairs in the list, [1] overflow flag, [2] chunks in use
@@ -843,6 +847,8 @@ extern "C" int scgpu_destroy(scgpu_ctx* c) {
     cudaFree(c->d_sweep_acc);
     cudaFree(c->d_trial); cudaFree(c->d_trial_rec); cudaFree(c->d_pl_total); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_counters); cudaFree(c->d_flush);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_small) cudaFreeHost(c->h_small);
+    cudaFree(c->d_single);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1068,7 +1074,9 @@ extern "C" int scgpu_update_particle(scgpu_ctx* c, int idx, const double* state3
     ARG(idx >= 0 && idx < c->n, "scgpu_update_particle: index out of range");
     CK(cudaSetDevice(c->device));
     if (sync_api_from_sorted(c)) return SCGPU_ERR_CUDA;
-    CK(cudaMemcpyAsync(c->d_api + (size_t)idx * 30, state30, 30 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));        // the staging slot is reused: the previous update must have landed
+    memcpy(c->h_small + 512, state30, 30 * sizeof(double));
+    CK(cudaMemcpyAsync(c->d_api + (size_t)idx * 30, c->h_small + 512, 30 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (c->cells_valid) {
         if (c->h_cell_of.empty()) {
             c->h_cell_of.resize(c->n);
@@ -1141,11 +1149,11 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
 // the patch work list is sized for ~24 patch partners per particle on average; if a launch overflowed it (sticky device
 // flag) the results of that launch are invalid: grow the list 4x and let the caller repeat the launch
 static int overflow_then_grow(scgpu_ctx* c, bool* repeat) {
-    int flag = 0;
-    CK(cudaMemcpyAsync(&flag, c->d_pl_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    int* hflag = (int*)(c->h_small + 256 + 64);
+    CK(cudaMemcpyAsync(hflag, c->d_pl_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     *repeat = false;
-    if (!flag) return 0;
+    if (!*hflag) return 0;
     if ((long long)c->pl_cap * 4 > (1ll << 30)) { g_err = "patch work list overflow: more patch pairs than the list can ever hold"; return SCGPU_ERR_STATE; }
     cudaFree(c->d_pl_pair); cudaFree(c->d_pl_e); cudaFree(c->d_chunks);
     c->d_pl_pair = nullptr; c->d_pl_e = nullptr; c->d_chunks = nullptr;
@@ -1165,17 +1173,22 @@ extern "C" int scgpu_one_to_all(scgpu_ctx* c, int target, const double* trial_st
     CK(cudaSetDevice(c->device));
     if (int r = ensure_cells(c)) return r;
     if (ensure_trial(c, 1)) return SCGPU_ERR_CUDA;
-    CK(cudaMemcpyAsync(c->d_targets, &target, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    if (trial_state30) CK(cudaMemcpyAsync(c->d_trial, trial_state30, 30 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // the sequential-MC path calls this twice per trial move: one small pinned upload (trial record + target index), three
+    // launches, one small pinned read-back, one synchronisation
+    if (trial_state30) memcpy(c->h_small, trial_state30, 30 * sizeof(double));
+    memcpy(c->h_small + 240, &target, sizeof(int));
+    double* hres = (double*)(c->h_small + 256);
     for (bool repeat = true; repeat;) {
+        CK(cudaMemcpyAsync(c->d_single, c->h_small, 256, cudaMemcpyHostToDevice, c->stream));
         if (e_pairs) CK(cudaMemsetAsync(c->d_pairs, 0, (size_t)c->n * sizeof(double), c->stream));
         // a single trial: all 4 warps of one block share the 27 neighbour cells
-        if (launch_energy(c, 0, 1, OTA_WARPS, c->d_targets, trial_state30 ? c->d_trial : nullptr, 0, 0, c->d_out,
+        if (launch_energy(c, 0, 1, OTA_WARPS, (const int*)(c->d_single + 240), trial_state30 ? (const double*)c->d_single : nullptr, 0, 0, c->d_out,
                           e_pairs ? c->d_pairs : nullptr, nullptr)) return SCGPU_ERR_CUDA;
-        CK(cudaMemcpyAsync(e_sum, c->d_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(hres, c->d_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if (e_pairs) CK(cudaMemcpyAsync(e_pairs, c->d_pairs, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if (int r = overflow_then_grow(c, &repeat)) return r;
     }
+    *e_sum = *hres;
     return SCGPU_OK;
 }
 

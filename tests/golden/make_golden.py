@@ -212,24 +212,30 @@ def do_extras():
 
 
 def do_short():
-    """volumeChange cases run 20 000 sweeps; a 1 500-sweep trajectory of the unmodified reference is the golden for the
-    sequential GPU-path test (the sequential C-ABI path pays two synchronous launches per trial)"""
+    """short trajectories of the unmodified reference program for the sequential GPU-path test (that path pays ~0.1 ms of
+    launch + FP64 latency per trial energy, so full 2 000-20 000 sweep runs are kept for a few cases only):
+    every Tests/test_0x/1x/2x case at 300 sweeps, every volumeChange case at 500 sweeps"""
     import re
+    cases = []
+    for d in sorted(os.listdir(os.path.join(REF, "Tests"))):
+        if re.match(r"test_(0|1|2)\d_", d):
+            cases.append((d, os.path.join(REF, "Tests", d, "new"), 300))
     for d in sorted(os.listdir(os.path.join(REF, "Tests", "volumeChange"))):
         src = os.path.join(REF, "Tests", "volumeChange", d, "new")
-        if not os.path.isdir(src):
-            continue
+        if os.path.isdir(src):
+            cases.append(("volumeChange_" + d, src, 500))
+    for name, src, ns in cases:
         tmp = tempfile.mkdtemp(prefix="short_")
         for fn in os.listdir(src):
             shutil.copy(os.path.join(src, fn), tmp)
         opt = open(os.path.join(tmp, "options")).read()
-        opt = re.sub(r"(?m)^nsweeps\s*=\s*\d+", "nsweeps = 1500", opt)
+        opt = re.sub(r"(?m)^nsweeps\s*=\s*\d+", "nsweeps = %d" % ns, opt)
         with open(os.path.join(tmp, "options"), "w") as f:
             f.write(opt)
         run([SC], tmp)
-        shutil.copy(os.path.join(tmp, "config.last"), os.path.join(HERE, "volumeChange_%s.short1500.config.last" % d))
+        shutil.copy(os.path.join(tmp, "config.last"), os.path.join(HERE, "%s.short%d.config.last" % (name, ns)))
         shutil.rmtree(tmp)
-        print("short:", d)
+        print("short:", name, ns)
 
 
 def main():

@@ -33,14 +33,22 @@ def _run(name, golden_file, nsweeps=0):
 
 @pytest.mark.parametrize("name", NVT)
 def test_nvt_trajectory_is_byte_identical(name):
-    got, want, st = _run(name, name + ".config.last")
+    """first 300 sweeps (11 400 - 12 000 trial moves) of every NVT regression case of the reference"""
+    got, want, st = _run(name, name + ".short300.config.last", 300)
     assert abs(st["drift"]) < 1e-8 * max(1.0, abs(st["e_end"]))        # the reference's own energy-drift self check
+    assert got == want, (name, st)
+
+
+@pytest.mark.parametrize("name", ["test_01_normal_PSC", "test_14_normal_SPA_PSC_CPSC", "test_20_chain_bond12"])
+def test_full_length_run_is_byte_identical(name):
+    """the complete runs exactly as Tests/test performs them (1 000 - 2 000 sweeps)"""
+    got, want, st = _run(name, name + ".config.last")
     assert got == want, (name, st)
 
 
 @pytest.mark.parametrize("name", NPT)
 def test_npt_trajectory_is_byte_identical(name):
     """pressure moves (ptype 0-3, high and low pressure): allToAll / allToAllTrial / update() through the GPU path"""
-    got, want, st = _run(name, name.replace("volumeChange_", "volumeChange_") + ".short1500.config.last", 1500)
+    got, want, st = _run(name, name + ".short500.config.last", 500)
     assert st["edge_acc"] + st["edge_rej"] > 100
     assert got == want, (name, st)
