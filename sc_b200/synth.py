@@ -197,3 +197,44 @@ E 100
         _gas(rnd, 100, box, lines)
         return top, "\n".join(lines) + "\n"
     raise ValueError(kind)
+
+
+def membrane(tiles_x, tiles_y, top_text, config_text):
+    """BASELINE.json configs[2] / SURVEY.md 8(d) "M": tile the 601-particle membrane of Tests/SC_PSC_MEMBRANE_WANG
+    (1 CPSC + 200 SPN-SPA-SPA lipids, box 10.888 x 10.888 x 50) tiles_x x tiles_y times in the bilayer plane.
+    21 x 21 -> 441 CPSC + 88 200 lipids = 265 041 particles. Returns (top_text, config_text, n)."""
+    lines = [l for l in config_text.split("\n") if l.strip()]
+    box = [float(x) for x in lines[0].split()[:3]]
+    parts = [l.split() for l in lines[1:]]
+    # [System] of the shipped topology: A 1 (the CPSC), B 200 (lipids of 3 beads)
+    head, tail = parts[:1], parts[1:]
+    out = [_fmt((box[0] * tiles_x, box[1] * tiles_y, box[2]))]
+
+    def emit(block):
+        for ty in range(tiles_y):
+            for tx in range(tiles_x):
+                for t in block:
+                    v = [float(x) for x in t[:9]]
+                    v[0] += tx * box[0]
+                    v[1] += ty * box[1]
+                    out.append(_fmt(v[0:3]) + "   " + _fmt(v[3:6]) + "   " + _fmt(v[6:9]) + " 0")
+    emit(head)
+    emit(tail)
+    nt = tiles_x * tiles_y
+    top = []
+    in_system = False
+    for l in top_text.split("\n"):
+        s_ = l.strip()
+        if s_.upper().startswith("[SYSTEM]"):
+            in_system = True
+            top.append(l)
+            continue
+        if in_system and s_ and not s_.startswith("#") and not s_.startswith("["):
+            name, cnt = s_.split()[:2]
+            top.append("%s %d" % (name, int(cnt) * nt))
+            continue
+        if s_.startswith("["):
+            in_system = False
+        top.append(l)
+    n = len(parts) * nt
+    return "\n".join(top) + "\n", "\n".join(out) + "\n", n

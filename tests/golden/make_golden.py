@@ -238,7 +238,31 @@ def do_short():
         print("short:", name, ns)
 
 
+def do_membrane():
+    """BASELINE.json configs[2]: the CPSC + SPN-SPA-SPA lipid membrane of Tests/SC_PSC_MEMBRANE_WANG (601 particles); the
+    inputs are committed so that sc_b200.synth.membrane() can tile them to 265 k particles on the GPU box"""
+    src = os.path.join(REF, "Tests", "SC_PSC_MEMBRANE_WANG", "scOOP_test")
+    with open(os.path.join(REF, "Tests", "test_01_normal_PSC", "new", "options")) as f:
+        opts = f.read()       # plain NVT options: the driver only evaluates energies (the shipped options switch Wang-Landau on)
+    inputs = {"options": opts}
+    for fn in ("top.init", "config.init"):
+        with open(os.path.join(src, fn)) as f:
+            inputs[fn] = f.read()
+    tmp = tempfile.mkdtemp(prefix="mem_")
+    for fn, txt in inputs.items():
+        with open(os.path.join(tmp, fn), "w") as f:
+            f.write(txt)
+    run([DRIVER, "dump", "ref_dump.txt"], tmp)
+    gz_copy(os.path.join(tmp, "ref_dump.txt"), os.path.join(HERE, "membrane601_init.ref.gz"))
+    with gzip.GzipFile(os.path.join(HERE, "membrane601.inputs.json.gz"), "wb", mtime=0) as g:
+        g.write(json.dumps(inputs).encode())
+    shutil.rmtree(tmp)
+    print("membrane601 done")
+
+
 def main():
+    if "membrane" in sys.argv[1:]:
+        return do_membrane()
     if "extras" in sys.argv[1:]:
         return do_extras()
     if "short" in sys.argv[1:]:
