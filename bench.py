@@ -301,6 +301,28 @@ def run_ours(args):
               "temper": 0.1, "transmx": 0.0212, "rotmx_deg": 7.5, "sweeps_timed": nsw,
               "note": "whole scgpu_sweep_checkerboard call: shifted cell build + 8 colour passes + statistics read-back"}
 
+    # several replicas on ONE GPU (the 8-replica parallel-tempering configuration on fewer than 8 GPUs): the sweeps of
+    # one 65k system are bound by the serial chain of trials inside a cell, so independent replicas on their own streams overlap
+    if world == 1:
+        R = 8
+        engines = [eng] + [Engine(local, "fast").load(hs) for _ in range(R - 1)]
+        for k in range(2):
+            for r, e in enumerate(engines):
+                e.sweep(mp, 777 + r, k, stats=False)
+        for e in engines:
+            e.sync()
+        t0 = time.perf_counter()
+        for k in range(nsw):
+            for r, e in enumerate(engines):
+                e.sweep(mp, 777 + r, 2 + k, stats=False)
+        for e in engines:
+            e.sync()
+        dt = time.perf_counter() - t0
+        sweeps["replicas_on_one_gpu"] = {"replicas": R, "aggregate_sweeps_per_s": R * nsw / dt, "ms_per_sweep_per_replica": dt / nsw * 1e3 / 1.0,
+                                          "trial_moves_per_s": R * nsw * n / dt}
+        for e in engines[1:]:
+            e.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

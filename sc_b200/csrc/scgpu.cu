@@ -1366,7 +1366,7 @@ extern "C" int scgpu_sweep_checkerboard(scgpu_ctx* c, const scgpu_moveparams* mp
         c->sweep_acc_cap = c->ncells;
     }
     CK(cudaMemsetAsync(c->d_sweep_acc, 0, (size_t)c->ncells * sizeof(SweepAcc), c->stream));
-    CK(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
+    if (stats) CK(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
     DevSys s = view(c);
     int nactive = (c->nc[0] / ncol.x) * (c->nc[1] / ncol.y) * (c->nc[2] / ncol.z);
     for (int k = 0; k < ncolours; k++) {
@@ -1376,13 +1376,13 @@ extern "C" int scgpu_sweep_checkerboard(scgpu_ctx* c, const scgpu_moveparams* mp
     CK(cudaGetLastError());
     c->api_stale = true;           // the cell-sorted arrays are now the newest copy of the configuration
     c->h_cell_of.clear();
-    int fail = 0;
-    std::vector<SweepAcc> acc;
-    if (stats) acc.resize(c->ncells);
-    CK(cudaMemcpyAsync(&fail, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    if (stats) CK(cudaMemcpyAsync(acc.data(), c->d_sweep_acc, (size_t)c->ncells * sizeof(SweepAcc), cudaMemcpyDeviceToHost, c->stream));
+    if (!stats) return SCGPU_OK;       // asynchronous form: nothing is read back; a too-dense cell is reported by the next call with stats / scgpu_sync
+    int* hfail = (int*)(c->h_small + 256 + 128);
+    std::vector<SweepAcc> acc(c->ncells);
+    CK(cudaMemcpyAsync(hfail, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(acc.data(), c->d_sweep_acc, (size_t)c->ncells * sizeof(SweepAcc), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (fail) { g_err = "scgpu_sweep_checkerboard: a cell neighbourhood holds more particles than the staged tile (SW_TILE); configuration too dense for this build"; return SCGPU_ERR_STATE; }
+    if (*hfail) { g_err = "scgpu_sweep_checkerboard: a cell neighbourhood holds more particles than the staged tile (SW_TILE); configuration too dense for this build"; return SCGPU_ERR_STATE; }
     if (stats) {
         memset(stats, 0, sizeof *stats);
         for (int i = 0; i < c->ncells; i++) {       // fixed order

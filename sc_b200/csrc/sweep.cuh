@@ -73,16 +73,21 @@ __device__ inline void rotate_record(double* r, int geotype, double angle, const
 }
 
 constexpr int SW_WARPS = 4;
+#ifndef SW_MINBLOCKS
+#define SW_MINBLOCKS 1
+#endif
 constexpr int SW_TILE = 1280;     // staged neighbourhood (FP32 relative coordinates + slot): 1280 x 20 B = 25 KB
 
 // one block per ACTIVE cell of the current colour
-__global__ void __launch_bounds__(SW_WARPS * 32)
+__global__ void __launch_bounds__(SW_WARPS * 32, SW_MINBLOCKS)
 k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long long sweep, int colour, int3 ncol,
                double4* posw, double* rec, SweepAcc* acc_out, int* fail_flag) {
     __shared__ float4 t_pf[SW_TILE];
     __shared__ int t_slot[SW_TILE];
     __shared__ double sh_old[REC], sh_new[REC];
     __shared__ int sh_queue[SW_WARPS][96];
+    __shared__ int sh_pl[SW_WARPS][32];       // per-warp lists of (slot, state) entries that owe a patch evaluation
+    __shared__ int sh_pc[SW_WARPS];
     __shared__ double sh_eo[SW_WARPS], sh_en[SW_WARPS];
     __shared__ int sh_b[28], sh_off[28];
     __shared__ int sh_ctl[4];     // [0] accept, [1] picked slot, [2] displacement?, [3] stayed in its cell?
@@ -188,19 +193,44 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
             int qn = 0;
             double lo = 0.0, ln = 0.0;
             // one queue entry = (partner slot, which state): the old and the new state of a trial are evaluated on DIFFERENT
-            // lanes, which halves the serial latency of a trial (the patch geometry is a long dependent FP64 chain)
-            auto eval = [&](int entry) {
+            // lanes. Phase A (all warps): exact gate + everything but the rod-rod patch term; entries that owe a patch term are
+            // collected per warp. Phase B (warp 0 only): the patch terms of the whole trial, packed on as few lanes as there
+            // are entries -- the other warps wait at the barrier instead of issuing 3-lanes-active patch code four times over.
+            int pc = 0;
+            auto patch_entry = [&](int entry) {
                 const int slot = entry >> 1;
                 const bool is_new = entry & 1;
                 double4 pw = posw[slot];
-                int orig = w_orig(pw.w);
-                const double* s1 = is_new ? sh_new : sh_old;
                 v3 r = image(s.box, is_new ? pn : po, mk(pw.x, pw.y, pw.z));
-                double d = dot(r, r);
-                bool bonded = !cl.is_empty && (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
-                if (d <= s.sqmaxcut || bonded) {
-                    double e = pair_energy_gated(s.box, s.ia, s.ntypes, s.mol, r, d, s1, type1, moltype1, rec + (size_t)slot * REC, w_type(pw.w), orig, cl);
-                    if (is_new) ln += e; else lo += e;
+                double e = pair_energy_patch(s.ia[type1 * s.ntypes + w_type(pw.w)], r, is_new ? sh_new : sh_old, rec + (size_t)slot * REC);
+                if (is_new) ln += e; else lo += e;
+            };
+            auto eval = [&](int entry, bool on) {
+                bool np = false;
+                if (on) {
+                    const int slot = entry >> 1;
+                    const bool is_new = entry & 1;
+                    double4 pw = posw[slot];
+                    int orig = w_orig(pw.w);
+                    v3 r = image(s.box, is_new ? pn : po, mk(pw.x, pw.y, pw.z));
+                    double d = dot(r, r);
+                    bool bonded = !cl.is_empty && (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
+                    if (d <= s.sqmaxcut || bonded) {
+                        double e = pair_energy_cheap<false>(s.box, s.ia, s.ntypes, s.mol, r, d, is_new ? sh_new : sh_old, type1, moltype1,
+                                                            rec + (size_t)slot * REC, w_type(pw.w), orig, cl, np);
+                        if (is_new) ln += e; else lo += e;
+                    }
+                }
+                unsigned m = __ballot_sync(0xffffffffu, np);
+                if (m) {
+                    int c = __popc(m);
+                    if (pc + c > 32) {                 // list full (never in physical configurations): evaluate in place
+                        if (np) patch_entry(entry);
+                    } else {
+                        if (np) sh_pl[wid][pc + __popc(m & lt_mask)] = entry;
+                        pc += c;
+                    }
+                    __syncwarp();
                 }
             };
             for (int base = wid * 32; base < C; base += SW_WARPS * 32) {
@@ -230,7 +260,7 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                 qn += no + __popc(mn);
                 __syncwarp();
                 while (qn >= 32) {
-                    eval(queue[lane]);
+                    eval(queue[lane], true);
                     int rest = qn - 32;
                     int mv0 = (lane < rest) ? queue[32 + lane] : 0;
                     int mv1 = (lane + 32 < rest) ? queue[64 + lane] : 0;
@@ -241,10 +271,26 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                     __syncwarp();
                 }
             }
-            if (lane < qn) eval(queue[lane]);
-            if (wid == 0 && !cl.is_empty && lane < 8 && cl.con[lane >> 1] >= 0) eval(s.slot_of[cl.con[lane >> 1]] * 2 + (lane & 1));
+            if (qn > 0) eval(lane < qn ? queue[lane] : 0, lane < qn);
+            if (wid == 0 && !cl.is_empty) {
+                bool on = lane < 8 && cl.con[lane >> 1] >= 0;
+                eval(on ? s.slot_of[cl.con[lane >> 1]] * 2 + (lane & 1) : 0, on);
+            }
+            if (lane == 0) sh_pc[wid] = pc;
+            __syncthreads();
+            if (wid == 0) {                            // phase B: all patch terms of this trial on one warp, in warp/list order
+                int tot = 0;
+                for (int w = 0; w < SW_WARPS; w++) tot += sh_pc[w];
+                for (int idx = lane; idx < tot; idx += 32) {
+                    int w = 0, k = idx;
+                    while (k >= sh_pc[w]) { k -= sh_pc[w]; w++; }
+                    patch_entry(sh_pl[w][k]);
+                }
+            }
             e_old = warp_sum(lo);
             e_new = warp_sum(ln);
+        } else {
+            __syncthreads();                           // keep the barrier count identical on both paths
         }
         __syncthreads();
         if (lane == 0) { sh_eo[wid] = e_old; sh_en[wid] = e_new; }

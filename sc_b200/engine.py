@@ -216,7 +216,11 @@ class Engine:
         self._ck(self.L.scgpu_overlap_all(self.h, int(variant), C.byref(f)))
         return f.value
 
-    def sweep(self, mp, seed, sweep):
+    def sweep(self, mp, seed, sweep, stats=True):
+        """one checkerboard sweep; stats=False enqueues it without any read-back (several engines can then overlap on one GPU)"""
+        if not stats:
+            self._ck(self.L.scgpu_sweep_checkerboard(self.h, C.byref(mp), int(seed), int(sweep), None))
+            return None
         st = SweepStats()
         self._ck(self.L.scgpu_sweep_checkerboard(self.h, C.byref(mp), int(seed), int(sweep), C.byref(st)))
         return st
