@@ -72,7 +72,10 @@ __device__ inline void rotate_record(double* r, int geotype, double angle, const
     }
 }
 
-constexpr int SW_WARPS = 4;
+#ifndef SW_WARPS_N
+#define SW_WARPS_N 2
+#endif
+constexpr int SW_WARPS = SW_WARPS_N;
 #ifndef SW_MINBLOCKS
 #define SW_MINBLOCKS 1
 #endif
@@ -278,13 +281,24 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
             }
             if (lane == 0) sh_pc[wid] = pc;
             __syncthreads();
-            if (wid == 0) {                            // phase B: all patch terms of this trial on one warp, in warp/list order
+            if (wid == 0) {        // phase B: all patch terms of this trial on one warp, two lanes per term, in warp/list order
                 int tot = 0;
                 for (int w = 0; w < SW_WARPS; w++) tot += sh_pc[w];
-                for (int idx = lane; idx < tot; idx += 32) {
-                    int w = 0, k = idx;
-                    while (k >= sh_pc[w]) { k -= sh_pc[w]; w++; }
-                    patch_entry(sh_pl[w][k]);
+                for (int base = 0; base < 2 * tot; base += 32) {
+                    const int idx = (base + lane) >> 1;
+                    const bool act = idx < tot;
+                    int entry = 0;
+                    if (act) {
+                        int w = 0, k = idx;
+                        while (k >= sh_pc[w]) { k -= sh_pc[w]; w++; }
+                        entry = sh_pl[w][k];
+                    }
+                    const int slot = entry >> 1;
+                    const bool is_new = entry & 1;
+                    double4 pw = posw[slot];
+                    v3 r = image(s.box, is_new ? pn : po, mk(pw.x, pw.y, pw.z));
+                    double e = pair_energy_patch_two_lanes(s.ia[type1 * s.ntypes + w_type(pw.w)], r, is_new ? sh_new : sh_old, rec + (size_t)slot * REC, act);
+                    if (is_new) ln += e; else lo += e;
                 }
             }
             e_old = warp_sum(lo);
