@@ -258,7 +258,7 @@ __device__ double warp_gate_cheap(const DevSys& s, const double* s1, int type1, 
             }
             if (head < 0) head = cid;
             last_chunk = cid;
-        } else if (lane == 0) atomicExch(pl.overflow, 1);
+        } else if (lane == 0) atomicOr(pl.overflow, 1);
         pn = 0;
         __syncwarp();
     };
@@ -490,7 +490,7 @@ k_gate_cheap_cells(DevSys s, PatchList pl, double* __restrict__ warp_partial, un
                     }
                     if (head < 0) head = cid;
                     last_chunk = cid;
-                } else if (lane == 0) atomicExch(pl.overflow, 1);
+                } else if (lane == 0) atomicOr(pl.overflow, 1);
                 pn = 0;
                 __syncwarp();
             };
@@ -584,6 +584,336 @@ k_gate_cheap_cells(DevSys s, PatchList pl, double* __restrict__ warp_partial, un
         }
         if (lane == 0) warp_partial[target] = part;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FLAT pipeline for "every particle" passes (MODE 1 one-to-all of everyone, MODE 2 allToAll rows): four launches, each dense
+//   k_gate_cells    block per cell; FP32 conservative pre-gate over the staged neighbourhood; survivors -> global pair list
+//                   (per-particle chunk chains, so that the final sum has a defined order)
+//   k_cheap_flat    thread per listed pair: exact FP64 gate + everything but the rod-rod patch term; pairs that owe a
+//                   patch term are appended (warp-aggregated) to a second list
+//   k_patch_flat    thread per patch pair
+//   k_combine_flat  per particle: sum of (cheap + patch) over its chunk chain, in list order
+// Compared with evaluating inside the gate kernel this keeps the gate kernel at ~40 registers (3x the resident warps) and
+// gives the FP64 work perfectly packed lanes.
+// ------------------------------------------------------------------------------------------------
+struct FlatList {
+    int2* pair;          // (slot of the first particle, slot of the second)
+    double2* e;          // {cheap part, patch part}
+    int* total; int cap;
+    int* head;           // per particle (original index): first chunk id or -1
+    int4* chunks; int* chunk_count; int chunk_cap;
+    int* plist; int* ptotal;     // indices into pair[] that owe a patch term
+    int* overflow;
+};
+
+constexpr int GT_TILE = 1024;     // staged candidates per cell neighbourhood: 1024 x 20 B = 20 KB (denser cells scan global memory)
+constexpr int GT_WARPS = 4;
+constexpr int GQ = 128;           // per-warp queue; flushed to the global list in chunks of 64
+
+template <int MODE, bool RODS>
+__global__ void __launch_bounds__(GT_WARPS * 32, 8)
+k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
+    __shared__ float4 t_pf[GT_TILE];
+    __shared__ int t_slot[GT_TILE];
+    __shared__ int sh_queue[GT_WARPS][GQ];
+    __shared__ int sh_b[28], sh_off[28];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int c0 = blockIdx.x;
+    const int tb = s.cell_start[c0], te = s.cell_start[c0 + 1];
+    if (tb == te) return;
+    const int cx = c0 % s.nc[0], cy = (c0 / s.nc[0]) % s.nc[1], cz = c0 / (s.nc[0] * s.nc[1]);
+    const int nx = s.nc[0] == 1 ? 1 : 3, ny = s.nc[1] == 1 ? 1 : 3, nz = s.nc[2] == 1 ? 1 : 3;
+    const int ncell_nb = nx * ny * nz;
+    if (wid == 0) {
+        int len = 0, b = 0;
+        if (lane < ncell_nb) {
+            int dx = lane % nx, dy = (lane / nx) % ny, dz = lane / (nx * ny);
+            int ccx = nx == 1 ? 0 : (cx + dx - 1 + s.nc[0]) % s.nc[0];
+            int ccy = ny == 1 ? 0 : (cy + dy - 1 + s.nc[1]) % s.nc[1];
+            int ccz = nz == 1 ? 0 : (cz + dz - 1 + s.nc[2]) % s.nc[2];
+            int c = (ccz * s.nc[1] + ccy) * s.nc[0] + ccx;
+            b = s.cell_start[c];
+            len = s.cell_start[c + 1] - b;
+        }
+        int x = len;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane < 28) { sh_b[lane] = b; sh_off[lane] = x - len; }
+    }
+    __syncthreads();
+    const int C = sh_off[ncell_nb];
+    const bool tiled = C <= GT_TILE;
+    const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
+    const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
+    const float pre_cut = (float)(s.sqmaxcut * 1.001);
+    auto slot_of_p = [&](int p) {
+        int k = 0;
+        while (k + 1 < ncell_nb && sh_off[k + 1] <= p) k++;
+        return sh_b[k] + (p - sh_off[k]);
+    };
+    auto staged = [&](int slot) {
+        double4 pw = s.posw[slot];
+        return make_float4((float)rel_frac(pw.x + s.shift[0], ccen[0]), (float)rel_frac(pw.y + s.shift[1], ccen[1]),
+                           (float)rel_frac(pw.z + s.shift[2], ccen[2]), __int_as_float(w_orig(pw.w)));
+    };
+    if (tiled) {
+        for (int p = threadIdx.x; p < C; p += blockDim.x) {
+            int slot = slot_of_p(p);
+            t_pf[p] = staged(slot);
+            t_slot[p] = slot;
+        }
+    }
+    __syncthreads();
+    int* queue = sh_queue[wid];
+    for (int ti = tb + wid; ti < te; ti += GT_WARPS) {
+        const double4 tpw = s.posw[ti];
+        const int target = w_orig(tpw.w);
+        int con0 = -1, con1 = -1, con2 = -1, con3 = -1;
+        if (!RODS) {
+            ConList cl;
+            get_conlist(s.mol, w_moltype(tpw.w), target, cl);
+            con0 = cl.con[0]; con1 = cl.con[1]; con2 = cl.con[2]; con3 = cl.con[3];
+        }
+        const int max_idx = (MODE == 2) ? target : 0x7fffffff;
+        const float t1x = (float)rel_frac(tpw.x + s.shift[0], ccen[0]), t1y = (float)rel_frac(tpw.y + s.shift[1], ccen[1]),
+                    t1z = (float)rel_frac(tpw.z + s.shift[2], ccen[2]);
+        int qn = 0, last_chunk = -1, head = -1;
+        unsigned n_cand = 0;
+        auto flush = [&](int cnt) {          // the first cnt queue entries become one chunk of the global list
+            int base = 0, cid = 0;
+            if (lane == 0) { base = atomicAdd(fl.total, cnt); cid = atomicAdd(fl.chunk_count, 1); }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            cid = __shfl_sync(0xffffffffu, cid, 0);
+            bool ok = (cid < fl.chunk_cap) && (base + cnt <= fl.cap);
+            if (ok) {
+                for (int k = lane; k < cnt; k += 32) fl.pair[base + k] = make_int2(ti, queue[k]);
+                if (lane == 0) {
+                    fl.chunks[cid] = make_int4(base, cnt, -1, 0);
+                    if (last_chunk >= 0) fl.chunks[last_chunk].z = cid;
+                }
+                if (head < 0) head = cid;
+                last_chunk = cid;
+            } else if (lane == 0) atomicOr(fl.overflow, 2);
+            __syncwarp();
+            int rest = qn - cnt;
+            int mv0 = (lane < rest) ? queue[cnt + lane] : 0;
+            int mv1 = (lane + 32 < rest) ? queue[cnt + 32 + lane] : 0;
+            __syncwarp();
+            if (lane < rest) queue[lane] = mv0;
+            if (lane + 32 < rest) queue[32 + lane] = mv1;
+            qn = rest;
+            __syncwarp();
+        };
+        for (int base = 0; base < C; base += 64) {
+            bool pa = false, pb = false;
+            int sa = 0, sb = 0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int p = base + 32 * h + lane;
+                bool pass = false;
+                int slot = 0;
+                if (p < C) {
+                    float4 q;
+                    if (tiled) { q = t_pf[p]; slot = t_slot[p]; } else { slot = slot_of_p(p); q = staged(slot); }
+                    int orig = __float_as_int(q.w);
+                    bool bonded = !RODS && (orig == con0 || orig == con1 || orig == con2 || orig == con3);
+                    if (orig != target && orig < max_idx && !bonded) {
+                        n_cand++;
+                        float dx = t1x - q.x, dy = t1y - q.y, dz = t1z - q.z;
+                        dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
+                        pass = dx * dx + dy * dy + dz * dz <= pre_cut;
+                    }
+                }
+                if (h == 0) { pa = pass; sa = slot; } else { pb = pass; sb = slot; }
+            }
+            unsigned ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
+            int na = __popc(ma);
+            if (pa) queue[qn + __popc(ma & lt_mask)] = sa;
+            if (pb) queue[qn + na + __popc(mb & lt_mask)] = sb;
+            qn += na + __popc(mb);
+            __syncwarp();
+            if (qn >= 64) flush(64);
+        }
+        if (!RODS) {       // bonded partners by index (never gated, mc/paire.h:1214)
+            int orig = lane == 0 ? con0 : lane == 1 ? con1 : lane == 2 ? con2 : lane == 3 ? con3 : -1;
+            bool on = orig >= 0 && orig != target && orig < max_idx;
+            if (on) n_cand++;
+            unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) queue[qn + __popc(m & lt_mask)] = s.slot_of[orig];
+            qn += __popc(m);
+            __syncwarp();
+        }
+        while (qn > 0) flush(qn < 64 ? qn : 64);
+        if (lane == 0) fl.head[target] = head;
+        if (counters) {
+            n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+            if (lane == 0) atomicAdd(&counters[0], (unsigned long long)n_cand);
+        }
+    }
+}
+
+template <bool RODS>
+__global__ void __launch_bounds__(256, RODS ? 3 : 2)
+k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int total = *fl.total;
+    if (total > fl.cap) total = fl.cap;
+    const int stride = gridDim.x * blockDim.x;
+    unsigned n_gate = 0;
+    for (int p0 = blockIdx.x * blockDim.x; p0 < total; p0 += stride) {      // warp-uniform trip count
+        const int p = p0 + threadIdx.x;
+        bool np = false;
+        if (p < total) {
+            int2 pr = fl.pair[p];
+            double4 pi = s.posw[pr.x], pj = s.posw[pr.y];
+            v3 r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
+            double dotrcm = dot(r_cm, r_cm);
+            int oi = w_orig(pi.w), oj = w_orig(pj.w);
+            ConList cl;
+            cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0;
+            bool bonded = false;
+            if (!RODS) {
+                get_conlist(s.mol, w_moltype(pi.w), oi, cl);
+                bonded = !cl.is_empty && (oj == cl.con[0] || oj == cl.con[1] || oj == cl.con[2] || oj == cl.con[3]);
+            }
+            double e = 0.0;
+            if (dotrcm <= s.sqmaxcut || bonded) {           // the exact PairE gate (mc/paire.h:1214)
+                e = pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r_cm, dotrcm, s.rec + (size_t)pr.x * REC, w_type(pi.w), w_moltype(pi.w),
+                                            s.rec + (size_t)pr.y * REC, w_type(pj.w), oj, cl, np);
+                n_gate++;
+            }
+            fl.e[p] = make_double2(e, 0.0);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, np);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(fl.ptotal, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (np) fl.plist[base + __popc(m & lt_mask)] = p;      // plist has the capacity of pair[]: cannot overflow
+        }
+    }
+    if (counters) {
+        n_gate = __reduce_add_sync(0xffffffffu, n_gate);
+        if (lane == 0 && n_gate) atomicAdd(&counters[1], (unsigned long long)n_gate);
+    }
+}
+
+// Patch terms in three dense phases per block of 128 listed pairs: most pairs drop out after the FIRST patch_intersect()
+// (the partner is simply not inside the patch wedge), so running intersect #1, intersect #2 and atr_e() as separate phases
+// with a block-level compaction of the survivors in between keeps the lanes of the expensive later phases full instead of
+// leaving a few lanes per warp on the long path.
+constexpr int PF_THREADS = 128;
+
+struct PatchItem {          // everything a phase needs to re-derive the geometry of a (pair, patch combination)
+    int p;                  // index into FlatList::pair / e
+    double T1, T2, S1, S2;
+};
+
+__device__ __forceinline__ void patch_setup(const DevSys& s, const FlatList& fl, int p, int combo, const scgpu_iaparam*& ia, v3& r_cm,
+                                            PatchArgs& P1, PatchArgs& P2, bool& first_psc, bool& second_psc, bool& applicable) {
+    int2 pr = fl.pair[p];
+    double4 pi = s.posw[pr.x], pj = s.posw[pr.y];
+    r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
+    ia = &s.ia[w_type(pi.w) * s.ntypes + w_type(pj.w)];
+    const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
+    const bool firstCH = is_chiral(g0), secondCH = is_chiral(g1), firstT = is_two_patch(g0), secondT = is_two_patch(g1);
+    first_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && is_psc_family(g0));
+    second_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && !is_psc_family(g0));
+    const int pn1 = combo & 1, pn2 = combo >> 1;
+    applicable = (combo == 0) || (combo == 1 && firstT) || (combo == 2 && secondT) || (combo == 3 && firstT && secondT);
+    const double* s1 = s.rec + (size_t)pr.x * REC;
+    const double* s2 = s.rec + (size_t)pr.y * REC;
+    P1.dir = firstCH ? ld3(s1 + (pn1 ? R_CH1 : R_CH0)) : ld3(s1 + R_DIR);
+    P1.pdir = ld3(s1 + (pn1 ? R_PD1 : R_PD0)); P1.s0 = ld3(s1 + (pn1 ? R_S2 : R_S0)); P1.s1 = ld3(s1 + (pn1 ? R_S3 : R_S1));
+    P2.dir = secondCH ? ld3(s2 + (pn2 ? R_CH1 : R_CH0)) : ld3(s2 + R_DIR);
+    P2.pdir = ld3(s2 + (pn2 ? R_PD1 : R_PD0)); P2.s0 = ld3(s2 + (pn2 ? R_S2 : R_S0)); P2.s1 = ld3(s2 + (pn2 ? R_S3 : R_S1));
+}
+
+// block-wide stable compaction: returns this thread's rank among the threads with flag set, total in *count (shared)
+__device__ __forceinline__ int block_rank(bool flag, int* sh_warp, int* count) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) sh_warp[wid] = __popc(m);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < PF_THREADS / 32; w++) { int c = sh_warp[w]; if (w < wid) off += c; tot += c; }
+    if (threadIdx.x == 0) *count = tot;
+    __syncthreads();
+    return off + __popc(m & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 4)
+k_patch_flat(DevSys s, FlatList fl, int any_two_patch) {
+    __shared__ PatchItem sh_a[PF_THREADS], sh_b[PF_THREADS];
+    __shared__ int sh_warp[PF_THREADS / 32];
+    __shared__ int sh_n1, sh_n2;
+    const int total = *fl.ptotal;
+    const int ncombo = any_two_patch ? 4 : 1;
+    for (int base = blockIdx.x * PF_THREADS; base < total; base += gridDim.x * PF_THREADS) {       // block-uniform trip count
+        const int q = base + threadIdx.x;
+        const int p = q < total ? fl.plist[q] : -1;
+        for (int combo = 0; combo < ncombo; combo++) {
+            // ---- phase 1: rod 2 against the patch of rod 1 (T1, T2)
+            bool keep = false;
+            double a = 0.0, b = 0.0;
+            if (p >= 0) {
+                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
+                patch_setup(s, fl, p, combo, ia, r_cm, P1, P2, fp, sp, ok);
+                if (ok) {
+                    const int pn1 = combo & 1;
+                    int n = fp ? patch_intersect<false>(P1.dir, P2.dir, P1, r_cm, a, b, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1])
+                               : patch_intersect<true>(P1.dir, P2.dir, P1, r_cm, a, b, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1]);
+                    keep = n >= 2;
+                }
+            }
+            int r = block_rank(keep, sh_warp, &sh_n1);
+            if (keep) { sh_a[r].p = p; sh_a[r].T1 = a; sh_a[r].T2 = b; }
+            __syncthreads();
+            const int n1 = sh_n1;
+            // ---- phase 2: rod 1 against the patch of rod 2 (S1, S2), survivors only
+            keep = false;
+            PatchItem it;
+            it.p = -1; it.T1 = it.T2 = it.S1 = it.S2 = 0.0;
+            if ((int)threadIdx.x < n1) {
+                it = sh_a[threadIdx.x];
+                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
+                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok);
+                const int pn2 = combo >> 1;
+                v3 vec1 = neg(r_cm);
+                int n = sp ? patch_intersect<false>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0])
+                           : patch_intersect<true>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0]);
+                keep = n >= 2;
+            }
+            r = block_rank(keep, sh_warp, &sh_n2);
+            if (keep) sh_b[r] = it;
+            __syncthreads();
+            const int n2 = sh_n2;
+            // ---- phase 3: attraction of the survivors
+            if ((int)threadIdx.x < n2) {
+                it = sh_b[threadIdx.x];
+                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
+                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok);
+                double e = atr_e(*ia, P1.dir, P2.dir, P1.pdir, P2.pdir, r_cm, combo & 1, combo >> 1, it.S1, it.S2, it.T1, it.T2);
+                fl.e[it.p].y += e;        // one writer per pair and phase; the combinations run one after another
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void k_combine_flat(int n, FlatList fl, double* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) { *fl.total = 0; *fl.chunk_count = 0; *fl.ptotal = 0; }   // lists consumed (stream order makes the reset safe)
+    if (t >= n) return;
+    double e = 0.0;
+    for (int cid = fl.head[t]; cid >= 0;) {
+        int4 ch = fl.chunks[cid];
+        for (int r = 0; r < ch.y; r++) { double2 v = fl.e[ch.x + r]; e += v.x + v.y; }     // per pair (cheap + patch), then accumulate
+        cid = ch.z;
+    }
+    out[t] = e;
 }
 
 #include "sweep.cuh"
@@ -750,11 +1080,19 @@ struct scgpu_ctx {
     int* d_pl_overflow = nullptr;
     int pl_cap = 0;
     bool rods_only = false;          // every particle an un-bonded rod: the specialised kernels apply
+    bool any_two_patch = false;      // some particle type present carries a second patch (TPSC/TCPSC/TCHPSC/TCHCPSC)
     int* d_warp_head = nullptr;
     int4* d_chunks = nullptr;
     int chunk_cap = 0;
     double* d_warp_partial = nullptr;
     double* d_trial_rec = nullptr;   // [trial_cap][REC]
+    // flat pipeline lists
+    int2* d_fl_pair = nullptr;
+    double2* d_fl_e = nullptr;
+    int* d_fl_plist = nullptr;
+    int* d_fl_head = nullptr;
+    int4* d_fl_chunks = nullptr;
+    int fl_cap = 0, fl_chunk_cap = 0;
     double* d_trial = nullptr;       // staging for trial states
     int* d_targets = nullptr;
     int trial_cap = 0;
@@ -819,8 +1157,8 @@ extern "C" int scgpu_create(scgpu_ctx** out, int device) {
     CK(cudaMalloc((void**)&c->d_single, 256));
     CK(cudaMalloc(&c->d_scalar, 16 * sizeof(double)));
     CK(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
-    CK(cudaMalloc(&c->d_pl_total, 4 * sizeof(int)));     // [0] pairs in the list, [1] overflow flag, [2] chunks in use
-    CK(cudaMemset(c->d_pl_total, 0, 4 * sizeof(int)));
+    CK(cudaMalloc(&c->d_pl_total, 8 * sizeof(int)));     // [0] patch pairs, [1] overflow flag, [2] patch chunks, [3] flat pairs, [4] flat chunks, [5] flat patch pairs
+    CK(cudaMemset(c->d_pl_total, 0, 8 * sizeof(int)));
     c->d_pl_overflow = c->d_pl_total + 1;
     CK(cudaMemset(c->d_scalar, 0, 16 * sizeof(double)));
     *out = c;
@@ -831,6 +1169,8 @@ static void free_particles(scgpu_ctx* c) {
     cudaFree(c->d_api); cudaFree(c->d_posw); cudaFree(c->d_rec); cudaFree(c->d_type); cudaFree(c->d_moltype);
     cudaFree(c->d_cell_of); cudaFree(c->d_order); cudaFree(c->d_slot_of); cudaFree(c->d_tmp); cudaFree(c->d_out);
     cudaFree(c->d_pairs); cudaFree(c->d_flags);
+    cudaFree(c->d_fl_pair); cudaFree(c->d_fl_e); cudaFree(c->d_fl_plist); cudaFree(c->d_fl_head); cudaFree(c->d_fl_chunks);
+    c->d_fl_pair = nullptr; c->d_fl_e = nullptr; c->d_fl_plist = nullptr; c->d_fl_head = nullptr; c->d_fl_chunks = nullptr;
     cudaFree(c->d_pl_pair); cudaFree(c->d_pl_e); cudaFree(c->d_warp_head); cudaFree(c->d_chunks); cudaFree(c->d_warp_partial);
     c->d_pl_pair = nullptr; c->d_pl_e = nullptr; c->d_warp_head = nullptr; c->d_chunks = nullptr; c->d_warp_partial = nullptr;
     c->d_api = nullptr; c->d_posw = nullptr; c->d_rec = nullptr; c->d_type = c->d_moltype = c->d_cell_of = c->d_order = c->d_slot_of = c->d_tmp = nullptr;
@@ -923,6 +1263,13 @@ extern "C" int scgpu_set_particles(scgpu_ctx* c, int n, const double* state30, c
         c->pl_cap = (int)(N * 24 < 16384 ? 16384 : N * 24);
         CK(cudaMalloc(&c->d_pl_pair, (size_t)c->pl_cap * sizeof(int2)));
         CK(cudaMalloc(&c->d_pl_e, (size_t)c->pl_cap * sizeof(double)));
+        c->fl_cap = (int)(N * 96 < 65536 ? 65536 : N * 96);
+        c->fl_chunk_cap = (int)(N + 64) + c->fl_cap / 64 + 64;
+        CK(cudaMalloc(&c->d_fl_pair, (size_t)c->fl_cap * sizeof(int2)));
+        CK(cudaMalloc(&c->d_fl_e, (size_t)c->fl_cap * sizeof(double2)));
+        CK(cudaMalloc(&c->d_fl_plist, (size_t)c->fl_cap * sizeof(int)));
+        CK(cudaMalloc(&c->d_fl_head, (N + 64) * sizeof(int)));
+        CK(cudaMalloc(&c->d_fl_chunks, (size_t)c->fl_chunk_cap * sizeof(int4)));
         c->chunk_cap = (int)(N + 64) + c->pl_cap / PCAP + 64;
         CK(cudaMalloc(&c->d_warp_head, (N + 64) * sizeof(int)));
         CK(cudaMalloc(&c->d_chunks, (size_t)c->chunk_cap * sizeof(int4)));
@@ -971,6 +1318,11 @@ extern "C" int scgpu_set_particles(scgpu_ctx* c, int n, const double* state30, c
         }
         for (int mm = 0; mm < c->nmol && rods; mm++) if (mu[mm] && c->h_mol[mm].mol_size != 1.0) rods = false;
         c->rods_only = rods;
+        c->any_two_patch = false;
+        for (int a = 0; a < c->ntypes; a++) if (tu[a]) {
+            int g = (int)c->h_ia[(size_t)a * c->ntypes + a].geotype[0];
+            if (g == SCGPU_TPSC || g == SCGPU_TCPSC || g == SCGPU_TCHPSC || g == SCGPU_TCHCPSC) c->any_two_patch = true;
+        }
     }
     c->cells_valid = false;
     c->api_stale = false;
@@ -1126,8 +1478,28 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
     pl.trial_rec = c->d_trial_rec; pl.overflow = c->d_pl_overflow;
     int groups_per_block = OTA_WARPS / gw;
     int blocks = (m + groups_per_block - 1) / groups_per_block;
+    if (mode == 1 || mode == 2) {        // every-particle passes: the flat four-launch pipeline
+        FlatList fl;
+        fl.pair = c->d_fl_pair; fl.e = c->d_fl_e; fl.total = c->d_pl_total + 3; fl.cap = c->fl_cap; fl.head = c->d_fl_head;
+        fl.chunks = c->d_fl_chunks; fl.chunk_count = c->d_pl_total + 4; fl.chunk_cap = c->fl_chunk_cap;
+        fl.plist = c->d_fl_plist; fl.ptotal = c->d_pl_total + 5; fl.overflow = c->d_pl_overflow;
+        if (c->rods_only) {
+            if (mode == 1) k_gate_cells<1, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters);
+            else k_gate_cells<2, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters);
+            k_cheap_flat<true><<<c->sm_count * 6, 256, 0, c->stream>>>(s, fl, d_counters);
+        } else {
+            if (mode == 1) k_gate_cells<1, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters);
+            else k_gate_cells<2, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters);
+            k_cheap_flat<false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters);
+        }
+        k_patch_flat<<<c->sm_count * 8, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0);
+        k_combine_flat<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, fl, d_out);
+        c->launches += 4;
+        CK(cudaGetLastError());
+        return 0;
+    }
 #define LAUNCH_CB(M, R) k_gate_cheap_cells<M, R><<<c->ncells, CB_WARPS * 32, 0, c->stream>>>(s, pl, c->d_warp_partial, d_counters)
-    if (mode == 1 || mode == 2) {
+    if (false) {
         if (c->rods_only) { if (mode == 1) LAUNCH_CB(1, true); else LAUNCH_CB(2, true); }
         else { if (mode == 1) LAUNCH_CB(1, false); else LAUNCH_CB(2, false); }
     } else
@@ -1154,15 +1526,29 @@ static int overflow_then_grow(scgpu_ctx* c, bool* repeat) {
     CK(cudaStreamSynchronize(c->stream));
     *repeat = false;
     if (!*hflag) return 0;
-    if ((long long)c->pl_cap * 4 > (1ll << 30)) { g_err = "patch work list overflow: more patch pairs than the list can ever hold"; return SCGPU_ERR_STATE; }
-    cudaFree(c->d_pl_pair); cudaFree(c->d_pl_e); cudaFree(c->d_chunks);
-    c->d_pl_pair = nullptr; c->d_pl_e = nullptr; c->d_chunks = nullptr;
-    c->pl_cap *= 4;
-    c->chunk_cap = c->cap + 64 + c->pl_cap / PCAP + 64;
-    CK(cudaMalloc(&c->d_pl_pair, (size_t)c->pl_cap * sizeof(int2)));
-    CK(cudaMalloc(&c->d_pl_e, (size_t)c->pl_cap * sizeof(double)));
-    CK(cudaMalloc(&c->d_chunks, (size_t)c->chunk_cap * sizeof(int4)));
-    CK(cudaMemsetAsync(c->d_pl_total, 0, 4 * sizeof(int), c->stream));
+    const int which = *hflag;      // bit 0: patch work list, bit 1: flat pair list
+    if (which & 2) {
+        if ((long long)c->fl_cap * 2 > (1ll << 30)) { g_err = "flat pair list overflow: more gated pairs than the list can ever hold"; return SCGPU_ERR_STATE; }
+        cudaFree(c->d_fl_pair); cudaFree(c->d_fl_e); cudaFree(c->d_fl_plist); cudaFree(c->d_fl_chunks);
+        c->d_fl_pair = nullptr; c->d_fl_e = nullptr; c->d_fl_plist = nullptr; c->d_fl_chunks = nullptr;
+        c->fl_cap *= 2;
+        c->fl_chunk_cap = c->cap + 64 + c->fl_cap / 64 + 64;
+        CK(cudaMalloc(&c->d_fl_pair, (size_t)c->fl_cap * sizeof(int2)));
+        CK(cudaMalloc(&c->d_fl_e, (size_t)c->fl_cap * sizeof(double2)));
+        CK(cudaMalloc(&c->d_fl_plist, (size_t)c->fl_cap * sizeof(int)));
+        CK(cudaMalloc(&c->d_fl_chunks, (size_t)c->fl_chunk_cap * sizeof(int4)));
+    }
+    if (which & 1) {
+        if ((long long)c->pl_cap * 4 > (1ll << 30)) { g_err = "patch work list overflow: more patch pairs than the list can ever hold"; return SCGPU_ERR_STATE; }
+        cudaFree(c->d_pl_pair); cudaFree(c->d_pl_e); cudaFree(c->d_chunks);
+        c->d_pl_pair = nullptr; c->d_pl_e = nullptr; c->d_chunks = nullptr;
+        c->pl_cap *= 4;
+        c->chunk_cap = c->cap + 64 + c->pl_cap / PCAP + 64;
+        CK(cudaMalloc(&c->d_pl_pair, (size_t)c->pl_cap * sizeof(int2)));
+        CK(cudaMalloc(&c->d_pl_e, (size_t)c->pl_cap * sizeof(double)));
+        CK(cudaMalloc(&c->d_chunks, (size_t)c->chunk_cap * sizeof(int4)));
+    }
+    CK(cudaMemsetAsync(c->d_pl_total, 0, 8 * sizeof(int), c->stream));
     *repeat = true;
     return 0;
 }
