@@ -246,20 +246,22 @@ def run_ours(args):
     value = pairs / (total_ms * 1e-3)
 
     # ---- end to end through the C ABI with HOST buffers: H2D of the configuration, cell build, energy pass, D2H of energies
-    # page-locked host buffer (the contract's "pinned host memory"): the library DMAs straight from it
+    # page-locked host buffers (the contract's "pinned host memory"): the library DMAs straight from them. The upload is what a
+    # configuration file holds -- 9 doubles per particle (position, direction, patch direction); patch sides are derived on the device
+    # exactly as the reference's partVecInit does after reading config.init.
     import torch as _t
-    pinned = _t.empty((n, 30), dtype=_t.float64).pin_memory()
+    pinned = _t.empty((n, 9), dtype=_t.float64).pin_memory()
     state_host = pinned.numpy()
-    state_host[:] = hs.state
+    state_host[:] = hs.state[:, :9]
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        eng.set_particles(state_host, hs.type, hs.moltype)
+        eng.set_particles_compact(state_host, hs.type, hs.moltype)
         eng.one_to_all_everyone(fetch=True)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.set_particles(state_host, hs.type, hs.moltype)
+        eng.set_particles_compact(state_host, hs.type, hs.moltype)
         e_host = eng.one_to_all_everyone(fetch=True)
     eng.sync()
     e2e_s = time.perf_counter() - t0

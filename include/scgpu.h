@@ -98,6 +98,10 @@ int scgpu_set_topology(scgpu_ctx* ctx, int ntypes, const scgpu_iaparam* table, d
                        int nmoltypes, const scgpu_molparam* mol);
 /* conf->pvec (scOOP/structures/Conf.h:305); also what initEM() / update(EMResize) need after a particle-count change */
 int scgpu_set_particles(scgpu_ctx* ctx, int n, const double* state30, const int* type, const int* moltype);
+/* the same from the 9 doubles per particle that config.init holds (pos[3] box-fractional, dir[3], patchdir[3]); patch sides,
+ * second patch and chiral axes are derived on the device as Conf::partVecInit / Particle::init do
+ * (scOOP/structures/Conf.cpp:98-103, scOOP/structures/particle.cpp:3-79) */
+int scgpu_set_particles_compact(scgpu_ctx* ctx, int n, const double* state9, const int* type, const int* moltype);
 /* conf->geo.box, read through PairE::pbc in the reference (scOOP/mc/paire.h:1205,1211) */
 int scgpu_set_box(scgpu_ctx* ctx, const double box[3]);
 /* update(int target) after an accepted single-particle move (totalenergycalculator.h:326-328) */

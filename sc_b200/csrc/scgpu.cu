@@ -63,6 +63,7 @@ struct DevSys {
     const int* moltype;
     const scgpu_iaparam* ia;
     const scgpu_molparam* mol;
+    const float* reach2;  // per ordered type pair: squared centre distance beyond which the pair energy is exactly 0 (x 1.001)
     double box[3];
     double shift[3];     // fractional grid shift used for the current cell assignment (0 for the energy API)
     double sqmaxcut;
@@ -159,6 +160,72 @@ __global__ void k_cell_place(DevSys s, const int* __restrict__ cell_of, const in
 #pragma unroll
     for (int k = 0; k < 30; k++) o[k] = a[c_api_of[k]];
     o[30] = 0.0; o[31] = 0.0;
+}
+
+// Particle::init on the device (scOOP/structures/particle.cpp:3-79): derive patch sides, second patch and chiral axes from
+// (dir, patchdir) and the type's own parameters -- what Conf::partVecInit does after config.init has been read. Lets a caller
+// upload the 9 doubles per particle that config.init holds instead of the 30-double record.
+__device__ __forceinline__ void rot_q(const double* p, const double* axis, double c, double sn, double* out) {   // Vector::rotate (Vector.h:138-160)
+    double qw = c, qx = axis[0] * sn, qy = axis[1] * sn, qz = axis[2] * sn;
+    double t2 = qw * qx, t3 = qw * qy, t4 = qw * qz, t5 = -qx * qx, t6 = qx * qy, t7 = qx * qz, t8 = -qy * qy, t9 = qy * qz, t10 = -qz * qz;
+    double x = p[0], y = p[1], z = p[2];
+    out[0] = 2.0 * ((t8 + t10) * x + (t6 - t4) * y + (t3 + t7) * z) + x;
+    out[1] = 2.0 * ((t4 + t6) * x + (t5 + t10) * y + (t9 - t2) * z) + y;
+    out[2] = 2.0 * ((t7 - t3) * x + (t2 + t9) * y + (t5 + t8) * z) + z;
+}
+__device__ __forceinline__ void normalise3(double* v) {
+    double tot = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (tot != 0.0) { tot = 1.0 / tot; v[0] *= tot; v[1] *= tot; v[2] *= tot; }
+}
+__device__ __forceinline__ void ortho3(double* a, const double* b) {
+    double dp = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    a[0] -= dp * b[0]; a[1] -= dp * b[1]; a[2] -= dp * b[2];
+}
+__global__ void k_particle_init(int n, int ntypes, const double* __restrict__ compact9, const int* __restrict__ type,
+                                const scgpu_iaparam* __restrict__ ia_tab, double* __restrict__ api) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double st[30];
+#pragma unroll
+    for (int k = 0; k < 9; k++) st[k] = compact9[(size_t)i * 9 + k];
+#pragma unroll
+    for (int k = 9; k < 30; k++) st[k] = 0.0;
+    const scgpu_iaparam& ia = ia_tab[type[i] * ntypes + type[i]];
+    const int g = (int)ia.geotype[0];
+    if (g < SCGPU_SPN && g != SCGPU_SCA && g != SCGPU_SCN) {
+        double* dir = st + 3; double* pd0 = st + 6; double* pd1 = st + 9;
+        normalise3(dir);
+        ortho3(pd0, dir);
+        normalise3(pd0);
+        const bool two = is_two_patch(g), chiral = is_chiral(g);
+        if (g == SCGPU_PSC || g == SCGPU_CPSC || g == SCGPU_TPSC || g == SCGPU_TCPSC) {
+            rot_q(pd0, dir, ia.pcoshalfi[0], ia.psinhalfi[0], st + 12);
+            rot_q(pd0, dir, ia.pcoshalfi[0], -1.0 * ia.psinhalfi[0], st + 15);
+        }
+        if (two) {
+            double tmp[3];
+            rot_q(pd0, dir, ia.csecpatchrot[0], ia.ssecpatchrot[0], tmp);
+            ortho3(tmp, dir);
+            normalise3(tmp);
+            pd1[0] = tmp[0]; pd1[1] = tmp[1]; pd1[2] = tmp[2];
+        }
+        if (g == SCGPU_TPSC || g == SCGPU_TCPSC) {
+            rot_q(pd1, dir, ia.pcoshalfi[2], ia.psinhalfi[2], st + 18);
+            rot_q(pd1, dir, ia.pcoshalfi[2], -1.0 * ia.psinhalfi[2], st + 21);
+        }
+        if (chiral) {
+            rot_q(dir, pd0, ia.chiral_cos[0], ia.chiral_sin[0], st + 24);
+            rot_q(pd0, st + 24, ia.pcoshalfi[0], ia.psinhalfi[0], st + 12);
+            rot_q(pd0, st + 24, ia.pcoshalfi[0], -1.0 * ia.psinhalfi[0], st + 15);
+        }
+        if (g == SCGPU_TCHPSC || g == SCGPU_TCHCPSC) {
+            rot_q(dir, pd1, ia.chiral_cos[0], ia.chiral_sin[0], st + 27);
+            rot_q(pd1, st + 27, ia.pcoshalfi[2], ia.psinhalfi[2], st + 18);
+            rot_q(pd1, st + 27, ia.pcoshalfi[2], -1.0 * ia.psinhalfi[2], st + 21);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 30; k++) api[(size_t)i * 30 + k] = st[k];
 }
 
 // rewrite one particle's sorted record in place (update(int target) when it stayed in its cell)
@@ -614,7 +681,7 @@ constexpr int GQ = 128;           // per-warp queue; flushed to the global list 
 template <int MODE, bool RODS>
 __global__ void __launch_bounds__(GT_WARPS * 32, 8)
 k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
-    __shared__ float4 t_pf[GT_TILE];
+    __shared__ float4 t_pf[GT_TILE];      // x,y,z: FP32 fractional coordinates relative to the cell centre; w: original index | type << 24
     __shared__ int t_slot[GT_TILE];
     __shared__ int sh_queue[GT_WARPS][GQ];
     __shared__ int sh_b[28], sh_off[28];
@@ -646,7 +713,7 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     const bool tiled = C <= GT_TILE;
     const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
     const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
-    const float pre_cut = (float)(s.sqmaxcut * 1.001);
+    const float cut_hi = (float)(s.sqmaxcut * 1.001), cut_lo = (float)(s.sqmaxcut * 0.999);
     auto slot_of_p = [&](int p) {
         int k = 0;
         while (k + 1 < ncell_nb && sh_off[k + 1] <= p) k++;
@@ -655,31 +722,35 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     auto staged = [&](int slot) {
         double4 pw = s.posw[slot];
         return make_float4((float)rel_frac(pw.x + s.shift[0], ccen[0]), (float)rel_frac(pw.y + s.shift[1], ccen[1]),
-                           (float)rel_frac(pw.z + s.shift[2], ccen[2]), __int_as_float(w_orig(pw.w)));
+                           (float)rel_frac(pw.z + s.shift[2], ccen[2]), __int_as_float(w_orig(pw.w) | (w_type(pw.w) << 24)));
     };
-    if (tiled) {
-        for (int p = threadIdx.x; p < C; p += blockDim.x) {
-            int slot = slot_of_p(p);
-            t_pf[p] = staged(slot);
-            t_slot[p] = slot;
+    if (tiled) {        // one warp per neighbour cell: contiguous 32-byte loads, no index search
+        for (int k = wid; k < ncell_nb; k += GT_WARPS) {
+            const int b = sh_b[k], off = sh_off[k], len = sh_off[k + 1] - off;
+            for (int idx = lane; idx < len; idx += 32) {
+                t_pf[off + idx] = staged(b + idx);
+                t_slot[off + idx] = b + idx;
+            }
         }
     }
     __syncthreads();
     int* queue = sh_queue[wid];
+    const bool count = counters != nullptr;
     for (int ti = tb + wid; ti < te; ti += GT_WARPS) {
         const double4 tpw = s.posw[ti];
         const int target = w_orig(tpw.w);
+        const float* reach_row = s.reach2 + w_type(tpw.w) * s.ntypes;
+        const float reach_same = reach_row[w_type(tpw.w)];
         int con0 = -1, con1 = -1, con2 = -1, con3 = -1;
         if (!RODS) {
             ConList cl;
             get_conlist(s.mol, w_moltype(tpw.w), target, cl);
             con0 = cl.con[0]; con1 = cl.con[1]; con2 = cl.con[2]; con3 = cl.con[3];
         }
-        const int max_idx = (MODE == 2) ? target : 0x7fffffff;
         const float t1x = (float)rel_frac(tpw.x + s.shift[0], ccen[0]), t1y = (float)rel_frac(tpw.y + s.shift[1], ccen[1]),
                     t1z = (float)rel_frac(tpw.z + s.shift[2], ccen[2]);
         int qn = 0, last_chunk = -1, head = -1;
-        unsigned n_cand = 0;
+        unsigned n_cand = 0, n_sure = 0;     // n_sure: pairs surely inside sqmaxcut AND surely beyond reach: gated, energy exactly 0, not listed
         auto flush = [&](int cnt) {          // the first cnt queue entries become one chunk of the global list
             int base = 0, cid = 0;
             if (lane == 0) { base = atomicAdd(fl.total, cnt); cid = atomicAdd(fl.chunk_count, 1); }
@@ -715,14 +786,21 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                 int slot = 0;
                 if (p < C) {
                     float4 q;
-                    if (tiled) { q = t_pf[p]; slot = t_slot[p]; } else { slot = slot_of_p(p); q = staged(slot); }
-                    int orig = __float_as_int(q.w);
-                    bool bonded = !RODS && (orig == con0 || orig == con1 || orig == con2 || orig == con3);
-                    if (orig != target && orig < max_idx && !bonded) {
-                        n_cand++;
+                    if (tiled) q = t_pf[p]; else { slot = slot_of_p(p); q = staged(slot); }
+                    const int wbits = __float_as_int(q.w);
+                    const int orig = wbits & 0xffffff;
+                    bool ok = orig != target;
+                    if (MODE == 2) ok = ok && orig < target;
+                    if (!RODS) ok = ok && !(orig == con0 || orig == con1 || orig == con2 || orig == con3);
+                    if (ok) {
                         float dx = t1x - q.x, dy = t1y - q.y, dz = t1z - q.z;
                         dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
-                        pass = dx * dx + dy * dy + dz * dz <= pre_cut;
+                        const float d2 = dx * dx + dy * dy + dz * dz;
+                        const float reach = RODS ? reach_same : reach_row[wbits >> 24];
+                        // listed: may interact (inside reach) or sits on the edge of the sqmaxcut gate (needs the exact FP64 test to be counted)
+                        pass = (d2 <= reach) || (d2 > cut_lo && d2 <= cut_hi);
+                        if (count) { n_cand++; if (!pass && d2 <= cut_lo) n_sure++; }
+                        if (pass && tiled) slot = t_slot[p];
                     }
                 }
                 if (h == 0) { pa = pass; sa = slot; } else { pb = pass; sb = slot; }
@@ -737,7 +815,7 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
         }
         if (!RODS) {       // bonded partners by index (never gated, mc/paire.h:1214)
             int orig = lane == 0 ? con0 : lane == 1 ? con1 : lane == 2 ? con2 : lane == 3 ? con3 : -1;
-            bool on = orig >= 0 && orig != target && orig < max_idx;
+            bool on = orig >= 0 && orig != target && (MODE != 2 || orig < target);
             if (on) n_cand++;
             unsigned m = __ballot_sync(0xffffffffu, on);
             if (on) queue[qn + __popc(m & lt_mask)] = s.slot_of[orig];
@@ -746,9 +824,10 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
         }
         while (qn > 0) flush(qn < 64 ? qn : 64);
         if (lane == 0) fl.head[target] = head;
-        if (counters) {
+        if (count) {
             n_cand = __reduce_add_sync(0xffffffffu, n_cand);
-            if (lane == 0) atomicAdd(&counters[0], (unsigned long long)n_cand);
+            n_sure = __reduce_add_sync(0xffffffffu, n_sure);
+            if (lane == 0) { atomicAdd(&counters[0], (unsigned long long)n_cand); atomicAdd(&counters[1], (unsigned long long)n_sure); }
         }
     }
 }
@@ -1051,6 +1130,7 @@ struct scgpu_ctx {
     int ntypes = 0, nmol = 0;
     std::vector<scgpu_iaparam> h_ia;
     std::vector<scgpu_molparam> h_mol;
+    float* d_reach2 = nullptr;
     scgpu_iaparam* d_ia = nullptr;
     scgpu_molparam* d_mol = nullptr;
     double sqmaxcut = 0, maxcut = 0;
@@ -1061,6 +1141,7 @@ struct scgpu_ctx {
     std::vector<double> h_api;       // unused host mirror (kept for ABI stability of the struct layout in debuggers)
     std::vector<int> h_cell_of;
     double* d_api = nullptr;
+    double* d_compact = nullptr;     // staging of 9-double records (scgpu_set_particles_compact)
     double4* d_posw = nullptr;
     double* d_rec = nullptr;
     int *d_type = nullptr, *d_moltype = nullptr, *d_cell_of = nullptr, *d_order = nullptr, *d_slot_of = nullptr, *d_tmp = nullptr;
@@ -1125,7 +1206,7 @@ static DevSys view(const scgpu_ctx* c) {
     for (int d = 0; d < 3; d++) { s.nc[d] = c->nc[d]; s.box[d] = c->box[d]; s.shift[d] = c->shift[d]; }
     s.ncells = c->ncells;
     s.api = c->d_api; s.posw = c->d_posw; s.rec = c->d_rec; s.cell_start = c->d_cell_start; s.order = c->d_order;
-    s.slot_of = c->d_slot_of; s.type = c->d_type; s.moltype = c->d_moltype; s.ia = c->d_ia; s.mol = c->d_mol;
+    s.slot_of = c->d_slot_of; s.type = c->d_type; s.moltype = c->d_moltype; s.ia = c->d_ia; s.mol = c->d_mol; s.reach2 = c->d_reach2;
     s.sqmaxcut = c->sqmaxcut;
     return s;
 }
@@ -1166,14 +1247,14 @@ extern "C" int scgpu_create(scgpu_ctx** out, int device) {
 }
 
 static void free_particles(scgpu_ctx* c) {
-    cudaFree(c->d_api); cudaFree(c->d_posw); cudaFree(c->d_rec); cudaFree(c->d_type); cudaFree(c->d_moltype);
+    cudaFree(c->d_api); cudaFree(c->d_compact); cudaFree(c->d_posw); cudaFree(c->d_rec); cudaFree(c->d_type); cudaFree(c->d_moltype);
     cudaFree(c->d_cell_of); cudaFree(c->d_order); cudaFree(c->d_slot_of); cudaFree(c->d_tmp); cudaFree(c->d_out);
     cudaFree(c->d_pairs); cudaFree(c->d_flags);
     cudaFree(c->d_fl_pair); cudaFree(c->d_fl_e); cudaFree(c->d_fl_plist); cudaFree(c->d_fl_head); cudaFree(c->d_fl_chunks);
     c->d_fl_pair = nullptr; c->d_fl_e = nullptr; c->d_fl_plist = nullptr; c->d_fl_head = nullptr; c->d_fl_chunks = nullptr;
     cudaFree(c->d_pl_pair); cudaFree(c->d_pl_e); cudaFree(c->d_warp_head); cudaFree(c->d_chunks); cudaFree(c->d_warp_partial);
     c->d_pl_pair = nullptr; c->d_pl_e = nullptr; c->d_warp_head = nullptr; c->d_chunks = nullptr; c->d_warp_partial = nullptr;
-    c->d_api = nullptr; c->d_posw = nullptr; c->d_rec = nullptr; c->d_type = c->d_moltype = c->d_cell_of = c->d_order = c->d_slot_of = c->d_tmp = nullptr;
+    c->d_api = nullptr; c->d_compact = nullptr; c->d_posw = nullptr; c->d_rec = nullptr; c->d_type = c->d_moltype = c->d_cell_of = c->d_order = c->d_slot_of = c->d_tmp = nullptr;
     c->d_out = c->d_pairs = nullptr; c->d_flags = nullptr;
     c->cap = 0;
 }
@@ -1183,7 +1264,7 @@ extern "C" int scgpu_destroy(scgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_particles(c);
-    cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_counts); cudaFree(c->d_cell_start); cudaFree(c->d_cursor);
+    cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_reach2); cudaFree(c->d_counts); cudaFree(c->d_cell_start); cudaFree(c->d_cursor);
     cudaFree(c->d_sweep_acc);
     cudaFree(c->d_trial); cudaFree(c->d_trial_rec); cudaFree(c->d_pl_total); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_counters); cudaFree(c->d_flush);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -1224,8 +1305,26 @@ extern "C" int scgpu_set_topology(scgpu_ctx* c, int ntypes, const scgpu_iaparam*
     c->h_ia.assign(table, table + (size_t)ntypes * ntypes);
     for (auto& p : c->h_ia) p.reserved[0] = (double)functor_kind((int)p.geotype[0], (int)p.geotype[1]);
     c->h_mol.assign(mol, mol + nmoltypes);
-    cudaFree(c->d_ia); cudaFree(c->d_mol);
-    c->d_ia = nullptr; c->d_mol = nullptr;
+    cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_reach2);
+    c->d_ia = nullptr; c->d_mol = nullptr; c->d_reach2 = nullptr;
+    {   // beyond `reach` (centre distance) every term of the pair energy is EXACTLY zero: rods are at least |r| - l1/2 - l2/2 apart,
+        // a rod and a sphere |r| - l/2, spheres |r|; the cutoffs are max(rcut, rcutwca). Stored squared, with a 0.1 % FP32 safety margin.
+        std::vector<float> reach((size_t)ntypes * ntypes);
+        for (int a = 0; a < ntypes; a++) for (int b = 0; b < ntypes; b++) {
+            const scgpu_iaparam& q = c->h_ia[(size_t)a * ntypes + b];
+            int k = (int)q.reserved[0];
+            double cut = sqrt(q.rcutSq > q.rcutwcaSq ? q.rcutSq : q.rcutwcaSq);
+            if (q.rcut > cut) cut = q.rcut;
+            if (q.rcutwca > cut) cut = q.rcutwca;
+            double r = 0.0;
+            if (k >= K_SC_PSCCPSC && k <= K_SC_SCA) r = cut + q.half_len[0] + q.half_len[1];
+            else if (k == K_SP_WCA || k == K_SP_COS2) r = cut;
+            else if (k >= K_MIX_SCASPA) r = cut + q.half_len[0] + q.half_len[1];    // one of the two half lengths is 0 (the sphere)
+            reach[(size_t)a * ntypes + b] = (float)(r * r * 1.001);
+        }
+        CK(cudaMalloc(&c->d_reach2, reach.size() * sizeof(float)));
+        CK(cudaMemcpy(c->d_reach2, reach.data(), reach.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&c->d_ia, c->h_ia.size() * sizeof(scgpu_iaparam)));
     CK(cudaMalloc(&c->d_mol, c->h_mol.size() * sizeof(scgpu_molparam)));
     CK(cudaMemcpyAsync(c->d_ia, c->h_ia.data(), c->h_ia.size() * sizeof(scgpu_iaparam), cudaMemcpyHostToDevice, c->stream));
@@ -1236,9 +1335,18 @@ extern "C" int scgpu_set_topology(scgpu_ctx* c, int ntypes, const scgpu_iaparam*
     return SCGPU_OK;
 }
 
+static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const int* type, const int* moltype, bool compact);
+
 extern "C" int scgpu_set_particles(scgpu_ctx* c, int n, const double* state30, const int* type, const int* moltype) {
+    return set_particles_impl(c, n, state30, type, moltype, false);
+}
+extern "C" int scgpu_set_particles_compact(scgpu_ctx* c, int n, const double* state9, const int* type, const int* moltype) {
+    return set_particles_impl(c, n, state9, type, moltype, true);
+}
+
+static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const int* type, const int* moltype, bool compact) {
     ARG(c && state30 && type && moltype, "scgpu_set_particles: NULL argument");
-    ARG(n > 0, "scgpu_set_particles: n must be positive");
+    ARG(n > 0 && n < (1 << 24), "scgpu_set_particles: n must be in 1 .. 16 777 215");
     ARG(c->ntypes > 0, "scgpu_set_particles: call scgpu_set_topology first");
     for (int i = 0; i < n; i++) {
         ARG(type[i] >= 0 && type[i] < c->ntypes, "scgpu_set_particles: particle type outside the topology table");
@@ -1249,6 +1357,7 @@ extern "C" int scgpu_set_particles(scgpu_ctx* c, int n, const double* state30, c
         free_particles(c);
         size_t N = (size_t)n;
         CK(cudaMalloc(&c->d_api, N * 30 * sizeof(double)));
+        CK(cudaMalloc(&c->d_compact, N * 9 * sizeof(double)));
         CK(cudaMalloc(&c->d_posw, N * sizeof(double4)));
         CK(cudaMalloc(&c->d_rec, N * REC * sizeof(double)));
         CK(cudaMalloc(&c->d_type, N * sizeof(int)));
@@ -1280,14 +1389,15 @@ extern "C" int scgpu_set_particles(scgpu_ctx* c, int n, const double* state30, c
     // Host -> device. If the caller's buffers are already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)
     // the DMA reads them directly; otherwise they are staged through a pinned bounce buffer in 2 MB chunks so that the
     // host memcpy of chunk k+1 overlaps the DMA of chunk k.
-    size_t bytes = (size_t)n * 30 * sizeof(double);
+    size_t bytes = (size_t)n * (compact ? 9 : 30) * sizeof(double);
+    double* d_dst = compact ? c->d_compact : c->d_api;
     auto is_pinned = [](const void* p) {
         cudaPointerAttributes a;
         if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
         return a.type == cudaMemoryTypeHost;
     };
     if (is_pinned(state30)) {
-        CK(cudaMemcpyAsync(c->d_api, state30, bytes, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d_dst, state30, bytes, cudaMemcpyHostToDevice, c->stream));
     } else {
         const size_t CH = 2u << 20;
         if (ensure_pinned(c, 2 * CH)) return SCGPU_ERR_CUDA;
@@ -1298,13 +1408,18 @@ extern "C" int scgpu_set_particles(scgpu_ctx* c, int n, const double* state30, c
             size_t len = bytes - off < CH ? bytes - off : CH;
             if (off >= 2 * CH) CK(cudaEventSynchronize(evs[k]));          // this half of the bounce buffer is free again
             memcpy(pin + k * CH, (const char*)state30 + off, len);
-            CK(cudaMemcpyAsync((char*)c->d_api + off, pin + k * CH, len, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync((char*)d_dst + off, pin + k * CH, len, cudaMemcpyHostToDevice, c->stream));
             CK(cudaEventRecord(evs[k], c->stream));
         }
     }
     CK(cudaMemcpyAsync(c->d_type, type, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_moltype, moltype, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    c->h_api.clear();            // host mirror (needed only by scgpu_update_particle) is refreshed lazily from the device
+    if (compact) {
+        k_particle_init<<<(n + 127) / 128, 128, 0, c->stream>>>(n, c->ntypes, c->d_compact, c->d_type, c->d_ia, c->d_api);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    c->h_api.clear();
     CK(cudaStreamSynchronize(c->stream));
     // specialisation switch: only rod-rod functors and no bonded molecule among the particles present
     {

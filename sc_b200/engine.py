@@ -33,7 +33,7 @@ class SweepStats(C.Structure):
 
 
 SYMBOLS = ["scgpu_last_error", "scgpu_device_count", "scgpu_create", "scgpu_destroy", "scgpu_set_topology",
-           "scgpu_set_particles", "scgpu_set_box", "scgpu_update_particle", "scgpu_download_particles",
+           "scgpu_set_particles", "scgpu_set_particles_compact", "scgpu_set_box", "scgpu_update_particle", "scgpu_download_particles",
            "scgpu_build_cells", "scgpu_cell_assignment", "scgpu_cell_order", "scgpu_one_to_all",
            "scgpu_one_to_all_batch", "scgpu_one_to_all_everyone", "scgpu_mol_to_others", "scgpu_all_to_all",
            "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_replica_record",
@@ -57,6 +57,7 @@ def load_library(variant="fast"):
     L.scgpu_destroy.argtypes = [vp]
     L.scgpu_set_topology.argtypes = [vp, C.c_int, _dp, C.c_double, C.c_double, C.c_int, _dp]
     L.scgpu_set_particles.argtypes = [vp, C.c_int, _dp, _ip, _ip]
+    L.scgpu_set_particles_compact.argtypes = [vp, C.c_int, _dp, _ip, _ip]
     L.scgpu_set_box.argtypes = [vp, _dp]
     L.scgpu_update_particle.argtypes = [vp, C.c_int, _dp]
     L.scgpu_download_particles.argtypes = [vp, _dp]
@@ -129,6 +130,14 @@ class Engine:
         moltypes = np.ascontiguousarray(moltypes, dtype=np.int32)
         self.n = state.shape[0]
         self._ck(self.L.scgpu_set_particles(self.h, self.n, _d(state), _i(types), _i(moltypes)))
+
+    def set_particles_compact(self, state9, types, moltypes):
+        """state9[n,9] = pos (box-fractional), dir, patchdir as config.init holds them; the rest is derived on the device"""
+        state9 = np.ascontiguousarray(state9, dtype=np.float64).reshape(-1, 9)
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        moltypes = np.ascontiguousarray(moltypes, dtype=np.int32)
+        self.n = state9.shape[0]
+        self._ck(self.L.scgpu_set_particles_compact(self.h, self.n, _d(state9), _i(types), _i(moltypes)))
 
     def set_box(self, box):
         box = np.ascontiguousarray(box, dtype=np.float64)

@@ -214,3 +214,22 @@ def test_errors_are_loud(engine):
         engine.set_box([0.0, 1.0, 1.0])
     with pytest.raises(ScgpuError):
         engine.overlap_all(7)
+
+
+@pytest.mark.parametrize("name", ["test_01_normal_PSC_init", "test_08_normal_TCHCPSC_init", "test_06_normal_TCPSC_init", "test_14_normal_SPA_PSC_CPSC_init",
+                                  "extra_mix_init", "extra_chains_init"])
+def test_compact_upload_derives_the_same_particles(engine, name):
+    """scgpu_set_particles_compact: 9 doubles per particle, Particle::init on the device == the host/reference derivation"""
+    r = O.load_ref_dump(os.path.join(G, name + ".ref.gz"))
+    s = r.system
+    engine.set_topology(s.ia, s.mol, s.sqmaxcut, s.maxcut)
+    engine.set_box(s.box)
+    engine.set_particles_compact(s.state[:, :9], s.type, s.moltype)
+    got = engine.download_particles()
+    from test_oracle_golden import used_fields
+    for i in range(s.n):
+        f = used_fields(int(s.ia[s.type[i], s.type[i], 0]))
+        assert np.max(np.abs(got[i, f] - s.state[i, f])) < 4e-16, (i, got[i, f] - s.state[i, f])
+    sc = eps_scale(s)
+    tl = list(range(0, s.n, max(1, s.n // 20)))
+    assert close(engine.one_to_all_batch(tl), [r.one[t] for t in tl], sc)
