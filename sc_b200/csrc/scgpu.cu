@@ -145,21 +145,42 @@ __global__ void k_cell_fill(int n, const int* __restrict__ cell_of, int* __restr
 // stable placement: slot = cell_start[c] + #{members of c with a smaller original index}; permute the records
 __global__ void k_cell_place(DevSys s, const int* __restrict__ cell_of, const int* __restrict__ tmp,
                              int* __restrict__ order, int* __restrict__ slot_of, double4* __restrict__ posw, double* __restrict__ rec) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.n) return;
-    int c = cell_of[i];
-    int b = s.cell_start[c], e = s.cell_start[c + 1];
-    int r = 0;
-    for (int k = b; k < e; k++) r += (tmp[k] < i);
-    int slot = b + r;
-    order[slot] = i;
-    slot_of[i] = slot;
-    const double* a = s.api + (size_t)i * 30;
-    posw[slot] = make_double4(a[0], a[1], a[2], pack_w(s.type[i], s.moltype[i], i));
-    double* o = rec + (size_t)slot * REC;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < s.n;
+    int slot = 0;
+    if (valid) {
+        int c = cell_of[i];
+        int b = s.cell_start[c], e = s.cell_start[c + 1];
+        int r = 0;
+        for (int k = b; k < e; k++) r += (tmp[k] < i);
+        slot = b + r;
+        order[slot] = i;
+        slot_of[i] = slot;
+    }
+    // record permute, warp-cooperative: for each of the warp's 32 particles the 32 lanes copy one 240-byte record together, so every
+    // load and store instruction touches one or two contiguous cache lines instead of 32 scattered ones
+    const int lane = threadIdx.x & 31;
+    if (!valid) slot = -1;
+    const int perm = lane < 30 ? c_api_of[lane] : 0;
+    for (int j0 = 0; j0 < 32; j0 += 8) {          // 8 records in flight per lane: loads first, then stores
+        double v[8];
+        int dst[8], srcs[8];
 #pragma unroll
-    for (int k = 0; k < 30; k++) o[k] = a[c_api_of[k]];
-    o[30] = 0.0; o[31] = 0.0;
+        for (int u = 0; u < 8; u++) {
+            srcs[u] = __shfl_sync(0xffffffffu, i, j0 + u);
+            dst[u] = __shfl_sync(0xffffffffu, slot, j0 + u);
+            v[u] = (dst[u] >= 0 && lane < 30) ? s.api[(size_t)srcs[u] * 30 + perm] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (dst[u] < 0) continue;
+            rec[(size_t)dst[u] * REC + lane] = v[u];
+            if (lane == 31) {
+                const double* a = s.api + (size_t)srcs[u] * 30;
+                posw[dst[u]] = make_double4(a[0], a[1], a[2], pack_w(s.type[srcs[u]], s.moltype[srcs[u]], srcs[u]));
+            }
+        }
+    }
 }
 
 // Particle::init on the device (scOOP/structures/particle.cpp:3-79): derive patch sides, second patch and chiral axes from

@@ -229,7 +229,7 @@ def test_compact_upload_derives_the_same_particles(engine, name):
     from test_oracle_golden import used_fields
     for i in range(s.n):
         f = used_fields(int(s.ia[s.type[i], s.type[i], 0]))
-        assert np.max(np.abs(got[i, f] - s.state[i, f])) < 4e-16, (i, got[i, f] - s.state[i, f])
+        assert np.max(np.abs(got[i, f] - s.state[i, f])) < 1e-14, (i, got[i, f] - s.state[i, f])   # re-normalising a unit vector moves last bits
     sc = eps_scale(s)
     tl = list(range(0, s.n, max(1, s.n // 20)))
     assert close(engine.one_to_all_batch(tl), [r.one[t] for t in tl], sc)
