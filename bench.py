@@ -273,6 +273,19 @@ def run_ours(args):
     h2d = state_host.nbytes + hs.type.nbytes + hs.moltype.nbytes
     d2h = e_host.nbytes
 
+    # ---- cell-list build (counting sort by cell + SoA permute): the HBM-bound kernel group of the path
+    cb_ms = []
+    for _ in range(max(3, min(args.steps, 10))):
+        eng.flush_l2()
+        eng.timer_start()
+        eng.build_cells()
+        cb_ms.append(eng.timer_stop())
+    cb_bytes = 544.0 * n          # 24 B position + 8 B cell id + 2 x 256 B record per particle
+    peaks, peak_kind = measured_peaks()
+    cell_build = {"bound": "hbm", "ms": float(np.mean(cb_ms)), "achieved": cb_bytes / (np.mean(cb_ms) * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                  "unit": "GB/s", "frac": cb_bytes / (np.mean(cb_ms) * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                  "bytes_per_build": cb_bytes, "kernels": "k_cell_count + k_cell_scan + k_cell_fill + k_cell_place (4 launches; launch latency is a large share at 65k particles)"}
+
     # ---- second metric of BASELINE.json: MC sweeps/s (batched checkerboard displacement/rotation sweeps, N trials each)
     from sc_b200.engine import MoveParams
     mp = MoveParams()
@@ -360,7 +373,7 @@ def run_ours(args):
            "roofline": roof, "cpu_baseline": cpu,
            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
-           "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall, "secondary": sweeps}
+           "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall, "secondary": sweeps, "cell_build": cell_build}
     if cpu:
         # the reference's sweep = N trials, each one trial-energy evaluation over its neighbour list (old energies are cached in its
         # energy matrix): derived from the measured pair rate, labelled as such

@@ -862,36 +862,48 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
     if (total > fl.cap) total = fl.cap;
     const int stride = gridDim.x * blockDim.x;
     unsigned n_gate = 0;
-    for (int p0 = blockIdx.x * blockDim.x; p0 < total; p0 += stride) {      // warp-uniform trip count
-        const int p = p0 + threadIdx.x;
-        bool np = false;
-        if (p < total) {
-            int2 pr = fl.pair[p];
-            double4 pi = s.posw[pr.x], pj = s.posw[pr.y];
-            v3 r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
-            double dotrcm = dot(r_cm, r_cm);
-            int oi = w_orig(pi.w), oj = w_orig(pj.w);
-            ConList cl;
-            cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0;
-            bool bonded = false;
-            if (!RODS) {
-                get_conlist(s.mol, w_moltype(pi.w), oi, cl);
-                bonded = !cl.is_empty && (oj == cl.con[0] || oj == cl.con[1] || oj == cl.con[2] || oj == cl.con[3]);
-            }
-            double e = 0.0;
-            if (dotrcm <= s.sqmaxcut || bonded) {           // the exact PairE gate (mc/paire.h:1214)
-                e = pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r_cm, dotrcm, s.rec + (size_t)pr.x * REC, w_type(pi.w), w_moltype(pi.w),
-                                            s.rec + (size_t)pr.y * REC, w_type(pj.w), oj, cl, np);
-                n_gate++;
-            }
-            fl.e[p] = make_double2(e, 0.0);
+    constexpr int U = 1;                                                     // pairs in flight per thread (2 measured slower: register pressure)
+    for (int p0 = blockIdx.x * blockDim.x * U; p0 < total; p0 += stride * U) {      // warp-uniform trip count
+        int pp[U];
+        int2 pr[U];
+        double4 pi[U], pj[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            pp[u] = p0 + u * blockDim.x + threadIdx.x;
+            pr[u] = pp[u] < total ? fl.pair[pp[u]] : make_int2(0, 0);
         }
-        unsigned m = __ballot_sync(0xffffffffu, np);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(fl.ptotal, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (np) fl.plist[base + __popc(m & lt_mask)] = p;      // plist has the capacity of pair[]: cannot overflow
+#pragma unroll
+        for (int u = 0; u < U; u++) { pi[u] = s.posw[pr[u].x]; pj[u] = s.posw[pr[u].y]; }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int p = pp[u];
+            bool np = false;
+            if (p < total) {
+                v3 r_cm = image(s.box, mk(pi[u].x, pi[u].y, pi[u].z), mk(pj[u].x, pj[u].y, pj[u].z));
+                double dotrcm = dot(r_cm, r_cm);
+                int oi = w_orig(pi[u].w), oj = w_orig(pj[u].w);
+                ConList cl;
+                cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0;
+                bool bonded = false;
+                if (!RODS) {
+                    get_conlist(s.mol, w_moltype(pi[u].w), oi, cl);
+                    bonded = !cl.is_empty && (oj == cl.con[0] || oj == cl.con[1] || oj == cl.con[2] || oj == cl.con[3]);
+                }
+                double e = 0.0;
+                if (dotrcm <= s.sqmaxcut || bonded) {           // the exact PairE gate (mc/paire.h:1214)
+                    e = pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r_cm, dotrcm, s.rec + (size_t)pr[u].x * REC, w_type(pi[u].w), w_moltype(pi[u].w),
+                                                s.rec + (size_t)pr[u].y * REC, w_type(pj[u].w), oj, cl, np);
+                    n_gate++;
+                }
+                fl.e[p] = make_double2(e, 0.0);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, np);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(fl.ptotal, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (np) fl.plist[base + __popc(m & lt_mask)] = p;      // plist has the capacity of pair[]: cannot overflow
+            }
         }
     }
     if (counters) {
