@@ -355,10 +355,11 @@ def run_ours(args):
         roof.update({"achieved": ach, "frac": ach / peak, "flops_per_launch": flops_step,
                      "flops_per_gated_pair": flops_sample / max(1, d["gated"]),
                      "peak_source": "DFMA-chain microbenchmark in this process (scgpu_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
-                     "kernel_ms": float(np.mean(kernel_ms))})
+                     "kernel_ms": float(np.mean(kernel_ms)),
+                     "kernels": "one step = k_gate_cells + k_cheap_flat + k_patch_flat + k_combine_flat (shares in profiles/launches_r1_summary.txt)"})
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
-            roof["traffic"] = json.load(open(prof)).get("k_one_to_all_dram_bytes_per_launch")
+            roof["traffic"] = json.load(open(prof)).get("pipeline_dram_bytes_per_step_total")
     except Exception as ex:      # the roofline numerator needs the oracle; never let it kill the bench line
         roof["error"] = repr(ex)
     cpu = None
