@@ -474,205 +474,7 @@ k_gate_cheap(DevSys s, int m, int gw, const int* __restrict__ targets, const dou
     if (lane == 0) warp_partial[wg] = part;
 }
 
-// ------------------------------------------------------------------------------------------------
-// cell-block variant of k_gate_cheap for "every particle" passes (MODE 1: one-to-all of everyone, MODE 2: allToAll rows):
-// one block per cell. The 27 neighbour cells' positions (and rod axes) are staged ONCE in shared memory with 32-byte
-// vector loads and reused by every particle of the cell (~17x fewer L1/L2 requests), and each warp then scans ONE dense
-// candidate array instead of 27 partially filled cell segments (lane utilisation of the gate ~100 % instead of ~55 %).
-// Cells whose neighbourhood does not fit the tile fall back to the per-warp global-memory scan.
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double rel_frac(double u, double cen) { double d = u - cen; return d - rint(d); }
-constexpr int TILE = 960;     // 960 x (16 + 24 + 4) B + per-warp scratch stays under the 48 KB static shared-memory limit     // 704 x (32 + 24 + 4) B + per-warp scratch stays under the 48 KB static shared-memory limit
-constexpr int CB_WARPS = 4;
-
-template <int MODE, bool RODS>
-__global__ void __launch_bounds__(CB_WARPS * 32, RODS ? 4 : 3)
-k_gate_cheap_cells(DevSys s, PatchList pl, double* __restrict__ warp_partial, unsigned long long* counters) {
-    __shared__ float4 t_pf[TILE];     // FP32 fractional coordinates relative to the cell centre (conservative pre-gate); w = original index
-    __shared__ double t_dir[RODS ? TILE * 3 : 3];
-    __shared__ int t_slot[TILE];
-    __shared__ double sh_rec[CB_WARPS][REC];
-    __shared__ int sh_queue[CB_WARPS][QCAP];
-    __shared__ int sh_pbuf[CB_WARPS][PCAP];
-    __shared__ int sh_b[28], sh_off[28];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const int c0 = blockIdx.x;
-    const int tb = s.cell_start[c0], te = s.cell_start[c0 + 1];
-    if (tb == te) return;
-    const int cx = c0 % s.nc[0], cy = (c0 / s.nc[0]) % s.nc[1], cz = c0 / (s.nc[0] * s.nc[1]);
-    const int nx = s.nc[0] == 1 ? 1 : 3, ny = s.nc[1] == 1 ? 1 : 3, nz = s.nc[2] == 1 ? 1 : 3;
-    const int ncell_nb = nx * ny * nz;
-    if (wid == 0) {
-        int len = 0, b = 0;
-        if (lane < ncell_nb) {
-            int dx = lane % nx, dy = (lane / nx) % ny, dz = lane / (nx * ny);
-            int ccx = nx == 1 ? 0 : (cx + dx - 1 + s.nc[0]) % s.nc[0];
-            int ccy = ny == 1 ? 0 : (cy + dy - 1 + s.nc[1]) % s.nc[1];
-            int ccz = nz == 1 ? 0 : (cz + dz - 1 + s.nc[2]) % s.nc[2];
-            int c = (ccz * s.nc[1] + ccy) * s.nc[0] + ccx;
-            b = s.cell_start[c];
-            len = s.cell_start[c + 1] - b;
-        }
-        int x = len;
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane < 28) { sh_b[lane] = b; sh_off[lane] = x - len; }      // exclusive prefix; entry ncell_nb = total
-    }
-    __syncthreads();
-    const int C = sh_off[ncell_nb];
-    const bool tiled = C <= TILE;
-    // centre of this cell in fractional coordinates; positions are staged relative to it so that FP32 keeps ~1e-8 of a cell
-    const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
-    const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
-    const float pre_cut = (float)(s.sqmaxcut * 1.001) ;   // conservative: the exact FP64 gate is re-applied before evaluation
-    if (tiled) {
-        for (int p = threadIdx.x; p < C; p += blockDim.x) {
-            int k = 0;
-            while (k + 1 < ncell_nb && sh_off[k + 1] <= p) k++;
-            int slot = sh_b[k] + (p - sh_off[k]);
-            double4 pw = s.posw[slot];
-            t_pf[p] = make_float4((float)rel_frac(pw.x + s.shift[0], ccen[0]), (float)rel_frac(pw.y + s.shift[1], ccen[1]),
-                                  (float)rel_frac(pw.z + s.shift[2], ccen[2]), __int_as_float(w_orig(pw.w)));
-            t_slot[p] = slot;
-            if (RODS) {
-                const double* r = s.rec + (size_t)slot * REC;
-                t_dir[3 * p] = r[0]; t_dir[3 * p + 1] = r[1]; t_dir[3 * p + 2] = r[2];
-            }
-        }
-    }
-    __syncthreads();
-    int* queue = sh_queue[wid];
-    int* pbuf = sh_pbuf[wid];
-    double* s1 = sh_rec[wid];
-    for (int ti = tb + wid; ti < te; ti += CB_WARPS) {
-        __syncwarp();
-        s1[lane] = s.rec[(size_t)ti * REC + lane];
-        const double4 tpw = s.posw[ti];
-        const int target = w_orig(tpw.w), type1 = w_type(tpw.w), moltype1 = w_moltype(tpw.w);
-        __syncwarp();
-        ConList cl;
-        if (RODS) { cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0; }
-        else get_conlist(s.mol, moltype1, target, cl);
-        Filter f;
-        f.self = target; f.excl_lo = 0; f.excl_hi = 0;
-        f.max_idx = (MODE == 2) ? target : 0x7fffffff;
-        double part;
-        if (!tiled) {
-            part = warp_gate_cheap<RODS>(s, s1, type1, moltype1, cl, f, 1, 0, queue, pbuf, ti, target, pl, nullptr, counters);
-        } else {
-            const v3 p1 = mk(tpw.x, tpw.y, tpw.z);
-            double acc = 0.0;
-            int qn = 0, pn = 0, last_chunk = -1, head = -1;
-            unsigned n_cand = 0, n_gate = 0;
-            auto flush_chunk = [&]() {
-                int base = 0, cid = 0;
-                if (lane == 0) { base = atomicAdd(pl.total, pn); cid = atomicAdd(pl.chunk_count, 1); }
-                base = __shfl_sync(0xffffffffu, base, 0);
-                cid = __shfl_sync(0xffffffffu, cid, 0);
-                bool ok = (cid < pl.chunk_cap) && (base + pn <= pl.cap);
-                if (ok) {
-                    for (int k = lane; k < pn; k += 32) pl.pair[base + k] = make_int2(ti, pbuf[k]);
-                    if (lane == 0) {
-                        pl.chunks[cid] = make_int4(base, pn, -1, 0);
-                        if (last_chunk >= 0) pl.chunks[last_chunk].z = cid;
-                    }
-                    if (head < 0) head = cid;
-                    last_chunk = cid;
-                } else if (lane == 0) atomicOr(pl.overflow, 1);
-                pn = 0;
-                __syncwarp();
-            };
-            auto eval_tile = [&](int p, bool on) {       // p: index into the staged tile
-                bool np = false;
-                int slot = 0;
-                if (on) {
-                    slot = t_slot[p];
-                    double4 pw = s.posw[slot];
-                    v3 r_cm = image(s.box, p1, mk(pw.x, pw.y, pw.z));
-                    double dotrcm = dot(r_cm, r_cm);
-                    if (dotrcm <= s.sqmaxcut) {            // the exact PairE gate (mc/paire.h:1214)
-                        const double* s2 = RODS ? &t_dir[3 * p] : s.rec + (size_t)slot * REC;
-                        acc += pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r_cm, dotrcm, s1, type1, moltype1, s2, w_type(pw.w), w_orig(pw.w), cl, np);
-                        n_gate++;
-                    }
-                }
-                unsigned m = __ballot_sync(0xffffffffu, np);
-                if (m) {
-                    int c = __popc(m);
-                    if (pn + c > PCAP) flush_chunk();
-                    if (np) pbuf[pn + __popc(m & lt_mask)] = slot;
-                    pn += c;
-                    __syncwarp();
-                }
-            };
-            const float t1x = (float)rel_frac(tpw.x + s.shift[0], ccen[0]), t1y = (float)rel_frac(tpw.y + s.shift[1], ccen[1]),
-                        t1z = (float)rel_frac(tpw.z + s.shift[2], ccen[2]);
-            auto pre_gate = [&](int p) -> bool {
-                if (p >= C) return false;
-                float4 q = t_pf[p];
-                int orig = __float_as_int(q.w);
-                bool bonded = !RODS && (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
-                if (!filt(f, orig) || bonded) return false;
-                n_cand++;
-                float dx = t1x - q.x, dy = t1y - q.y, dz = t1z - q.z;
-                dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
-                return dx * dx + dy * dy + dz * dz <= pre_cut;
-            };
-            for (int base = 0; base < C; base += 64) {
-                bool pa = pre_gate(base + lane), pb = pre_gate(base + 32 + lane);
-                unsigned ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
-                int na = __popc(ma);
-                if (pa) queue[qn + __popc(ma & lt_mask)] = base + lane;
-                if (pb) queue[qn + na + __popc(mb & lt_mask)] = base + 32 + lane;
-                qn += na + __popc(mb);
-                __syncwarp();
-                while (qn >= 32) {
-                    eval_tile(queue[lane], true);
-                    int rest = qn - 32;
-                    int mv0 = (lane < rest) ? queue[32 + lane] : 0;
-                    int mv1 = (lane + 32 < rest) ? queue[64 + lane] : 0;
-                    __syncwarp();
-                    if (lane < rest) queue[lane] = mv0;
-                    if (lane + 32 < rest) queue[32 + lane] = mv1;
-                    qn = rest;
-                    __syncwarp();
-                }
-            }
-            if (qn > 0) eval_tile(lane < qn ? queue[lane] : 0, lane < qn);
-            if (!RODS && !cl.is_empty) {     // bonded partners by index, through the global records
-                int orig = lane < 4 ? cl.con[lane] : -1;
-                bool on = orig >= 0 && filt(f, orig);
-                bool np = false;
-                int slot = 0;
-                if (on) {
-                    n_cand++; n_gate++;
-                    slot = s.slot_of[orig];
-                    double4 pw = s.posw[slot];
-                    v3 r_cm = image(s.box, p1, mk(pw.x, pw.y, pw.z));
-                    acc += pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r_cm, dot(r_cm, r_cm), s1, type1, moltype1,
-                                                   s.rec + (size_t)slot * REC, w_type(pw.w), orig, cl, np);
-                }
-                unsigned m = __ballot_sync(0xffffffffu, np);
-                if (m) {
-                    int c = __popc(m);
-                    if (pn + c > PCAP) flush_chunk();
-                    if (np) pbuf[pn + __popc(m & lt_mask)] = slot;
-                    pn += c;
-                    __syncwarp();
-                }
-            }
-            if (pn > 0) flush_chunk();
-            if (lane == 0) pl.warp_head[target] = head;
-            if (counters) {
-                n_cand = __reduce_add_sync(0xffffffffu, n_cand);
-                n_gate = __reduce_add_sync(0xffffffffu, n_gate);
-                if (lane == 0) { atomicAdd(&counters[0], (unsigned long long)n_cand); atomicAdd(&counters[1], (unsigned long long)n_gate); }
-            }
-            part = warp_sum(acc);
-        }
-        if (lane == 0) warp_partial[target] = part;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // FLAT pipeline for "every particle" passes (MODE 1 one-to-all of everyone, MODE 2 allToAll rows): four launches, each dense
@@ -1646,11 +1448,6 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
         CK(cudaGetLastError());
         return 0;
     }
-#define LAUNCH_CB(M, R) k_gate_cheap_cells<M, R><<<c->ncells, CB_WARPS * 32, 0, c->stream>>>(s, pl, c->d_warp_partial, d_counters)
-    if (false) {
-        if (c->rods_only) { if (mode == 1) LAUNCH_CB(1, true); else LAUNCH_CB(2, true); }
-        else { if (mode == 1) LAUNCH_CB(1, false); else LAUNCH_CB(2, false); }
-    } else
 #define LAUNCH_GC(M, R) k_gate_cheap<M, R><<<blocks, OTA_THREADS, 0, c->stream>>>(s, m, gw, d_targets, d_trial, excl_lo, excl_hi, pl, c->d_warp_partial, d_pairs, d_counters)
     if (c->rods_only) {
         switch (mode) { case 0: LAUNCH_GC(0, true); break; case 1: LAUNCH_GC(1, true); break; case 2: LAUNCH_GC(2, true); break; default: LAUNCH_GC(3, true); break; }

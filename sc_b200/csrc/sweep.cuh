@@ -125,21 +125,26 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
     }
     __syncthreads();
     const int C = sh_off[ncell_nb];
-    if (C > SW_TILE) {      // neighbourhood does not fit: leave the cell untouched and tell the host (it falls back to fewer, larger tiles)
-        if (threadIdx.x == 0) { atomicExch(fail_flag, 1); acc_out[c0] = acc; }
-        return;
-    }
+    const bool tiled = C <= SW_TILE;        // denser neighbourhoods are scanned from global memory (slower, same results)
+    (void)fail_flag;
     const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
     const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
     const float pre_cut = (float)(s.sqmaxcut * 1.001);
-    for (int p = threadIdx.x; p < C; p += blockDim.x) {
+    auto slot_of_p = [&](int p) {
         int k = 0;
         while (k + 1 < ncell_nb && sh_off[k + 1] <= p) k++;
-        int slot = sh_b[k] + (p - sh_off[k]);
+        return sh_b[k] + (p - sh_off[k]);
+    };
+    auto staged = [&](int slot) {
         double4 pw = posw[slot];
-        t_pf[p] = make_float4((float)rel_frac(pw.x + s.shift[0], ccen[0]), (float)rel_frac(pw.y + s.shift[1], ccen[1]),
-                              (float)rel_frac(pw.z + s.shift[2], ccen[2]), 0.f);
-        t_slot[p] = slot;
+        return make_float4((float)rel_frac(pw.x + s.shift[0], ccen[0]), (float)rel_frac(pw.y + s.shift[1], ccen[1]),
+                           (float)rel_frac(pw.z + s.shift[2], ccen[2]), 0.f);
+    };
+    if (tiled) {
+        for (int k = wid; k < ncell_nb; k += SW_WARPS) {
+            const int b = sh_b[k], off = sh_off[k], len = sh_off[k + 1] - off;
+            for (int idx = lane; idx < len; idx += 32) { t_pf[off + idx] = staged(b + idx); t_slot[off + idx] = b + idx; }
+        }
     }
     __syncthreads();
     const int ntrial = npart * sp.n_sub;
@@ -241,9 +246,9 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                 bool pass_o = false, pass_n = false;
                 int slot = 0;
                 if (p < C) {
-                    slot = t_slot[p];
+                    slot = tiled ? t_slot[p] : slot_of_p(p);
                     if (slot != tslot) {
-                        float4 q = t_pf[p];
+                        float4 q = tiled ? t_pf[p] : staged(slot);
                         float dx = ox - q.x, dy = oy - q.y, dz = oz - q.z;
                         dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
                         float ex = nxf - q.x, ey = nyf - q.y, ez = nzf - q.z;
@@ -327,7 +332,7 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
         if (sh_ctl[0]) {          // commit in place: sorted record, position word, staged FP32 copy
             if (threadIdx.x < REC) rec[(size_t)tslot * REC + threadIdx.x] = sh_new[threadIdx.x];
             if (threadIdx.x == 32) posw[tslot] = make_double4(sh_new[R_POS], sh_new[R_POS + 1], sh_new[R_POS + 2], tpw.w);
-            for (int p = threadIdx.x; p < C; p += blockDim.x)
+            for (int p = threadIdx.x; tiled && p < C; p += blockDim.x)
                 if (t_slot[p] == tslot)
                     t_pf[p] = make_float4((float)rel_frac(sh_new[R_POS] + s.shift[0], ccen[0]), (float)rel_frac(sh_new[R_POS + 1] + s.shift[1], ccen[1]),
                                           (float)rel_frac(sh_new[R_POS + 2] + s.shift[2], ccen[2]), 0.f);

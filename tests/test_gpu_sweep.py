@@ -138,3 +138,24 @@ def test_average_energy_matches_reference_sequential_sweeps():
     print("reference <E> = %.3f +- %.3f ; checkerboard <E> = %.3f +- %.3f ; acceptance trans %.3f rot %.3f"
           % (ref_mean, ref_err, gpu_mean, gpu_err, acc_t / tot_t, acc_r / tot_r))
     assert abs(gpu_mean - ref_mean) <= 4.0 * sigma + 2e-3 * abs(ref_mean), (gpu_mean, ref_mean, sigma)
+
+
+def test_dense_membrane_sweeps_fall_back_to_global_scan():
+    """CPSC + lipid membrane (bonded 3-bead chains, neighbourhoods far larger than the staged tile): sweeps still keep exact books"""
+    import gzip
+    inp = json.loads(gzip.open(os.path.join(G, "membrane601.inputs.json.gz")).read().decode())
+    top, cfg, n = synth.membrane(4, 4, inp["top.init"], inp["config.init"])
+    hs = HostSystem(top, cfg)
+    eng = Engine(0, "fast").load(hs)
+    e0 = eng.all_to_all()
+    mp = move_params(1.0, 0.05, 10.0)
+    tot = 0.0
+    acc = 0
+    for sw in range(4):
+        st = eng.sweep(mp, 99, sw)
+        tot += st.energy_delta
+        acc += st.trans_acc + st.rot_acc
+    e1 = eng.all_to_all()
+    assert acc > 0
+    assert abs((e1 - e0) - tot) <= 1e-9 * max(abs(e0), abs(e1)), (e0, e1, tot)
+    eng.close()
