@@ -286,6 +286,34 @@ def run_ours(args):
                   "unit": "GB/s", "frac": cb_bytes / (np.mean(cb_ms) * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                   "bytes_per_build": cb_bytes, "kernels": "k_cell_count + k_cell_scan + k_cell_fill + k_cell_place (4 launches; launch latency is a large share at 65k particles)"}
 
+    # ---- full-system energy (allToAll: what every NPT volume move and every replica exchange needs): every pair once
+    fe_ms = []
+    for _ in range(max(3, min(args.steps, 10))):
+        eng.flush_l2()
+        eng.timer_start()
+        eng.all_to_all(fetch=False)
+        fe_ms.append(eng.timer_stop())
+    full_energy = {"workload": "allToAll over 65536 PSC (every unordered pair once, conlist of the higher index)", "ms": float(np.mean(fe_ms)),
+                   "gated_pairs": int(ngate) // 2, "pair_evals_per_s": (int(ngate) // 2) / (np.mean(fe_ms) * 1e-3)}
+    if args.with_membrane and world == 1:
+        import gzip as _gz
+        inp = json.loads(_gz.open(os.path.join(ROOT, "tests", "golden", "membrane601.inputs.json.gz")).read().decode())
+        from sc_b200 import synth as _synth
+        mtop, mcfg, mn = _synth.membrane(21, 21, inp["top.init"], inp["config.init"])
+        mhs = HostSystem(mtop, mcfg)
+        meng = Engine(local, "fast").load(mhs)
+        meng.all_to_all()
+        mm = []
+        for _ in range(3):
+            meng.flush_l2()
+            meng.timer_start()
+            meng.all_to_all(fetch=False)
+            mm.append(meng.timer_stop())
+        full_energy["membrane_265041"] = {"workload": "BASELINE configs[2]: CPSC + SPN-SPA-SPA lipid membrane tiled 21x21 (265 041 particles), one allToAll = one NPT trial energy",
+                                          "ms": float(np.mean(mm))}
+        meng.close()
+        mhs.close()
+
     # ---- second metric of BASELINE.json: MC sweeps/s (batched checkerboard displacement/rotation sweeps, N trials each)
     from sc_b200.engine import MoveParams
     mp = MoveParams()
@@ -374,7 +402,7 @@ def run_ours(args):
            "roofline": roof, "cpu_baseline": cpu,
            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
-           "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall, "secondary": sweeps, "cell_build": cell_build}
+           "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall, "secondary": sweeps, "cell_build": cell_build, "full_energy": full_energy}
     if cpu:
         # the reference's sweep = N trials, each one trial-energy evaluation over its neighbour list (old energies are cached in its
         # energy matrix): derived from the measured pair rate, labelled as such
@@ -417,6 +445,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--with-membrane", action="store_true", help="also time the 265k-particle membrane full-energy pass (configs[2])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
