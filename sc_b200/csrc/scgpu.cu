@@ -500,6 +500,7 @@ struct FlatList {
 constexpr int GT_TILE = 1024;     // staged candidates per cell neighbourhood: 1024 x 20 B = 20 KB (denser cells scan global memory)
 constexpr int GT_WARPS = 4;
 constexpr int GQ = 128;           // per-warp queue; flushed to the global list in chunks of 64
+constexpr int GT_MAXP = 512;      // particles of one cell whose chunk-chain ends are kept in shared memory across tiles
 
 template <int MODE, bool RODS>
 __global__ void __launch_bounds__(GT_WARPS * 32, 8)
@@ -507,6 +508,7 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     __shared__ float4 t_pf[GT_TILE];      // x,y,z: FP32 fractional coordinates relative to the cell centre; w: original index | type << 24
     __shared__ int t_slot[GT_TILE];
     __shared__ int sh_queue[GT_WARPS][GQ];
+    __shared__ int sh_head[GT_MAXP], sh_last[GT_MAXP];
     __shared__ int sh_b[28], sh_off[28];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -533,7 +535,11 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     }
     __syncthreads();
     const int C = sh_off[ncell_nb];
-    const bool tiled = C <= GT_TILE;
+    const int npart = te - tb;
+    // neighbourhoods larger than one tile are processed tile by tile (the per-particle chunk chains persist in shared memory);
+    // only cells with more than GT_MAXP particles of their own fall back to scanning global memory in one pass
+    const bool use_tiles = npart <= GT_MAXP;
+    const int ntiles = use_tiles ? (C + GT_TILE - 1) / GT_TILE : 1;
     const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
     const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
     const float cut_hi = (float)(s.sqmaxcut * 1.001), cut_lo = (float)(s.sqmaxcut * 0.999);
@@ -547,110 +553,119 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
         return make_float4((float)rel_frac(pw.x + s.shift[0], ccen[0]), (float)rel_frac(pw.y + s.shift[1], ccen[1]),
                            (float)rel_frac(pw.z + s.shift[2], ccen[2]), __int_as_float(w_orig(pw.w) | (w_type(pw.w) << 24)));
     };
-    if (tiled) {        // one warp per neighbour cell: contiguous 32-byte loads, no index search
-        for (int k = wid; k < ncell_nb; k += GT_WARPS) {
-            const int b = sh_b[k], off = sh_off[k], len = sh_off[k + 1] - off;
-            for (int idx = lane; idx < len; idx += 32) {
-                t_pf[off + idx] = staged(b + idx);
-                t_slot[off + idx] = b + idx;
-            }
-        }
-    }
-    __syncthreads();
+    if (use_tiles) for (int k = threadIdx.x; k < npart; k += blockDim.x) { sh_head[k] = -1; sh_last[k] = -1; }
     int* queue = sh_queue[wid];
     const bool count = counters != nullptr;
-    for (int ti = tb + wid; ti < te; ti += GT_WARPS) {
-        const double4 tpw = s.posw[ti];
-        const int target = w_orig(tpw.w);
-        const float* reach_row = s.reach2 + w_type(tpw.w) * s.ntypes;
-        const float reach_same = reach_row[w_type(tpw.w)];
-        int con0 = -1, con1 = -1, con2 = -1, con3 = -1;
-        if (!RODS) {
-            ConList cl;
-            get_conlist(s.mol, w_moltype(tpw.w), target, cl);
-            con0 = cl.con[0]; con1 = cl.con[1]; con2 = cl.con[2]; con3 = cl.con[3];
-        }
-        const float t1x = (float)rel_frac(tpw.x + s.shift[0], ccen[0]), t1y = (float)rel_frac(tpw.y + s.shift[1], ccen[1]),
-                    t1z = (float)rel_frac(tpw.z + s.shift[2], ccen[2]);
-        int qn = 0, last_chunk = -1, head = -1;
-        unsigned n_cand = 0, n_sure = 0;     // n_sure: pairs surely inside sqmaxcut AND surely beyond reach: gated, energy exactly 0, not listed
-        auto flush = [&](int cnt) {          // the first cnt queue entries become one chunk of the global list
-            int base = 0, cid = 0;
-            if (lane == 0) { base = atomicAdd(fl.total, cnt); cid = atomicAdd(fl.chunk_count, 1); }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            cid = __shfl_sync(0xffffffffu, cid, 0);
-            bool ok = (cid < fl.chunk_cap) && (base + cnt <= fl.cap);
-            if (ok) {
-                for (int k = lane; k < cnt; k += 32) fl.pair[base + k] = make_int2(ti, queue[k]);
-                if (lane == 0) {
-                    fl.chunks[cid] = make_int4(base, cnt, -1, 0);
-                    if (last_chunk >= 0) fl.chunks[last_chunk].z = cid;
+    for (int tile = 0; tile < ntiles; tile++) {
+        const int t0 = tile * GT_TILE;
+        const int TC = use_tiles ? min(GT_TILE, C - t0) : C;       // candidates handled in this pass
+        __syncthreads();                                           // previous tile fully consumed
+        if (use_tiles) {        // one warp per neighbour cell: contiguous 32-byte loads, no index search
+            for (int k = wid; k < ncell_nb; k += GT_WARPS) {
+                const int b = sh_b[k], off = sh_off[k], len = sh_off[k + 1] - off;
+                int lo = max(off, t0), hi = min(off + len, t0 + TC);
+                for (int p = lo + lane; p < hi; p += 32) {
+                    t_pf[p - t0] = staged(b + (p - off));
+                    t_slot[p - t0] = b + (p - off);
                 }
-                if (head < 0) head = cid;
-                last_chunk = cid;
-            } else if (lane == 0) atomicOr(fl.overflow, 2);
-            __syncwarp();
-            int rest = qn - cnt;
-            int mv0 = (lane < rest) ? queue[cnt + lane] : 0;
-            int mv1 = (lane + 32 < rest) ? queue[cnt + 32 + lane] : 0;
-            __syncwarp();
-            if (lane < rest) queue[lane] = mv0;
-            if (lane + 32 < rest) queue[32 + lane] = mv1;
-            qn = rest;
-            __syncwarp();
-        };
-        for (int base = 0; base < C; base += 64) {
-            bool pa = false, pb = false;
-            int sa = 0, sb = 0;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                int p = base + 32 * h + lane;
-                bool pass = false;
-                int slot = 0;
-                if (p < C) {
-                    float4 q;
-                    if (tiled) q = t_pf[p]; else { slot = slot_of_p(p); q = staged(slot); }
-                    const int wbits = __float_as_int(q.w);
-                    const int orig = wbits & 0xffffff;
-                    bool ok = orig != target;
-                    if (MODE == 2) ok = ok && orig < target;
-                    if (!RODS) ok = ok && !(orig == con0 || orig == con1 || orig == con2 || orig == con3);
-                    if (ok) {
-                        float dx = t1x - q.x, dy = t1y - q.y, dz = t1z - q.z;
-                        dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
-                        const float d2 = dx * dx + dy * dy + dz * dz;
-                        const float reach = RODS ? reach_same : reach_row[wbits >> 24];
-                        // listed: may interact (inside reach) or sits on the edge of the sqmaxcut gate (needs the exact FP64 test to be counted)
-                        pass = (d2 <= reach) || (d2 > cut_lo && d2 <= cut_hi);
-                        if (count) { n_cand++; if (!pass && d2 <= cut_lo) n_sure++; }
-                        if (pass && tiled) slot = t_slot[p];
-                    }
-                }
-                if (h == 0) { pa = pass; sa = slot; } else { pb = pass; sb = slot; }
             }
-            unsigned ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
-            int na = __popc(ma);
-            if (pa) queue[qn + __popc(ma & lt_mask)] = sa;
-            if (pb) queue[qn + na + __popc(mb & lt_mask)] = sb;
-            qn += na + __popc(mb);
-            __syncwarp();
-            if (qn >= 64) flush(64);
         }
-        if (!RODS) {       // bonded partners by index (never gated, mc/paire.h:1214)
-            int orig = lane == 0 ? con0 : lane == 1 ? con1 : lane == 2 ? con2 : lane == 3 ? con3 : -1;
-            bool on = orig >= 0 && orig != target && (MODE != 2 || orig < target);
-            if (on) n_cand++;
-            unsigned m = __ballot_sync(0xffffffffu, on);
-            if (on) queue[qn + __popc(m & lt_mask)] = s.slot_of[orig];
-            qn += __popc(m);
-            __syncwarp();
-        }
-        while (qn > 0) flush(qn < 64 ? qn : 64);
-        if (lane == 0) fl.head[target] = head;
-        if (count) {
-            n_cand = __reduce_add_sync(0xffffffffu, n_cand);
-            n_sure = __reduce_add_sync(0xffffffffu, n_sure);
-            if (lane == 0) { atomicAdd(&counters[0], (unsigned long long)n_cand); atomicAdd(&counters[1], (unsigned long long)n_sure); }
+        __syncthreads();
+        for (int ti = tb + wid; ti < te; ti += GT_WARPS) {
+            const double4 tpw = s.posw[ti];
+            const int target = w_orig(tpw.w);
+            const float* reach_row = s.reach2 + w_type(tpw.w) * s.ntypes;
+            const float reach_same = reach_row[w_type(tpw.w)];
+            int con0 = -1, con1 = -1, con2 = -1, con3 = -1;
+            if (!RODS) {
+                ConList cl;
+                get_conlist(s.mol, w_moltype(tpw.w), target, cl);
+                con0 = cl.con[0]; con1 = cl.con[1]; con2 = cl.con[2]; con3 = cl.con[3];
+            }
+            const float t1x = (float)rel_frac(tpw.x + s.shift[0], ccen[0]), t1y = (float)rel_frac(tpw.y + s.shift[1], ccen[1]),
+                        t1z = (float)rel_frac(tpw.z + s.shift[2], ccen[2]);
+            int qn = 0;
+            int last_chunk = use_tiles ? sh_last[ti - tb] : -1, head = use_tiles ? sh_head[ti - tb] : -1;
+            unsigned n_cand = 0, n_sure = 0;     // n_sure: pairs surely inside sqmaxcut AND surely beyond reach: gated, energy exactly 0, not listed
+            auto flush = [&](int cnt) {          // the first cnt queue entries become one chunk of the global list
+                int base = 0, cid = 0;
+                if (lane == 0) { base = atomicAdd(fl.total, cnt); cid = atomicAdd(fl.chunk_count, 1); }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                cid = __shfl_sync(0xffffffffu, cid, 0);
+                bool ok = (cid < fl.chunk_cap) && (base + cnt <= fl.cap);
+                if (ok) {
+                    for (int k = lane; k < cnt; k += 32) fl.pair[base + k] = make_int2(ti, queue[k]);
+                    if (lane == 0) {
+                        fl.chunks[cid] = make_int4(base, cnt, -1, 0);
+                        if (last_chunk >= 0) fl.chunks[last_chunk].z = cid;
+                    }
+                    if (head < 0) head = cid;
+                    last_chunk = cid;
+                } else if (lane == 0) atomicOr(fl.overflow, 2);
+                __syncwarp();
+                int rest = qn - cnt;
+                int mv0 = (lane < rest) ? queue[cnt + lane] : 0;
+                int mv1 = (lane + 32 < rest) ? queue[cnt + 32 + lane] : 0;
+                __syncwarp();
+                if (lane < rest) queue[lane] = mv0;
+                if (lane + 32 < rest) queue[32 + lane] = mv1;
+                qn = rest;
+                __syncwarp();
+            };
+            for (int base = 0; base < TC; base += 64) {
+                bool pa = false, pb = false;
+                int sa = 0, sb = 0;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    int p = base + 32 * h + lane;
+                    bool pass = false;
+                    int slot = 0;
+                    if (p < TC) {
+                        float4 q;
+                        if (use_tiles) q = t_pf[p]; else { slot = slot_of_p(p); q = staged(slot); }
+                        const int wbits = __float_as_int(q.w);
+                        const int orig = wbits & 0xffffff;
+                        bool ok = orig != target;
+                        if (MODE == 2) ok = ok && orig < target;
+                        if (!RODS) ok = ok && !(orig == con0 || orig == con1 || orig == con2 || orig == con3);
+                        if (ok) {
+                            float dx = t1x - q.x, dy = t1y - q.y, dz = t1z - q.z;
+                            dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
+                            const float d2 = dx * dx + dy * dy + dz * dz;
+                            const float reach = RODS ? reach_same : reach_row[wbits >> 24];
+                            // listed: may interact (inside reach) or sits on the edge of the sqmaxcut gate (needs the exact FP64 test to be counted)
+                            pass = (d2 <= reach) || (d2 > cut_lo && d2 <= cut_hi);
+                            if (count) { n_cand++; if (!pass && d2 <= cut_lo) n_sure++; }
+                            if (pass && use_tiles) slot = t_slot[p];
+                        }
+                    }
+                    if (h == 0) { pa = pass; sa = slot; } else { pb = pass; sb = slot; }
+                }
+                unsigned ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
+                int na = __popc(ma);
+                if (pa) queue[qn + __popc(ma & lt_mask)] = sa;
+                if (pb) queue[qn + na + __popc(mb & lt_mask)] = sb;
+                qn += na + __popc(mb);
+                __syncwarp();
+                if (qn >= 64) flush(64);
+            }
+            if (!RODS && tile == ntiles - 1) {       // bonded partners by index (never gated, mc/paire.h:1214)
+                int orig = lane == 0 ? con0 : lane == 1 ? con1 : lane == 2 ? con2 : lane == 3 ? con3 : -1;
+                bool on = orig >= 0 && orig != target && (MODE != 2 || orig < target);
+                if (on) n_cand++;
+                unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) queue[qn + __popc(m & lt_mask)] = s.slot_of[orig];
+                qn += __popc(m);
+                __syncwarp();
+            }
+            while (qn > 0) flush(qn < 64 ? qn : 64);
+            if (use_tiles && lane == 0) { sh_head[ti - tb] = head; sh_last[ti - tb] = last_chunk; }
+            if (tile == ntiles - 1 && lane == 0) fl.head[target] = head;
+            if (count) {
+                n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+                n_sure = __reduce_add_sync(0xffffffffu, n_sure);
+                if (lane == 0) { atomicAdd(&counters[0], (unsigned long long)n_cand); atomicAdd(&counters[1], (unsigned long long)n_sure); }
+            }
         }
     }
 }
