@@ -340,7 +340,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sweep_s = float(t.item())
     sweeps = {"metric": "mc_sweeps_per_s", "value": nsw * world / sweep_s, "unit": "sweeps/s (1 sweep = N = 65536 trial moves per replica)",
-              "ms_per_sweep": sweep_s / nsw * 1e3, "trial_moves_per_s": nsw * world * n / sweep_s, "acceptance": acc / max(1, tot),
+              "ms_per_sweep": sweep_s / nsw * 1e3, "trial_moves_per_s": tot * world / sweep_s, "acceptance": acc / max(1, tot),
               "temper": 0.1, "transmx": 0.0212, "rotmx_deg": 7.5, "sweeps_timed": nsw,
               "note": "whole scgpu_sweep_checkerboard call: shifted cell build + 8 colour passes + statistics read-back"}
 

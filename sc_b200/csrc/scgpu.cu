@@ -21,6 +21,7 @@
 #include <string.h>
 #include <math.h>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "pair_energy.cuh"
@@ -132,6 +133,14 @@ __global__ void k_cell_scan(int ncells, const int* __restrict__ counts, int* __r
         __syncthreads();
     }
     if (threadIdx.x == 0) cell_start[ncells] = carry;
+    // [ncells + 1]: number of non-empty cells (the sweep kernel spreads its trials over them)
+    __syncthreads();
+    int ne = 0;
+    for (int i = threadIdx.x; i < ncells; i += blockDim.x) ne += counts[i] > 0;
+    ne = __reduce_add_sync(0xffffffffu, ne);
+    if (lane == 0) warp_tot[wid] = ne;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += warp_tot[w]; cell_start[ncells + 1] = t; }
 }
 
 // unordered fill of each cell's segment with original indices (order fixed afterwards by k_cell_place)
@@ -502,10 +511,13 @@ constexpr int GT_WARPS = 4;
 constexpr int GQ = 128;           // per-warp queue; flushed to the global list in chunks of 64
 constexpr int GT_MAXP = 512;      // particles of one cell whose chunk-chain ends are kept in shared memory across tiles
 
-template <int MODE, bool RODS>
+// WRAP: some axis has fewer than 5 cells, so a neighbour can be more than half a box away from the target and the FP32
+// separation needs the minimum-image fold. With >= 5 cells per axis every candidate of the 27-cell neighbourhood is within
+// 2/5 of the box of the target once both are taken relative to the cell centre, and the fold is skipped.
+template <int MODE, bool RODS, bool WRAP>
 __global__ void __launch_bounds__(GT_WARPS * 32, 8)
 k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
-    __shared__ float4 t_pf[GT_TILE];      // x,y,z: FP32 fractional coordinates relative to the cell centre; w: original index | type << 24
+    __shared__ float4 t_pf[GT_TILE];      // x,y,z: FP32 coordinates relative to the cell centre, in length units; w: original index | type << 24
     __shared__ int t_slot[GT_TILE];
     __shared__ int sh_queue[GT_WARPS][GQ];
     __shared__ int sh_head[GT_MAXP], sh_last[GT_MAXP];
@@ -542,6 +554,7 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     const int ntiles = use_tiles ? (C + GT_TILE - 1) / GT_TILE : 1;
     const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
     const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
+    const float ibox[3] = {(float)(1.0 / s.box[0]), (float)(1.0 / s.box[1]), (float)(1.0 / s.box[2])};
     const float cut_hi = (float)(s.sqmaxcut * 1.001), cut_lo = (float)(s.sqmaxcut * 0.999);
     auto slot_of_p = [&](int p) {
         int k = 0;
@@ -550,8 +563,8 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     };
     auto staged = [&](int slot) {
         double4 pw = s.posw[slot];
-        return make_float4((float)rel_frac(pw.x + s.shift[0], ccen[0]), (float)rel_frac(pw.y + s.shift[1], ccen[1]),
-                           (float)rel_frac(pw.z + s.shift[2], ccen[2]), __int_as_float(w_orig(pw.w) | (w_type(pw.w) << 24)));
+        return make_float4((float)(rel_frac(pw.x + s.shift[0], ccen[0]) * s.box[0]), (float)(rel_frac(pw.y + s.shift[1], ccen[1]) * s.box[1]),
+                           (float)(rel_frac(pw.z + s.shift[2], ccen[2]) * s.box[2]), __int_as_float(w_orig(pw.w) | (w_type(pw.w) << 24)));
     };
     if (use_tiles) for (int k = threadIdx.x; k < npart; k += blockDim.x) { sh_head[k] = -1; sh_last[k] = -1; }
     int* queue = sh_queue[wid];
@@ -569,6 +582,11 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                     t_slot[p - t0] = b + (p - off);
                 }
             }
+            for (int p = TC + threadIdx.x; p < ((TC + 63) & ~63); p += blockDim.x) {     // padding: NaN coordinates fail every comparison of the gate
+                const float qnan = __int_as_float(0x7fc00000);
+                t_pf[p] = make_float4(qnan, qnan, qnan, __int_as_float(0xffffff));
+                t_slot[p] = 0;
+            }
         }
         __syncthreads();
         for (int ti = tb + wid; ti < te; ti += GT_WARPS) {
@@ -582,8 +600,8 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                 get_conlist(s.mol, w_moltype(tpw.w), target, cl);
                 con0 = cl.con[0]; con1 = cl.con[1]; con2 = cl.con[2]; con3 = cl.con[3];
             }
-            const float t1x = (float)rel_frac(tpw.x + s.shift[0], ccen[0]), t1y = (float)rel_frac(tpw.y + s.shift[1], ccen[1]),
-                        t1z = (float)rel_frac(tpw.z + s.shift[2], ccen[2]);
+            const float t1x = (float)(rel_frac(tpw.x + s.shift[0], ccen[0]) * s.box[0]), t1y = (float)(rel_frac(tpw.y + s.shift[1], ccen[1]) * s.box[1]),
+                        t1z = (float)(rel_frac(tpw.z + s.shift[2], ccen[2]) * s.box[2]);
             int qn = 0;
             int last_chunk = use_tiles ? sh_last[ti - tb] : -1, head = use_tiles ? sh_head[ti - tb] : -1;
             unsigned n_cand = 0, n_sure = 0;     // n_sure: pairs surely inside sqmaxcut AND surely beyond reach: gated, energy exactly 0, not listed
@@ -612,43 +630,48 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                 qn = rest;
                 __syncwarp();
             };
-            for (int base = 0; base < TC; base += 64) {
-                bool pa = false, pb = false;
-                int sa = 0, sb = 0;
+            // the scan, specialised at compile time on where the candidates come from and on whether work is being counted
+            auto scan = [&](auto tiles_c, auto count_c) {
+                constexpr bool TILES = decltype(tiles_c)::value, COUNT = decltype(count_c)::value;
+                for (int base = 0; base < TC; base += 64) {
+                    bool pa = false, pb = false;
+                    int sa = 0, sb = 0;
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    int p = base + 32 * h + lane;
-                    bool pass = false;
-                    int slot = 0;
-                    if (p < TC) {
-                        float4 q;
-                        if (use_tiles) q = t_pf[p]; else { slot = slot_of_p(p); q = staged(slot); }
-                        const int wbits = __float_as_int(q.w);
-                        const int orig = wbits & 0xffffff;
-                        bool ok = orig != target;
-                        if (MODE == 2) ok = ok && orig < target;
-                        if (!RODS) ok = ok && !(orig == con0 || orig == con1 || orig == con2 || orig == con3);
-                        if (ok) {
+                    for (int h = 0; h < 2; h++) {
+                        const int p = base + 32 * h + lane;
+                        bool pass = false;
+                        int slot = 0;
+                        if (TILES || p < TC) {           // a staged tile is padded to a multiple of 64 with NaN entries: no bounds test
+                            float4 q;
+                            if (TILES) q = t_pf[p]; else { slot = slot_of_p(p); q = staged(slot); }
+                            const int wbits = __float_as_int(q.w);
+                            const int orig = wbits & 0xffffff;
                             float dx = t1x - q.x, dy = t1y - q.y, dz = t1z - q.z;
-                            dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
+                            if (WRAP) {
+                                dx -= boxf[0] * rintf(dx * ibox[0]); dy -= boxf[1] * rintf(dy * ibox[1]); dz -= boxf[2] * rintf(dz * ibox[2]);
+                            }
                             const float d2 = dx * dx + dy * dy + dz * dz;
                             const float reach = RODS ? reach_same : reach_row[wbits >> 24];
+                            bool ok = MODE == 2 ? orig < target : orig != target;
+                            if (!RODS) ok = ok & !((orig == con0) | (orig == con1) | (orig == con2) | (orig == con3));
                             // listed: may interact (inside reach) or sits on the edge of the sqmaxcut gate (needs the exact FP64 test to be counted)
-                            pass = (d2 <= reach) || (d2 > cut_lo && d2 <= cut_hi);
-                            if (count) { n_cand++; if (!pass && d2 <= cut_lo) n_sure++; }
-                            if (pass && use_tiles) slot = t_slot[p];
+                            pass = ok & ((d2 <= reach) | ((d2 > cut_lo) & (d2 <= cut_hi)));      // bitwise on purpose: no branches in this loop
+                            if (COUNT && ok && p < TC) { n_cand++; if (!pass && d2 <= cut_lo) n_sure++; }
+                            if (TILES) slot = t_slot[p];
                         }
+                        if (h == 0) { pa = pass; sa = slot; } else { pb = pass; sb = slot; }
                     }
-                    if (h == 0) { pa = pass; sa = slot; } else { pb = pass; sb = slot; }
+                    const unsigned ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
+                    const int na = __popc(ma);
+                    if (pa) queue[qn + __popc(ma & lt_mask)] = sa;
+                    if (pb) queue[qn + na + __popc(mb & lt_mask)] = sb;
+                    qn += na + __popc(mb);
+                    __syncwarp();
+                    if (qn >= 64) flush(64);
                 }
-                unsigned ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
-                int na = __popc(ma);
-                if (pa) queue[qn + __popc(ma & lt_mask)] = sa;
-                if (pb) queue[qn + na + __popc(mb & lt_mask)] = sb;
-                qn += na + __popc(mb);
-                __syncwarp();
-                if (qn >= 64) flush(64);
-            }
+            };
+            if (use_tiles) { if (count) scan(std::true_type{}, std::true_type{}); else scan(std::true_type{}, std::false_type{}); }
+            else { if (count) scan(std::false_type{}, std::true_type{}); else scan(std::false_type{}, std::false_type{}); }
             if (!RODS && tile == ntiles - 1) {       // bonded partners by index (never gated, mc/paire.h:1214)
                 int orig = lane == 0 ? con0 : lane == 1 ? con1 : lane == 2 ? con2 : lane == 3 ? con3 : -1;
                 bool on = orig >= 0 && orig != target && (MODE != 2 || orig < target);
@@ -1337,9 +1360,9 @@ static int build_cells_impl(scgpu_ctx* c, const double shift[3], bool even_grid)
     long long ncells = (long long)c->nc[0] * c->nc[1] * c->nc[2];
     ARG(ncells < (1ll << 30), "scgpu_build_cells: too many cells");
     c->ncells = (int)ncells;
-    if (c->ncells + 1 > c->cells_cap) {
+    if (c->ncells + 2 > c->cells_cap) {
         cudaFree(c->d_counts); cudaFree(c->d_cell_start); cudaFree(c->d_cursor);
-        c->cells_cap = c->ncells + 1;
+        c->cells_cap = c->ncells + 2;
         CK(cudaMalloc(&c->d_counts, (size_t)c->cells_cap * sizeof(int)));
         CK(cudaMalloc(&c->d_cell_start, (size_t)c->cells_cap * sizeof(int)));
         CK(cudaMalloc(&c->d_cursor, (size_t)c->cells_cap * sizeof(int)));
@@ -1448,13 +1471,14 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
         fl.pair = c->d_fl_pair; fl.e = c->d_fl_e; fl.total = c->d_pl_total + 3; fl.cap = c->fl_cap; fl.head = c->d_fl_head;
         fl.chunks = c->d_fl_chunks; fl.chunk_count = c->d_pl_total + 4; fl.chunk_cap = c->fl_chunk_cap;
         fl.plist = c->d_fl_plist; fl.ptotal = c->d_pl_total + 5; fl.overflow = c->d_pl_overflow;
+        const bool wrap = c->nc[0] < 5 || c->nc[1] < 5 || c->nc[2] < 5;
         if (c->rods_only) {
-            if (mode == 1) k_gate_cells<1, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters);
-            else k_gate_cells<2, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters);
+            if (mode == 1) { if (wrap) k_gate_cells<1, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
+            else { if (wrap) k_gate_cells<2, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             k_cheap_flat<true><<<c->sm_count * 6, 256, 0, c->stream>>>(s, fl, d_counters);
         } else {
-            if (mode == 1) k_gate_cells<1, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters);
-            else k_gate_cells<2, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters);
+            if (mode == 1) { if (wrap) k_gate_cells<1, false, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
+            else { if (wrap) k_gate_cells<2, false, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             k_cheap_flat<false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters);
         }
         k_patch_flat<<<c->sm_count * 8, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0);
@@ -1716,7 +1740,8 @@ extern "C" int scgpu_sweep_checkerboard(scgpu_ctx* c, const scgpu_moveparams* mp
     DevSys s = view(c);
     int nactive = (c->nc[0] / ncol.x) * (c->nc[1] / ncol.y) * (c->nc[2] / ncol.z);
     for (int k = 0; k < ncolours; k++) {
-        k_sweep_colour<<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags);
+        if (c->rods_only) k_sweep_colour<true><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags);
+        else k_sweep_colour<false><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags);
         c->launches++;
     }
     CK(cudaGetLastError());
@@ -1805,3 +1830,12 @@ extern "C" int scgpu_flush_l2(scgpu_ctx* c) {
     CK(cudaGetLastError());
     return SCGPU_OK;
 }
+
+#ifdef SW_PROFILE
+extern "C" int scgpu_sweep_profile(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (out16) cudaMemcpyFromSymbol(out16, sw_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(sw_prof, z, sizeof z); }
+    return 0;
+}
+#endif

@@ -48,28 +48,33 @@ __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {    // 53-bit uni
     return ((double)(((unsigned long long)a << 21) ^ (unsigned long long)(b >> 11)) + 0.5) * (1.0 / 9007199254740992.0) * 0.99999999999999989;
 }
 
-// Particle::pscRotate on an internal record (quaternion half-angle convention of the reference: vc = cos(angle))
-__device__ inline void rotate_record(double* r, int geotype, double angle, const v3& axis, bool positive) {
+// Particle::pscRotate on an internal record (quaternion half-angle convention of the reference: vc = cos(angle)),
+// split into the coefficients (which depend on angle and axis only) and their application to one vector of the record
+__device__ inline void rotation_coefficients(double* d, double angle, const v3& axis, bool positive) {
     double vc = cos(angle);
     double vs = positive ? sqrt(1.0 - vc * vc) : -sqrt(1.0 - vc * vc);
     double qw = vc, qx = axis.x * vs, qy = axis.y * vs, qz = axis.z * vs;
     double t2 = qw * qx, t3 = qw * qy, t4 = qw * qz, t5 = -qx * qx, t6 = qx * qy, t7 = qx * qz, t8 = -qy * qy, t9 = qy * qz, t10 = -qz * qz;
-    double d1 = t8 + t10, d2 = t6 - t4, d3 = t3 + t7, d4 = t4 + t6, d5 = t5 + t10, d6 = t9 - t2, d7 = t7 - t3, d8 = t2 + t9, d9 = t5 + t8;
-    auto rot = [&](int off) {
-        double x = r[off], y = r[off + 1], z = r[off + 2];
-        r[off] = 2.0 * (d1 * x + d2 * y + d3 * z) + x;
-        r[off + 1] = 2.0 * (d4 * x + d5 * y + d6 * z) + y;
-        r[off + 2] = 2.0 * (d7 * x + d8 * y + d9 * z) + z;
-    };
-    rot(R_DIR);
-    if (geotype != SCGPU_SCN && geotype != SCGPU_SCA) {
-        rot(R_PD0); rot(R_S0); rot(R_S1);
-        if (is_two_patch(geotype)) { rot(R_PD1); rot(R_S2); rot(R_S3); }
-    }
-    if (is_chiral(geotype)) {
-        rot(R_CH0);
-        if (geotype == SCGPU_TCHPSC || geotype == SCGPU_TCHCPSC) rot(R_CH1);
-    }
+    d[0] = t8 + t10; d[1] = t6 - t4; d[2] = t3 + t7; d[3] = t4 + t6; d[4] = t5 + t10; d[5] = t9 - t2; d[6] = t7 - t3; d[7] = t2 + t9; d[8] = t5 + t8;
+}
+__device__ __forceinline__ void rotate_vector(double* r, const double* d) {
+    double x = r[0], y = r[1], z = r[2];
+    r[0] = 2.0 * (d[0] * x + d[1] * y + d[2] * z) + x;
+    r[1] = 2.0 * (d[3] * x + d[4] * y + d[5] * z) + y;
+    r[2] = 2.0 * (d[6] * x + d[7] * y + d[8] * z) + z;
+}
+// which vectors of the record (index = offset / 3: dir, pd0, s0, s1, pd1, s2, s3, ch0, ch1) a rotation touches for a geotype
+__device__ __forceinline__ bool record_vector_rotates(int geotype, int v) {
+    if (v == 0) return true;
+    if (v <= 3) return geotype != SCGPU_SCN && geotype != SCGPU_SCA;
+    if (v <= 6) return geotype != SCGPU_SCN && geotype != SCGPU_SCA && is_two_patch(geotype);
+    if (v == 7) return is_chiral(geotype);
+    return geotype == SCGPU_TCHPSC || geotype == SCGPU_TCHCPSC;
+}
+__device__ inline void rotate_record(double* r, int geotype, double angle, const v3& axis, bool positive) {
+    double d[9];
+    rotation_coefficients(d, angle, axis, positive);
+    for (int v = 0; v < 9; v++) if (record_vector_rotates(geotype, v)) rotate_vector(r + 3 * v, d);
 }
 
 #ifndef SW_WARPS_N
@@ -80,8 +85,23 @@ constexpr int SW_WARPS = SW_WARPS_N;
 #define SW_MINBLOCKS 1
 #endif
 constexpr int SW_TILE = 1280;     // staged neighbourhood (FP32 relative coordinates + slot): 1280 x 20 B = 25 KB
+constexpr int SW_BATCH = 32;      // trials whose random numbers and proposal geometry are prepared together, one thread each
+
+struct SweepProposal {            // everything of a trial that does not depend on the outcome of earlier trials
+    int slot, displace;
+    double u_acc;
+    double m[9];                  // displacement (m[0..2], box-fractional) or the rotation coefficients d1..d9 of pscRotate
+};
+
+#ifdef SW_PROFILE      // debug build only: cycles per phase of a trial, summed over blocks (thread 0's view)
+__device__ unsigned long long sw_prof[16];
+#define SWP_MARK(k) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&sw_prof[k], (unsigned long long)(t_ - swp_t)); swp_t = t_; } } while (0)
+#else
+#define SWP_MARK(k) do { } while (0)
+#endif
 
 // one block per ACTIVE cell of the current colour
+template <bool RODS>
 __global__ void __launch_bounds__(SW_WARPS * 32, SW_MINBLOCKS)
 k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long long sweep, int colour, int3 ncol,
                double4* posw, double* rec, SweepAcc* acc_out, int* fail_flag) {
@@ -90,11 +110,10 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
     __shared__ double sh_old[REC], sh_new[REC];
     __shared__ int sh_queue[SW_WARPS][96];
     __shared__ int sh_pl[SW_WARPS][32];       // per-warp lists of (slot, state) entries that owe a patch evaluation
-    __shared__ int sh_pc[SW_WARPS];
     __shared__ double sh_eo[SW_WARPS], sh_en[SW_WARPS];
     __shared__ int sh_b[28], sh_off[28];
-    __shared__ int sh_ctl[4];     // [0] accept, [1] picked slot, [2] displacement?, [3] stayed in its cell?
-    __shared__ double sh_u[12];   // the trial's uniforms
+    __shared__ SweepProposal sh_prop[SW_BATCH];
+    static_assert(SW_WARPS * 32 >= SW_BATCH && SW_WARPS * 32 >= REC + 1, "block too small");
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     // active cell of this block
@@ -146,54 +165,85 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
             for (int idx = lane; idx < len; idx += 32) { t_pf[off + idx] = staged(b + idx); t_slot[off + idx] = b + idx; }
         }
     }
-    __syncthreads();
-    const int ntrial = npart * sp.n_sub;
+    // the active cell is the centre of its own neighbourhood: where its particles sit in the staged tile
+    const int k_centre = (nz == 1 ? 0 : nx * ny) + (ny == 1 ? 0 : nx) + (nx == 1 ? 0 : 1);
+    const int centre_off = sh_off[k_centre];
+    // every non-empty cell performs the same number of trials (n_sub * N / non-empty cells, stochastically rounded): the count
+    // does not depend on anything a trial can change (particles never leave their cell within a pass), so detailed balance
+    // holds, and all blocks of a pass finish together instead of waiting for the fullest cell
+    int ntrial;
+    {
+        const double avg = (double)sp.n_sub * (double)s.n / (double)s.cell_start[s.ncells + 1];
+        const uint4 r = philox4x32((uint32_t)sweep, (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 28), (uint32_t)c0, 0xffffffffu, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double fl = floor(avg);
+        ntrial = (int)fl + (u01(r.x, r.y) < avg - fl ? 1 : 0);
+    }
+#ifdef SW_PROFILE
+    long long swp_t = clock64();
+    if (threadIdx.x == 0) atomicAdd(&sw_prof[15], (unsigned long long)ntrial);
+#endif
     for (int trial = 0; trial < ntrial; trial++) {
-        // ---- random numbers of this trial (thread 0), Philox counter = (sweep, colour, cell, 3*trial + k)
-        if (threadIdx.x == 0) {
-            const uint32_t c1 = (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 28);
-            for (int k = 0; k < 3; k++) {
-                uint4 r = philox4x32((uint32_t)sweep, c1, (uint32_t)c0, (uint32_t)(3 * trial + k), (uint32_t)seed, (uint32_t)(seed >> 32));
-                sh_u[2 * k] = u01(r.x, r.y);
-                sh_u[2 * k + 1] = u01(r.z, r.w);
+        const int bi = trial % SW_BATCH;
+        if (bi == 0) {
+            // ---- random numbers and proposal geometry of the next SW_BATCH trials, one thread per trial.
+            // Philox counter = (sweep, colour, cell, 3*trial + k); nothing here depends on earlier acceptances.
+            __syncthreads();
+            const int tr = trial + (int)threadIdx.x;
+            if (threadIdx.x < SW_BATCH && tr < ntrial) {
+                double u[6];
+                const uint32_t c1 = (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 28);
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    uint4 r = philox4x32((uint32_t)sweep, c1, (uint32_t)c0, (uint32_t)(3 * tr + k), (uint32_t)seed, (uint32_t)(seed >> 32));
+                    u[2 * k] = u01(r.x, r.y);
+                    u[2 * k + 1] = u01(r.z, r.w);
+                }
+                int pick = tb + (int)(u[0] * npart);          // uniformly chosen particle of this cell, with replacement
+                if (pick >= te) pick = te - 1;
+                const int ty = w_type(posw[pick].w);
+                const int g = sp.geotype_of_type[ty];
+                const bool displace = (g >= SCGPU_SPN) || (u[1] < 0.5);                 // particleMove (movecreator.cpp:11-33)
+                const double z = 1.0 - 2.0 * u[2], phi = 6.283185307179586476925 * u[3];
+                const double rr = sqrt(fmax(0.0, 1.0 - z * z));
+                const v3 ax3 = mk(rr * cos(phi), rr * sin(phi), z);                     // uniform on the unit sphere
+                SweepProposal& P = sh_prop[threadIdx.x];
+                P.slot = pick;
+                P.displace = displace ? 1 : 0;
+                P.u_acc = u[1] < 0.5 ? 2.0 * u[1] : 2.0 * u[1] - 1.0;   // the move-type bit is used up; the rest is still uniform
+                if (displace) {            // partDisplace (movecreator.cpp:947-994): fixed length trans_mx, uniform direction
+                    const double mx = sp.trans_mx[ty];
+                    P.m[0] = ax3.x * mx / s.box[0]; P.m[1] = ax3.y * mx / s.box[1]; P.m[2] = ax3.z * mx / s.box[2];
+                } else {                   // partRotate (movecreator.cpp:996-1028)
+                    rotation_coefficients(P.m, sp.rot_angle[ty] * u[4], ax3, u[5] < 0.5);
+                }
             }
-            int pick = tb + (int)(sh_u[0] * npart);          // uniformly chosen particle of this cell, with replacement
-            if (pick >= te) pick = te - 1;
-            sh_ctl[1] = pick;
+            __syncthreads();
         }
-        __syncthreads();
-        const int tslot = sh_ctl[1];
+        SWP_MARK(0);
+        const int tslot = sh_prop[bi].slot;
+        const bool displace = sh_prop[bi].displace != 0;
+        const double u_acc = sh_prop[bi].u_acc;
         if (threadIdx.x < REC) { double v = rec[(size_t)tslot * REC + threadIdx.x]; sh_old[threadIdx.x] = v; sh_new[threadIdx.x] = v; }
         const double4 tpw = posw[tslot];
         const int target = w_orig(tpw.w), type1 = w_type(tpw.w), moltype1 = w_moltype(tpw.w);
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int g = sp.geotype_of_type[type1];
-            bool displace = (g >= SCGPU_SPN) || (sh_u[1] < 0.5);                 // particleMove (movecreator.cpp:11-33)
-            double z = 1.0 - 2.0 * sh_u[2], phi = 6.283185307179586476925 * sh_u[3];
-            double rr = sqrt(fmax(0.0, 1.0 - z * z));
-            v3 u = mk(rr * cos(phi), rr * sin(phi), z);                           // uniform on the unit sphere
-            if (displace) {            // partDisplace (movecreator.cpp:947-994): fixed length trans_mx, uniform direction
-                double mx = sp.trans_mx[type1];
-                sh_new[R_POS] += u.x * mx / s.box[0];
-                sh_new[R_POS + 1] += u.y * mx / s.box[1];
-                sh_new[R_POS + 2] += u.z * mx / s.box[2];
-            } else {                   // partRotate (movecreator.cpp:996-1028)
-                rotate_record(sh_new, g, sp.rot_angle[type1] * sh_u[4], u, sh_u[5] < 0.5);
-            }
-            sh_ctl[2] = displace ? 1 : 0;
-            // a move that leaves the cell would break the independence of the active cells: reject it
-            sh_ctl[3] = (cell_index(sh_new + R_POS, s.shift, s.nc) == c0) ? 1 : 0;
-            sh_ctl[0] = 0;
+        SWP_MARK(1);
+        if (displace) {
+            if (threadIdx.x < 3) sh_new[R_POS + threadIdx.x] += sh_prop[bi].m[threadIdx.x];
+        } else if (threadIdx.x < 9) {      // one thread per vector of the record
+            const int g = sp.geotype_of_type[type1];
+            const int off = 3 * threadIdx.x;                   // R_DIR, R_PD0, R_S0, R_S1, R_PD1, R_S2, R_S3, R_CH0, R_CH1
+            if (record_vector_rotates(g, threadIdx.x)) rotate_vector(sh_new + off, sh_prop[bi].m);
         }
         __syncthreads();
-        const bool in_cell = sh_ctl[3] != 0;
-        const bool displace = sh_ctl[2] != 0;
-        const double u_acc = sh_u[1] < 0.5 ? 2.0 * sh_u[1] : 2.0 * sh_u[1] - 1.0;   // the move-type bit is used up; the rest is still uniform
+        SWP_MARK(2);
+        // a move that leaves the cell would break the independence of the active cells: reject it
+        const bool in_cell = cell_index(sh_new + R_POS, s.shift, s.nc) == c0;
         double e_old = 0.0, e_new = 0.0;
         if (in_cell) {
             ConList cl;
-            get_conlist(s.mol, moltype1, target, cl);
+            if (RODS) { cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0; }
+            else get_conlist(s.mol, moltype1, target, cl);
             const v3 po = ld3(sh_old + R_POS), pn = ld3(sh_new + R_POS);
             const float ox = (float)rel_frac(po.x + s.shift[0], ccen[0]), oy = (float)rel_frac(po.y + s.shift[1], ccen[1]), oz = (float)rel_frac(po.z + s.shift[2], ccen[2]);
             const float nxf = (float)rel_frac(pn.x + s.shift[0], ccen[0]), nyf = (float)rel_frac(pn.y + s.shift[1], ccen[1]), nzf = (float)rel_frac(pn.z + s.shift[2], ccen[2]);
@@ -201,9 +251,8 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
             int qn = 0;
             double lo = 0.0, ln = 0.0;
             // one queue entry = (partner slot, which state): the old and the new state of a trial are evaluated on DIFFERENT
-            // lanes. Phase A (all warps): exact gate + everything but the rod-rod patch term; entries that owe a patch term are
-            // collected per warp. Phase B (warp 0 only): the patch terms of the whole trial, packed on as few lanes as there
-            // are entries -- the other warps wait at the barrier instead of issuing 3-lanes-active patch code four times over.
+            // lanes. Phase A: exact gate + everything but the rod-rod patch term; entries that owe a patch term are collected
+            // per warp. Phase B: each warp evaluates its own patch terms, two lanes per term.
             int pc = 0;
             auto patch_entry = [&](int entry) {
                 const int slot = entry >> 1;
@@ -222,10 +271,10 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                     int orig = w_orig(pw.w);
                     v3 r = image(s.box, is_new ? pn : po, mk(pw.x, pw.y, pw.z));
                     double d = dot(r, r);
-                    bool bonded = !cl.is_empty && (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
+                    bool bonded = !RODS && !cl.is_empty && (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
                     if (d <= s.sqmaxcut || bonded) {
-                        double e = pair_energy_cheap<false>(s.box, s.ia, s.ntypes, s.mol, r, d, is_new ? sh_new : sh_old, type1, moltype1,
-                                                            rec + (size_t)slot * REC, w_type(pw.w), orig, cl, np);
+                        double e = pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r, d, is_new ? sh_new : sh_old, type1, moltype1,
+                                                           rec + (size_t)slot * REC, w_type(pw.w), orig, cl, np);
                         if (is_new) ln += e; else lo += e;
                     }
                 }
@@ -255,7 +304,7 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                         ex = (ex - rintf(ex)) * boxf[0]; ey = (ey - rintf(ey)) * boxf[1]; ez = (ez - rintf(ez)) * boxf[2];
                         pass_o = (dx * dx + dy * dy + dz * dz <= pre_cut);
                         pass_n = (ex * ex + ey * ey + ez * ez <= pre_cut);
-                        if (!cl.is_empty) {       // bonded partners are evaluated by index below
+                        if (!RODS && !cl.is_empty) {       // bonded partners are evaluated by index below
                             int orig = w_orig(posw[slot].w);
                             if (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]) { pass_o = false; pass_n = false; }
                         }
@@ -280,65 +329,56 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                 }
             }
             if (qn > 0) eval(lane < qn ? queue[lane] : 0, lane < qn);
-            if (wid == 0 && !cl.is_empty) {
+            if (!RODS && wid == 0 && !cl.is_empty) {
                 bool on = lane < 8 && cl.con[lane >> 1] >= 0;
                 eval(on ? s.slot_of[cl.con[lane >> 1]] * 2 + (lane & 1) : 0, on);
             }
-            if (lane == 0) sh_pc[wid] = pc;
-            __syncthreads();
-            if (wid == 0) {        // phase B: all patch terms of this trial on one warp, two lanes per term, in warp/list order
-                int tot = 0;
-                for (int w = 0; w < SW_WARPS; w++) tot += sh_pc[w];
-                for (int base = 0; base < 2 * tot; base += 32) {
-                    const int idx = (base + lane) >> 1;
-                    const bool act = idx < tot;
-                    int entry = 0;
-                    if (act) {
-                        int w = 0, k = idx;
-                        while (k >= sh_pc[w]) { k -= sh_pc[w]; w++; }
-                        entry = sh_pl[w][k];
-                    }
-                    const int slot = entry >> 1;
-                    const bool is_new = entry & 1;
-                    double4 pw = posw[slot];
-                    v3 r = image(s.box, is_new ? pn : po, mk(pw.x, pw.y, pw.z));
-                    double e = pair_energy_patch_two_lanes(s.ia[type1 * s.ntypes + w_type(pw.w)], r, is_new ? sh_new : sh_old, rec + (size_t)slot * REC, act);
-                    if (is_new) ln += e; else lo += e;
-                }
+            SWP_MARK(3);
+            for (int base = 0; base < 2 * pc; base += 32) {      // phase B: this warp's patch terms, two lanes per term, in list order
+                const int idx = (base + lane) >> 1;
+                const bool act = idx < pc;
+                const int entry = act ? sh_pl[wid][idx] : 0;
+                const int slot = entry >> 1;
+                const bool is_new = entry & 1;
+                double4 pw = posw[slot];
+                v3 r = image(s.box, is_new ? pn : po, mk(pw.x, pw.y, pw.z));
+                double e = pair_energy_patch_two_lanes(s.ia[type1 * s.ntypes + w_type(pw.w)], r, is_new ? sh_new : sh_old, rec + (size_t)slot * REC, act);
+                if (is_new) ln += e; else lo += e;
             }
+            SWP_MARK(5);
             e_old = warp_sum(lo);
             e_new = warp_sum(ln);
-        } else {
-            __syncthreads();                           // keep the barrier count identical on both paths
         }
-        __syncthreads();
         if (lane == 0) { sh_eo[wid] = e_old; sh_en[wid] = e_new; }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            double eo = 0.0, en = 0.0;
-            for (int k = 0; k < SW_WARPS; k++) { eo += sh_eo[k]; en += sh_en[k]; }     // fixed order
-            bool accept = false;
-            if (!in_cell) acc.cell_rej++;
-            else {
-                double de = en - eo;
-                accept = (de <= 0.0) || (exp(-de / sp.temper) > u_acc);                // moveTry (movecreator.h:175-187)
-                if (accept) acc.de += de;
+        SWP_MARK(6);
+        bool accept = false;
+        if (in_cell) {
+            double de = 0.0;
+            if (lane == 0) {          // every warp takes the same decision from the same numbers (no broadcast barrier)
+                double eo = 0.0, en = 0.0;
+                for (int k = 0; k < SW_WARPS; k++) { eo += sh_eo[k]; en += sh_en[k]; }     // fixed order
+                de = en - eo;
+                accept = (de <= 0.0) || (exp(-de / sp.temper) > u_acc);                    // moveTry (movecreator.h:175-187)
             }
+            accept = __shfl_sync(0xffffffffu, accept ? 1 : 0, 0) != 0;
+            if (threadIdx.x == 0 && accept) acc.de += de;
+        }
+        if (threadIdx.x == 0) {
+            if (!in_cell) acc.cell_rej++;
             if (displace) { if (accept) acc.trans_acc++; else acc.trans_rej++; }
             else { if (accept) acc.rot_acc++; else acc.rot_rej++; }
-            sh_ctl[0] = accept ? 1 : 0;
         }
-        __syncthreads();
-        if (sh_ctl[0]) {          // commit in place: sorted record, position word, staged FP32 copy
+        if (accept) {          // commit in place: sorted record, position word, staged FP32 copy
             if (threadIdx.x < REC) rec[(size_t)tslot * REC + threadIdx.x] = sh_new[threadIdx.x];
-            if (threadIdx.x == 32) posw[tslot] = make_double4(sh_new[R_POS], sh_new[R_POS + 1], sh_new[R_POS + 2], tpw.w);
-            for (int p = threadIdx.x; tiled && p < C; p += blockDim.x)
-                if (t_slot[p] == tslot)
-                    t_pf[p] = make_float4((float)rel_frac(sh_new[R_POS] + s.shift[0], ccen[0]), (float)rel_frac(sh_new[R_POS + 1] + s.shift[1], ccen[1]),
-                                          (float)rel_frac(sh_new[R_POS + 2] + s.shift[2], ccen[2]), 0.f);
-            __threadfence_block();
+            if (threadIdx.x == REC) {
+                posw[tslot] = make_double4(sh_new[R_POS], sh_new[R_POS + 1], sh_new[R_POS + 2], tpw.w);
+                if (tiled) t_pf[centre_off + (tslot - tb)] = make_float4((float)rel_frac(sh_new[R_POS] + s.shift[0], ccen[0]), (float)rel_frac(sh_new[R_POS + 1] + s.shift[1], ccen[1]),
+                                                                         (float)rel_frac(sh_new[R_POS + 2] + s.shift[2], ccen[2]), 0.f);
+            }
         }
         __syncthreads();
+        SWP_MARK(7);
     }
     if (threadIdx.x == 0) acc_out[c0] = acc;
 }

@@ -42,13 +42,15 @@ def test_energy_bookkeeping_and_invariants(kind):
     e0 = eng.all_to_all()
     mp = move_params(0.5 if kind != "psc_lattice" else 0.25, 0.05, 8.0)
     tot_de, acc, rej, cell_rej = 0.0, 0, 0, 0
-    for sw in range(12):
+    nsw = 12
+    for sw in range(nsw):
         st = eng.sweep(mp, 777, sw)
         tot_de += st.energy_delta
         acc += st.trans_acc + st.rot_acc
         rej += st.trans_rej + st.rot_rej
         cell_rej += st.cell_rej
-        assert st.trans_acc + st.trans_rej + st.rot_acc + st.rot_rej == hs.n      # one sweep = N trials
+    # one sweep = N trials in expectation: every non-empty cell does N / (non-empty cells) of them, stochastically rounded
+    assert abs((acc + rej) - nsw * hs.n) <= 6.0 * np.sqrt(nsw * 0.25 * hs.n) + 1
     e1 = eng.all_to_all()
     assert acc > 0 and rej > 0
     assert cell_rej < 0.2 * (acc + rej)
