@@ -96,7 +96,9 @@ int scgpu_destroy(scgpu_ctx* ctx);
  * row-major by (type of first particle, type of second particle) */
 int scgpu_set_topology(scgpu_ctx* ctx, int ntypes, const scgpu_iaparam* table, double sqmaxcut, double maxcut,
                        int nmoltypes, const scgpu_molparam* mol);
-/* conf->pvec (scOOP/structures/Conf.h:305); also what initEM() / update(EMResize) need after a particle-count change */
+/* conf->pvec (scOOP/structures/Conf.h:305); also what initEM() / update(EMResize) need after a particle-count change.
+ * type == moltype == NULL: n and every particle's type are those of the previous upload (only coordinates travel).
+ * Page-locked host buffers are read by DMA directly; pageable ones are staged through the library's own pinned buffer. */
 int scgpu_set_particles(scgpu_ctx* ctx, int n, const double* state30, const int* type, const int* moltype);
 /* the same from the 9 doubles per particle that config.init holds (pos[3] box-fractional, dir[3], patchdir[3]); patch sides,
  * second patch and chiral axes are derived on the device as Conf::partVecInit / Particle::init do

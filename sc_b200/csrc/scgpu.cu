@@ -506,22 +506,27 @@ struct FlatList {
     int* overflow;
 };
 
-constexpr int GT_TILE = 1024;     // staged candidates per cell neighbourhood: 1024 x 20 B = 20 KB (denser cells scan global memory)
+constexpr int GT_TILE = 1024;     // staged candidates per tile of a cell neighbourhood: 1024 x 20 B = 20 KB
 constexpr int GT_WARPS = 4;
-constexpr int GQ = 128;           // per-warp queue; flushed to the global list in chunks of 64
-constexpr int GT_MAXP = 512;      // particles of one cell whose chunk-chain ends are kept in shared memory across tiles
+constexpr int GT_MAXP = 512;      // particles of one cell handled as one batch (counts and write cursors live in shared memory)
 
 // WRAP: some axis has fewer than 5 cells, so a neighbour can be more than half a box away from the target and the FP32
 // separation needs the minimum-image fold. With >= 5 cells per axis every candidate of the 27-cell neighbourhood is within
 // 2/5 of the box of the target once both are taken relative to the cell centre, and the fold is skipped.
+//
+// One block per cell, two passes over the same staged neighbourhood: pass 0 COUNTS the listed partners of every particle
+// of the cell, the block then reserves one contiguous span of the global list with a single atomicAdd (thousands of
+// same-address atomics per launch instead of hundreds of thousands -- they serialise in L2), and pass 1 repeats the scan and
+// writes each particle's partners, in candidate order, into its own sub-span. The FP32 scan is a few instructions per
+// candidate, so running it twice is cheaper than any queue + flush scheme; spans make the per-particle sum trivial.
 template <int MODE, bool RODS, bool WRAP>
 __global__ void __launch_bounds__(GT_WARPS * 32, 8)
 k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     __shared__ float4 t_pf[GT_TILE];      // x,y,z: FP32 coordinates relative to the cell centre, in length units; w: original index | type << 24
     __shared__ int t_slot[GT_TILE];
-    __shared__ int sh_queue[GT_WARPS][GQ];
-    __shared__ int sh_head[GT_MAXP], sh_last[GT_MAXP];
+    __shared__ int sh_cnt[GT_MAXP], sh_pos[GT_MAXP];     // per particle of the current batch: listed partners, write cursor
     __shared__ int sh_b[28], sh_off[28];
+    __shared__ int sh_ok;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int c0 = blockIdx.x;
@@ -547,147 +552,143 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     }
     __syncthreads();
     const int C = sh_off[ncell_nb];
-    const int npart = te - tb;
-    // neighbourhoods larger than one tile are processed tile by tile (the per-particle chunk chains persist in shared memory);
-    // only cells with more than GT_MAXP particles of their own fall back to scanning global memory in one pass
-    const bool use_tiles = npart <= GT_MAXP;
-    const int ntiles = use_tiles ? (C + GT_TILE - 1) / GT_TILE : 1;
+    const int ntiles = (C + GT_TILE - 1) / GT_TILE;      // neighbourhoods larger than one tile are processed tile by tile
     const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
     const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
     const float ibox[3] = {(float)(1.0 / s.box[0]), (float)(1.0 / s.box[1]), (float)(1.0 / s.box[2])};
     const float cut_hi = (float)(s.sqmaxcut * 1.001), cut_lo = (float)(s.sqmaxcut * 0.999);
-    auto slot_of_p = [&](int p) {
-        int k = 0;
-        while (k + 1 < ncell_nb && sh_off[k + 1] <= p) k++;
-        return sh_b[k] + (p - sh_off[k]);
-    };
     auto staged = [&](int slot) {
         double4 pw = s.posw[slot];
         return make_float4((float)(rel_frac(pw.x + s.shift[0], ccen[0]) * s.box[0]), (float)(rel_frac(pw.y + s.shift[1], ccen[1]) * s.box[1]),
                            (float)(rel_frac(pw.z + s.shift[2], ccen[2]) * s.box[2]), __int_as_float(w_orig(pw.w) | (w_type(pw.w) << 24)));
     };
-    if (use_tiles) for (int k = threadIdx.x; k < npart; k += blockDim.x) { sh_head[k] = -1; sh_last[k] = -1; }
-    int* queue = sh_queue[wid];
-    const bool count = counters != nullptr;
-    for (int tile = 0; tile < ntiles; tile++) {
-        const int t0 = tile * GT_TILE;
-        const int TC = use_tiles ? min(GT_TILE, C - t0) : C;       // candidates handled in this pass
-        __syncthreads();                                           // previous tile fully consumed
-        if (use_tiles) {        // one warp per neighbour cell: contiguous 32-byte loads, no index search
-            for (int k = wid; k < ncell_nb; k += GT_WARPS) {
-                const int b = sh_b[k], off = sh_off[k], len = sh_off[k + 1] - off;
-                int lo = max(off, t0), hi = min(off + len, t0 + TC);
-                for (int p = lo + lane; p < hi; p += 32) {
-                    t_pf[p - t0] = staged(b + (p - off));
-                    t_slot[p - t0] = b + (p - off);
-                }
-            }
-            for (int p = TC + threadIdx.x; p < ((TC + 63) & ~63); p += blockDim.x) {     // padding: NaN coordinates fail every comparison of the gate
-                const float qnan = __int_as_float(0x7fc00000);
-                t_pf[p] = make_float4(qnan, qnan, qnan, __int_as_float(0xffffff));
-                t_slot[p] = 0;
+    int staged_tile = -1;
+    auto stage = [&](int tile) {        // block-wide; one warp per neighbour cell: contiguous 32-byte loads, no index search
+        if (tile == staged_tile) return;
+        const int t0 = tile * GT_TILE, TC = min(GT_TILE, C - t0);
+        __syncthreads();                // previous tile fully consumed
+        for (int k = wid; k < ncell_nb; k += GT_WARPS) {
+            const int b = sh_b[k], off = sh_off[k], len = sh_off[k + 1] - off;
+            const int lo = max(off, t0), hi = min(off + len, t0 + TC);
+            for (int p = lo + lane; p < hi; p += 32) {
+                t_pf[p - t0] = staged(b + (p - off));
+                t_slot[p - t0] = b + (p - off);
             }
         }
+        for (int p = TC + threadIdx.x; p < ((TC + 63) & ~63); p += blockDim.x) {     // padding: NaN coordinates fail every comparison of the gate
+            const float qnan = __int_as_float(0x7fc00000);
+            t_pf[p] = make_float4(qnan, qnan, qnan, __int_as_float(0xffffff));
+            t_slot[p] = 0;
+        }
+        staged_tile = tile;
         __syncthreads();
-        for (int ti = tb + wid; ti < te; ti += GT_WARPS) {
-            const double4 tpw = s.posw[ti];
-            const int target = w_orig(tpw.w);
-            const float* reach_row = s.reach2 + w_type(tpw.w) * s.ntypes;
-            const float reach_same = reach_row[w_type(tpw.w)];
-            int con0 = -1, con1 = -1, con2 = -1, con3 = -1;
-            if (!RODS) {
-                ConList cl;
-                get_conlist(s.mol, w_moltype(tpw.w), target, cl);
-                con0 = cl.con[0]; con1 = cl.con[1]; con2 = cl.con[2]; con3 = cl.con[3];
-            }
-            const float t1x = (float)(rel_frac(tpw.x + s.shift[0], ccen[0]) * s.box[0]), t1y = (float)(rel_frac(tpw.y + s.shift[1], ccen[1]) * s.box[1]),
-                        t1z = (float)(rel_frac(tpw.z + s.shift[2], ccen[2]) * s.box[2]);
-            int qn = 0;
-            int last_chunk = use_tiles ? sh_last[ti - tb] : -1, head = use_tiles ? sh_head[ti - tb] : -1;
-            unsigned n_cand = 0, n_sure = 0;     // n_sure: pairs surely inside sqmaxcut AND surely beyond reach: gated, energy exactly 0, not listed
-            auto flush = [&](int cnt) {          // the first cnt queue entries become one chunk of the global list
-                int base = 0, cid = 0;
-                if (lane == 0) { base = atomicAdd(fl.total, cnt); cid = atomicAdd(fl.chunk_count, 1); }
-                base = __shfl_sync(0xffffffffu, base, 0);
-                cid = __shfl_sync(0xffffffffu, cid, 0);
-                bool ok = (cid < fl.chunk_cap) && (base + cnt <= fl.cap);
-                if (ok) {
-                    for (int k = lane; k < cnt; k += 32) fl.pair[base + k] = make_int2(ti, queue[k]);
-                    if (lane == 0) {
-                        fl.chunks[cid] = make_int4(base, cnt, -1, 0);
-                        if (last_chunk >= 0) fl.chunks[last_chunk].z = cid;
+    };
+    const bool count = counters != nullptr;
+    for (int bt = tb; bt < te; bt += GT_MAXP) {          // batches of particles of this cell (one batch unless the cell is huge)
+        const int nb = min(GT_MAXP, te - bt);
+        __syncthreads();
+        for (int k = threadIdx.x; k < nb; k += blockDim.x) sh_cnt[k] = 0;
+        __syncthreads();
+        for (int pass = 0; pass < 2; pass++) {
+            for (int tile = 0; tile < ntiles; tile++) {
+                stage(tile);
+                const int TC = min(GT_TILE, C - tile * GT_TILE);
+                for (int ti = bt + wid; ti < bt + nb; ti += GT_WARPS) {
+                    const double4 tpw = s.posw[ti];
+                    const int target = w_orig(tpw.w);
+                    const float* reach_row = s.reach2 + w_type(tpw.w) * s.ntypes;
+                    const float reach_same = reach_row[w_type(tpw.w)];
+                    int con0 = -1, con1 = -1, con2 = -1, con3 = -1;
+                    if (!RODS) {
+                        ConList cl;
+                        get_conlist(s.mol, w_moltype(tpw.w), target, cl);
+                        con0 = cl.con[0]; con1 = cl.con[1]; con2 = cl.con[2]; con3 = cl.con[3];
                     }
-                    if (head < 0) head = cid;
-                    last_chunk = cid;
-                } else if (lane == 0) atomicOr(fl.overflow, 2);
-                __syncwarp();
-                int rest = qn - cnt;
-                int mv0 = (lane < rest) ? queue[cnt + lane] : 0;
-                int mv1 = (lane + 32 < rest) ? queue[cnt + 32 + lane] : 0;
-                __syncwarp();
-                if (lane < rest) queue[lane] = mv0;
-                if (lane + 32 < rest) queue[32 + lane] = mv1;
-                qn = rest;
-                __syncwarp();
-            };
-            // the scan, specialised at compile time on where the candidates come from and on whether work is being counted
-            auto scan = [&](auto tiles_c, auto count_c) {
-                constexpr bool TILES = decltype(tiles_c)::value, COUNT = decltype(count_c)::value;
-                for (int base = 0; base < TC; base += 64) {
-                    bool pa = false, pb = false;
-                    int sa = 0, sb = 0;
+                    const float t1x = (float)(rel_frac(tpw.x + s.shift[0], ccen[0]) * s.box[0]), t1y = (float)(rel_frac(tpw.y + s.shift[1], ccen[1]) * s.box[1]),
+                                t1z = (float)(rel_frac(tpw.z + s.shift[2], ccen[2]) * s.box[2]);
+                    unsigned n_cand = 0, n_sure = 0;     // n_sure: pairs surely inside sqmaxcut AND surely beyond reach: gated, energy exactly 0, not listed
+                    int cur = pass ? sh_pos[ti - bt] : 0;      // pass 0: partners counted so far in this tile; pass 1: write cursor
+                    auto scan = [&](auto write_c, auto count_c) {
+                        constexpr bool WRITE = decltype(write_c)::value, COUNT = decltype(count_c)::value;
+                        for (int base = 0; base < TC; base += 64) {
+                            bool pa = false, pb = false;
+                            int sa = 0, sb = 0;
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int p = base + 32 * h + lane;
-                        bool pass = false;
-                        int slot = 0;
-                        if (TILES || p < TC) {           // a staged tile is padded to a multiple of 64 with NaN entries: no bounds test
-                            float4 q;
-                            if (TILES) q = t_pf[p]; else { slot = slot_of_p(p); q = staged(slot); }
-                            const int wbits = __float_as_int(q.w);
-                            const int orig = wbits & 0xffffff;
-                            float dx = t1x - q.x, dy = t1y - q.y, dz = t1z - q.z;
-                            if (WRAP) {
-                                dx -= boxf[0] * rintf(dx * ibox[0]); dy -= boxf[1] * rintf(dy * ibox[1]); dz -= boxf[2] * rintf(dz * ibox[2]);
+                            for (int h = 0; h < 2; h++) {
+                                const int p = base + 32 * h + lane;        // the tile is padded to a multiple of 64: no bounds test
+                                const float4 q = t_pf[p];
+                                const int wbits = __float_as_int(q.w);
+                                const int orig = wbits & 0xffffff;
+                                float dx = t1x - q.x, dy = t1y - q.y, dz = t1z - q.z;
+                                if (WRAP) {
+                                    dx -= boxf[0] * rintf(dx * ibox[0]); dy -= boxf[1] * rintf(dy * ibox[1]); dz -= boxf[2] * rintf(dz * ibox[2]);
+                                }
+                                const float d2 = dx * dx + dy * dy + dz * dz;
+                                const float reach = RODS ? reach_same : reach_row[wbits >> 24];
+                                bool ok = MODE == 2 ? orig < target : orig != target;
+                                if (!RODS) ok = ok & !((orig == con0) | (orig == con1) | (orig == con2) | (orig == con3));
+                                // listed: may interact (inside reach) or sits on the edge of the sqmaxcut gate (needs the exact FP64 test to be counted)
+                                const bool pass_gate = ok & ((d2 <= reach) | ((d2 > cut_lo) & (d2 <= cut_hi)));      // bitwise on purpose: no branches in this loop
+                                if (COUNT && ok && p < TC) { n_cand++; if (!pass_gate && d2 <= cut_lo) n_sure++; }
+                                if (h == 0) { pa = pass_gate; if (WRITE) sa = t_slot[p]; } else { pb = pass_gate; if (WRITE) sb = t_slot[p]; }
                             }
-                            const float d2 = dx * dx + dy * dy + dz * dz;
-                            const float reach = RODS ? reach_same : reach_row[wbits >> 24];
-                            bool ok = MODE == 2 ? orig < target : orig != target;
-                            if (!RODS) ok = ok & !((orig == con0) | (orig == con1) | (orig == con2) | (orig == con3));
-                            // listed: may interact (inside reach) or sits on the edge of the sqmaxcut gate (needs the exact FP64 test to be counted)
-                            pass = ok & ((d2 <= reach) | ((d2 > cut_lo) & (d2 <= cut_hi)));      // bitwise on purpose: no branches in this loop
-                            if (COUNT && ok && p < TC) { n_cand++; if (!pass && d2 <= cut_lo) n_sure++; }
-                            if (TILES) slot = t_slot[p];
+                            const unsigned ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
+                            const int na = __popc(ma);
+                            if (WRITE) {
+                                if (pa) fl.pair[cur + __popc(ma & lt_mask)] = make_int2(ti, sa);
+                                if (pb) fl.pair[cur + na + __popc(mb & lt_mask)] = make_int2(ti, sb);
+                            }
+                            cur += na + __popc(mb);
                         }
-                        if (h == 0) { pa = pass; sa = slot; } else { pb = pass; sb = slot; }
+                    };
+                    if (pass) scan(std::true_type{}, std::false_type{});
+                    else if (count) scan(std::false_type{}, std::true_type{});
+                    else scan(std::false_type{}, std::false_type{});
+                    if (!RODS && tile == ntiles - 1) {       // bonded partners by index (never gated, mc/paire.h:1214)
+                        int orig = lane == 0 ? con0 : lane == 1 ? con1 : lane == 2 ? con2 : lane == 3 ? con3 : -1;
+                        bool on = orig >= 0 && orig != target && (MODE != 2 || orig < target);
+                        if (on && !pass) n_cand++;
+                        unsigned m = __ballot_sync(0xffffffffu, on);
+                        if (pass && on) fl.pair[cur + __popc(m & lt_mask)] = make_int2(ti, s.slot_of[orig]);
+                        cur += __popc(m);
                     }
-                    const unsigned ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
-                    const int na = __popc(ma);
-                    if (pa) queue[qn + __popc(ma & lt_mask)] = sa;
-                    if (pb) queue[qn + na + __popc(mb & lt_mask)] = sb;
-                    qn += na + __popc(mb);
-                    __syncwarp();
-                    if (qn >= 64) flush(64);
+                    if (lane == 0) { if (pass) sh_pos[ti - bt] = cur; else sh_cnt[ti - bt] += cur; }
+                    if (!pass && count) {
+                        n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+                        n_sure = __reduce_add_sync(0xffffffffu, n_sure);
+                        if (lane == 0) { atomicAdd(&counters[0], (unsigned long long)n_cand); atomicAdd(&counters[1], (unsigned long long)n_sure); }
+                    }
                 }
-            };
-            if (use_tiles) { if (count) scan(std::true_type{}, std::true_type{}); else scan(std::true_type{}, std::false_type{}); }
-            else { if (count) scan(std::false_type{}, std::true_type{}); else scan(std::false_type{}, std::false_type{}); }
-            if (!RODS && tile == ntiles - 1) {       // bonded partners by index (never gated, mc/paire.h:1214)
-                int orig = lane == 0 ? con0 : lane == 1 ? con1 : lane == 2 ? con2 : lane == 3 ? con3 : -1;
-                bool on = orig >= 0 && orig != target && (MODE != 2 || orig < target);
-                if (on) n_cand++;
-                unsigned m = __ballot_sync(0xffffffffu, on);
-                if (on) queue[qn + __popc(m & lt_mask)] = s.slot_of[orig];
-                qn += __popc(m);
-                __syncwarp();
             }
-            while (qn > 0) flush(qn < 64 ? qn : 64);
-            if (use_tiles && lane == 0) { sh_head[ti - tb] = head; sh_last[ti - tb] = last_chunk; }
-            if (tile == ntiles - 1 && lane == 0) fl.head[target] = head;
-            if (count) {
-                n_cand = __reduce_add_sync(0xffffffffu, n_cand);
-                n_sure = __reduce_add_sync(0xffffffffu, n_sure);
-                if (lane == 0) { atomicAdd(&counters[0], (unsigned long long)n_cand); atomicAdd(&counters[1], (unsigned long long)n_sure); }
+            if (pass == 0) {      // reserve the batch's span, hand every particle its sub-span
+                __syncthreads();
+                if (wid == 0) {
+                    int carry = 0;
+                    for (int k0 = 0; k0 < nb; k0 += 32) {
+                        const int k = k0 + lane;
+                        const int v = k < nb ? sh_cnt[k] : 0;
+                        int x = v;
+                        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                        if (k < nb) sh_pos[k] = carry + x - v;
+                        carry += __shfl_sync(0xffffffffu, x, 31);
+                    }
+                    int base = 0;
+                    if (lane == 0) {
+                        base = atomicAdd(fl.total, carry);
+                        const bool ok = base + carry <= fl.cap;
+                        if (!ok) atomicOr(fl.overflow, 2);
+                        sh_ok = ok ? 1 : 0;
+                    }
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    for (int k = lane; k < nb; k += 32) {
+                        const int target = w_orig(s.posw[bt + k].w);
+                        sh_pos[k] += base;
+                        fl.chunks[target] = make_int4(sh_pos[k], sh_cnt[k], -1, 0);      // the particle's span of the list
+                        fl.head[target] = target;
+                    }
+                }
+                __syncthreads();
+                if (!sh_ok) return;          // list too short: the host grows it and repeats the launch
             }
         }
     }
@@ -702,50 +703,56 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
     if (total > fl.cap) total = fl.cap;
     const int stride = gridDim.x * blockDim.x;
     unsigned n_gate = 0;
-    constexpr int U = 1;                                                     // pairs in flight per thread (2 measured slower: register pressure)
-    for (int p0 = blockIdx.x * blockDim.x * U; p0 < total; p0 += stride * U) {      // warp-uniform trip count
-        int pp[U];
-        int2 pr[U];
-        double4 pi[U], pj[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            pp[u] = p0 + u * blockDim.x + threadIdx.x;
-            pr[u] = pp[u] < total ? fl.pair[pp[u]] : make_int2(0, 0);
+    // software pipeline: the pair of the NEXT trip is fetched while this trip computes, and the patch-list append of the
+    // PREVIOUS trip (an atomicAdd whose return value is needed) is issued right after this trip's gathers, so that its
+    // latency overlaps theirs instead of stalling the warp at the end of every trip
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int2 pr_next = p < total ? fl.pair[p] : make_int2(0, 0);
+    unsigned m_prev = 0;
+    bool np_prev = false;
+    int p_prev = 0;
+    auto append_prev = [&]() {
+        if (m_prev) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(fl.ptotal, __popc(m_prev));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (np_prev) fl.plist[base + __popc(m_prev & lt_mask)] = p_prev;      // plist has the capacity of pair[]: cannot overflow
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) { pi[u] = s.posw[pr[u].x]; pj[u] = s.posw[pr[u].y]; }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int p = pp[u];
-            bool np = false;
-            if (p < total) {
-                v3 r_cm = image(s.box, mk(pi[u].x, pi[u].y, pi[u].z), mk(pj[u].x, pj[u].y, pj[u].z));
-                double dotrcm = dot(r_cm, r_cm);
-                int oi = w_orig(pi[u].w), oj = w_orig(pj[u].w);
-                ConList cl;
-                cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0;
-                bool bonded = false;
-                if (!RODS) {
-                    get_conlist(s.mol, w_moltype(pi[u].w), oi, cl);
-                    bonded = !cl.is_empty && (oj == cl.con[0] || oj == cl.con[1] || oj == cl.con[2] || oj == cl.con[3]);
-                }
-                double e = 0.0;
-                if (dotrcm <= s.sqmaxcut || bonded) {           // the exact PairE gate (mc/paire.h:1214)
-                    e = pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r_cm, dotrcm, s.rec + (size_t)pr[u].x * REC, w_type(pi[u].w), w_moltype(pi[u].w),
-                                                s.rec + (size_t)pr[u].y * REC, w_type(pj[u].w), oj, cl, np);
-                    n_gate++;
-                }
-                fl.e[p] = make_double2(e, 0.0);
+    };
+    for (int p0 = blockIdx.x * blockDim.x; p0 < total; p0 += stride, p += stride) {      // warp-uniform trip count
+        const int2 pr = pr_next;
+        // everything the rod path reads from memory, issued together: one L2 round trip, not three
+        const double4 pi = s.posw[pr.x], pj = s.posw[pr.y];
+        v3 di, dj;
+        if (RODS) { di = ld3(s.rec + (size_t)pr.x * REC + R_DIR); dj = ld3(s.rec + (size_t)pr.y * REC + R_DIR); }
+        pr_next = (p + stride < total) ? fl.pair[p + stride] : make_int2(0, 0);
+        append_prev();
+        bool np = false;
+        if (p < total) {
+            v3 r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
+            double dotrcm = dot(r_cm, r_cm);
+            int oi = w_orig(pi.w), oj = w_orig(pj.w);
+            ConList cl;
+            cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0;
+            bool bonded = false;
+            if (!RODS) {
+                get_conlist(s.mol, w_moltype(pi.w), oi, cl);
+                bonded = !cl.is_empty && (oj == cl.con[0] || oj == cl.con[1] || oj == cl.con[2] || oj == cl.con[3]);
             }
-            unsigned m = __ballot_sync(0xffffffffu, np);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(fl.ptotal, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (np) fl.plist[base + __popc(m & lt_mask)] = p;      // plist has the capacity of pair[]: cannot overflow
+            double e = 0.0;
+            if (dotrcm <= s.sqmaxcut || bonded) {           // the exact PairE gate (mc/paire.h:1214)
+                if (RODS) e = pair_energy_cheap_rods(s.ia[w_type(pi.w) * s.ntypes + w_type(pj.w)], r_cm, dotrcm, di, dj, np);
+                else e = pair_energy_cheap<false>(s.box, s.ia, s.ntypes, s.mol, r_cm, dotrcm, s.rec + (size_t)pr.x * REC, w_type(pi.w), w_moltype(pi.w),
+                                                  s.rec + (size_t)pr.y * REC, w_type(pj.w), oj, cl, np);
+                n_gate++;
             }
+            fl.e[p] = make_double2(e, 0.0);
         }
+        m_prev = __ballot_sync(0xffffffffu, np);
+        np_prev = np;
+        p_prev = p;
     }
+    append_prev();
     if (counters) {
         n_gate = __reduce_add_sync(0xffffffffu, n_gate);
         if (lane == 0 && n_gate) atomicAdd(&counters[1], (unsigned long long)n_gate);
@@ -1023,6 +1030,7 @@ struct scgpu_ctx {
     int nc[3] = {1, 1, 1};
     int ncells = 1;
     bool cells_valid = false;
+    bool types_valid = false;        // d_type / d_moltype hold the types of the current n particles
     bool api_stale = false;          // sorted arrays are newer than d_api (after device sweeps)
     // scratch
     double* d_out = nullptr;         // n doubles
@@ -1175,8 +1183,14 @@ extern "C" int scgpu_set_topology(scgpu_ctx* c, int ntypes, const scgpu_iaparam*
     ARG(ntypes > 0 && ntypes <= 255 && nmoltypes > 0, "scgpu_set_topology: bad counts");
     ARG(maxcut > 0 && sqmaxcut > 0, "scgpu_set_topology: cutoff must be positive");
     CK(cudaSetDevice(c->device));
+    c->types_valid = false;          // rods_only / any_two_patch are derived from (topology, types): the next upload must bring types
     c->h_ia.assign(table, table + (size_t)ntypes * ntypes);
-    for (auto& p : c->h_ia) p.reserved[0] = (double)functor_kind((int)p.geotype[0], (int)p.geotype[1]);
+    for (auto& p : c->h_ia) {
+        p.reserved[0] = (double)functor_kind((int)p.geotype[0], (int)p.geotype[1]);
+        // rod pairs: squared centre distance beyond which every term is exactly 0 (pair_energy_cheap's shortcut)
+        const double reach = sqrt(fmax(p.rcutSq, p.rcutwcaSq)) + p.half_len[0] + p.half_len[1];
+        p.reserved[1] = reach * reach * 1.000001;
+    }
     c->h_mol.assign(mol, mol + nmoltypes);
     cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_reach2);
     c->d_ia = nullptr; c->d_mol = nullptr; c->d_reach2 = nullptr;
@@ -1218,10 +1232,15 @@ extern "C" int scgpu_set_particles_compact(scgpu_ctx* c, int n, const double* st
 }
 
 static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const int* type, const int* moltype, bool compact) {
-    ARG(c && state30 && type && moltype, "scgpu_set_particles: NULL argument");
+    ARG(c && state30, "scgpu_set_particles: NULL argument");
+    ARG((type == nullptr) == (moltype == nullptr), "scgpu_set_particles: type and moltype must both be given or both be NULL");
     ARG(n > 0 && n < (1 << 24), "scgpu_set_particles: n must be in 1 .. 16 777 215");
     ARG(c->ntypes > 0, "scgpu_set_particles: call scgpu_set_topology first");
-    for (int i = 0; i < n; i++) {
+    // type == moltype == NULL: same particle count and the same types as the previous upload (a Monte Carlo caller's types
+    // never change between configurations); only the coordinates travel
+    const bool same_types = type == nullptr;
+    ARG(!same_types || (n == c->n && c->types_valid), "scgpu_set_particles: NULL types need a previous upload of the same particle count");
+    for (int i = 0; i < n && !same_types; i++) {
         ARG(type[i] >= 0 && type[i] < c->ntypes, "scgpu_set_particles: particle type outside the topology table");
         ARG(moltype[i] >= 0 && moltype[i] < c->nmol, "scgpu_set_particles: molecule type outside the topology table");
     }
@@ -1285,8 +1304,10 @@ static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const 
             CK(cudaEventRecord(evs[k], c->stream));
         }
     }
-    CK(cudaMemcpyAsync(c->d_type, type, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_moltype, moltype, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (!same_types) {
+        CK(cudaMemcpyAsync(c->d_type, type, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_moltype, moltype, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
     if (compact) {
         k_particle_init<<<(n + 127) / 128, 128, 0, c->stream>>>(n, c->ntypes, c->d_compact, c->d_type, c->d_ia, c->d_api);
         c->launches++;
@@ -1295,7 +1316,8 @@ static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const 
     c->h_api.clear();
     CK(cudaStreamSynchronize(c->stream));
     // specialisation switch: only rod-rod functors and no bonded molecule among the particles present
-    {
+    if (!same_types) {
+        c->types_valid = true;
         std::vector<char> tu(c->ntypes, 0), mu(c->nmol, 0);
         for (int i = 0; i < n; i++) { tu[type[i]] = 1; mu[moltype[i]] = 1; }
         bool rods = true;

@@ -134,9 +134,12 @@ class Engine:
     def set_particles_compact(self, state9, types, moltypes):
         """state9[n,9] = pos (box-fractional), dir, patchdir as config.init holds them; the rest is derived on the device"""
         state9 = np.ascontiguousarray(state9, dtype=np.float64).reshape(-1, 9)
+        self.n = state9.shape[0]
+        if types is None and moltypes is None:       # same particle count and types as the previous upload: only coordinates travel
+            self._ck(self.L.scgpu_set_particles_compact(self.h, self.n, _d(state9), None, None))
+            return
         types = np.ascontiguousarray(types, dtype=np.int32)
         moltypes = np.ascontiguousarray(moltypes, dtype=np.int32)
-        self.n = state9.shape[0]
         self._ck(self.L.scgpu_set_particles_compact(self.h, self.n, _d(state9), _i(types), _i(moltypes)))
 
     def set_box(self, box):
@@ -193,8 +196,10 @@ class Engine:
         self._ck(self.L.scgpu_one_to_all_batch(self.h, len(targets), _i(targets), None if ts is None else _d(ts), _d(out)))
         return out
 
-    def one_to_all_everyone(self, fetch=True, count=False):
-        out = np.zeros(self.n) if fetch else None
+    def one_to_all_everyone(self, fetch=True, count=False, out=None):
+        """out: optional caller-owned float64[n] result buffer (page-locked memory is read back by DMA without staging)"""
+        if out is None:
+            out = np.zeros(self.n) if fetch else None
         nc, ng = C.c_int64(0), C.c_int64(0)
         self._ck(self.L.scgpu_one_to_all_everyone(self.h, None if out is None else _d(out),
                                                   C.byref(nc) if count else None, C.byref(ng) if count else None))

@@ -233,3 +233,10 @@ def test_compact_upload_derives_the_same_particles(engine, name):
     sc = eps_scale(s)
     tl = list(range(0, s.n, max(1, s.n // 20)))
     assert close(engine.one_to_all_batch(tl), [r.one[t] for t in tl], sc)
+    # types NULL = "unchanged since the previous upload": only coordinates travel
+    engine.set_particles_compact(s.state[:, :9], None, None)
+    assert close(engine.one_to_all_batch(tl), [r.one[t] for t in tl], sc)
+    from sc_b200 import ScgpuError
+    with pytest.raises(ScgpuError):
+        engine.set_particles_compact(s.state[:-1, :9], None, None)        # a different particle count needs the types again
+    engine.set_particles_compact(s.state[:, :9], s.type, s.moltype)
