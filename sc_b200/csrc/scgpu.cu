@@ -694,8 +694,11 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     }
 }
 
+#ifndef CHEAP_MINB
+#define CHEAP_MINB 3
+#endif
 template <bool RODS>
-__global__ void __launch_bounds__(256, RODS ? 3 : 2)
+__global__ void __launch_bounds__(256, RODS ? CHEAP_MINB : 2)
 k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -722,9 +725,12 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
     for (int p0 = blockIdx.x * blockDim.x; p0 < total; p0 += stride, p += stride) {      // warp-uniform trip count
         const int2 pr = pr_next;
         // everything the rod path reads from memory, issued together: one L2 round trip, not three
-        const double4 pi = s.posw[pr.x], pj = s.posw[pr.y];
+        const double4 pi = ldg256(s.posw + pr.x), pj = ldg256(s.posw + pr.y);
         v3 di, dj;
-        if (RODS) { di = ld3(s.rec + (size_t)pr.x * REC + R_DIR); dj = ld3(s.rec + (size_t)pr.y * REC + R_DIR); }
+        if (RODS) {      // dir + one more double of the record: a single 32-byte request per particle
+            const double4 ri = ldg256(s.rec + (size_t)pr.x * REC + R_DIR), rj = ldg256(s.rec + (size_t)pr.y * REC + R_DIR);
+            di = mk(ri.x, ri.y, ri.z); dj = mk(rj.x, rj.y, rj.z);
+        }
         pr_next = (p + stride < total) ? fl.pair[p + stride] : make_int2(0, 0);
         append_prev();
         bool np = false;
@@ -770,10 +776,25 @@ struct PatchItem {          // everything a phase needs to re-derive the geometr
     double T1, T2, S1, S2;
 };
 
+// the four vectors of one patch out of a cell-sorted record (layout: dir | pd0 | s0 | s1 | pd1 | s2 | s3 | ch0 | ch1 | pos) in
+// three or four 32-byte requests instead of a dozen narrower ones: the gathers of this kernel are bound by L1 requests
+__device__ __forceinline__ void load_patch_args(const double* rec, int pn, bool chiral, PatchArgs& P) {
+    if (!pn) {
+        const double4 a = ldg256(rec), b = ldg256(rec + 4), c = ldg256(rec + 8);
+        P.dir = mk(a.x, a.y, a.z); P.pdir = mk(a.w, b.x, b.y); P.s0 = mk(b.z, b.w, c.x); P.s1 = mk(c.y, c.z, c.w);
+        if (chiral) { const double4 d = ldg256(rec + 20); P.dir = mk(d.y, d.z, d.w); }                       // R_CH0 = 21
+    } else {
+        const double4 a = ldg256(rec + 12), b = ldg256(rec + 16), c = ldg256(rec + 20);
+        P.pdir = mk(a.x, a.y, a.z); P.s0 = mk(a.w, b.x, b.y); P.s1 = mk(b.z, b.w, c.x);                       // R_PD1 = 12, R_S2 = 15, R_S3 = 18
+        if (chiral) { const double4 d = ldg256(rec + 24); P.dir = mk(d.x, d.y, d.z); }                       // R_CH1 = 24
+        else { const double4 d = ldg256(rec); P.dir = mk(d.x, d.y, d.z); }
+    }
+}
+
 __device__ __forceinline__ void patch_setup(const DevSys& s, const FlatList& fl, int p, int combo, const scgpu_iaparam*& ia, v3& r_cm,
                                             PatchArgs& P1, PatchArgs& P2, bool& first_psc, bool& second_psc, bool& applicable) {
     int2 pr = fl.pair[p];
-    double4 pi = s.posw[pr.x], pj = s.posw[pr.y];
+    double4 pi = ldg256(s.posw + pr.x), pj = ldg256(s.posw + pr.y);
     r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
     ia = &s.ia[w_type(pi.w) * s.ntypes + w_type(pj.w)];
     const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
@@ -784,10 +805,8 @@ __device__ __forceinline__ void patch_setup(const DevSys& s, const FlatList& fl,
     applicable = (combo == 0) || (combo == 1 && firstT) || (combo == 2 && secondT) || (combo == 3 && firstT && secondT);
     const double* s1 = s.rec + (size_t)pr.x * REC;
     const double* s2 = s.rec + (size_t)pr.y * REC;
-    P1.dir = firstCH ? ld3(s1 + (pn1 ? R_CH1 : R_CH0)) : ld3(s1 + R_DIR);
-    P1.pdir = ld3(s1 + (pn1 ? R_PD1 : R_PD0)); P1.s0 = ld3(s1 + (pn1 ? R_S2 : R_S0)); P1.s1 = ld3(s1 + (pn1 ? R_S3 : R_S1));
-    P2.dir = secondCH ? ld3(s2 + (pn2 ? R_CH1 : R_CH0)) : ld3(s2 + R_DIR);
-    P2.pdir = ld3(s2 + (pn2 ? R_PD1 : R_PD0)); P2.s0 = ld3(s2 + (pn2 ? R_S2 : R_S0)); P2.s1 = ld3(s2 + (pn2 ? R_S3 : R_S1));
+    load_patch_args(s1, pn1, firstCH, P1);
+    load_patch_args(s2, pn2, secondCH, P2);
 }
 
 // block-wide stable compaction: returns this thread's rank among the threads with flag set, total in *count (shared)
@@ -803,7 +822,10 @@ __device__ __forceinline__ int block_rank(bool flag, int* sh_warp, int* count) {
     return off + __popc(m & ((1u << lane) - 1u));
 }
 
-__global__ void __launch_bounds__(PF_THREADS, 4)
+#ifndef PATCH_MINB
+#define PATCH_MINB 7
+#endif
+__global__ void __launch_bounds__(PF_THREADS, PATCH_MINB)
 k_patch_flat(DevSys s, FlatList fl, int any_two_patch) {
     __shared__ PatchItem sh_a[PF_THREADS], sh_b[PF_THREADS];
     __shared__ int sh_warp[PF_THREADS / 32];
@@ -1497,13 +1519,13 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
         if (c->rods_only) {
             if (mode == 1) { if (wrap) k_gate_cells<1, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             else { if (wrap) k_gate_cells<2, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
-            k_cheap_flat<true><<<c->sm_count * 6, 256, 0, c->stream>>>(s, fl, d_counters);
+            k_cheap_flat<true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters);
         } else {
             if (mode == 1) { if (wrap) k_gate_cells<1, false, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             else { if (wrap) k_gate_cells<2, false, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             k_cheap_flat<false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters);
         }
-        k_patch_flat<<<c->sm_count * 8, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0);
+        k_patch_flat<<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0);
         k_combine_flat<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, fl, d_out);
         c->launches += 4;
         CK(cudaGetLastError());

@@ -11,9 +11,14 @@ from sc_b200.host import HostSystem                  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else "everyone"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+variant = "fast"
+if len(sys.argv) > 3:                                # experiment builds: python scripts/profile_step.py everyone 3 libscgpu_x46.so
+    import sc_b200 as _pkg                           # noqa: F401
+    sys.modules["sc_b200.build"].VARIANTS["x"] = (sys.argv[3], [])
+    variant = "x"
 top, cfg, n = synth.psc_bulk()
 hs = HostSystem(top, cfg)
-eng = Engine(0, "fast").load(hs)
+eng = Engine(0, variant).load(hs)
 eng.build_cells()
 for _ in range(reps):
     if what == "everyone":
