@@ -508,7 +508,8 @@ struct FlatList {
 
 constexpr int GT_TILE = 1024;     // staged candidates per tile of a cell neighbourhood: 1024 x 20 B = 20 KB
 constexpr int GT_WARPS = 4;
-constexpr int GT_MAXP = 512;      // particles of one cell handled as one batch (counts and write cursors live in shared memory)
+constexpr int GT_NMASK = 512;     // 64-bit gate masks kept from the counting pass (4 KB): the writing pass replays them instead of re-testing
+constexpr int GT_MAXP = 256;      // particles of one cell handled as one batch (counts and write cursors live in shared memory)
 
 // WRAP: some axis has fewer than 5 cells, so a neighbour can be more than half a box away from the target and the FP32
 // separation needs the minimum-image fold. With >= 5 cells per axis every candidate of the 27-cell neighbourhood is within
@@ -525,6 +526,7 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     __shared__ float4 t_pf[GT_TILE];      // x,y,z: FP32 coordinates relative to the cell centre, in length units; w: original index | type << 24
     __shared__ int t_slot[GT_TILE];
     __shared__ int sh_cnt[GT_MAXP], sh_pos[GT_MAXP];     // per particle of the current batch: listed partners, write cursor
+    __shared__ unsigned long long sh_mask[GT_NMASK];
     __shared__ int sh_b[28], sh_off[28];
     __shared__ int sh_ok;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -586,6 +588,8 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     const bool count = counters != nullptr;
     for (int bt = tb; bt < te; bt += GT_MAXP) {          // batches of particles of this cell (one batch unless the cell is huge)
         const int nb = min(GT_MAXP, te - bt);
+        const int W = (C + 63) >> 6;                               // 64-candidate groups of a single-tile neighbourhood
+        const bool use_masks = ntiles == 1 && nb * W <= GT_NMASK;  // the usual case; otherwise pass 1 re-tests
         __syncthreads();
         for (int k = threadIdx.x; k < nb; k += blockDim.x) sh_cnt[k] = 0;
         __syncthreads();
@@ -637,11 +641,25 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                             if (WRITE) {
                                 if (pa) fl.pair[cur + __popc(ma & lt_mask)] = make_int2(ti, sa);
                                 if (pb) fl.pair[cur + na + __popc(mb & lt_mask)] = make_int2(ti, sb);
+                            } else if (use_masks && lane == 0) {
+                                sh_mask[(ti - bt) * W + (base >> 6)] = (unsigned long long)ma | ((unsigned long long)mb << 32);
                             }
                             cur += na + __popc(mb);
                         }
                     };
-                    if (pass) scan(std::true_type{}, std::false_type{});
+                    if (pass && use_masks) {       // replay the masks of the counting pass
+                        const unsigned long long* mrow = sh_mask + (ti - bt) * W;
+                        for (int it = 0; it < W; it++) {
+                            const unsigned long long m = mrow[it];
+                            if (m == 0) continue;
+                            const unsigned ma = (unsigned)m, mb = (unsigned)(m >> 32);
+                            const int na = __popc(ma);
+                            if ((ma >> lane) & 1u) fl.pair[cur + __popc(ma & lt_mask)] = make_int2(ti, t_slot[it * 64 + lane]);
+                            if ((mb >> lane) & 1u) fl.pair[cur + na + __popc(mb & lt_mask)] = make_int2(ti, t_slot[it * 64 + 32 + lane]);
+                            cur += na + __popc(mb);
+                        }
+                    }
+                    else if (pass) scan(std::true_type{}, std::false_type{});
                     else if (count) scan(std::false_type{}, std::true_type{});
                     else scan(std::false_type{}, std::false_type{});
                     if (!RODS && tile == ntiles - 1) {       // bonded partners by index (never gated, mc/paire.h:1214)
@@ -884,17 +902,22 @@ k_patch_flat(DevSys s, FlatList fl, int any_two_patch) {
     }
 }
 
-__global__ void k_combine_flat(int n, FlatList fl, double* __restrict__ out) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t == 0) { *fl.total = 0; *fl.chunk_count = 0; *fl.ptotal = 0; }   // lists consumed (stream order makes the reset safe)
-    if (t >= n) return;
+// eight lanes per particle: each group reads its particle's span of the list 128 bytes at a time, lane k of the group sums
+// entries k, k+8, ... in order, then a fixed three-step shuffle tree -> the same bits on every run
+__global__ void __launch_bounds__(256) k_combine_flat(int n, FlatList fl, double* __restrict__ out) {
+    const int sub = threadIdx.x & 7;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *fl.total = 0; *fl.chunk_count = 0; *fl.ptotal = 0; }   // lists consumed (stream order makes the reset safe)
     double e = 0.0;
-    for (int cid = fl.head[t]; cid >= 0;) {
-        int4 ch = fl.chunks[cid];
-        for (int r = 0; r < ch.y; r++) { double2 v = fl.e[ch.x + r]; e += v.x + v.y; }     // per pair (cheap + patch), then accumulate
-        cid = ch.z;
+    if (t < n) {
+        for (int cid = fl.head[t]; cid >= 0;) {
+            const int4 ch = fl.chunks[cid];
+            for (int r = sub; r < ch.y; r += 8) { const double2 v = fl.e[ch.x + r]; e += v.x + v.y; }     // per pair (cheap + patch), then accumulate
+            cid = ch.z;
+        }
     }
-    out[t] = e;
+    for (int o = 4; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if (t < n && sub == 0) out[t] = e;
 }
 
 #include "sweep.cuh"
@@ -1526,7 +1549,7 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
             k_cheap_flat<false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters);
         }
         k_patch_flat<<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0);
-        k_combine_flat<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, fl, d_out);
+        k_combine_flat<<<(c->n + 31) / 32, 256, 0, c->stream>>>(c->n, fl, d_out);
         c->launches += 4;
         CK(cudaGetLastError());
         return 0;
