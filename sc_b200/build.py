@@ -1,6 +1,7 @@
 """Build recipe: nvcc, sm_100a only, in-tree shared libraries (they travel to the GPU box with the snapshot).
 
-  libscgpu.so       default: -fmad=true (FMA contraction, what the FP64 pipe is built for)
+  libscgpu.so       default: -fmad=true (FMA contraction, what the FP64 pipe is built for) and -DSCG_FAST_DIV (division
+                    by Newton iteration without the IEEE special-operand tail, <= 1 ulp; see fdiv() in pair_energy.cuh)
   libscgpu_strict.so  -fmad=false: same operation order AND same roundings as the reference / oracle
 """
 import os
@@ -10,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "scgpu.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "pair_energy.cuh"), os.path.join(HERE, "csrc", "sweep.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "scgpu.h")]
-VARIANTS = {"fast": ("libscgpu.so", ["-fmad=true"]), "strict": ("libscgpu_strict.so", ["-fmad=false"])}
+VARIANTS = {"fast": ("libscgpu.so", ["-fmad=true", "-DSCG_FAST_DIV"]), "strict": ("libscgpu_strict.so", ["-fmad=false"])}
 
 
 def lib_path(variant="fast"):

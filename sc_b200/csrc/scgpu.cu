@@ -715,6 +715,7 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
 #ifndef CHEAP_MINB
 #define CHEAP_MINB 3
 #endif
+constexpr int CHEAP_BUF = 2048;   // patch-list entries buffered per block between global appends
 template <bool RODS>
 __global__ void __launch_bounds__(256, RODS ? CHEAP_MINB : 2)
 k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
@@ -722,25 +723,27 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
     const unsigned lt_mask = (1u << lane) - 1u;
     int total = *fl.total;
     if (total > fl.cap) total = fl.cap;
-    const int stride = gridDim.x * blockDim.x;
     unsigned n_gate = 0;
-    // software pipeline: the pair of the NEXT trip is fetched while this trip computes, and the patch-list append of the
-    // PREVIOUS trip (an atomicAdd whose return value is needed) is issued right after this trip's gathers, so that its
-    // latency overlaps theirs instead of stalling the warp at the end of every trip
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    int2 pr_next = p < total ? fl.pair[p] : make_int2(0, 0);
-    unsigned m_prev = 0;
-    bool np_prev = false;
-    int p_prev = 0;
-    auto append_prev = [&]() {
-        if (m_prev) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(fl.ptotal, __popc(m_prev));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (np_prev) fl.plist[base + __popc(m_prev & lt_mask)] = p_prev;      // plist has the capacity of pair[]: cannot overflow
-        }
+    // Each block owns one contiguous slice of the list. Pairs that owe a patch term are collected in a shared-memory buffer
+    // and appended to the global patch list with ONE atomicAdd per buffer-full (normally once per block): an append per warp
+    // and trip meant ~130 000 atomics on a single address per launch, which serialise in L2 and cost a third of the kernel.
+    __shared__ int sh_pl[CHEAP_BUF];
+    __shared__ int sh_n, sh_base;
+    if (threadIdx.x == 0) sh_n = 0;
+    const int per_block = (((total + (int)gridDim.x - 1) / (int)gridDim.x) + 255) & ~255;
+    const int lo = blockIdx.x * per_block, hi = min(total, lo + per_block);
+    auto flush = [&]() {              // block-wide; callers guarantee a barrier since the last append
+        const int n = sh_n;
+        if (threadIdx.x == 0 && n) sh_base = atomicAdd(fl.ptotal, n);
+        __syncthreads();
+        const int gbase = sh_base;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) fl.plist[gbase + k] = sh_pl[k];      // plist has the capacity of pair[]: cannot overflow
+        __syncthreads();
+        if (threadIdx.x == 0) sh_n = 0;
     };
-    for (int p0 = blockIdx.x * blockDim.x; p0 < total; p0 += stride, p += stride) {      // warp-uniform trip count
+    int p = lo + threadIdx.x;
+    int2 pr_next = p < hi ? fl.pair[p] : make_int2(0, 0);
+    for (int p0 = lo; p0 < hi; p0 += 256, p += 256) {      // block-uniform trip count
         const int2 pr = pr_next;
         // everything the rod path reads from memory, issued together: one L2 round trip, not three
         const double4 pi = ldg256(s.posw + pr.x), pj = ldg256(s.posw + pr.y);
@@ -749,10 +752,11 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
             const double4 ri = ldg256(s.rec + (size_t)pr.x * REC + R_DIR), rj = ldg256(s.rec + (size_t)pr.y * REC + R_DIR);
             di = mk(ri.x, ri.y, ri.z); dj = mk(rj.x, rj.y, rj.z);
         }
-        pr_next = (p + stride < total) ? fl.pair[p + stride] : make_int2(0, 0);
-        append_prev();
+        pr_next = (p + 256 < hi) ? fl.pair[p + 256] : make_int2(0, 0);
+        __syncthreads();                                   // appends of the previous trip are complete
+        if (sh_n > CHEAP_BUF - 256) flush();               // block-uniform decision
         bool np = false;
-        if (p < total) {
+        if (p < hi) {
             v3 r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
             double dotrcm = dot(r_cm, r_cm);
             int oi = w_orig(pi.w), oj = w_orig(pj.w);
@@ -772,11 +776,16 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
             }
             fl.e[p] = make_double2(e, 0.0);
         }
-        m_prev = __ballot_sync(0xffffffffu, np);
-        np_prev = np;
-        p_prev = p;
+        const unsigned m = __ballot_sync(0xffffffffu, np);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sh_n, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (np) sh_pl[base + __popc(m & lt_mask)] = p;
+        }
     }
-    append_prev();
+    __syncthreads();
+    flush();
     if (counters) {
         n_gate = __reduce_add_sync(0xffffffffu, n_gate);
         if (lane == 0 && n_gate) atomicAdd(&counters[1], (unsigned long long)n_gate);

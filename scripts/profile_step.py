@@ -39,3 +39,10 @@ for _ in range(reps):
         eng.sweep(mp, 12345, _)
 eng.sync()
 print("done", what, reps)
+if what == "sweep":                                  # wall-clock per sweep (not under a profiler)
+    import time
+    t0 = time.perf_counter()
+    for k in range(reps, reps + 10):
+        eng.sweep(mp, 12345, k)
+    eng.sync()
+    print("ms_per_sweep %.3f" % ((time.perf_counter() - t0) / 10 * 1e3))
