@@ -585,6 +585,8 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
         staged_tile = tile;
         __syncthreads();
     };
+    // the block's own cell is the centre of its neighbourhood: where its particles sit in the (first) staged tile
+    const int centre_off = sh_off[(nz == 1 ? 0 : nx * ny) + (ny == 1 ? 0 : nx) + (nx == 1 ? 0 : 1)];
     const bool count = counters != nullptr;
     for (int bt = tb; bt < te; bt += GT_MAXP) {          // batches of particles of this cell (one batch unless the cell is huge)
         const int nb = min(GT_MAXP, te - bt);
@@ -598,18 +600,42 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                 stage(tile);
                 const int TC = min(GT_TILE, C - tile * GT_TILE);
                 for (int ti = bt + wid; ti < bt + nb; ti += GT_WARPS) {
-                    const double4 tpw = s.posw[ti];
-                    const int target = w_orig(tpw.w);
-                    const float* reach_row = s.reach2 + w_type(tpw.w) * s.ntypes;
-                    const float reach_same = reach_row[w_type(tpw.w)];
-                    int con0 = -1, con1 = -1, con2 = -1, con3 = -1;
-                    if (!RODS) {
-                        ConList cl;
-                        get_conlist(s.mol, w_moltype(tpw.w), target, cl);
-                        con0 = cl.con[0]; con1 = cl.con[1]; con2 = cl.con[2]; con3 = cl.con[3];
+                    if (RODS && pass && use_masks) {       // replay the masks of the counting pass: nothing about the target is needed
+                        int cur = sh_pos[ti - bt];
+                        const unsigned long long* mrow = sh_mask + (ti - bt) * W;
+                        for (int it = 0; it < W; it++) {
+                            const unsigned long long m = mrow[it];
+                            if (m == 0) continue;
+                            const unsigned ma = (unsigned)m, mb = (unsigned)(m >> 32);
+                            const int na = __popc(ma);
+                            if ((ma >> lane) & 1u) fl.pair[cur + __popc(ma & lt_mask)] = make_int2(ti, t_slot[it * 64 + lane]);
+                            if ((mb >> lane) & 1u) fl.pair[cur + na + __popc(mb & lt_mask)] = make_int2(ti, t_slot[it * 64 + 32 + lane]);
+                            cur += na + __popc(mb);
+                        }
+                        continue;
                     }
-                    const float t1x = (float)(rel_frac(tpw.x + s.shift[0], ccen[0]) * s.box[0]), t1y = (float)(rel_frac(tpw.y + s.shift[1], ccen[1]) * s.box[1]),
-                                t1z = (float)(rel_frac(tpw.z + s.shift[2], ccen[2]) * s.box[2]);
+                    int target, ttype;
+                    float t1x, t1y, t1z;
+                    int con0 = -1, con1 = -1, con2 = -1, con3 = -1;
+                    if (RODS && ntiles == 1) {             // the target is itself an entry of the staged tile (its cell is the centre one)
+                        const float4 q = t_pf[centre_off + (ti - tb)];
+                        t1x = q.x; t1y = q.y; t1z = q.z;
+                        target = __float_as_int(q.w) & 0xffffff;
+                        ttype = __float_as_int(q.w) >> 24;
+                    } else {
+                        const double4 tpw = s.posw[ti];
+                        target = w_orig(tpw.w);
+                        ttype = w_type(tpw.w);
+                        if (!RODS) {
+                            ConList cl;
+                            get_conlist(s.mol, w_moltype(tpw.w), target, cl);
+                            con0 = cl.con[0]; con1 = cl.con[1]; con2 = cl.con[2]; con3 = cl.con[3];
+                        }
+                        t1x = (float)(rel_frac(tpw.x + s.shift[0], ccen[0]) * s.box[0]); t1y = (float)(rel_frac(tpw.y + s.shift[1], ccen[1]) * s.box[1]);
+                        t1z = (float)(rel_frac(tpw.z + s.shift[2], ccen[2]) * s.box[2]);
+                    }
+                    const float* reach_row = s.reach2 + ttype * s.ntypes;
+                    const float reach_same = reach_row[ttype];
                     unsigned n_cand = 0, n_sure = 0;     // n_sure: pairs surely inside sqmaxcut AND surely beyond reach: gated, energy exactly 0, not listed
                     int cur = pass ? sh_pos[ti - bt] : 0;      // pass 0: partners counted so far in this tile; pass 1: write cursor
                     auto scan = [&](auto write_c, auto count_c) {
@@ -796,7 +822,10 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
 // (the partner is simply not inside the patch wedge), so running intersect #1, intersect #2 and atr_e() as separate phases
 // with a block-level compaction of the survivors in between keeps the lanes of the expensive later phases full instead of
 // leaving a few lanes per warp on the long path.
-constexpr int PF_THREADS = 128;
+#ifndef PF_THREADS_N
+#define PF_THREADS_N 128
+#endif
+constexpr int PF_THREADS = PF_THREADS_N;
 
 struct PatchItem {          // everything a phase needs to re-derive the geometry of a (pair, patch combination)
     int p;                  // index into FlatList::pair / e

@@ -16,14 +16,20 @@ if len(sys.argv) > 3:                                # experiment builds: python
     import sc_b200 as _pkg                           # noqa: F401
     sys.modules["sc_b200.build"].VARIANTS["x"] = (sys.argv[3], [])
     variant = "x"
-top, cfg, n = synth.psc_bulk()
+if what.startswith("membrane"):                       # BASELINE configs[2]: 265 041-particle lipid membrane + CPSC, allToAll
+    import gzip
+    import json
+    inp = json.loads(gzip.open(os.path.join(ROOT, "tests", "golden", "membrane601.inputs.json.gz")).read().decode())
+    top, cfg, n = synth.membrane(21, 21, inp["top.init"], inp["config.init"])
+else:
+    top, cfg, n = synth.psc_bulk()
 hs = HostSystem(top, cfg)
 eng = Engine(0, variant).load(hs)
 eng.build_cells()
 for _ in range(reps):
     if what == "everyone":
         eng.one_to_all_everyone(fetch=False)
-    elif what == "all_to_all":
+    elif what in ("all_to_all", "membrane"):
         eng.all_to_all(fetch=False)
     elif what == "cells":
         eng.set_particles(hs.state, hs.type, hs.moltype)
