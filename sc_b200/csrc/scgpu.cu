@@ -527,6 +527,10 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     __shared__ int t_slot[GT_TILE];
     __shared__ int sh_cnt[GT_MAXP], sh_pos[GT_MAXP];     // per particle of the current batch: listed partners, write cursor
     __shared__ unsigned long long sh_mask[GT_NMASK];
+    __shared__ unsigned sh_grp[GT_TILE / 64];          // per 64-candidate group of the staged tile: which neighbour cells it holds
+    __shared__ unsigned sh_ctypes[28];                 // per neighbour cell: bit t set = a particle of type t lives there
+    __shared__ unsigned sh_tcm[GT_MAXP];               // per particle of the batch: neighbour cells within its reach (computed once)
+    __shared__ unsigned sh_tilecells;                  // neighbour cells with entries in the staged tile
     __shared__ int sh_b[28], sh_off[28];
     __shared__ int sh_ok;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -555,10 +559,21 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     __syncthreads();
     const int C = sh_off[ncell_nb];
     const int ntiles = (C + GT_TILE - 1) / GT_TILE;      // neighbourhoods larger than one tile are processed tile by tile
+    if (!RODS || ntiles > 1) {       // culling data: the particle types present in every neighbour cell (types >= 32: assume all)
+        for (int k = wid; k < ncell_nb; k += GT_WARPS) {
+            const int b = sh_b[k], len = sh_off[k + 1] - sh_off[k];
+            unsigned m = 0;
+            for (int idx = lane; idx < len; idx += 32) { const int ty = w_type(s.posw[b + idx].w); m |= ty < 32 ? 1u << ty : 0xffffffffu; }
+            m = __reduce_or_sync(0xffffffffu, m);
+            if (lane == 0) sh_ctypes[k] = s.ntypes > 32 ? 0xffffffffu : m;
+        }
+        __syncthreads();
+    }
     const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
     const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
     const float ibox[3] = {(float)(1.0 / s.box[0]), (float)(1.0 / s.box[1]), (float)(1.0 / s.box[2])};
     const float cut_hi = (float)(s.sqmaxcut * 1.001), cut_lo = (float)(s.sqmaxcut * 0.999);
+    const float hcell[3] = {(float)(0.5 * s.box[0] / s.nc[0]), (float)(0.5 * s.box[1] / s.nc[1]), (float)(0.5 * s.box[2] / s.nc[2])};
     auto staged = [&](int slot) {
         double4 pw = s.posw[slot];
         return make_float4((float)(rel_frac(pw.x + s.shift[0], ccen[0]) * s.box[0]), (float)(rel_frac(pw.y + s.shift[1], ccen[1]) * s.box[1]),
@@ -581,6 +596,17 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
             const float qnan = __int_as_float(0x7fc00000);
             t_pf[p] = make_float4(qnan, qnan, qnan, __int_as_float(0xffffff));
             t_slot[p] = 0;
+        }
+        if (threadIdx.x < GT_TILE / 64) {
+            const int g0 = t0 + 64 * (int)threadIdx.x, g1 = g0 + 64;
+            unsigned m = 0;
+            for (int k = 0; k < ncell_nb; k++) if (sh_off[k + 1] > sh_off[k] && sh_off[k] < g1 && sh_off[k + 1] > g0) m |= 1u << k;
+            sh_grp[threadIdx.x] = m;
+        }
+        if (threadIdx.x == 0) {
+            unsigned m = 0;
+            for (int k = 0; k < ncell_nb; k++) if (sh_off[k + 1] > sh_off[k] && sh_off[k] < t0 + TC && sh_off[k + 1] > t0) m |= 1u << k;
+            sh_tilecells = m;
         }
         staged_tile = tile;
         __syncthreads();
@@ -614,6 +640,11 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                         }
                         continue;
                     }
+                    const bool cull = !count && (!RODS || ntiles > 1);      // rods in reach-sized cells need nearly all 27 cells: not worth the test
+                    const bool first_visit = pass == 0 && tile == 0;
+                    // a particle whose reach touches none of the cells of this tile has nothing to do here (except on the last
+                    // tile, where bonded partners are appended by index)
+                    if (cull && !first_visit && !(sh_tcm[ti - bt] & sh_tilecells) && (RODS || tile != ntiles - 1)) continue;
                     int target, ttype;
                     float t1x, t1y, t1z;
                     int con0 = -1, con1 = -1, con2 = -1, con3 = -1;
@@ -636,11 +667,35 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                     }
                     const float* reach_row = s.reach2 + ttype * s.ntypes;
                     const float reach_same = reach_row[ttype];
+                    // neighbour cells whose nearest face is beyond the largest reach of this particle hold no partner: their
+                    // 64-candidate groups are skipped. Not while counting work: the reference's sqmaxcut gate is wider than reach.
+                    unsigned cellmask = 0xffffffffu;
+                    if (cull && !first_visit) cellmask = sh_tcm[ti - bt];
+                    else if (cull) {
+                        float rmax2 = 0.f;          // the largest reach of this particle towards the types present in neighbour cell `lane`
+                        float g2 = 0.f;
+                        if (lane < ncell_nb) {
+                            unsigned tm = sh_ctypes[lane];
+                            if (tm == 0xffffffffu) rmax2 = s.reach2[s.ntypes * s.ntypes + ttype];
+                            else while (tm) { const int b = __ffs(tm) - 1; tm &= tm - 1; rmax2 = fmaxf(rmax2, reach_row[b]); }
+                            const int ox = nx == 1 ? 0 : lane % nx - 1, oy = ny == 1 ? 0 : (lane / nx) % ny - 1, oz = nz == 1 ? 0 : lane / (nx * ny) - 1;
+                            const float gx = ox < 0 ? t1x + hcell[0] : ox > 0 ? hcell[0] - t1x : 0.f;
+                            const float gy = oy < 0 ? t1y + hcell[1] : oy > 0 ? hcell[1] - t1y : 0.f;
+                            const float gz = oz < 0 ? t1z + hcell[2] : oz > 0 ? hcell[2] - t1z : 0.f;
+                            g2 = fmaxf(gx, 0.f) * fmaxf(gx, 0.f) + fmaxf(gy, 0.f) * fmaxf(gy, 0.f) + fmaxf(gz, 0.f) * fmaxf(gz, 0.f);
+                        }
+                        cellmask = __ballot_sync(0xffffffffu, lane < ncell_nb && g2 <= rmax2 * 1.001f);
+                        if (lane == 0) sh_tcm[ti - bt] = cellmask;
+                    }
                     unsigned n_cand = 0, n_sure = 0;     // n_sure: pairs surely inside sqmaxcut AND surely beyond reach: gated, energy exactly 0, not listed
                     int cur = pass ? sh_pos[ti - bt] : 0;      // pass 0: partners counted so far in this tile; pass 1: write cursor
-                    auto scan = [&](auto write_c, auto count_c) {
-                        constexpr bool WRITE = decltype(write_c)::value, COUNT = decltype(count_c)::value;
+                    auto scan = [&](auto write_c, auto count_c, auto cull_c) {        // the edge band is listed exactly when work is being counted, in BOTH passes
+                        constexpr bool WRITE = decltype(write_c)::value, BAND = decltype(count_c)::value, COUNT = BAND && !WRITE, CULL = decltype(cull_c)::value;
                         for (int base = 0; base < TC; base += 64) {
+                            if (CULL && !(sh_grp[base >> 6] & cellmask)) {       // warp-uniform
+                                if (!WRITE && use_masks && lane == 0) sh_mask[(ti - bt) * W + (base >> 6)] = 0ull;
+                                continue;
+                            }
                             bool pa = false, pb = false;
                             int sa = 0, sb = 0;
 #pragma unroll
@@ -658,7 +713,9 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                                 bool ok = MODE == 2 ? orig < target : orig != target;
                                 if (!RODS) ok = ok & !((orig == con0) | (orig == con1) | (orig == con2) | (orig == con3));
                                 // listed: may interact (inside reach) or sits on the edge of the sqmaxcut gate (needs the exact FP64 test to be counted)
-                                const bool pass_gate = ok & ((d2 <= reach) | ((d2 > cut_lo) & (d2 <= cut_hi)));      // bitwise on purpose: no branches in this loop
+                                // (the edge band only matters for the work counters: without them, beyond reach means exactly zero energy)
+                                const bool pass_gate = BAND ? (ok & ((d2 <= reach) | ((d2 > cut_lo) & (d2 <= cut_hi))))
+                                                            : (ok & (d2 <= reach));      // bitwise on purpose: no branches in this loop
                                 if (COUNT && ok && p < TC) { n_cand++; if (!pass_gate && d2 <= cut_lo) n_sure++; }
                                 if (h == 0) { pa = pass_gate; if (WRITE) sa = t_slot[p]; } else { pb = pass_gate; if (WRITE) sb = t_slot[p]; }
                             }
@@ -685,9 +742,14 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                             cur += na + __popc(mb);
                         }
                     }
-                    else if (pass) scan(std::true_type{}, std::false_type{});
-                    else if (count) scan(std::false_type{}, std::true_type{});
-                    else scan(std::false_type{}, std::false_type{});
+                    else if (pass) {
+                        if (count) scan(std::true_type{}, std::true_type{}, std::false_type{});
+                        else if (cull) scan(std::true_type{}, std::false_type{}, std::true_type{});
+                        else scan(std::true_type{}, std::false_type{}, std::false_type{});
+                    }
+                    else if (count) scan(std::false_type{}, std::true_type{}, std::false_type{});
+                    else if (cull) scan(std::false_type{}, std::false_type{}, std::true_type{});
+                    else scan(std::false_type{}, std::false_type{}, std::false_type{});
                     if (!RODS && tile == ntiles - 1) {       // bonded partners by index (never gated, mc/paire.h:1214)
                         int orig = lane == 0 ? con0 : lane == 1 ? con1 : lane == 2 ? con2 : lane == 3 ? con3 : -1;
                         bool on = orig >= 0 && orig != target && (MODE != 2 || orig < target);
@@ -1001,17 +1063,41 @@ __global__ void k_combine(int m, int gw, PatchList pl, const double* __restrict_
 }
 
 // deterministic total: one block, each thread strides in a fixed pattern, fixed tree
-__global__ void k_reduce_fixed(int n, const double* __restrict__ v, double* __restrict__ out) {
-    __shared__ double sh[1024];
-    double a = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) a += v[i];
-    sh[threadIdx.x] = a;
+// Sum of n doubles in an order that depends on n alone: block b of RF_BLOCKS sums its contiguous chunk (thread t takes every
+// RF_THREADS-th element, then a shared-memory tree), and whichever block finishes last adds the RF_BLOCKS partial sums in index
+// order. scratch: RF_BLOCKS doubles followed by one unsigned counter that the last block leaves at zero again.
+constexpr int RF_BLOCKS = 128, RF_THREADS = 256;
+__global__ void __launch_bounds__(RF_THREADS) k_reduce_fixed(int n, const double* __restrict__ v, double* __restrict__ out, double* __restrict__ scratch) {
+    __shared__ double sh[RF_THREADS];
+    __shared__ bool last;
+    const int chunk = (n + RF_BLOCKS - 1) / RF_BLOCKS;
+    const int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int i = lo + threadIdx.x;
+    for (; i + 3 * RF_THREADS < hi; i += 4 * RF_THREADS) { a0 += v[i]; a1 += v[i + RF_THREADS]; a2 += v[i + 2 * RF_THREADS]; a3 += v[i + 3 * RF_THREADS]; }
+    for (; i < hi; i += RF_THREADS) a0 += v[i];
+    sh[threadIdx.x] = (a0 + a1) + (a2 + a3);
     __syncthreads();
-    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    for (int o = RF_THREADS >> 1; o > 0; o >>= 1) {
         if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = sh[0];
+    unsigned* counter = (unsigned*)(scratch + RF_BLOCKS);
+    if (threadIdx.x == 0) {
+        scratch[blockIdx.x] = sh[0];
+        __threadfence();
+        last = atomicAdd(counter, 1u) == RF_BLOCKS - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    sh[threadIdx.x] = threadIdx.x < RF_BLOCKS ? ((volatile double*)scratch)[threadIdx.x] : 0.0;
+    __syncthreads();
+    for (int o = RF_THREADS >> 1; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = sh[0]; *counter = 0u; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1142,6 +1228,7 @@ struct scgpu_ctx {
     int* d_targets = nullptr;
     int trial_cap = 0;
     double* d_scalar = nullptr;      // 16 doubles: [0] total, [8..] replica record
+    double* d_reduce = nullptr;      // k_reduce_fixed scratch: RF_BLOCKS partial sums + counter
     int* d_flags = nullptr;          // n ints
     unsigned long long* d_counters = nullptr;   // 8
     void* d_sweep_acc = nullptr;
@@ -1201,6 +1288,8 @@ extern "C" int scgpu_create(scgpu_ctx** out, int device) {
     CK(cudaMallocHost((void**)&c->h_small, 1024));
     CK(cudaMalloc((void**)&c->d_single, 256));
     CK(cudaMalloc(&c->d_scalar, 16 * sizeof(double)));
+    CK(cudaMalloc(&c->d_reduce, (RF_BLOCKS + 2) * sizeof(double)));
+    CK(cudaMemset(c->d_reduce, 0, (RF_BLOCKS + 2) * sizeof(double)));
     CK(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     CK(cudaMalloc(&c->d_pl_total, 8 * sizeof(int)));     // [0] patch pairs, [1] overflow flag, [2] patch chunks, [3] flat pairs, [4] flat chunks, [5] flat patch pairs
     CK(cudaMemset(c->d_pl_total, 0, 8 * sizeof(int)));
@@ -1230,7 +1319,7 @@ extern "C" int scgpu_destroy(scgpu_ctx* c) {
     free_particles(c);
     cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_reach2); cudaFree(c->d_counts); cudaFree(c->d_cell_start); cudaFree(c->d_cursor);
     cudaFree(c->d_sweep_acc);
-    cudaFree(c->d_trial); cudaFree(c->d_trial_rec); cudaFree(c->d_pl_total); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_counters); cudaFree(c->d_flush);
+    cudaFree(c->d_trial); cudaFree(c->d_trial_rec); cudaFree(c->d_pl_total); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_reduce); cudaFree(c->d_counters); cudaFree(c->d_flush);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_small) cudaFreeHost(c->h_small);
     cudaFree(c->d_single);
@@ -1280,6 +1369,7 @@ extern "C" int scgpu_set_topology(scgpu_ctx* c, int ntypes, const scgpu_iaparam*
     {   // beyond `reach` (centre distance) every term of the pair energy is EXACTLY zero: rods are at least |r| - l1/2 - l2/2 apart,
         // a rod and a sphere |r| - l/2, spheres |r|; the cutoffs are max(rcut, rcutwca). Stored squared, with a 0.1 % FP32 safety margin.
         std::vector<float> reach((size_t)ntypes * ntypes);
+        reach.reserve((size_t)ntypes * ntypes + ntypes);
         for (int a = 0; a < ntypes; a++) for (int b = 0; b < ntypes; b++) {
             const scgpu_iaparam& q = c->h_ia[(size_t)a * ntypes + b];
             int k = (int)q.reserved[0];
@@ -1291,6 +1381,12 @@ extern "C" int scgpu_set_topology(scgpu_ctx* c, int ntypes, const scgpu_iaparam*
             else if (k == K_SP_WCA || k == K_SP_COS2) r = cut;
             else if (k >= K_MIX_SCASPA) r = cut + q.half_len[0] + q.half_len[1];    // one of the two half lengths is 0 (the sphere)
             reach[(size_t)a * ntypes + b] = (float)(r * r * 1.001);
+        }
+        // [ntypes*ntypes + a]: the largest of row a -- no partner of a type-a particle interacts beyond it (neighbour-cell culling)
+        for (int a = 0; a < ntypes; a++) {
+            float m = 0.f;
+            for (int b = 0; b < ntypes; b++) m = fmaxf(m, reach[(size_t)a * ntypes + b]);
+            reach.push_back(m);
         }
         CK(cudaMalloc(&c->d_reach2, reach.size() * sizeof(float)));
         CK(cudaMemcpy(c->d_reach2, reach.data(), reach.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1722,7 +1818,7 @@ extern "C" int scgpu_mol_to_others(scgpu_ctx* c, int first, int m, const double*
     }
     for (bool repeat = true; repeat;) {
         if (launch_energy(c, 3, m, 1, nullptr, trial_states30 ? c->d_trial : nullptr, first, first + m, c->d_out, nullptr, nullptr)) return SCGPU_ERR_CUDA;
-        k_reduce_fixed<<<1, 256, 0, c->stream>>>(m, c->d_out, c->d_scalar);
+        k_reduce_fixed<<<RF_BLOCKS, RF_THREADS, 0, c->stream>>>(m, c->d_out, c->d_scalar, c->d_reduce);
         c->launches += 1;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(e_sum, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1733,7 +1829,7 @@ extern "C" int scgpu_mol_to_others(scgpu_ctx* c, int first, int m, const double*
 
 static int launch_all_to_all(scgpu_ctx* c) {
     if (launch_energy(c, 2, c->n, 1, nullptr, nullptr, 0, 0, c->d_out, nullptr, nullptr)) return SCGPU_ERR_CUDA;
-    k_reduce_fixed<<<1, 1024, 0, c->stream>>>(c->n, c->d_out, c->d_scalar);
+    k_reduce_fixed<<<RF_BLOCKS, RF_THREADS, 0, c->stream>>>(c->n, c->d_out, c->d_scalar, c->d_reduce);
     c->launches += 1;
     CK(cudaGetLastError());
     return 0;
