@@ -803,7 +803,7 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
 #ifndef CHEAP_MINB
 #define CHEAP_MINB 3
 #endif
-constexpr int CHEAP_BUF = 2048;   // patch-list entries buffered per block between global appends
+constexpr int CHEAP_BUF = 256;    // patch-list entries buffered per warp between global appends
 template <bool RODS>
 __global__ void __launch_bounds__(256, RODS ? CHEAP_MINB : 2)
 k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
@@ -812,22 +812,22 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
     int total = *fl.total;
     if (total > fl.cap) total = fl.cap;
     unsigned n_gate = 0;
-    // Each block owns one contiguous slice of the list. Pairs that owe a patch term are collected in a shared-memory buffer
-    // and appended to the global patch list with ONE atomicAdd per buffer-full (normally once per block): an append per warp
-    // and trip meant ~130 000 atomics on a single address per launch, which serialise in L2 and cost a third of the kernel.
-    __shared__ int sh_pl[CHEAP_BUF];
-    __shared__ int sh_n, sh_base;
-    if (threadIdx.x == 0) sh_n = 0;
+    // Each block owns one contiguous slice of the list. Pairs that owe a patch term are collected in a per-warp shared-memory
+    // buffer and appended to the global patch list with ONE atomicAdd per buffer-full (normally once per warp and launch): an
+    // append per warp and trip meant ~130 000 atomics on a single address per launch, which serialise in L2 and cost a third
+    // of the kernel. No block barrier anywhere: warps whose pairs take the long path do not hold the others up.
+    __shared__ int sh_pl[256 / 32][CHEAP_BUF];
+    int* wbuf = sh_pl[threadIdx.x >> 5];
+    int wn = 0;                       // entries in this warp's buffer (warp-uniform)
     const int per_block = (((total + (int)gridDim.x - 1) / (int)gridDim.x) + 255) & ~255;
     const int lo = blockIdx.x * per_block, hi = min(total, lo + per_block);
-    auto flush = [&]() {              // block-wide; callers guarantee a barrier since the last append
-        const int n = sh_n;
-        if (threadIdx.x == 0 && n) sh_base = atomicAdd(fl.ptotal, n);
-        __syncthreads();
-        const int gbase = sh_base;
-        for (int k = threadIdx.x; k < n; k += blockDim.x) fl.plist[gbase + k] = sh_pl[k];      // plist has the capacity of pair[]: cannot overflow
-        __syncthreads();
-        if (threadIdx.x == 0) sh_n = 0;
+    auto flush = [&]() {              // warp-wide
+        int gbase = 0;
+        if (lane == 0) gbase = atomicAdd(fl.ptotal, wn);
+        gbase = __shfl_sync(0xffffffffu, gbase, 0);
+        for (int k = lane; k < wn; k += 32) fl.plist[gbase + k] = wbuf[k];      // plist has the capacity of pair[]: cannot overflow
+        __syncwarp();
+        wn = 0;
     };
     int p = lo + threadIdx.x;
     int2 pr_next = p < hi ? fl.pair[p] : make_int2(0, 0);
@@ -841,8 +841,7 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
             di = mk(ri.x, ri.y, ri.z); dj = mk(rj.x, rj.y, rj.z);
         }
         pr_next = (p + 256 < hi) ? fl.pair[p + 256] : make_int2(0, 0);
-        __syncthreads();                                   // appends of the previous trip are complete
-        if (sh_n > CHEAP_BUF - 256) flush();               // block-uniform decision
+        if (wn > CHEAP_BUF - 32) flush();
         bool np = false;
         if (p < hi) {
             v3 r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
@@ -865,15 +864,11 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
             fl.e[p] = make_double2(e, 0.0);
         }
         const unsigned m = __ballot_sync(0xffffffffu, np);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&sh_n, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (np) sh_pl[base + __popc(m & lt_mask)] = p;
-        }
+        if (np) wbuf[wn + __popc(m & lt_mask)] = p;
+        wn += __popc(m);
+        __syncwarp();
     }
-    __syncthreads();
-    flush();
+    if (wn) flush();
     if (counters) {
         n_gate = __reduce_add_sync(0xffffffffu, n_gate);
         if (lane == 0 && n_gate) atomicAdd(&counters[1], (unsigned long long)n_gate);
