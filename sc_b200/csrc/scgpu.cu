@@ -666,7 +666,7 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                         t1z = (float)(rel_frac(tpw.z + s.shift[2], ccen[2]) * s.box[2]);
                     }
                     const float* reach_row = s.reach2 + ttype * s.ntypes;
-                    const float reach_same = reach_row[ttype];
+                    const float reach_same = s.reach2[s.ntypes * s.ntypes + ttype];      // RODS: the largest reach of this type (conservative for mixed rod types)
                     // neighbour cells whose nearest face is beyond the largest reach of this particle hold no partner: their
                     // 64-candidate groups are skipped. Not while counting work: the reference's sqmaxcut gate is wider than reach.
                     unsigned cellmask = 0xffffffffu;
@@ -796,6 +796,183 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                 __syncthreads();
                 if (!sh_ok) return;          // list too short: the host grows it and repeats the launch
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_gate_rows: the gate of the flat pipeline for rods-only systems on grids without wrap (>= 5 cells per axis), THREAD per
+// target. k_gate_cells gives a warp to every target and spends ~60 warp instructions per 32 candidate tests on ballots,
+// compaction, mask replay and per-cell set-up (cells hold ~17 particles, a block amortises its prologue over very few
+// targets). Here a block takes 32 CONSECUTIVE slots of one cell row (cells of a row are contiguous in the sorted arrays, so a
+// unit is always full whatever the cell populations are) and stages the union of their neighbourhoods: the cells
+// [cxa-1, cxb+1] of the 9 neighbouring rows, <= 18 contiguous slot ranges. Lane t owns target t; the four warps split the
+// staged candidates round-robin (warp w takes c = w, w+4, ...), so every lane of a warp reads the SAME candidate (one
+// broadcast LDS.128) and runs the FP32 test privately: ~9 instructions per test, no votes. Hits go to a per-(target, warp)
+// buffer in shared memory; afterwards the block reserves one span of the global list and every target's hits are written
+// contiguously (warp-0 hits first, then warp 1, ...: a fixed order, so the combine step stays bit-reproducible).
+// Anything the layout cannot hold (a unit spanning too many cells for the box, a neighbourhood above the tile, a buffer
+// overflow in a very dense spot) raises bit 2 of the overflow word: the host then repeats the launch with k_gate_cells.
+// ------------------------------------------------------------------------------------------------
+constexpr int GR_T = 32;            // targets per unit (= lanes)
+constexpr int GR_SL = 4;            // candidate slices (= warps per block)
+constexpr int GR_TILE = 1024;       // staged candidates per unit
+#ifndef GR_CAP_N
+#define GR_CAP_N 40
+#endif
+constexpr int GR_CAP = GR_CAP_N;    // hits per (target, slice)
+constexpr int GR_STRIDE = 34;       // halfwords per buffer row: row k of target t at k * 34 + t -> the write-out (fixed t, k = lane) is conflict-free
+
+template <int MODE>
+__global__ void __launch_bounds__(GR_SL * 32, 6)
+k_gate_rows(DevSys s, FlatList fl) {
+    __shared__ float4 t_pf[GR_TILE];                // x, y, z: FP32 coordinates relative to the unit centre, length units; w = x^2 + y^2 + z^2
+    __shared__ int t_orig[GR_TILE], t_slot[GR_TILE];
+    __shared__ unsigned short sh_hit[GR_SL][GR_CAP * GR_STRIDE];
+    __shared__ int sh_cnt[GR_SL][GR_T];
+    __shared__ int sh_off[GR_SL][GR_T];
+    __shared__ int sh_sb[20], sh_soff[20];          // staged segments: first slot, offset in the tile
+    __shared__ int sh_cx[2];
+    __shared__ int sh_ok;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int row = blockIdx.y;
+    const int nx = s.nc[0], ny = s.nc[1];
+    const int cy = row % ny, cz = row / ny;
+    const int rs = s.cell_start[row * nx], re = s.cell_start[(row + 1) * nx];
+    for (int first = rs + GR_T * blockIdx.x; first < re; first += GR_T * gridDim.x) {
+        const int count = min(GR_T, re - first);
+        const int last = first + count - 1;
+        __syncthreads();                 // previous unit fully written out
+        // ---- cells of the first and the last target (warp 0: lanes over the cells of the row)
+        if (wid == 0) {
+            int cxa = 0, cxb = 0;
+            for (int c0 = 0; c0 < nx; c0 += 32) {
+                const int cxl = c0 + lane;
+                int b = 0, e = 0;
+                if (cxl < nx) { b = s.cell_start[row * nx + cxl]; e = s.cell_start[row * nx + cxl + 1]; }
+                const unsigned ma = __ballot_sync(0xffffffffu, cxl < nx && b <= first && first < e);
+                const unsigned mb = __ballot_sync(0xffffffffu, cxl < nx && b <= last && last < e);
+                if (ma) cxa = c0 + __ffs(ma) - 1;
+                if (mb) cxb = c0 + __ffs(mb) - 1;
+            }
+            // ---- the <= 18 contiguous slot ranges of the neighbourhood: 9 rows x (one range, or two when the x range wraps)
+            const int k = cxb - cxa + 1;
+            const bool fits = nx >= k + 3;
+            int b = 0, len = 0;
+            if (fits && lane < 18) {
+                const int rr = lane >> 1, part = lane & 1;
+                const int yy = (cy + rr % 3 - 1 + ny) % ny, zz = (cz + rr / 3 - 1 + s.nc[2]) % s.nc[2];
+                const int rbase = (zz * ny + yy) * nx;
+                const int lo = cxa - 1, hi = cxb + 1;                // inclusive cell range, may stick out of [0, nx)
+                int a0, a1;                                          // this part's range, empty when a0 > a1
+                if (lo < 0) { if (part == 0) { a0 = 0; a1 = hi; } else { a0 = lo + nx; a1 = nx - 1; } }
+                else if (hi >= nx) { if (part == 0) { a0 = lo; a1 = nx - 1; } else { a0 = 0; a1 = hi - nx; } }
+                else { a0 = part == 0 ? lo : 1; a1 = part == 0 ? hi : 0; }
+                if (a0 <= a1) { b = s.cell_start[rbase + a0]; len = s.cell_start[rbase + a1 + 1] - b; }
+            }
+            int x = len;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane < 19) { sh_sb[lane] = b; sh_soff[lane] = x - len; }
+            if (lane == 0) { sh_cx[0] = cxa; sh_cx[1] = cxb; }
+            const int C = __shfl_sync(0xffffffffu, x, 18);
+            if (lane == 0) {
+                sh_ok = (fits && C <= GR_TILE) ? 1 : 0;
+                if (!sh_ok) atomicOr(fl.overflow, 4);
+            }
+        }
+        __syncthreads();
+        if (!sh_ok) return;
+        const int C = sh_soff[18];
+        const int Cpad = (C + 4 * GR_SL - 1) / (4 * GR_SL) * (4 * GR_SL);
+        const double ccen[3] = {0.5 * (sh_cx[0] + sh_cx[1] + 1) / nx, (cy + 0.5) / ny, (cz + 0.5) / s.nc[2]};
+        auto staged = [&](const double4& pw) {
+            const float x = (float)(rel_frac(pw.x + s.shift[0], ccen[0]) * s.box[0]), y = (float)(rel_frac(pw.y + s.shift[1], ccen[1]) * s.box[1]),
+                        z = (float)(rel_frac(pw.z + s.shift[2], ccen[2]) * s.box[2]);
+            return make_float4(x, y, z, x * x + y * y + z * z);
+        };
+        // ---- stage: a warp per segment, contiguous 32-byte loads
+        for (int k = wid; k < 18; k += GR_SL) {
+            const int b = sh_sb[k], off = sh_soff[k], len = sh_soff[k + 1] - off;
+            for (int idx = lane; idx < len; idx += 32) {
+                const double4 pw = s.posw[b + idx];
+                t_pf[off + idx] = staged(pw); t_orig[off + idx] = w_orig(pw.w); t_slot[off + idx] = b + idx;
+            }
+        }
+        for (int p = C + threadIdx.x; p < Cpad; p += blockDim.x) {          // padding: an infinite |q|^2 fails the comparison
+            t_pf[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+            t_orig[p] = -1; t_slot[p] = 0;
+        }
+        // ---- this lane's target: |t - q|^2 <= reach  <=>  |q|^2 - 2 t.q <= reach - |t|^2 (three FMAs and a compare per test; the
+        // rounding error, ~1e-6 relative at these magnitudes, is far inside the 0.1 % margin carried by reach)
+        float m2x = 0.f, m2y = 0.f, m2z = 0.f, thr = __int_as_float(0xff800000);
+        int target = -2;
+        if (lane < count) {
+            const double4 pw = s.posw[first + lane];
+            const float4 q = staged(pw);
+            m2x = -2.f * q.x; m2y = -2.f * q.y; m2z = -2.f * q.z;
+            target = w_orig(pw.w);
+            thr = s.reach2[s.ntypes * s.ntypes + w_type(pw.w)] - q.w;     // the largest reach of this type: conservative for mixed rod types
+        }
+        __syncthreads();
+        // ---- scan: every lane tests its own target against the candidates of this warp's slice. Hits are appended through a
+        // per-lane cursor that saturates four entries below the capacity (then the launch is repeated by k_gate_cells).
+        unsigned short* buf = sh_hit[wid];
+        int cur = lane;
+        const int cur_max = lane + (GR_CAP - 4) * GR_STRIDE;
+        for (int c0 = wid; c0 < Cpad; c0 += 4 * GR_SL) {
+            bool hit[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {        // four independent tests first (instruction-level parallelism), appends afterwards
+                const float4 q = t_pf[c0 + GR_SL * u];
+                const int ob = t_orig[c0 + GR_SL * u];
+                const float sq = fmaf(m2z, q.z, fmaf(m2y, q.y, fmaf(m2x, q.x, q.w)));
+                hit[u] = (sq <= thr) & (MODE == 2 ? ob < target : ob != target);
+            }
+            if (hit[0] | hit[1] | hit[2] | hit[3]) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) { buf[cur] = (unsigned short)(c0 + GR_SL * u); cur += hit[u] ? GR_STRIDE : 0; }
+                cur = min(cur, cur_max);
+            }
+        }
+        if (__any_sync(0xffffffffu, cur == cur_max) && lane == 0) atomicOr(fl.overflow, 4);
+        const int cnt = (cur - lane) / GR_STRIDE;
+        sh_cnt[wid][lane] = cnt;
+        __syncthreads();
+        // ---- reserve the unit's span of the list, hand every (target, slice) its sub-span
+        if (wid == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < GR_SL; w++) tot += sh_cnt[w][lane];
+            int x = tot;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            const int total = __shfl_sync(0xffffffffu, x, 31);
+            int base = 0;
+            if (lane == 0) {
+                base = atomicAdd(fl.total, total);
+                const bool ok = base + total <= fl.cap;
+                if (!ok) atomicOr(fl.overflow, 2);
+                sh_ok = ok ? 1 : 0;
+            }
+            base = __shfl_sync(0xffffffffu, base, 0) + x - tot;
+            {
+                int o = base;
+#pragma unroll
+                for (int w = 0; w < GR_SL; w++) { sh_off[w][lane] = o; o += sh_cnt[w][lane]; }
+            }
+            if (lane < count) {
+                fl.chunks[target] = make_int4(base, tot, -1, 0);
+                fl.head[target] = target;
+            }
+        }
+        __syncthreads();
+        if (!sh_ok) return;
+        // ---- write-out: warp w appends its slice's hits of every target behind those of the warps before it
+        const int my_off = sh_off[wid][lane];       // lane t holds the sub-span of target t
+#pragma unroll 4
+        for (int t = 0; t < count; t++) {
+            const int nh = __shfl_sync(0xffffffffu, cnt, t), off = __shfl_sync(0xffffffffu, my_off, t);
+            if (lane < nh) fl.pair[off + lane] = make_int2(first + t, t_slot[buf[lane * GR_STRIDE + t]]);
+            if (lane + 32 < nh) fl.pair[off + lane + 32] = make_int2(first + t, t_slot[buf[(lane + 32) * GR_STRIDE + t]]);
         }
     }
 }
@@ -1206,6 +1383,7 @@ struct scgpu_ctx {
     int* d_pl_overflow = nullptr;
     int pl_cap = 0;
     bool rods_only = false;          // every particle an un-bonded rod: the specialised kernels apply
+    bool use_rows = true;            // k_gate_rows until a launch reports a layout it cannot hold (then k_gate_cells for good)
     bool any_two_patch = false;      // some particle type present carries a second patch (TPSC/TCPSC/TCHPSC/TCHCPSC)
     int* d_warp_head = nullptr;
     int4* d_chunks = nullptr;
@@ -1492,6 +1670,7 @@ static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const 
     // specialisation switch: only rod-rod functors and no bonded molecule among the particles present
     if (!same_types) {
         c->types_valid = true;
+        c->use_rows = true;
         std::vector<char> tu(c->ntypes, 0), mu(c->nmol, 0);
         for (int i = 0; i < n; i++) { tu[type[i]] = 1; mu[moltype[i]] = 1; }
         bool rods = true;
@@ -1668,7 +1847,13 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
         fl.chunks = c->d_fl_chunks; fl.chunk_count = c->d_pl_total + 4; fl.chunk_cap = c->fl_chunk_cap;
         fl.plist = c->d_fl_plist; fl.ptotal = c->d_pl_total + 5; fl.overflow = c->d_pl_overflow;
         const bool wrap = c->nc[0] < 5 || c->nc[1] < 5 || c->nc[2] < 5;
-        if (c->rods_only) {
+        const int nrows = c->nc[1] * c->nc[2];
+        if (c->rods_only && c->use_rows && !wrap && !d_counters && nrows <= 65535) {
+            const dim3 grid((unsigned)(c->n / nrows / GR_T + 2), (unsigned)nrows);
+            if (mode == 1) k_gate_rows<1><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
+            else k_gate_rows<2><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
+            k_cheap_flat<true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters);
+        } else if (c->rods_only) {
             if (mode == 1) { if (wrap) k_gate_cells<1, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             else { if (wrap) k_gate_cells<2, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             k_cheap_flat<true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters);
@@ -1706,7 +1891,8 @@ static int overflow_then_grow(scgpu_ctx* c, bool* repeat) {
     CK(cudaStreamSynchronize(c->stream));
     *repeat = false;
     if (!*hflag) return 0;
-    const int which = *hflag;      // bit 0: patch work list, bit 1: flat pair list
+    const int which = *hflag;      // bit 0: patch work list, bit 1: flat pair list, bit 2: k_gate_rows cannot hold this configuration
+    if (which & 4) c->use_rows = false;
     if (which & 2) {
         if ((long long)c->fl_cap * 2 > (1ll << 30)) { g_err = "flat pair list overflow: more gated pairs than the list can ever hold"; return SCGPU_ERR_STATE; }
         cudaFree(c->d_fl_pair); cudaFree(c->d_fl_e); cudaFree(c->d_fl_plist); cudaFree(c->d_fl_chunks);
