@@ -125,6 +125,14 @@ int scgpu_one_to_all_batch(scgpu_ctx* ctx, int m, const int* targets, const doub
 /* same over every particle's current state, results stay on the device (bench: inputs resident in HBM);
  * e_host may be NULL. n_gated / n_candidates (optional) return the pair counters of that launch. */
 int scgpu_one_to_all_everyone(scgpu_ctx* ctx, double* e_host, int64_t* n_candidates, int64_t* n_gated);
+/* ASYNCHRONOUS whole-configuration pass for callers that stream configurations (replica workers, analysis of stored
+ * trajectories): upload a configuration of the SAME particle count and types as the previous upload (state9 = what
+ * config.init holds per particle: pos, dir, patchdir), derive the patch vectors on the device (Particle::init,
+ * structures/particle.cpp:3-79), rebuild the cell list, evaluate oneToAll of every particle (the loop a TotalE<>::initEM()
+ * + per-particle oneToAll performs, totalenergycalculator.h:135-297) and copy the n energies to e_out. Both buffers must be
+ * page-locked; the call returns at once, the data is valid after scgpu_sync(ctx) returns SCGPU_OK, and state9 must not be
+ * modified before that. Two contexts used alternately overlap the copies of one configuration with the kernels of another. */
+int scgpu_submit_everyone(scgpu_ctx* ctx, const double* state9_pinned, double* e_out_pinned);
 /* mol2others(mol) / mol2othersTrial(mol) for a molecule of m consecutive particles starting at `first`
  * (totalenergycalculator.h:417-499): members x non-members with an EMPTY conlist. trial_states30 (m*30, optional)
  * = the members' states as mutated by the caller. */

@@ -827,7 +827,8 @@ template <int MODE>
 __global__ void __launch_bounds__(GR_SL * 32, 6)
 k_gate_rows(DevSys s, FlatList fl) {
     __shared__ float4 t_pf[GR_TILE];                // x, y, z: FP32 coordinates relative to the unit centre, length units; w = x^2 + y^2 + z^2
-    __shared__ int t_orig[GR_TILE], t_slot[GR_TILE];
+    __shared__ __align__(16) int t_orig[GR_TILE];
+    __shared__ int t_slot[GR_TILE];
     __shared__ unsigned short sh_hit[GR_SL][GR_CAP * GR_STRIDE];
     __shared__ int sh_cnt[GR_SL][GR_T];
     __shared__ int sh_off[GR_SL][GR_T];
@@ -919,18 +920,20 @@ k_gate_rows(DevSys s, FlatList fl) {
         unsigned short* buf = sh_hit[wid];
         int cur = lane;
         const int cur_max = lane + (GR_CAP - 4) * GR_STRIDE;
-        for (int c0 = wid; c0 < Cpad; c0 += 4 * GR_SL) {
+        // warp w takes the candidates 16 i + 4 w .. 16 i + 4 w + 3: four float4 reads and ONE int4 read of the original indices
+        for (int c0 = 4 * wid; c0 < Cpad; c0 += 4 * GR_SL) {
+            const int4 ob4 = *reinterpret_cast<const int4*>(t_orig + c0);
+            const int ob[4] = {ob4.x, ob4.y, ob4.z, ob4.w};
             bool hit[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {        // four independent tests first (instruction-level parallelism), appends afterwards
-                const float4 q = t_pf[c0 + GR_SL * u];
-                const int ob = t_orig[c0 + GR_SL * u];
+                const float4 q = t_pf[c0 + u];
                 const float sq = fmaf(m2z, q.z, fmaf(m2y, q.y, fmaf(m2x, q.x, q.w)));
-                hit[u] = (sq <= thr) & (MODE == 2 ? ob < target : ob != target);
+                hit[u] = (sq <= thr) & (MODE == 2 ? ob[u] < target : ob[u] != target);
             }
             if (hit[0] | hit[1] | hit[2] | hit[3]) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) { buf[cur] = (unsigned short)(c0 + GR_SL * u); cur += hit[u] ? GR_STRIDE : 0; }
+                for (int u = 0; u < 4; u++) { buf[cur] = (unsigned short)(c0 + u); cur += hit[u] ? GR_STRIDE : 0; }
                 cur = min(cur, cur_max);
             }
         }
@@ -968,11 +971,12 @@ k_gate_rows(DevSys s, FlatList fl) {
         if (!sh_ok) return;
         // ---- write-out: warp w appends its slice's hits of every target behind those of the warps before it
         const int my_off = sh_off[wid][lane];       // lane t holds the sub-span of target t
+        const bool big = __any_sync(0xffffffffu, cnt > 32);
 #pragma unroll 4
         for (int t = 0; t < count; t++) {
             const int nh = __shfl_sync(0xffffffffu, cnt, t), off = __shfl_sync(0xffffffffu, my_off, t);
             if (lane < nh) fl.pair[off + lane] = make_int2(first + t, t_slot[buf[lane * GR_STRIDE + t]]);
-            if (lane + 32 < nh) fl.pair[off + lane + 32] = make_int2(first + t, t_slot[buf[(lane + 32) * GR_STRIDE + t]]);
+            if (big && lane + 32 < nh) fl.pair[off + lane + 32] = make_int2(first + t, t_slot[buf[(lane + 32) * GR_STRIDE + t]]);
         }
     }
 }
@@ -1575,6 +1579,11 @@ extern "C" int scgpu_set_topology(scgpu_ctx* c, int ntypes, const scgpu_iaparam*
 }
 
 static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const int* type, const int* moltype, bool compact);
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
 
 extern "C" int scgpu_set_particles(scgpu_ctx* c, int n, const double* state30, const int* type, const int* moltype) {
     return set_particles_impl(c, n, state30, type, moltype, false);
@@ -1986,6 +1995,24 @@ extern "C" int scgpu_one_to_all_everyone(scgpu_ctx* c, double* e_host, int64_t* 
     if (n_candidates) *n_candidates = (int64_t)h[0];
     if (n_gated) *n_gated = (int64_t)h[1];
     return SCGPU_OK;
+}
+
+extern "C" int scgpu_submit_everyone(scgpu_ctx* c, const double* state9, double* e_out) {
+    ARG(c && state9 && e_out, "scgpu_submit_everyone: NULL argument");
+    ARG(c->n > 0 && c->types_valid, "scgpu_submit_everyone: needs a previous upload that brought the particle types");
+    ARG(is_pinned_host(state9) && is_pinned_host(e_out), "scgpu_submit_everyone: both buffers must be page-locked host memory");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->d_compact, state9, (size_t)c->n * 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_particle_init<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->n, c->ntypes, c->d_compact, c->d_type, c->d_ia, c->d_api);
+    c->launches++;
+    CK(cudaGetLastError());
+    c->h_api.clear();
+    c->cells_valid = false;
+    c->api_stale = false;
+    if (int r = scgpu_build_cells(c)) return r;
+    if (launch_energy(c, 1, c->n, 1, nullptr, nullptr, 0, 0, c->d_out, nullptr, nullptr)) return SCGPU_ERR_CUDA;
+    CK(cudaMemcpyAsync(e_out, c->d_out, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return SCGPU_OK;          // list overflows are reported by scgpu_sync
 }
 
 extern "C" int scgpu_mol_to_others(scgpu_ctx* c, int first, int m, const double* trial_states30, double* e_sum) {

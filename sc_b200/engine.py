@@ -35,7 +35,7 @@ class SweepStats(C.Structure):
 SYMBOLS = ["scgpu_last_error", "scgpu_device_count", "scgpu_create", "scgpu_destroy", "scgpu_set_topology",
            "scgpu_set_particles", "scgpu_set_particles_compact", "scgpu_set_box", "scgpu_update_particle", "scgpu_download_particles",
            "scgpu_build_cells", "scgpu_cell_assignment", "scgpu_cell_order", "scgpu_one_to_all",
-           "scgpu_one_to_all_batch", "scgpu_one_to_all_everyone", "scgpu_mol_to_others", "scgpu_all_to_all",
+           "scgpu_one_to_all_batch", "scgpu_one_to_all_everyone", "scgpu_submit_everyone", "scgpu_mol_to_others", "scgpu_all_to_all",
            "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_replica_record",
            "scgpu_timer_start", "scgpu_timer_stop", "scgpu_sync", "scgpu_fp64_peak", "scgpu_flush_l2",
            "scgpu_kernel_launches"]
@@ -67,6 +67,7 @@ def load_library(variant="fast"):
     L.scgpu_one_to_all.argtypes = [vp, C.c_int, _dp, _dp, _dp]
     L.scgpu_one_to_all_batch.argtypes = [vp, C.c_int, _ip, _dp, _dp]
     L.scgpu_one_to_all_everyone.argtypes = [vp, _dp, _i64p, _i64p]
+    L.scgpu_submit_everyone.argtypes = [vp, _dp, _dp]
     L.scgpu_mol_to_others.argtypes = [vp, C.c_int, C.c_int, _dp, _dp]
     L.scgpu_all_to_all.argtypes = [vp, _dp, _dp]
     L.scgpu_overlap_one.argtypes = [vp, C.c_int, _dp, C.c_int, _ip]
@@ -206,6 +207,13 @@ class Engine:
         if count:
             return out, nc.value, ng.value
         return out
+
+    def submit_everyone(self, state9_pinned, out_pinned):
+        """asynchronous: upload a configuration (page-locked float64[n,9]), rebuild cells, oneToAll of every particle, energies into
+        the page-locked float64[n] buffer; valid after sync(). The caller keeps both arrays alive and untouched until then."""
+        assert state9_pinned.dtype == np.float64 and state9_pinned.flags.c_contiguous and state9_pinned.size == 9 * self.n
+        assert out_pinned.dtype == np.float64 and out_pinned.flags.c_contiguous and out_pinned.size == self.n
+        self._ck(self.L.scgpu_submit_everyone(self.h, _d(state9_pinned), _d(out_pinned)))
 
     def mol_to_others(self, first, m, trial_states=None):
         e = C.c_double(0.0)

@@ -88,6 +88,44 @@ def small_case(kind, seed=2024):
     if kind == "psc_gas":
         _gas(rnd, 700, box, lines)
         return TOP_PSC % 700, "\n".join(lines) + "\n"
+    if kind == "rods_wide":
+        # un-bonded rods of four types with different cutoffs on a grid of >= 7 x 5 x 5 cells: the configuration the thread-per-target
+        # gate (k_gate_rows) takes; clustered along x so that cell populations are very uneven (empty cells, cells beyond 32 rods)
+        top = """[Types]
+P1 1 PSC    1.333333  1.2  1.346954458  0.3  90  5.0  3  0.5
+C2 2 CPSC   1.1       1.1  1.30         0.45 120 5.0  3  0.5
+T3 3 TCPSC  1.0       1.0  1.2          0.4  80  8.0  3  -0.4 150.0 90 5.0
+H4 4 CHPSC  1.2       1.2  1.346954458  0.3  90  5.0  3  0.0  10.0
+[Molecules]
+A: {
+particles: 1
+}
+B: {
+particles: 2
+}
+C: {
+particles: 3
+}
+D: {
+particles: 4
+}
+[System]
+A 900
+B 700
+C 600
+D 500
+"""
+        box = (44.0, 29.0, 31.0)
+        lines = [_fmt(box)]
+        for i in range(2700):
+            if i % 3 == 0:
+                pos = (rnd.gauss(0.3, 0.07) % 1.0 * box[0], rnd.uniform(0, box[1]), rnd.gauss(0.5, 0.2) % 1.0 * box[2])
+            else:
+                pos = (rnd.uniform(0, box[0]), rnd.uniform(0, box[1]), rnd.uniform(0, box[2]))
+            d = _rand_unit(rnd)
+            p = _perp(rnd, d)
+            lines.append(_fmt(pos) + "   " + _fmt(d) + "   " + _fmt(p) + " 0")
+        return top, "\n".join(lines) + "\n"
     if kind == "mix":
         top = """[Types]
 S1 1 SPA    1.333333  1.2  1.346954458  0.3

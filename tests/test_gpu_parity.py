@@ -184,6 +184,45 @@ def test_multicell_systems(engine, kind):
     assert engine.overlap_all(1) == s.overlap_all(1)
 
 
+def _pinned(shape):
+    import torch
+    return torch.empty(shape, dtype=torch.float64).pin_memory()
+
+
+def test_row_unit_gate_matches_cell_gate_and_oracle(engine):
+    """rods-only system on a grid without wrap: the every-particle passes run k_gate_rows (thread per target); with work counters
+    requested they run k_gate_cells. Same pair set -> energies agree to rounding (the summation order differs), both agree
+    with the oracle; the asynchronous whole-configuration call returns the same bits as the synchronous one."""
+    top, cfg = synth.small_case("rods_wide")
+    s = O.system_from_text(top, cfg)
+    engine.load(s)
+    sc = eps_scale(s)
+    ncell = s.cells()[0]
+    assert ncell[0] >= 7 and ncell[1] >= 5 and ncell[2] >= 5
+    ev_cells, ncand, ngate = engine.one_to_all_everyone(count=True)
+    ev_rows = engine.one_to_all_everyone()
+    assert close(ev_rows, ev_cells, sc * 10), worst(ev_rows, ev_cells)
+    assert np.array_equal(ev_rows, engine.one_to_all_everyone())          # run-to-run identical
+    for t in range(0, s.n, max(1, s.n // 150)):
+        assert close(ev_rows[t], s.one_to_all(t), sc), (t, ev_rows[t], s.one_to_all(t))
+    tot, rows = engine.all_to_all(rows=True)
+    assert close(np.sum(rows), tot, sc * 10)
+    assert close(2 * tot, np.sum(ev_rows), sc * 100)
+    assert close(tot, s.all_to_all(), sc * 10)
+    # a shrunk box (NPT): fewer cells per axis, the wrap variant of the cell gate takes over
+    state9, out = _pinned((s.n, 9)), _pinned((s.n,))
+    state9.numpy()[:] = s.state[:, :9]
+    engine.set_particles_compact(s.state[:, :9], s.type, s.moltype)
+    ref = engine.one_to_all_everyone()
+    for _ in range(3):
+        engine.submit_everyone(state9.numpy(), out.numpy())
+        engine.sync()
+        assert np.array_equal(out.numpy(), ref)
+    from sc_b200 import ScgpuError
+    with pytest.raises(ScgpuError):
+        engine.submit_everyone(np.zeros((s.n, 9)), out.numpy())          # pageable memory is refused
+
+
 def test_determinism_and_box_change(engine):
     top, cfg = synth.small_case("psc_gas")
     s = O.system_from_text(top, cfg)
