@@ -920,15 +920,31 @@ k_gate_rows(DevSys s, FlatList fl) {
         unsigned short* buf = sh_hit[wid];
         int cur = lane;
         const int cur_max = lane + (GR_CAP - 4) * GR_STRIDE;
-        // warp w takes the candidates 16 i + 4 w .. 16 i + 4 w + 3: four float4 reads and ONE int4 read of the original indices
+        // warp w takes the candidates 16 i + 4 w .. 16 i + 4 w + 3: four float4 reads and ONE int4 read of the original indices,
+        // fetched one trip ahead so that the shared-memory latency hides behind the arithmetic of the current trip
+        float4 qn[4];
+        int4 on = make_int4(-1, -1, -1, -1);
+        {
+            const int c0 = 4 * wid;       // Cpad >= 16: always inside the padded tile
+#pragma unroll
+            for (int u = 0; u < 4; u++) qn[u] = t_pf[c0 + u];
+            on = *reinterpret_cast<const int4*>(t_orig + c0);
+        }
         for (int c0 = 4 * wid; c0 < Cpad; c0 += 4 * GR_SL) {
-            const int4 ob4 = *reinterpret_cast<const int4*>(t_orig + c0);
-            const int ob[4] = {ob4.x, ob4.y, ob4.z, ob4.w};
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) q[u] = qn[u];
+            const int ob[4] = {on.x, on.y, on.z, on.w};
+            {
+                const int cn = min(c0 + 4 * GR_SL, Cpad - 4 * GR_SL + 4 * wid);      // the last trip re-reads its own entries
+#pragma unroll
+                for (int u = 0; u < 4; u++) qn[u] = t_pf[cn + u];
+                on = *reinterpret_cast<const int4*>(t_orig + cn);
+            }
             bool hit[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {        // four independent tests first (instruction-level parallelism), appends afterwards
-                const float4 q = t_pf[c0 + u];
-                const float sq = fmaf(m2z, q.z, fmaf(m2y, q.y, fmaf(m2x, q.x, q.w)));
+                const float sq = fmaf(m2z, q[u].z, fmaf(m2y, q[u].y, fmaf(m2x, q[u].x, q[u].w)));
                 hit[u] = (sq <= thr) & (MODE == 2 ? ob[u] < target : ob[u] != target);
             }
             if (hit[0] | hit[1] | hit[2] | hit[3]) {
@@ -972,11 +988,13 @@ k_gate_rows(DevSys s, FlatList fl) {
         // ---- write-out: warp w appends its slice's hits of every target behind those of the warps before it
         const int my_off = sh_off[wid][lane];       // lane t holds the sub-span of target t
         const bool big = __any_sync(0xffffffffu, cnt > 32);
-#pragma unroll 4
-        for (int t = 0; t < count; t++) {
+        const unsigned short* my_row = buf + lane * GR_STRIDE;
+#pragma unroll
+        for (int t = 0; t < GR_T; t++) {      // fully unrolled: lane indices and buffer offsets become immediates
+            if (t >= count) break;
             const int nh = __shfl_sync(0xffffffffu, cnt, t), off = __shfl_sync(0xffffffffu, my_off, t);
-            if (lane < nh) fl.pair[off + lane] = make_int2(first + t, t_slot[buf[lane * GR_STRIDE + t]]);
-            if (big && lane + 32 < nh) fl.pair[off + lane + 32] = make_int2(first + t, t_slot[buf[(lane + 32) * GR_STRIDE + t]]);
+            if (lane < nh) fl.pair[off + lane] = make_int2(first + t, t_slot[my_row[t]]);
+            if (big && lane + 32 < nh) fl.pair[off + lane + 32] = make_int2(first + t, t_slot[my_row[32 * GR_STRIDE + t]]);
         }
     }
 }
@@ -1015,6 +1033,8 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
     for (int p0 = lo; p0 < hi; p0 += 256, p += 256) {      // block-uniform trip count
         const int2 pr = pr_next;
         // everything the rod path reads from memory, issued together: one L2 round trip, not three
+        // (staging these operands through shared memory with cp.async one trip ahead was measured: 25 % slower -- eight 16-byte
+        // copies per thread throttle the memory pipe harder than the exposed latency of four 32-byte loads costs)
         const double4 pi = ldg256(s.posw + pr.x), pj = ldg256(s.posw + pr.y);
         v3 di, dj;
         if (RODS) {      // dir + one more double of the record: a single 32-byte request per particle

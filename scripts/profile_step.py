@@ -45,6 +45,17 @@ for _ in range(reps):
         eng.sweep(mp, 12345, _)
 eng.sync()
 print("done", what, reps)
+if what in ("everyone", "all_to_all"):                # device time per pass (not under a profiler)
+    ms = []
+    for k in range(20):
+        eng.flush_l2()
+        eng.timer_start()
+        if what == "everyone":
+            eng.one_to_all_everyone(fetch=False)
+        else:
+            eng.all_to_all(fetch=False)
+        ms.append(eng.timer_stop())
+    print("ms_per_pass %.4f (min %.4f)" % (sum(ms) / len(ms), min(ms)))
 if what == "sweep":                                  # wall-clock per sweep (not under a profiler)
     import time
     t0 = time.perf_counter()
