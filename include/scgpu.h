@@ -85,6 +85,19 @@ typedef struct scgpu_sweepstats {
     double energy_delta;                                       /* sum of accepted dE */
 } scgpu_sweepstats;
 
+/* Chain moves of the same sweep (MoveCreator::chainMove / chainDisplace / chainRotate, scOOP/mc/movecreator.cpp:304-328,
+ * 1075-1256): whole molecules are displaced or rotated rigidly, energy = mol2others before and after. */
+typedef struct scgpu_chainmoves {
+    double chainprob;              /* Sim::chainprob: share of the sweep's trials that are chain moves (updater.cpp:215) */
+    double chainm_mx[32];          /* per molecule type: stat.chainm[molType].mx    (= 2*chainmmx, sim.h:366) */
+    double chainr_angle[32];       /* per molecule type: stat.chainr[molType].angle (radians, sim.h:362) */
+} scgpu_chainmoves;
+
+typedef struct scgpu_chainstats {
+    int64_t chainm_acc, chainm_rej, chainr_acc, chainr_rej, cell_rej; /* cell_rej: a member outside the active cell before or after */
+    double energy_delta;                                               /* sum of accepted dE */
+} scgpu_chainstats;
+
 const char* scgpu_last_error(void);
 int scgpu_device_count(void);
 
@@ -149,6 +162,10 @@ int scgpu_overlap_all(scgpu_ctx* ctx, int variant, int* flag);
 /* one checkerboard sweep of displacement/rotation trials, validated statistically against sequential sweeps */
 int scgpu_sweep_checkerboard(scgpu_ctx* ctx, const scgpu_moveparams* mp, uint64_t seed, uint64_t sweep,
                              scgpu_sweepstats* stats);
+
+/* the same sweep with a share `chainprob` of its trials made chain moves (cm == NULL or chainprob == 0: identical to the call above) */
+int scgpu_sweep_checkerboard_chains(scgpu_ctx* ctx, const scgpu_moveparams* mp, const scgpu_chainmoves* cm, uint64_t seed, uint64_t sweep,
+                                    scgpu_sweepstats* stats, scgpu_chainstats* chain_stats);
 
 /* replica exchange helper (MoveCreator::replicaExchangeMove, scOOP/mc/movecreator.cpp:552-795): full energy stays on
  * the device; returns the device address of a packed double[8] record {E, V, N, 0...} for an NCCL all-gather */

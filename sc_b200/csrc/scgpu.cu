@@ -1559,6 +1559,9 @@ extern "C" int scgpu_set_topology(scgpu_ctx* c, int ntypes, const scgpu_iaparam*
         // rod pairs: squared centre distance beyond which every term is exactly 0 (pair_energy_cheap's shortcut)
         const double reach = sqrt(fmax(p.rcutSq, p.rcutwcaSq)) + p.half_len[0] + p.half_len[1];
         p.reserved[1] = reach * reach * 1.000001;
+        // Ia_param::volume (mc/inicializer.cpp:840-844), the weight of clusterCM (mc/movecreator.cpp:1323-1337); meaningful on the diagonal
+        const double hs = p.sigma / 2.0;
+        p.reserved[2] = 4.0 / 3.0 * 3.14159265358979323846 * hs * hs * hs + ((int)p.geotype[0] < SCGPU_SPN ? 3.14159265358979323846 / 2.0 * p.len[0] * hs * hs : 0.0);
     }
     c->h_mol.assign(mol, mol + nmoltypes);
     cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_reach2);
@@ -2135,8 +2138,22 @@ static inline unsigned long long splitmix64(unsigned long long& x) {
     return z ^ (z >> 31);
 }
 
+static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chainmoves* cm, uint64_t seed, uint64_t sweep, scgpu_sweepstats* stats,
+                      scgpu_chainstats* cstats);
 extern "C" int scgpu_sweep_checkerboard(scgpu_ctx* c, const scgpu_moveparams* mp, uint64_t seed, uint64_t sweep, scgpu_sweepstats* stats) {
+    return sweep_impl(c, mp, nullptr, seed, sweep, stats, nullptr);
+}
+extern "C" int scgpu_sweep_checkerboard_chains(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chainmoves* cm, uint64_t seed, uint64_t sweep,
+                                               scgpu_sweepstats* stats, scgpu_chainstats* cstats) {
+    return sweep_impl(c, mp, cm, seed, sweep, stats, cstats);
+}
+
+static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chainmoves* cm, uint64_t seed, uint64_t sweep, scgpu_sweepstats* stats,
+                      scgpu_chainstats* cstats) {
     ARG(c && mp, "scgpu_sweep_checkerboard: NULL argument");
+    const bool chains = cm && cm->chainprob > 0.0;
+    ARG(!chains || (cm->chainprob <= 1.0 && c->nmol <= CH_MAXMT), "scgpu_sweep_checkerboard_chains: chainprob must be in [0, 1] and at most 32 molecule types");
+    if (chains) for (int t = 0; t < c->nmol; t++) ARG(c->h_mol[t].mol_size <= CH_MAX, "scgpu_sweep_checkerboard_chains: a molecule is longer than MAXCHL = 20");
     ARG(mp->temper > 0 && mp->n_sub >= 1, "scgpu_sweep_checkerboard: temperature and n_sub must be positive");
     ARG(c->n > 0 && c->ntypes > 0 && c->ntypes <= 40, "scgpu_sweep_checkerboard: set topology (<= 40 types) and particles first");
     CK(cudaSetDevice(c->device));
@@ -2153,35 +2170,57 @@ extern "C" int scgpu_sweep_checkerboard(scgpu_ctx* c, const scgpu_moveparams* mp
     SweepParams sp;
     sp.temper = mp->temper;
     sp.n_sub = mp->n_sub;
+    sp.trial_scale = chains ? 1.0 - cm->chainprob : 1.0;
+    ChainParams cp;
+    memset(&cp, 0, sizeof cp);
+    if (chains) {
+        cp.temper = mp->temper;
+        cp.total_trials = cm->chainprob * (double)mp->n_sub * (double)c->n;
+        for (int t = 0; t < CH_MAXMT; t++) { cp.chainm_mx[t] = cm->chainm_mx[t]; cp.chainr_angle[t] = cm->chainr_angle[t]; }
+    }
     for (int t = 0; t < 40; t++) {
         sp.trans_mx[t] = mp->trans_mx[t];
         sp.rot_angle[t] = mp->rot_angle[t];
         sp.geotype_of_type[t] = (t < c->ntypes) ? (int)c->h_ia[(size_t)t * c->ntypes + t].geotype[0] : 0;
     }
-    if (c->sweep_acc_cap < c->ncells) {
+    if (c->sweep_acc_cap < c->ncells) {        // [0, ncells): single-particle passes, [ncells, 2 ncells): chain passes
         cudaFree(c->d_sweep_acc);
         c->d_sweep_acc = nullptr;
-        CK(cudaMalloc(&c->d_sweep_acc, (size_t)c->ncells * sizeof(SweepAcc)));
+        CK(cudaMalloc(&c->d_sweep_acc, (size_t)2 * c->ncells * sizeof(SweepAcc)));
         c->sweep_acc_cap = c->ncells;
     }
-    CK(cudaMemsetAsync(c->d_sweep_acc, 0, (size_t)c->ncells * sizeof(SweepAcc), c->stream));
-    if (stats) CK(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->d_sweep_acc, 0, (size_t)2 * c->ncells * sizeof(SweepAcc), c->stream));
+    SweepAcc* d_chain_acc = (SweepAcc*)c->d_sweep_acc + c->sweep_acc_cap;
+    if (stats || cstats) CK(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
     DevSys s = view(c);
     int nactive = (c->nc[0] / ncol.x) * (c->nc[1] / ncol.y) * (c->nc[2] / ncol.z);
     for (int k = 0; k < ncolours; k++) {
         if (c->rods_only) k_sweep_colour<true><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags);
         else k_sweep_colour<false><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags);
         c->launches++;
+        if (chains) {
+            k_sweep_chain_colour<<<nactive, CH_THREADS, 0, c->stream>>>(s, cp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, d_chain_acc);
+            c->launches++;
+        }
     }
     CK(cudaGetLastError());
     c->api_stale = true;           // the cell-sorted arrays are now the newest copy of the configuration
     c->h_cell_of.clear();
-    if (!stats) return SCGPU_OK;       // asynchronous form: nothing is read back; a too-dense cell is reported by the next call with stats / scgpu_sync
+    if (!stats && !cstats) return SCGPU_OK;       // asynchronous form: nothing is read back; a too-dense cell is reported by the next call with stats / scgpu_sync
     int* hfail = (int*)(c->h_small + 256 + 128);
-    std::vector<SweepAcc> acc(c->ncells);
+    std::vector<SweepAcc> acc(c->ncells), cacc(chains ? c->ncells : 0);
     CK(cudaMemcpyAsync(hfail, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(acc.data(), c->d_sweep_acc, (size_t)c->ncells * sizeof(SweepAcc), cudaMemcpyDeviceToHost, c->stream));
+    if (chains) CK(cudaMemcpyAsync(cacc.data(), d_chain_acc, (size_t)c->ncells * sizeof(SweepAcc), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (cstats) {
+        memset(cstats, 0, sizeof *cstats);
+        for (size_t i = 0; i < cacc.size(); i++) {       // fixed order
+            cstats->chainm_acc += cacc[i].trans_acc; cstats->chainm_rej += cacc[i].trans_rej;
+            cstats->chainr_acc += cacc[i].rot_acc; cstats->chainr_rej += cacc[i].rot_rej;
+            cstats->cell_rej += cacc[i].cell_rej; cstats->energy_delta += cacc[i].de;
+        }
+    }
     if (*hfail) { g_err = "scgpu_sweep_checkerboard: a cell neighbourhood holds more particles than the staged tile (SW_TILE); configuration too dense for this build"; return SCGPU_ERR_STATE; }
     if (stats) {
         memset(stats, 0, sizeof *stats);

@@ -21,6 +21,7 @@ struct SweepParams {
     double rot_angle[40];
     int n_sub;
     int geotype_of_type[40];
+    double trial_scale;             // share of the sweep's trials that are single-particle moves (1 - chainprob)
 };
 
 struct SweepAcc {      // per cell, written once per colour pass (summed on the host side in a fixed order)
@@ -173,7 +174,7 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
     // holds, and all blocks of a pass finish together instead of waiting for the fullest cell
     int ntrial;
     {
-        const double avg = (double)sp.n_sub * (double)s.n / (double)s.cell_start[s.ncells + 1];
+        const double avg = sp.trial_scale * (double)sp.n_sub * (double)s.n / (double)s.cell_start[s.ncells + 1];
         const uint4 r = philox4x32((uint32_t)sweep, (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 28), (uint32_t)c0, 0xffffffffu, (uint32_t)seed, (uint32_t)(seed >> 32));
         const double fl = floor(avg);
         ntrial = (int)fl + (u01(r.x, r.y) < avg - fl ? 1 : 0);
@@ -383,3 +384,204 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
     if (threadIdx.x == 0) acc_out[c0] = acc;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Chain moves on the device: MoveCreator::chainMove / chainDisplace / chainRotate /
+// clusterRotate / clusterCM (scOOP/mc/movecreator.cpp:304-328, 1075-1256, 1308-1392) as checkerboard passes.
+// A trial picks a uniformly random particle of the active cell and moves the WHOLE molecule it belongs to: with p = 1/2 a
+// displacement of fixed length chainm[molType].mx in a uniform direction, else a rotation by chainr[molType].angle * u about a
+// uniform axis through the volume-weighted centre (all ten vectors of every member turn, positions in real units, exactly as
+// clusterRotate does). Energy before and after is mol2others (totalenergycalculator.h:436-494): every member against every
+// NON-member, with an empty connectivity list; the intramolecular terms do not change under a rigid move. Acceptance is
+// moveTry. The independence argument of the checkerboard needs every member of the molecule inside the active cell before
+// AND after the move, otherwise the trial is rejected (the grid is re-drawn with a random shift every sweep, so every
+// molecule that fits into a cell is mobile). A molecule is picked with probability (members in the cell) / (cell population)
+// in both directions of a move -- detailed balance holds; particles of one-particle molecules make the trial a no-op.
+// Chain passes are separate launches between the single-particle passes of the same sweep: a composition of moves that
+// each satisfy detailed balance. Validated by the energy-drift identity, rigid-body invariants and against <E> of the
+// reference's sequential sweeps with chainprob > 0.
+// ------------------------------------------------------------------------------------------------
+constexpr int CH_MAX = 20;          // MAXCHL (scOOP/structures/macros.h:62)
+constexpr int CH_THREADS = 128;
+constexpr int CH_MAXMT = 32;        // molecule types with their own chain step sizes
+
+struct ChainParams {
+    double temper;
+    double total_trials;            // expected chain trials of the whole sweep (chainprob * n_sub * N), spread evenly over the non-empty cells
+    double chainm_mx[CH_MAXMT];     // stat.chainm[molType].mx (= 2 * chainmmx, sim.h:366)
+    double chainr_angle[CH_MAXMT];  // stat.chainr[molType].angle (radians, sim.h:362)
+};
+
+__global__ void __launch_bounds__(CH_THREADS)
+k_sweep_chain_colour(DevSys s, ChainParams cp, unsigned long long seed, unsigned long long sweep, int colour, int3 ncol,
+                     double4* posw, double* rec, SweepAcc* acc_out) {
+    __shared__ double sh_old[CH_MAX][REC], sh_new[CH_MAX][REC];
+    __shared__ int sh_mslot[CH_MAX], sh_mtype[CH_MAX];
+    __shared__ double sh_red[2][CH_THREADS / 32];
+    __shared__ int sh_b[28], sh_off[28];
+    __shared__ double sh_u[8];
+    __shared__ double sh_rot[9], sh_cm[3];
+    __shared__ int sh_ok, sh_accept;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ax = s.nc[0] / ncol.x, ay = s.nc[1] / ncol.y;
+    const int bx = blockIdx.x % ax, by = (blockIdx.x / ax) % ay, bz = blockIdx.x / (ax * ay);
+    const int cx = bx * ncol.x + (colour % ncol.x), cy = by * ncol.y + ((colour / ncol.x) % ncol.y), cz = bz * ncol.z + (colour / (ncol.x * ncol.y));
+    const int c0 = (cz * s.nc[1] + cy) * s.nc[0] + cx;
+    const int tb = s.cell_start[c0], te = s.cell_start[c0 + 1];
+    const int npart = te - tb;
+    SweepAcc acc = {0, 0, 0, 0, 0, 0, 0.0};
+    if (npart == 0) { if (threadIdx.x == 0) acc_out[c0] = acc; return; }
+    const int nx = s.nc[0] == 1 ? 1 : 3, ny = s.nc[1] == 1 ? 1 : 3, nz = s.nc[2] == 1 ? 1 : 3;
+    const int ncell_nb = nx * ny * nz;
+    if (wid == 0) {
+        int len = 0, b = 0;
+        if (lane < ncell_nb) {
+            int dx = lane % nx, dy = (lane / nx) % ny, dz = lane / (nx * ny);
+            int ccx = nx == 1 ? 0 : (cx + dx - 1 + s.nc[0]) % s.nc[0];
+            int ccy = ny == 1 ? 0 : (cy + dy - 1 + s.nc[1]) % s.nc[1];
+            int ccz = nz == 1 ? 0 : (cz + dz - 1 + s.nc[2]) % s.nc[2];
+            int c = (ccz * s.nc[1] + ccy) * s.nc[0] + ccx;
+            b = s.cell_start[c];
+            len = s.cell_start[c + 1] - b;
+        }
+        if (lane < 28) { sh_b[lane] = b; sh_off[lane] = len; }
+    }
+    __syncthreads();
+    int ntrial;
+    {
+        const uint4 r = philox4x32((uint32_t)sweep, (uint32_t)(sweep >> 32) ^ ((uint32_t)(colour | 8) << 28), (uint32_t)c0, 0xffffffffu, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double avg = cp.total_trials / (double)s.cell_start[s.ncells + 1];
+        const double fl = floor(avg);
+        ntrial = (int)fl + (u01(r.x, r.y) < avg - fl ? 1 : 0);
+    }
+    ConList cl;        // mol2others evaluates with an EMPTY connectivity list (totalenergycalculator.h:442-446)
+    cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0;
+    for (int trial = 0; trial < ntrial; trial++) {
+        __syncthreads();
+        if (threadIdx.x < 3) {      // Philox counter = (sweep, colour | chain flag, cell, 3 * trial + k)
+            const uint4 r = philox4x32((uint32_t)sweep, (uint32_t)(sweep >> 32) ^ ((uint32_t)(colour | 8) << 28), (uint32_t)c0, (uint32_t)(3 * trial + threadIdx.x),
+                                       (uint32_t)seed, (uint32_t)(seed >> 32));
+            sh_u[2 * threadIdx.x] = u01(r.x, r.y);
+            sh_u[2 * threadIdx.x + 1] = u01(r.z, r.w);
+        }
+        __syncthreads();
+        int pick = tb + (int)(sh_u[0] * npart);
+        if (pick >= te) pick = te - 1;
+        const double4 ppw = posw[pick];
+        const int moltype = w_moltype(ppw.w);
+        const scgpu_molparam& mpar = s.mol[moltype];
+        const int m = (int)mpar.mol_size;
+        if (m <= 1 || m > CH_MAX) continue;        // block-uniform: not a chain (or longer than the reference allows)
+        const int mfirst = (int)mpar.first + ((w_orig(ppw.w) - (int)mpar.first) / m) * m;
+        const bool displace = sh_u[1] < 0.5;
+        const double u_acc = sh_u[1] < 0.5 ? 2.0 * sh_u[1] : 2.0 * sh_u[1] - 1.0;
+        // ---- members: records into shared memory (old and new copy)
+        if (threadIdx.x < m) {
+            const int sl = s.slot_of[mfirst + threadIdx.x];
+            sh_mslot[threadIdx.x] = sl;
+            sh_mtype[threadIdx.x] = w_type(posw[sl].w);
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < m * REC; idx += blockDim.x) {
+            const int k = idx / REC, f = idx % REC;
+            const double v = rec[(size_t)sh_mslot[k] * REC + f];
+            sh_old[k][f] = v; sh_new[k][f] = v;
+        }
+        __syncthreads();
+        // ---- proposal
+        if (threadIdx.x == 0) {
+            const double z = 1.0 - 2.0 * sh_u[2], phi = 6.283185307179586476925 * sh_u[3];
+            const double rr = sqrt(fmax(0.0, 1.0 - z * z));
+            const v3 ax3 = mk(rr * cos(phi), rr * sin(phi), z);
+            if (displace) {           // chainDisplace (movecreator.cpp:1091-1094)
+                const double mx = cp.chainm_mx[moltype];
+                sh_cm[0] = ax3.x * mx / s.box[0]; sh_cm[1] = ax3.y * mx / s.box[1]; sh_cm[2] = ax3.z * mx / s.box[2];
+            } else {                  // clusterCM (:1323-1337) + the quaternion of clusterRotate (:1347-1353)
+                double cmx = 0.0, cmy = 0.0, cmz = 0.0, vol = 0.0;
+                for (int k = 0; k < m; k++) {
+                    const double v = s.ia[sh_mtype[k] * s.ntypes + sh_mtype[k]].reserved[2];
+                    cmx += sh_old[k][R_POS] * v; cmy += sh_old[k][R_POS + 1] * v; cmz += sh_old[k][R_POS + 2] * v;
+                    vol += v;
+                }
+                sh_cm[0] = cmx / vol; sh_cm[1] = cmy / vol; sh_cm[2] = cmz / vol;
+                double d[9];
+                rotation_coefficients(d, cp.chainr_angle[moltype] * sh_u[4], ax3, sh_u[5] < 0.5);
+                for (int k = 0; k < 9; k++) sh_rot[k] = d[k];
+            }
+        }
+        __syncthreads();
+        if (displace) {
+            if (threadIdx.x < 3 * m) sh_new[threadIdx.x / 3][R_POS + threadIdx.x % 3] += sh_cm[threadIdx.x % 3];
+        } else {
+            for (int idx = threadIdx.x; idx < 10 * m; idx += blockDim.x) {
+                const int k = idx / 10, v = idx % 10;
+                if (v < 9) rotate_vector(&sh_new[k][3 * v], sh_rot);       // dir, patchdir[2], patchsides[4], chdir[2]: all of them, as clusterRotate does
+                else {
+                    double p[3] = {(sh_old[k][R_POS] - sh_cm[0]) * s.box[0], (sh_old[k][R_POS + 1] - sh_cm[1]) * s.box[1], (sh_old[k][R_POS + 2] - sh_cm[2]) * s.box[2]};
+                    rotate_vector(p, sh_rot);
+                    sh_new[k][R_POS] = p[0] / s.box[0] + sh_cm[0]; sh_new[k][R_POS + 1] = p[1] / s.box[1] + sh_cm[1]; sh_new[k][R_POS + 2] = p[2] / s.box[2] + sh_cm[2];
+                }
+            }
+        }
+        if (threadIdx.x == 0) sh_ok = 1;
+        __syncthreads();
+        if (threadIdx.x < 2 * m) {      // every member inside the active cell, before and after
+            const double* r = (threadIdx.x < m) ? sh_old[threadIdx.x] : sh_new[threadIdx.x - m];
+            if (cell_index(r + R_POS, s.shift, s.nc) != c0) sh_ok = 0;
+        }
+        __syncthreads();
+        const bool in_cell = sh_ok != 0;
+        double eo = 0.0, en = 0.0;
+        if (in_cell) {
+            for (int seg = 0; seg < ncell_nb; seg++) {
+                const int b = sh_b[seg], len = sh_off[seg];
+                for (int i = threadIdx.x; i < len; i += blockDim.x) {
+                    const int slot = b + i;
+                    const double4 pw = posw[slot];
+                    const int orig = w_orig(pw.w);
+                    if (orig >= mfirst && orig < mfirst + m) continue;
+                    const v3 pc = mk(pw.x, pw.y, pw.z);
+                    const int type2 = w_type(pw.w);
+                    for (int k = 0; k < m; k++) {
+                        v3 r = image(s.box, ld3(&sh_old[k][R_POS]), pc);
+                        double d = dot(r, r);
+                        if (d <= s.sqmaxcut) eo += pair_energy_gated(s.box, s.ia, s.ntypes, s.mol, r, d, sh_old[k], sh_mtype[k], moltype, rec + (size_t)slot * REC, type2, orig, cl);
+                        r = image(s.box, ld3(&sh_new[k][R_POS]), pc);
+                        d = dot(r, r);
+                        if (d <= s.sqmaxcut) en += pair_energy_gated(s.box, s.ia, s.ntypes, s.mol, r, d, sh_new[k], sh_mtype[k], moltype, rec + (size_t)slot * REC, type2, orig, cl);
+                    }
+                }
+            }
+        }
+        eo = warp_sum(eo); en = warp_sum(en);
+        if (lane == 0) { sh_red[0][wid] = eo; sh_red[1][wid] = en; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bool accept = false;
+            double de = 0.0;
+            if (in_cell) {
+                double a = 0.0, b2 = 0.0;
+                for (int k = 0; k < CH_THREADS / 32; k++) { a += sh_red[0][k]; b2 += sh_red[1][k]; }      // fixed order
+                de = b2 - a;
+                accept = (de <= 0.0) || (exp(-de / cp.temper) > u_acc);       // moveTry (movecreator.h:175-187)
+            } else acc.cell_rej++;
+            if (accept) acc.de += de;
+            if (displace) { if (accept) acc.trans_acc++; else acc.trans_rej++; }
+            else { if (accept) acc.rot_acc++; else acc.rot_rej++; }
+            sh_accept = accept ? 1 : 0;
+        }
+        __syncthreads();
+        if (sh_accept) {
+            for (int idx = threadIdx.x; idx < m * REC; idx += blockDim.x) {
+                const int k = idx / REC, f = idx % REC;
+                rec[(size_t)sh_mslot[k] * REC + f] = sh_new[k][f];
+            }
+            if (threadIdx.x < m) {
+                const int sl = sh_mslot[threadIdx.x];
+                const double w = posw[sl].w;
+                posw[sl] = make_double4(sh_new[threadIdx.x][R_POS], sh_new[threadIdx.x][R_POS + 1], sh_new[threadIdx.x][R_POS + 2], w);
+            }
+        }
+    }
+    if (threadIdx.x == 0) acc_out[c0] = acc;
+}

@@ -32,11 +32,20 @@ class SweepStats(C.Structure):
                 ("cell_rej", C.c_int64), ("energy_delta", C.c_double)]
 
 
+class ChainMoves(C.Structure):
+    _fields_ = [("chainprob", C.c_double), ("chainm_mx", C.c_double * 32), ("chainr_angle", C.c_double * 32)]
+
+
+class ChainStats(C.Structure):
+    _fields_ = [("chainm_acc", C.c_int64), ("chainm_rej", C.c_int64), ("chainr_acc", C.c_int64), ("chainr_rej", C.c_int64),
+                ("cell_rej", C.c_int64), ("energy_delta", C.c_double)]
+
+
 SYMBOLS = ["scgpu_last_error", "scgpu_device_count", "scgpu_create", "scgpu_destroy", "scgpu_set_topology",
            "scgpu_set_particles", "scgpu_set_particles_compact", "scgpu_set_box", "scgpu_update_particle", "scgpu_download_particles",
            "scgpu_build_cells", "scgpu_cell_assignment", "scgpu_cell_order", "scgpu_one_to_all",
            "scgpu_one_to_all_batch", "scgpu_one_to_all_everyone", "scgpu_submit_everyone", "scgpu_mol_to_others", "scgpu_all_to_all",
-           "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_replica_record",
+           "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_sweep_checkerboard_chains", "scgpu_replica_record",
            "scgpu_timer_start", "scgpu_timer_stop", "scgpu_sync", "scgpu_fp64_peak", "scgpu_flush_l2",
            "scgpu_kernel_launches"]
 
@@ -73,6 +82,8 @@ def load_library(variant="fast"):
     L.scgpu_overlap_one.argtypes = [vp, C.c_int, _dp, C.c_int, _ip]
     L.scgpu_overlap_all.argtypes = [vp, C.c_int, _ip]
     L.scgpu_sweep_checkerboard.argtypes = [vp, C.POINTER(MoveParams), C.c_uint64, C.c_uint64, C.POINTER(SweepStats)]
+    L.scgpu_sweep_checkerboard_chains.argtypes = [vp, C.POINTER(MoveParams), C.POINTER(ChainMoves), C.c_uint64, C.c_uint64,
+                                                  C.POINTER(SweepStats), C.POINTER(ChainStats)]
     L.scgpu_replica_record.argtypes = [vp, C.POINTER(vp)]
     L.scgpu_timer_start.argtypes = [vp]
     L.scgpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
@@ -246,6 +257,15 @@ class Engine:
         st = SweepStats()
         self._ck(self.L.scgpu_sweep_checkerboard(self.h, C.byref(mp), int(seed), int(sweep), C.byref(st)))
         return st
+
+    def sweep_chains(self, mp, cm, seed, sweep, stats=True):
+        """one checkerboard sweep in which a share cm.chainprob of the trials are chain moves -> (SweepStats, ChainStats)"""
+        if not stats:
+            self._ck(self.L.scgpu_sweep_checkerboard_chains(self.h, C.byref(mp), C.byref(cm), int(seed), int(sweep), None, None))
+            return None
+        st, cst = SweepStats(), ChainStats()
+        self._ck(self.L.scgpu_sweep_checkerboard_chains(self.h, C.byref(mp), C.byref(cm), int(seed), int(sweep), C.byref(st), C.byref(cst)))
+        return st, cst
 
     def replica_record_ptr(self):
         p = C.c_void_p()

@@ -126,6 +126,46 @@ D 500
             p = _perp(rnd, d)
             lines.append(_fmt(pos) + "   " + _fmt(d) + "   " + _fmt(p) + " 0")
         return top, "\n".join(lines) + "\n"
+    if kind == "chain_fluid":
+        # 480 bonded SPN-SPA-SPA trimers + 160 PSC rods on a lattice without overlaps: the system of the chain-move sweep tests
+        top = """[Types]
+H2 2 SPN    1.0 0.95
+T3 3 SPA    1.0 1.0 1.12246205 0.6
+Q4 4 PSC    1.0 1.2 1.346954458 0.3 120 5.0 3 0.3
+[Molecules]
+B: {
+bond1: 10.0 1.0
+particles: 2
+particles: 3
+particles: 3
+}
+E: {
+particles: 4
+}
+[System]
+B 480
+E 160
+"""
+        box = (26.0, 25.6, 33.0)
+        sx, sy, sz = box[0] / 8, box[1] / 8, box[2] / 10
+        rods, trimers = [], []
+        for iz in range(10):
+            for iy in range(8):
+                for ix in range(8):
+                    c = ((ix + 0.5) * sx, (iy + 0.5) * sy, (iz + 0.5) * sz)
+                    if (ix + iy) % 2 == 0 and iz % 2 == 0:
+                        rods.append(c)
+                    else:
+                        trimers.append(c)
+        lines = [_fmt(box)]
+        for c in trimers:
+            for k in (-1, 0, 1):
+                pos = (c[0] + k * 1.0, c[1], c[2])
+                lines.append(_fmt(pos) + "   " + _fmt((0.0, 0.0, 1.0)) + "   " + _fmt((1.0, 0.0, 0.0)) + " 0")
+        for c in rods:
+            az = rnd.uniform(0.0, 2.0 * math.pi)
+            lines.append(_fmt(c) + "   " + _fmt((0.0, 1.0, 0.0)) + "   " + _fmt((math.cos(az), 0.0, math.sin(az))) + " 0")
+        return top, "\n".join(lines) + "\n"
     if kind == "mix":
         top = """[Types]
 S1 1 SPA    1.333333  1.2  1.346954458  0.3

@@ -161,3 +161,146 @@ def test_dense_membrane_sweeps_fall_back_to_global_scan():
     assert acc > 0
     assert abs((e1 - e0) - tot) <= 1e-9 * max(abs(e0), abs(e1)), (e0, e1, tot)
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# chain moves on the device (scOOP/mc/movecreator.cpp:304-328, 1075-1256, 1308-1392)
+# ------------------------------------------------------------------------------------------------
+def chain_moves(chainprob, chainmmx, chainrmx):
+    from sc_b200.engine import ChainMoves
+    cm = ChainMoves()
+    cm.chainprob = chainprob
+    for k in range(32):
+        cm.chainm_mx[k] = 2.0 * chainmmx                   # sim.h:366  chainmmx *= 2
+        cm.chainr_angle[k] = chainrmx / 180.0 * PIH        # sim.h:362
+    return cm
+
+
+def _molecules(hs):
+    """(first index, size) of every molecule, from the molecule-type table the engine itself uses"""
+    out, i = [], 0
+    while i < hs.n:
+        m = int(hs.mol[hs.moltype[i], 12])
+        out.append((i, m))
+        i += m
+    return out
+
+
+def _intramolecular(state, box, mols):
+    d = []
+    for first, m in mols:
+        for a in range(first, first + m):
+            for b in range(a + 1, first + m):
+                r = (state[a, 0:3] - state[b, 0:3]) * box      # chains live in unwrapped coordinates: no image
+                d.append(math.sqrt(float(np.dot(r, r))))
+            if m > 1:
+                d.append(float(np.dot(state[first, 3:6], state[first + 1, 3:6])))
+    return np.array(d)
+
+
+@pytest.mark.parametrize("kind", ["chain_fluid", "chains"])
+def test_chain_moves_only_are_rigid_and_keep_exact_books(kind):
+    """chainprob = 1: every trial is a chain move. Molecules move rigidly (all intramolecular distances and relative
+    orientations unchanged), the summed accepted dE equals the change of the recomputed total energy, and the oracle agrees on
+    the evolved configuration."""
+    top, cfg = synth.small_case(kind)
+    hs = HostSystem(top, cfg)
+    eng = Engine(0, "fast").load(hs)
+    mols = _molecules(hs)
+    assert any(m > 1 for _, m in mols)
+    s0 = eng.download_particles()
+    g0 = _intramolecular(s0, hs.box, mols)
+    e0 = eng.all_to_all()
+    mp = move_params(1.0, 0.1, 10.0)
+    cm = chain_moves(1.0, 0.2, 15.0)
+    tot, acc_m, acc_r, tried, cell_rej = 0.0, 0, 0, 0, 0
+    for sw in range(10):
+        st, cst = eng.sweep_chains(mp, cm, 4242, sw)
+        assert st.trans_acc + st.trans_rej + st.rot_acc + st.rot_rej == 0          # no single-particle trials at chainprob = 1
+        tot += cst.energy_delta
+        acc_m += cst.chainm_acc; acc_r += cst.chainr_acc
+        tried += cst.chainm_acc + cst.chainm_rej + cst.chainr_acc + cst.chainr_rej
+        cell_rej += cst.cell_rej
+    assert acc_m > 0 and acc_r > 0 and tried > 0
+    assert cell_rej < tried
+    e1 = eng.all_to_all()
+    assert abs((e1 - e0) - tot) <= 1e-9 * max(abs(e0), abs(e1), 1.0), (e0, e1, tot)
+    s1 = eng.download_particles()
+    assert np.max(np.abs(s1[:, 0:3] - s0[:, 0:3])) > 1e-3                             # something moved
+    g1 = _intramolecular(s1, hs.box, mols)
+    assert np.max(np.abs(g1 - g0)) < 1e-9, float(np.max(np.abs(g1 - g0)))
+    for i in range(hs.n):
+        g = int(hs.ia[hs.type[i], hs.type[i], 0])
+        if g < 30:
+            d = s1[i, 3:6]
+            assert abs(np.dot(d, d) - 1.0) < 1e-9
+    s = O.system_from_text(top, cfg)
+    s.state[:] = s1
+    for t in range(0, hs.n, max(1, hs.n // 16)):
+        a, b = eng.one_to_all(t), s.one_to_all(t)
+        assert abs(a - b) <= 1e-10 * max(abs(a), abs(b)) + 1e-10
+    eng.close()
+
+
+def test_mixed_sweeps_with_chain_moves_keep_exact_books_and_are_reproducible():
+    top, cfg = synth.small_case("chain_fluid")
+    hs = HostSystem(top, cfg)
+    finals = []
+    for rep in range(2):
+        eng = Engine(0, "fast").load(hs)
+        e0 = eng.all_to_all()
+        mp = move_params(1.0, 0.12, 15.0)
+        cm = chain_moves(0.3, 0.15, 12.0)
+        tot, n_part, n_chain = 0.0, 0, 0
+        for sw in range(8):
+            st, cst = eng.sweep_chains(mp, cm, 777, sw)
+            tot += st.energy_delta + cst.energy_delta
+            n_part += st.trans_acc + st.trans_rej + st.rot_acc + st.rot_rej
+            n_chain += cst.chainm_acc + cst.chainm_rej + cst.chainr_acc + cst.chainr_rej
+        e1 = eng.all_to_all()
+        assert abs((e1 - e0) - tot) <= 1e-9 * max(abs(e0), abs(e1), 1.0), (e0, e1, tot)
+        # the trial mix of Updater::simulate (updater.cpp:206-230): a share chainprob of the N trials of a sweep are chain moves;
+        # picks that land on a one-particle molecule (the rods: 160 of 1600 particles) are no-ops and not counted
+        assert abs(n_part - 0.7 * 8 * hs.n) <= 6.0 * math.sqrt(8 * hs.n) + 8
+        assert abs(n_chain - 0.3 * 8 * hs.n * 0.9) <= 6.0 * math.sqrt(8 * hs.n) + 8
+        finals.append(eng.download_particles())
+        eng.close()
+    assert np.array_equal(finals[0], finals[1])
+
+
+def test_average_energy_with_chain_moves_matches_reference_sequential_sweeps():
+    gold = json.load(open(os.path.join(G, "sweep_chain_fluid.json")))
+    P = gold["params"]
+    top, cfg = synth.small_case("chain_fluid")
+    hs = HostSystem(top, cfg)
+    skip = P["nsweeps"] // 3
+    ref_means, ref_errs = [], []
+    for run in gold["runs"]:
+        sw, e = np.array(run["sweep"]), np.array(run["energy"])
+        w = e[sw > skip]
+        ref_means.append(w.mean())
+        ref_errs.append(_block_stderr(w))
+    ref_mean = float(np.mean(ref_means))
+    ref_err = max(float(np.std(ref_means, ddof=1) / math.sqrt(len(ref_means))), float(np.mean(ref_errs)) / math.sqrt(len(ref_means)))
+    gpu_means, gpu_errs = [], []
+    for seed in (101, 202, 303, 404):
+        eng = Engine(0, "fast").load(hs)
+        mp = move_params(P["temper"], P["transmx"], P["rotmx"])
+        cm = chain_moves(P["chainprob"], P["chainmmx"], P["chainrmx"])
+        e = eng.all_to_all()
+        series = []
+        for sw in range(1, P["nsweeps"] + 1):
+            st, cst = eng.sweep_chains(mp, cm, seed, sw)
+            e += st.energy_delta + cst.energy_delta
+            if sw > skip and sw % P["report"] == 0:
+                series.append(e)
+        e_check = eng.all_to_all()
+        assert abs(e_check - e) <= 1e-7 * max(abs(e_check), 1.0)
+        gpu_means.append(np.mean(series))
+        gpu_errs.append(_block_stderr(series))
+        eng.close()
+    gpu_mean = float(np.mean(gpu_means))
+    gpu_err = max(float(np.std(gpu_means, ddof=1) / math.sqrt(len(gpu_means))), float(np.mean(gpu_errs)) / math.sqrt(len(gpu_means)))
+    sigma = math.sqrt(ref_err ** 2 + gpu_err ** 2)
+    print("reference <E> = %.3f +- %.3f ; checkerboard with chain moves <E> = %.3f +- %.3f" % (ref_mean, ref_err, gpu_mean, gpu_err))
+    assert abs(gpu_mean - ref_mean) <= 4.0 * sigma + 2e-3 * abs(ref_mean), (gpu_mean, ref_mean, sigma)
