@@ -449,7 +449,7 @@ def run_ours(args):
         # the reference's sweep = N trials, each one trial-energy evaluation over its neighbour list (old energies are cached in its
         # energy matrix): derived from the measured pair rate, labelled as such
         out["secondary"]["cpu_reference_derived_sweeps_per_s"] = cpu["value"] / (float(ngate))
-    print(json.dumps(out))
+    print(json.dumps(out), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -477,7 +477,10 @@ def run_reference(args):
            "data": "synthetic", "config": {"workload": WORKLOAD, "particles_per_replica": 65536, "step_sample": cb["sample"]},
            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    print(json.dumps(out), file=_REAL_STDOUT, flush=True)
+
+
+_REAL_STDOUT = sys.stdout
 
 
 def main():
@@ -489,10 +492,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--with-membrane", action="store_true", help="also time the 265k-particle membrane full-energy pass (configs[2])")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries that write to file descriptor 1 on their own (NCCL prints its version banner
+    # there when NCCL_DEBUG is set) are sent to stderr for the duration of the run, the JSON line goes to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    _REAL_STDOUT.flush()
 
 
 if __name__ == "__main__":
