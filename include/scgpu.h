@@ -96,6 +96,7 @@ typedef struct scgpu_chainmoves {
 typedef struct scgpu_chainstats {
     int64_t chainm_acc, chainm_rej, chainr_acc, chainr_rej, cell_rej; /* cell_rej: a member outside the active cell before or after */
     double energy_delta;                                               /* sum of accepted dE */
+    int64_t noop;                                                      /* picks that landed on a one-particle molecule: no move */
 } scgpu_chainstats;
 
 const char* scgpu_last_error(void);

@@ -2175,7 +2175,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     memset(&cp, 0, sizeof cp);
     if (chains) {
         cp.temper = mp->temper;
-        cp.total_trials = cm->chainprob * (double)mp->n_sub * (double)c->n;
+        cp.trials_per_particle = cm->chainprob * (double)mp->n_sub;
         for (int t = 0; t < CH_MAXMT; t++) { cp.chainm_mx[t] = cm->chainm_mx[t]; cp.chainr_angle[t] = cm->chainr_angle[t]; }
     }
     for (int t = 0; t < 40; t++) {
@@ -2218,7 +2218,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
         for (size_t i = 0; i < cacc.size(); i++) {       // fixed order
             cstats->chainm_acc += cacc[i].trans_acc; cstats->chainm_rej += cacc[i].trans_rej;
             cstats->chainr_acc += cacc[i].rot_acc; cstats->chainr_rej += cacc[i].rot_rej;
-            cstats->cell_rej += cacc[i].cell_rej; cstats->energy_delta += cacc[i].de;
+            cstats->cell_rej += cacc[i].cell_rej; cstats->energy_delta += cacc[i].de; cstats->noop += cacc[i].pad;
         }
     }
     if (*hfail) { g_err = "scgpu_sweep_checkerboard: a cell neighbourhood holds more particles than the staged tile (SW_TILE); configuration too dense for this build"; return SCGPU_ERR_STATE; }

@@ -396,7 +396,8 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
 // moveTry. The independence argument of the checkerboard needs every member of the molecule inside the active cell before
 // AND after the move, otherwise the trial is rejected (the grid is re-drawn with a random shift every sweep, so every
 // molecule that fits into a cell is mobile). A molecule is picked with probability (members in the cell) / (cell population)
-// in both directions of a move -- detailed balance holds; particles of one-particle molecules make the trial a no-op.
+// in both directions of a move -- detailed balance holds; particles of one-particle molecules make the trial a no-op
+// (counted in scgpu_chainstats::noop).
 // Chain passes are separate launches between the single-particle passes of the same sweep: a composition of moves that
 // each satisfy detailed balance. Validated by the energy-drift identity, rigid-body invariants and against <E> of the
 // reference's sequential sweeps with chainprob > 0.
@@ -407,7 +408,7 @@ constexpr int CH_MAXMT = 32;        // molecule types with their own chain step 
 
 struct ChainParams {
     double temper;
-    double total_trials;            // expected chain trials of the whole sweep (chainprob * n_sub * N), spread evenly over the non-empty cells
+    double trials_per_particle;     // chainprob * n_sub: a cell performs (this x its population) trials, stochastically rounded
     double chainm_mx[CH_MAXMT];     // stat.chainm[molType].mx (= 2 * chainmmx, sim.h:366)
     double chainr_angle[CH_MAXMT];  // stat.chainr[molType].angle (radians, sim.h:362)
 };
@@ -450,7 +451,9 @@ k_sweep_chain_colour(DevSys s, ChainParams cp, unsigned long long seed, unsigned
     int ntrial;
     {
         const uint4 r = philox4x32((uint32_t)sweep, (uint32_t)(sweep >> 32) ^ ((uint32_t)(colour | 8) << 28), (uint32_t)c0, 0xffffffffu, (uint32_t)seed, (uint32_t)(seed >> 32));
-        const double avg = cp.total_trials / (double)s.cell_start[s.ncells + 1];
+        // proportional to the cell population (constant during a pass: no particle leaves its cell), so that cells holding only
+        // one-particle molecules do not burn trials on no-ops
+        const double avg = cp.trials_per_particle * (double)npart;
         const double fl = floor(avg);
         ntrial = (int)fl + (u01(r.x, r.y) < avg - fl ? 1 : 0);
     }
@@ -471,7 +474,7 @@ k_sweep_chain_colour(DevSys s, ChainParams cp, unsigned long long seed, unsigned
         const int moltype = w_moltype(ppw.w);
         const scgpu_molparam& mpar = s.mol[moltype];
         const int m = (int)mpar.mol_size;
-        if (m <= 1 || m > CH_MAX) continue;        // block-uniform: not a chain (or longer than the reference allows)
+        if (m <= 1 || m > CH_MAX) { if (threadIdx.x == 0) acc.pad++; continue; }        // block-uniform: not a chain (or longer than the reference allows)
         const int mfirst = (int)mpar.first + ((w_orig(ppw.w) - (int)mpar.first) / m) * m;
         const bool displace = sh_u[1] < 0.5;
         const double u_acc = sh_u[1] < 0.5 ? 2.0 * sh_u[1] : 2.0 * sh_u[1] - 1.0;

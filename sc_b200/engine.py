@@ -38,7 +38,7 @@ class ChainMoves(C.Structure):
 
 class ChainStats(C.Structure):
     _fields_ = [("chainm_acc", C.c_int64), ("chainm_rej", C.c_int64), ("chainr_acc", C.c_int64), ("chainr_rej", C.c_int64),
-                ("cell_rej", C.c_int64), ("energy_delta", C.c_double)]
+                ("cell_rej", C.c_int64), ("energy_delta", C.c_double), ("noop", C.c_int64)]
 
 
 SYMBOLS = ["scgpu_last_error", "scgpu_device_count", "scgpu_create", "scgpu_destroy", "scgpu_set_topology",

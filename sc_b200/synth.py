@@ -316,3 +316,69 @@ def membrane(tiles_x, tiles_y, top_text, config_text):
         top.append(l)
     n = len(parts) * nt
     return "\n".join(top) + "\n", "\n".join(out) + "\n", n
+
+
+def tile(top_text, config_text, kx, ky, kz):
+    """Replicate ANY (top.init, config.init) pair kx x ky x kz times (SURVEY.md 8(d) "X": Tests/test_14 and Tests/test_20 tiled
+    12^3 -> 65 664 / 69 120 particles). Particles stay grouped by the molecule blocks of [System], so molecule indices,
+    chain positions and connectivity lists of every copy are those of the original. Returns (top_text, config_text, n)."""
+    lines = [l for l in config_text.split("\n") if l.strip()]
+    box = [float(x) for x in lines[0].split()[:3]]
+    parts = [l.split() for l in lines[1:]]
+    # molecule sizes from [Molecules], block counts from [System]
+    sizes, counts, order = {}, [], []
+    section, cur = "", None
+    for l in top_text.split("\n"):
+        s_ = l.split("#")[0].strip()
+        if not s_:
+            continue
+        if s_.startswith("["):
+            section = s_.upper()
+            continue
+        if section.startswith("[MOLECULES]"):
+            if s_.endswith("{"):
+                cur = s_.split(":")[0].strip()
+                sizes[cur] = 0
+            elif s_.startswith("}"):
+                cur = None
+            elif cur is not None and s_.lower().startswith("particles"):
+                sizes[cur] += 1
+        elif section.startswith("[SYSTEM]"):
+            name, cnt = s_.split()[:2]
+            counts.append((name, int(cnt)))
+    out = [_fmt((box[0] * kx, box[1] * ky, box[2] * kz))]
+    at = 0
+    for name, cnt in counts:
+        blk = [list(t) for t in parts[at:at + cnt * sizes[name]]]
+        at += cnt * sizes[name]
+        # config files hold positions wrapped into the box: bring every chain member next to its predecessor first, otherwise a
+        # bond that crosses the boundary of the small box would be stretched over it in the large one
+        for m0 in range(0, len(blk), sizes[name]):
+            for k in range(m0 + 1, m0 + sizes[name]):
+                for d in range(3):
+                    delta = float(blk[k][d]) - float(blk[k - 1][d])
+                    blk[k][d] = repr(float(blk[k][d]) - box[d] * round(delta / box[d]))
+        for tz in range(kz):
+            for ty in range(ky):
+                for tx in range(kx):
+                    for t in blk:
+                        v = [float(x) for x in t[:9]]
+                        v[0] += tx * box[0]; v[1] += ty * box[1]; v[2] += tz * box[2]
+                        out.append(_fmt(v[0:3]) + "   " + _fmt(v[3:6]) + "   " + _fmt(v[6:9]) + " 0")
+    assert at == len(parts), "config.init does not match the [System] block of top.init"
+    nt = kx * ky * kz
+    top, in_system = [], False
+    for l in top_text.split("\n"):
+        s_ = l.split("#")[0].strip()
+        if s_.upper().startswith("[SYSTEM]"):
+            in_system = True
+            top.append(l)
+            continue
+        if in_system and s_ and not s_.startswith("["):
+            name, cnt = s_.split()[:2]
+            top.append("%s %d" % (name, int(cnt) * nt))
+            continue
+        if s_.startswith("["):
+            in_system = False
+        top.append(l)
+    return "\n".join(top) + "\n", "\n".join(out) + "\n", len(parts) * nt

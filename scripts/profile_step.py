@@ -21,6 +21,12 @@ if what.startswith("membrane"):                       # BASELINE configs[2]: 265
     import json
     inp = json.loads(gzip.open(os.path.join(ROOT, "tests", "golden", "membrane601.inputs.json.gz")).read().decode())
     top, cfg, n = synth.membrane(21, 21, inp["top.init"], inp["config.init"])
+elif what.startswith("mix14") or what.startswith("chains20"):          # BASELINE configs[3] tiled 12^3
+    import json
+    name = "test_14_normal_SPA_PSC_CPSC" if what.startswith("mix14") else "test_20_chain_bond12"
+    inp = json.load(open(os.path.join(ROOT, "tests", "golden", name + ".inputs.json")))
+    top, cfg, n = synth.tile(inp["top.init"], inp["config.init"], 12, 12, 12)
+    what = "everyone"
 else:
     top, cfg, n = synth.psc_bulk()
 hs = HostSystem(top, cfg)
@@ -43,8 +49,31 @@ for _ in range(reps):
             mp.rot_angle[k] = 7.5 / 180.0 * 1.5707963267948966 * 0.5
         mp.n_sub = 1
         eng.sweep(mp, 12345, _)
+    elif what == "membrane_chainsweep":               # configs[2] with the reference's move mix for lipids: chain moves of whole 3-bead molecules
+        from sc_b200.engine import MoveParams, ChainMoves
+        mp = MoveParams()
+        mp.temper = 1.0
+        cm = ChainMoves()
+        cm.chainprob = 0.5
+        for k in range(40):
+            mp.trans_mx[k] = 0.1
+            mp.rot_angle[k] = 10.0 / 180.0 * 1.5707963267948966 * 0.5
+        for k in range(32):
+            cm.chainm_mx[k] = 0.2
+            cm.chainr_angle[k] = 10.0 / 180.0 * 1.5707963267948966
+        mp.n_sub = 1
+        st, cst = eng.sweep_chains(mp, cm, 4242, _)
+        print("sweep", _, "particle acc/rej", st.trans_acc + st.rot_acc, st.trans_rej + st.rot_rej, "chain acc/rej", cst.chainm_acc + cst.chainr_acc,
+              cst.chainm_rej + cst.chainr_rej, "chain cell_rej", cst.cell_rej)
 eng.sync()
 print("done", what, reps)
+if what == "membrane_chainsweep":
+    import time
+    t0 = time.perf_counter()
+    for k in range(reps, reps + 3):
+        eng.sweep_chains(mp, cm, 4242, k)
+    eng.sync()
+    print("ms_per_sweep %.3f (N = %d, chainprob 0.5)" % ((time.perf_counter() - t0) / 3 * 1e3, n))
 if what in ("everyone", "all_to_all"):                # device time per pass (not under a profiler)
     ms = []
     for k in range(20):

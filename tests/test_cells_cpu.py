@@ -53,3 +53,19 @@ def test_small_box_degrades_to_one_cell():
     assert cells[0].tolist() == [1, 1, 1]
     for t in range(s.n):
         assert s.one_to_all_cells(t, cells)[0] == r.one[t]
+
+
+def test_tiler_keeps_energy_per_copy():
+    """synth.tile (configs[3] at throughput size): a periodic 2 x 2 x 2 replication has 8 times the energy of the original,
+    also for bonded chains whose members sit on opposite sides of the small box"""
+    import json
+    import os
+    from oracle import oracle as O
+    from sc_b200 import synth
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name in ("test_14_normal_SPA_PSC_CPSC", "test_20_chain_bond12"):
+        inp = json.load(open(os.path.join(g, name + ".inputs.json")))
+        top, cfg, n = synth.tile(inp["top.init"], inp["config.init"], 2, 2, 2)
+        s1, s2 = O.system_from_text(inp["top.init"], inp["config.init"]), O.system_from_text(top, cfg)
+        assert s2.n == 8 * s1.n == n
+        assert abs(s2.all_to_all() - 8 * s1.all_to_all()) <= 1e-6 * abs(s2.all_to_all())

@@ -1,6 +1,7 @@
 """GPU: the BASELINE.json configurations at FULL size, checked through size-independent properties and sampled oracle
 comparisons (the oracle finishes a one-to-all over cell lists in microseconds even at 265 k particles):
   L  65 536 PSC bulk (configs[1])             M  265 041-particle CPSC + lipid membrane, NPT box changes (configs[2])
+  X  Tests/test_14 (SPA + PSC + CPSC) and Tests/test_20 (bonded TCPSC chains) tiled 12^3 -> 65 664 / 69 120 particles (configs[3])
 properties: cell ids / sort order bit-exact; sampled one-to-all energies <= 1e-10; sum of row sums == total;
 sum of all one-to-all energies == 2 x total (every pair is in exactly two of them); run-to-run bit reproducibility.
 """
@@ -93,3 +94,17 @@ def test_M_molecule_energies():
         f = first_lipid + 3 * k
         assert close(eng.mol_to_others(f, 3), s.mol_to_others(f, 3))
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["test_14_normal_SPA_PSC_CPSC", "test_20_chain_bond12"])
+def test_X_mixed_types_and_bonded_chains_tiled(name):
+    """BASELINE configs[3] at throughput size: every pair-potential branch (sphere-sphere, rod-sphere, PSC-CPSC) and bonded chains
+    (bond1 + bond2 along five-rod molecules) through the flat pipeline of the general (non rods-only) kernels"""
+    inp = json.load(open(os.path.join(G, name + ".inputs.json")))
+    top, cfg, n = synth.tile(inp["top.init"], inp["config.init"], 12, 12, 12)
+    assert n in (65664, 69120)
+    ncand, ngate, tot = _check_system(top, cfg, "fast", 96, box_scales=[(0.98, 0.98, 0.98)])
+    # periodic tiling: the total is 12^3 times the energy of the shipped configuration (coordinates are printed with 9 digits)
+    s0 = O.system_from_text(inp["top.init"], inp["config.init"])
+    assert abs(tot - 1728 * s0.all_to_all()) <= 1e-6 * abs(tot)
+    assert 0 < ngate <= ncand

@@ -251,18 +251,20 @@ def test_mixed_sweeps_with_chain_moves_keep_exact_books_and_are_reproducible():
         e0 = eng.all_to_all()
         mp = move_params(1.0, 0.12, 15.0)
         cm = chain_moves(0.3, 0.15, 12.0)
-        tot, n_part, n_chain = 0.0, 0, 0
+        tot, n_part, n_chain, n_noop = 0.0, 0, 0, 0
         for sw in range(8):
             st, cst = eng.sweep_chains(mp, cm, 777, sw)
             tot += st.energy_delta + cst.energy_delta
             n_part += st.trans_acc + st.trans_rej + st.rot_acc + st.rot_rej
             n_chain += cst.chainm_acc + cst.chainm_rej + cst.chainr_acc + cst.chainr_rej
+            n_noop += cst.noop
         e1 = eng.all_to_all()
         assert abs((e1 - e0) - tot) <= 1e-9 * max(abs(e0), abs(e1), 1.0), (e0, e1, tot)
         # the trial mix of Updater::simulate (updater.cpp:206-230): a share chainprob of the N trials of a sweep are chain moves;
         # picks that land on a one-particle molecule (the rods: 160 of 1600 particles) are no-ops and not counted
         assert abs(n_part - 0.7 * 8 * hs.n) <= 6.0 * math.sqrt(8 * hs.n) + 8
-        assert abs(n_chain - 0.3 * 8 * hs.n * 0.9) <= 6.0 * math.sqrt(8 * hs.n) + 8
+        assert abs(n_chain + n_noop - 0.3 * 8 * hs.n) <= 6.0 * math.sqrt(8 * hs.n) + 8
+        assert abs(n_noop - 0.3 * 8 * hs.n * 0.1) <= 6.0 * math.sqrt(8 * hs.n) + 8
         finals.append(eng.download_particles())
         eng.close()
     assert np.array_equal(finals[0], finals[1])
@@ -304,3 +306,43 @@ def test_average_energy_with_chain_moves_matches_reference_sequential_sweeps():
     sigma = math.sqrt(ref_err ** 2 + gpu_err ** 2)
     print("reference <E> = %.3f +- %.3f ; checkerboard with chain moves <E> = %.3f +- %.3f" % (ref_mean, ref_err, gpu_mean, gpu_err))
     assert abs(gpu_mean - ref_mean) <= 4.0 * sigma + 2e-3 * abs(ref_mean), (gpu_mean, ref_mean, sigma)
+
+
+def test_membrane_lipids_chain_sweeps():
+    """the move mix the reference uses on the lipid membrane (configs[2]): single-bead moves plus rigid moves of whole SPN-SPA-SPA
+    lipids, in neighbourhoods far denser than the staged tile of the single-particle kernel"""
+    import gzip
+    inp = json.loads(gzip.open(os.path.join(G, "membrane601.inputs.json.gz")).read().decode())
+    top, cfg, n = synth.membrane(4, 4, inp["top.init"], inp["config.init"])
+    hs = HostSystem(top, cfg)
+    eng = Engine(0, "fast").load(hs)
+    mols = _molecules(hs)
+    s0 = eng.download_particles()
+    g0 = _intramolecular(s0, hs.box, mols)
+    e0 = eng.all_to_all()
+    mp = move_params(1.0, 0.05, 10.0)
+    mp_none = move_params(1.0, 0.05, 10.0)
+    cm = chain_moves(1.0, 0.1, 10.0)
+    tot = 0.0
+    for sw in range(5):
+        st, cst = eng.sweep_chains(mp_none, cm, 99, sw)
+        tried = cst.chainm_acc + cst.chainm_rej + cst.chainr_acc + cst.chainr_rej
+        # every pick lands on a lipid bead except those on the 16 CPSC rods (no-ops)
+        assert abs(tried + cst.noop - n) <= 6.0 * math.sqrt(n) + 20, (sw, tried, cst.noop, n)
+        assert cst.noop < 0.02 * n
+        assert cst.chainm_acc > 0 and cst.chainr_acc > 0
+        tot += cst.energy_delta
+    s1 = eng.download_particles()
+    assert np.all(np.isfinite(s1))
+    assert np.max(np.abs(_intramolecular(s1, hs.box, mols) - g0)) < 1e-9
+    e1 = eng.all_to_all()
+    assert abs((e1 - e0) - tot) <= 1e-9 * max(abs(e0), abs(e1)), (e0, e1, tot)
+    cm = chain_moves(0.5, 0.1, 10.0)
+    for sw in range(5, 8):
+        st, cst = eng.sweep_chains(mp, cm, 99, sw)
+        tot += st.energy_delta + cst.energy_delta
+        tried = cst.chainm_acc + cst.chainm_rej + cst.chainr_acc + cst.chainr_rej
+        assert abs(tried + cst.noop - 0.5 * n) <= 6.0 * math.sqrt(n) + 20, (sw, tried, cst.noop, n)
+    e2 = eng.all_to_all()
+    assert abs((e2 - e0) - tot) <= 1e-9 * max(abs(e0), abs(e2)), (e0, e2, tot)
+    eng.close()
