@@ -128,41 +128,56 @@ def cpu_port_fallback(ntargets):
 # clocks sampler (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------------
 class Clocks:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region. The region is a few milliseconds long, far shorter than the
+    start-up of an `nvidia-smi -lms` child, so the samples come from NVML in this process (what nvidia-smi itself reads): one
+    sample when the region opens, a polling thread while it runs, one sample when it closes."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.samples = []
-        self.p = None
+        self.sm, self.mx, self.reasons = [], None, set()
+        self.h = None
+        self.run = False
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.p = None
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as ex:
+            self.err = repr(ex)
+            self.h = None
+            return
+        self._sample()
+        self.run = True
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.samples.append(line.strip())
+    def _sample(self):
+        try:
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            try:
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _poll(self):
+        while self.run:
+            self._sample()
+            time.sleep(0.0005)
 
     def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            t = [x.strip() for x in s.split(",")]
-            try:
-                sm.append(float(t[0])); mx.append(float(t[1]))
-            except Exception:
-                continue
-            for k, nm in enumerate(names):
-                if len(t) > 2 + k and t[2 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")], "samples": 0}
+        self.run = False
+        self.t.join(timeout=1.0)
+        self._sample()
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": "NVML (nvmlDeviceGetClockInfo / CurrentClocksEventReasons) polled in-process over the timed region"}
 
 
 def measured_peaks():
