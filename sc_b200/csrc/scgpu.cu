@@ -1003,9 +1003,11 @@ k_gate_rows(DevSys s, FlatList fl) {
 #define CHEAP_MINB 3
 #endif
 constexpr int CHEAP_BUF = 256;    // patch-list entries buffered per warp between global appends
-template <bool RODS>
+// ONE: every particle present has the same type, so there is a single interaction-table entry: it travels as a kernel parameter
+// (constant bank, read by LDC on the uniform path) instead of being fetched field by field through the load/store unit
+template <bool RODS, bool ONE>
 __global__ void __launch_bounds__(256, RODS ? CHEAP_MINB : 2)
-k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
+k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters, const __grid_constant__ scgpu_iaparam ia1) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     int total = *fl.total;
@@ -1057,7 +1059,7 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters) {
             }
             double e = 0.0;
             if (dotrcm <= s.sqmaxcut || bonded) {           // the exact PairE gate (mc/paire.h:1214)
-                if (RODS) e = pair_energy_cheap_rods(s.ia[w_type(pi.w) * s.ntypes + w_type(pj.w)], r_cm, dotrcm, di, dj, np);
+                if (RODS) e = pair_energy_cheap_rods(ONE ? ia1 : s.ia[w_type(pi.w) * s.ntypes + w_type(pj.w)], r_cm, dotrcm, di, dj, np);
                 else e = pair_energy_cheap<false>(s.box, s.ia, s.ntypes, s.mol, r_cm, dotrcm, s.rec + (size_t)pr.x * REC, w_type(pi.w), w_moltype(pi.w),
                                                   s.rec + (size_t)pr.y * REC, w_type(pj.w), oj, cl, np);
                 n_gate++;
@@ -1106,11 +1108,12 @@ __device__ __forceinline__ void load_patch_args(const double* rec, int pn, bool 
 }
 
 __device__ __forceinline__ void patch_setup(const DevSys& s, const FlatList& fl, int p, int combo, const scgpu_iaparam*& ia, v3& r_cm,
-                                            PatchArgs& P1, PatchArgs& P2, bool& first_psc, bool& second_psc, bool& applicable) {
+                                            PatchArgs& P1, PatchArgs& P2, bool& first_psc, bool& second_psc, bool& applicable,
+                                            const scgpu_iaparam* ia_one = nullptr) {
     int2 pr = fl.pair[p];
     double4 pi = ldg256(s.posw + pr.x), pj = ldg256(s.posw + pr.y);
     r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
-    ia = &s.ia[w_type(pi.w) * s.ntypes + w_type(pj.w)];
+    ia = ia_one ? ia_one : &s.ia[w_type(pi.w) * s.ntypes + w_type(pj.w)];
     const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
     const bool firstCH = is_chiral(g0), secondCH = is_chiral(g1), firstT = is_two_patch(g0), secondT = is_two_patch(g1);
     first_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && is_psc_family(g0));
@@ -1139,8 +1142,10 @@ __device__ __forceinline__ int block_rank(bool flag, int* sh_warp, int* count) {
 #ifndef PATCH_MINB
 #define PATCH_MINB 7
 #endif
+template <bool ONE>
 __global__ void __launch_bounds__(PF_THREADS, PATCH_MINB)
-k_patch_flat(DevSys s, FlatList fl, int any_two_patch) {
+k_patch_flat(DevSys s, FlatList fl, int any_two_patch, const __grid_constant__ scgpu_iaparam ia1) {
+    const scgpu_iaparam* ia_one = ONE ? &ia1 : nullptr;
     __shared__ PatchItem sh_a[PF_THREADS], sh_b[PF_THREADS];
     __shared__ int sh_warp[PF_THREADS / 32];
     __shared__ int sh_n1, sh_n2;
@@ -1155,7 +1160,7 @@ k_patch_flat(DevSys s, FlatList fl, int any_two_patch) {
             double a = 0.0, b = 0.0;
             if (p >= 0) {
                 const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
-                patch_setup(s, fl, p, combo, ia, r_cm, P1, P2, fp, sp, ok);
+                patch_setup(s, fl, p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
                 if (ok) {
                     const int pn1 = combo & 1;
                     int n = fp ? patch_intersect<false>(P1.dir, P2.dir, P1, r_cm, a, b, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1])
@@ -1174,7 +1179,7 @@ k_patch_flat(DevSys s, FlatList fl, int any_two_patch) {
             if ((int)threadIdx.x < n1) {
                 it = sh_a[threadIdx.x];
                 const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
-                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok);
+                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
                 const int pn2 = combo >> 1;
                 v3 vec1 = neg(r_cm);
                 int n = sp ? patch_intersect<false>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0])
@@ -1189,7 +1194,7 @@ k_patch_flat(DevSys s, FlatList fl, int any_two_patch) {
             if ((int)threadIdx.x < n2) {
                 it = sh_b[threadIdx.x];
                 const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
-                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok);
+                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
                 double e = atr_e(*ia, P1.dir, P2.dir, P1.pdir, P2.pdir, r_cm, combo & 1, combo >> 1, it.S1, it.S2, it.T1, it.T2);
                 fl.e[it.p].y += e;        // one writer per pair and phase; the combinations run one after another
             }
@@ -1407,6 +1412,7 @@ struct scgpu_ctx {
     int* d_pl_overflow = nullptr;
     int pl_cap = 0;
     bool rods_only = false;          // every particle an un-bonded rod: the specialised kernels apply
+    int one_type = -1;               // >= 0: every particle present has this type (single table entry -> kernel parameter)
     bool use_rows = true;            // k_gate_rows until a launch reports a layout it cannot hold (then k_gate_cells for good)
     bool any_two_patch = false;      // some particle type present carries a second patch (TPSC/TCPSC/TCHPSC/TCHCPSC)
     int* d_warp_head = nullptr;
@@ -1713,6 +1719,11 @@ static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const 
         }
         for (int mm = 0; mm < c->nmol && rods; mm++) if (mu[mm] && c->h_mol[mm].mol_size != 1.0) rods = false;
         c->rods_only = rods;
+        {
+            int nt = 0, last = -1;
+            for (int a = 0; a < c->ntypes; a++) if (tu[a]) { nt++; last = a; }
+            c->one_type = nt == 1 ? last : -1;
+        }
         c->any_two_patch = false;
         for (int a = 0; a < c->ntypes; a++) if (tu[a]) {
             int g = (int)c->h_ia[(size_t)a * c->ntypes + a].geotype[0];
@@ -1879,22 +1890,24 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
         fl.chunks = c->d_fl_chunks; fl.chunk_count = c->d_pl_total + 4; fl.chunk_cap = c->fl_chunk_cap;
         fl.plist = c->d_fl_plist; fl.ptotal = c->d_pl_total + 5; fl.overflow = c->d_pl_overflow;
         const bool wrap = c->nc[0] < 5 || c->nc[1] < 5 || c->nc[2] < 5;
+        const bool one = c->one_type >= 0 && c->rods_only;
+        const scgpu_iaparam& ia1 = c->h_ia[one ? (size_t)c->one_type * c->ntypes + c->one_type : 0];
         const int nrows = c->nc[1] * c->nc[2];
         if (c->rods_only && c->use_rows && !wrap && !d_counters && nrows <= 65535) {
             const dim3 grid((unsigned)(c->n / nrows / GR_T + 2), (unsigned)nrows);
             if (mode == 1) k_gate_rows<1><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
             else k_gate_rows<2><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
-            k_cheap_flat<true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters);
+            if (one) k_cheap_flat<true, true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<true, false><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         } else if (c->rods_only) {
             if (mode == 1) { if (wrap) k_gate_cells<1, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             else { if (wrap) k_gate_cells<2, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
-            k_cheap_flat<true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters);
+            if (one) k_cheap_flat<true, true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<true, false><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         } else {
             if (mode == 1) { if (wrap) k_gate_cells<1, false, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             else { if (wrap) k_gate_cells<2, false, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
-            k_cheap_flat<false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters);
+            k_cheap_flat<false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         }
-        k_patch_flat<<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0);
+        if (one) k_patch_flat<true><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, ia1); else k_patch_flat<false><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, ia1);
         k_combine_flat<<<(c->n + 31) / 32, 256, 0, c->stream>>>(c->n, fl, d_out);
         c->launches += 4;
         CK(cudaGetLastError());
