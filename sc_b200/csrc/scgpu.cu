@@ -2207,9 +2207,12 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     if (stats || cstats) CK(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
     DevSys s = view(c);
     int nactive = (c->nc[0] / ncol.x) * (c->nc[1] / ncol.y) * (c->nc[2] / ncol.z);
+    const bool one = c->one_type >= 0 && c->rods_only;
+    const scgpu_iaparam& ia1 = c->h_ia[one ? (size_t)c->one_type * c->ntypes + c->one_type : 0];
     for (int k = 0; k < ncolours; k++) {
-        if (c->rods_only) k_sweep_colour<true><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags);
-        else k_sweep_colour<false><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags);
+        if (c->rods_only && one) k_sweep_colour<true, true><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags, ia1);
+        else if (c->rods_only) k_sweep_colour<true, false><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags, ia1);
+        else k_sweep_colour<false, false><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags, ia1);
         c->launches++;
         if (chains) {
             k_sweep_chain_colour<<<nactive, CH_THREADS, 0, c->stream>>>(s, cp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, d_chain_acc);

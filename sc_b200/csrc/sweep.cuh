@@ -102,10 +102,12 @@ __device__ unsigned long long sw_prof[16];
 #endif
 
 // one block per ACTIVE cell of the current colour
-template <bool RODS>
+// ONE (with RODS): a single particle type is present -> its interaction-table entry is a kernel parameter (constant bank); in this
+// latency-bound kernel every field fetched through the load/store unit sits on the serial path of a trial
+template <bool RODS, bool ONE>
 __global__ void __launch_bounds__(SW_WARPS * 32, SW_MINBLOCKS)
 k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long long sweep, int colour, int3 ncol,
-               double4* posw, double* rec, SweepAcc* acc_out, int* fail_flag) {
+               double4* posw, double* rec, SweepAcc* acc_out, int* fail_flag, const __grid_constant__ scgpu_iaparam ia1) {
     __shared__ float4 t_pf[SW_TILE];
     __shared__ int t_slot[SW_TILE];
     __shared__ double sh_old[REC], sh_new[REC];
@@ -260,7 +262,7 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                 const bool is_new = entry & 1;
                 double4 pw = posw[slot];
                 v3 r = image(s.box, is_new ? pn : po, mk(pw.x, pw.y, pw.z));
-                double e = pair_energy_patch(s.ia[type1 * s.ntypes + w_type(pw.w)], r, is_new ? sh_new : sh_old, rec + (size_t)slot * REC);
+                double e = pair_energy_patch(ONE ? ia1 : s.ia[type1 * s.ntypes + w_type(pw.w)], r, is_new ? sh_new : sh_old, rec + (size_t)slot * REC);
                 if (is_new) ln += e; else lo += e;
             };
             auto eval = [&](int entry, bool on) {
@@ -274,8 +276,10 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                     double d = dot(r, r);
                     bool bonded = !RODS && !cl.is_empty && (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]);
                     if (d <= s.sqmaxcut || bonded) {
-                        double e = pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r, d, is_new ? sh_new : sh_old, type1, moltype1,
-                                                           rec + (size_t)slot * REC, w_type(pw.w), orig, cl, np);
+                        double e;
+                        if (RODS && ONE) e = pair_energy_cheap_rods(ia1, r, d, ld3((is_new ? sh_new : sh_old) + R_DIR), ld3(rec + (size_t)slot * REC + R_DIR), np);
+                        else e = pair_energy_cheap<RODS>(s.box, s.ia, s.ntypes, s.mol, r, d, is_new ? sh_new : sh_old, type1, moltype1,
+                                                         rec + (size_t)slot * REC, w_type(pw.w), orig, cl, np);
                         if (is_new) ln += e; else lo += e;
                     }
                 }
@@ -343,7 +347,7 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                 const bool is_new = entry & 1;
                 double4 pw = posw[slot];
                 v3 r = image(s.box, is_new ? pn : po, mk(pw.x, pw.y, pw.z));
-                double e = pair_energy_patch_two_lanes(s.ia[type1 * s.ntypes + w_type(pw.w)], r, is_new ? sh_new : sh_old, rec + (size_t)slot * REC, act);
+                double e = pair_energy_patch_two_lanes(ONE ? ia1 : s.ia[type1 * s.ntypes + w_type(pw.w)], r, is_new ? sh_new : sh_old, rec + (size_t)slot * REC, act);
                 if (is_new) ln += e; else lo += e;
             }
             SWP_MARK(5);
