@@ -88,7 +88,7 @@ def small_case(kind, seed=2024):
     if kind == "psc_gas":
         _gas(rnd, 700, box, lines)
         return TOP_PSC % 700, "\n".join(lines) + "\n"
-    if kind == "rods_wide":
+    if kind in ("rods_wide", "rods_dense"):
         # un-bonded rods of four types with different cutoffs on a grid of >= 7 x 5 x 5 cells: the configuration the thread-per-target
         # gate (k_gate_rows) takes; clustered along x so that cell populations are very uneven (empty cells, cells beyond 32 rods)
         top = """[Types]
@@ -110,14 +110,17 @@ D: {
 particles: 4
 }
 [System]
-A 900
-B 700
-C 600
-D 500
+A %d
+B %d
+C %d
+D %d
 """
+        # rods_dense: four times the particles -> neighbourhoods above the staged tile of k_gate_rows: the launch must fall back
+        mult = 4 if kind == "rods_dense" else 1
+        top = top % (900 * mult, 700 * mult, 600 * mult, 500 * mult)
         box = (44.0, 29.0, 31.0)
         lines = [_fmt(box)]
-        for i in range(2700):
+        for i in range(2700 * mult):
             if i % 3 == 0:
                 pos = (rnd.gauss(0.3, 0.07) % 1.0 * box[0], rnd.uniform(0, box[1]), rnd.gauss(0.5, 0.2) % 1.0 * box[2])
             else:

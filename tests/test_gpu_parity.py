@@ -223,6 +223,26 @@ def test_row_unit_gate_matches_cell_gate_and_oracle(engine):
         engine.submit_everyone(np.zeros((s.n, 9)), out.numpy())          # pageable memory is refused
 
 
+def test_row_unit_gate_falls_back_when_the_layout_does_not_fit(engine):
+    """four times denser: a unit's neighbourhood exceeds the staged tile of k_gate_rows, the launch raises the fallback flag and
+    is repeated with k_gate_cells -- silently for the caller, with the same results as the counting pass and the oracle"""
+    top, cfg = synth.small_case("rods_dense")
+    s = O.system_from_text(top, cfg)
+    engine.load(s)
+    sc = eps_scale(s)
+    l0 = engine.launches()
+    ev = engine.one_to_all_everyone()
+    l1 = engine.launches()
+    ev2 = engine.one_to_all_everyone()
+    l2 = engine.launches()
+    assert l1 - l0 > l2 - l1 > 0                       # the first call launched twice (rows, then cells); later calls go straight to cells
+    assert np.array_equal(ev, ev2)
+    ev_cells, _, _ = engine.one_to_all_everyone(count=True)
+    assert close(ev, ev_cells, sc * 10)
+    for t in range(0, s.n, max(1, s.n // 100)):
+        assert close(ev[t], s.one_to_all(t), sc), (t, ev[t], s.one_to_all(t))
+
+
 def test_determinism_and_box_change(engine):
     top, cfg = synth.small_case("psc_gas")
     s = O.system_from_text(top, cfg)
