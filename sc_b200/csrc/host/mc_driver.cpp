@@ -97,22 +97,36 @@ class SequentialMC {
     Ran2 ran2;
     double temper, press, shprob, chainprob;
     int ptype;
-    double trans_mx, rot_angle, chainm_mx, chainr_angle, edge_mx;
+    // Disp (structures/statistics.h:55-71): step size + acceptance counters per particle type / molecule type, adapted during
+    // equilibration by optimizeStep / optimizeRot (mc/updater.cpp:395-465)
+    struct Disp {
+        double mx = 0.0, angle = 0.0, oldrmsd = 0.0, oldmx = 0.0;
+        long acc = 0, rej = 0;
+        double ratio() const { return (acc + rej) > 0 ? 1.0 * acc / (acc + rej) : 0.0; }
+    };
+    Disp trans[40], rot[40], chainm[100], chainr[100], edge;      // MAXT, MAXMT (structures/macros.h:87-88)
+    long nequil = 0, adjust = 0;
     std::vector<std::pair<int, int>> chains;   // (first index, size) of every molecule with more than one particle
 public:
     McStats st;
     SequentialMC(System* c, TotalEGpu* calc_, const Options& o)
         : conf(c), calc(calc_), ran2((long)o.get("seed")) {
-        if (o.get("nequil") != 0 || o.get("adjust") != 0) throw Error("sequential driver: nequil/adjust (step-size adaptation) are not mirrored; set them to 0");
+        nequil = (long)o.get("nequil"); adjust = (long)o.get("adjust");
         if (o.get("wlm") != 0 || o.get("nGrandCanon") != 0 || o.get("nClustMove") != 0 || o.get("switchprob") != 0 || o.get("nrepchange") != 0)
             throw Error("sequential driver: Wang-Landau / muVT / cluster / switch / replica moves are outside the mirrored callers");
         if (conf->topo.exterExist) throw Error("sequential driver: the [EXTER] wall potential is outside the hot path");
         temper = o.get("temper"); press = o.get("press"); ptype = (int)o.get("ptype");
-        trans_mx = 2.0 * o.get("transmx");                      // sim.h:365
-        rot_angle = o.get("rotmx") / 180.0 * PIH * 0.5;         // sim.h:360
-        chainm_mx = 2.0 * o.get("chainmmx");                    // sim.h:366
-        chainr_angle = o.get("chainrmx") / 180.0 * PIH;         // sim.h:362
-        edge_mx = 2.0 * o.get("edge_mx");                       // sim.h:364
+        for (int i = 0; i < 40; i++) {                          // sim.h:358-374
+            trans[i].mx = 2.0 * o.get("transmx");
+            rot[i].mx = cos(o.get("rotmx") / 180.0 * PIH);      // the cosine is what optimizeRot adapts; the moves read .angle, which it never touches
+            rot[i].angle = o.get("rotmx") / 180.0 * PIH * 0.5;
+        }
+        for (int i = 0; i < 100; i++) {                         // sim.h:376-382
+            chainm[i].mx = 2.0 * o.get("chainmmx");
+            chainr[i].mx = cos(o.get("chainrmx") / 180.0 * PIH);
+            chainr[i].angle = o.get("chainrmx") / 180.0 * PIH;
+        }
+        edge.mx = 2.0 * o.get("edge_mx");                       // sim.h:364
         for (int i = 0; i < conf->n;) {
             int msz = conf->topo.mols[conf->moltype[i]].molSize();
             if (msz > 1) chains.emplace_back(i, msz);
@@ -155,15 +169,16 @@ public:
         double energy = calc->oneToAll(target);
         double dr[3];
         randomUnitSphere(dr);
-        dr[0] *= trans_mx / conf->box[0]; dr[1] *= trans_mx / conf->box[1]; dr[2] *= trans_mx / conf->box[2];
+        Disp& ds = trans[conf->type[target]];
+        dr[0] *= ds.mx / conf->box[0]; dr[1] *= ds.mx / conf->box[1]; dr[2] *= ds.mx / conf->box[2];
         P(target)[0] += dr[0]; P(target)[1] += dr[1]; P(target)[2] += dr[2];
         double enermove = calc->oneToAllTrial(target);
         if (moveTry(energy, enermove)) {
             P(target)[0] = orig[0]; P(target)[1] = orig[1]; P(target)[2] = orig[2];
-            st.trans_rej++;
+            st.trans_rej++; ds.rej++;
             return 0.0;
         }
-        st.trans_acc++;
+        st.trans_acc++; ds.acc++;
         calc->update(target);
         return enermove - energy;
     }
@@ -192,7 +207,8 @@ public:
         // evaluates the arguments right to left: the axis is drawn BEFORE the angle (particle.h:171-173)
         double axis[3];
         randomUnitSphere(axis);
-        double angle = rot_angle * ran2();
+        Disp& ds = rot[conf->type[target]];
+        double angle = ds.angle * ran2();
         pscRotate(P(target), angle, geotype(target), axis);
         {   // patchdir[0].ortogonalise(dir)
             double* p = P(target);
@@ -202,10 +218,10 @@ public:
         double enermove = calc->oneToAllTrial(target);
         if (moveTry(energy, enermove)) {
             memcpy(P(target), orig, sizeof orig);
-            st.rot_rej++;
+            st.rot_rej++; ds.rej++;
             return 0.0;
         }
-        st.rot_acc++;
+        st.rot_acc++; ds.acc++;
         calc->update(target);
         return enermove - energy;
     }
@@ -224,15 +240,16 @@ public:
         double energy = calc->mol2others(mol);
         double dr[3];
         randomUnitSphere(dr);
-        dr[0] *= chainm_mx / conf->box[0]; dr[1] *= chainm_mx / conf->box[1]; dr[2] *= chainm_mx / conf->box[2];
+        Disp& ds = chainm[conf->moltype[mol[0]]];
+        dr[0] *= ds.mx / conf->box[0]; dr[1] *= ds.mx / conf->box[1]; dr[2] *= ds.mx / conf->box[2];
         for (int i : mol) { P(i)[0] += dr[0]; P(i)[1] += dr[1]; P(i)[2] += dr[2]; }
         double enermove = calc->mol2othersTrial(mol);
         if (moveTry(energy, enermove)) {
             for (size_t k = 0; k < mol.size(); k++) memcpy(P(mol[k]), &orig[3 * k], 3 * sizeof(double));
-            st.chainm_rej++;
+            st.chainm_rej++; ds.rej++;
             return 0.0;
         }
-        st.chainm_acc++;
+        st.chainm_acc++; ds.acc++;
         calc->update(mol);
         return enermove - energy;
     }
@@ -252,7 +269,8 @@ public:
         cm[0] /= vol; cm[1] /= vol; cm[2] /= vol;
         double axis[3];
         randomUnitSphere(axis);
-        double vc = cos(chainr_angle * ran2()), vs;
+        Disp& ds = chainr[conf->moltype[mol[0]]];
+        double vc = cos(ds.angle * ran2()), vs;
         if (ran2() < 0.5) vs = sqrt(1.0 - vc * vc); else vs = -sqrt(1.0 - vc * vc);
         double d[9];
         quatMatrix(vc, axis[0] * vs, axis[1] * vs, axis[2] * vs, d);
@@ -269,10 +287,10 @@ public:
         double enermove = calc->mol2othersTrial(mol);
         if (moveTry(energy, enermove)) {
             for (size_t k = 0; k < mol.size(); k++) memcpy(P(mol[k]), &orig[30 * k], 30 * sizeof(double));
-            st.chainr_rej++;
+            st.chainr_rej++; ds.rej++;
             return 0.0;
         }
-        st.chainr_acc++;
+        st.chainr_acc++; ds.acc++;
         calc->update(mol);
         return enermove - energy;
     }
@@ -298,13 +316,13 @@ public:
             else if (rsave < 2.0 / 3.0) { side = 1; area = box[0] * box[2]; }
             else { side = 2; area = box[0] * box[1]; }
             double old_side = box[side];
-            box[side] += edge_mx * (ran2() - 0.5);
+            box[side] += edge.mx * (ran2() - 0.5);
             enermove = press * area * (box[side] - old_side) - N * temper * log(box[side] / old_side);
             enermove += calc->allToAllTrial();
             reject = box[side] <= 0.0 || moveTry(energy, enermove);
             if (reject) box[side] = old_side;
         } else if (ptype == 1) {
-            double psch = edge_mx * (ran2() - 0.5);
+            double psch = edge.mx * (ran2() - 0.5);
             double pvol = box[0] * box[1] * box[2];
             box[0] += psch; box[1] += psch; box[2] += psch;
             double pvoln = box[0] * box[1] * box[2];
@@ -313,7 +331,7 @@ public:
             reject = moveTry(energy, enermove);
             if (reject) { box[0] -= psch; box[1] -= psch; box[2] -= psch; }
         } else if (ptype == 2) {
-            double psch = edge_mx * (ran2() - 0.5);
+            double psch = edge.mx * (ran2() - 0.5);
             double pvol = box[0] * box[1];
             box[0] += psch; box[1] += psch;
             double pvoln = box[0] * box[1];
@@ -322,7 +340,7 @@ public:
             reject = moveTry(energy, enermove);
             if (reject) { box[0] -= psch; box[1] -= psch; }
         } else if (ptype == 3) {
-            double psch = edge_mx * (ran2() - 0.5);
+            double psch = edge.mx * (ran2() - 0.5);
             double pvol = box[0] * box[1] * box[2];
             box[0] += psch; box[1] += psch;
             box[2] = pvol / box[0] / box[1];
@@ -330,16 +348,50 @@ public:
             reject = moveTry(energy, enermove);
             if (reject) { box[0] -= psch; box[1] -= psch; box[2] = pvol / box[0] / box[1]; }
         } else throw Error("sequential driver: ptype 4/5 are not mirrored");
-        if (reject) { st.edge_rej++; return 0.0; }     // the calculator re-reads the restored box on its next call
-        st.edge_acc++;
+        if (reject) { st.edge_rej++; edge.rej++; return 0.0; }     // the calculator re-reads the restored box on its next call
+        st.edge_acc++; edge.acc++;
         calc->update();
         return enermove - energy;
     }
 
-    void simulate(long nsweeps) {              // updater.cpp:45-389 (production part)
+    static void optimizeStep(Disp& x, double hi, double lo) {      // updater.cpp:395-429
+        const double newrmsd = x.mx * x.ratio();
+        if (x.oldrmsd > 0) {
+            if (newrmsd < x.oldrmsd) {
+                if (x.oldmx > 1) { x.mx /= 1.05; x.oldmx = 0.95; } else { x.mx *= 1.05; x.oldmx = 1.05; }
+            } else {
+                if (x.oldmx > 1) { x.mx *= 1.05; x.oldmx = 1.05; } else { x.mx /= 1.05; x.oldmx = 0.95; }
+            }
+        }
+        if (newrmsd > 0) x.oldrmsd = newrmsd;
+        else { x.oldrmsd = 0.0; x.mx /= 1.05; x.oldmx = 0.95; }
+        if (x.mx > hi) x.mx = hi;
+        if (x.mx < lo) x.mx = lo;
+        x.acc = x.rej = 0;
+    }
+    static void optimizeRot(Disp& x, double hi, double lo) {       // updater.cpp:431-465 (adapts the cosine .mx; the moves read .angle)
+        const double newrmsd = x.mx * x.ratio();
+        if (x.oldrmsd > 0) {
+            if (newrmsd > x.oldrmsd) {
+                if (x.oldmx > 1) { x.mx *= 0.99; x.oldmx *= 0.99; } else { x.mx *= 1.01; x.oldmx *= 1.01; }
+            } else {
+                if (x.oldmx > 1) { x.mx *= 1.01; x.oldmx *= 1.01; } else { x.mx *= 0.99; x.oldmx *= 0.99; }
+            }
+        }
+        if (newrmsd > 0) x.oldrmsd = newrmsd;
+        else { x.oldrmsd = 0.0; x.mx *= 1.01; x.oldmx = 1.01; }
+        if (x.mx > hi) x.mx = hi;
+        if (x.mx < lo) x.mx = lo;
+        x.acc = x.rej = 0;
+    }
+
+    // one Updater::simulate call (updater.cpp:45-389): `adjust` > 0 adapts the step sizes every `adjust` sweeps (:238-253)
+    void simulate(long nsweeps, long adjust_every = 0, bool reinit = false) {
         double edriftchanges = 0.0;
+        if (reinit) for (int i = 0; i < conf->n; i++) conf->initParticle(i);      // Updater::initValues -> partVecInit (:31)
         calc->initEM();
         st.e_start = calc->allToAll();
+        long next_adjust = adjust_every;
         for (long sweep = 1; sweep <= nsweeps; sweep++) {
             for (long step = 1; step <= (long)conf->n; step++) {
                 double moveprobab = ran2();
@@ -347,11 +399,35 @@ public:
                 if (moveprobab < shprob + chainprob) { edriftchanges += chainMove(); continue; }
                 edriftchanges += particleMove();
             }
+            if (sweep == next_adjust) {
+                for (int i = 0; i < 40; i++) {
+                    if (trans[i].acc > 0 || trans[i].rej > 0) optimizeStep(trans[i], 1.5, 0.0);
+                    if (rot[i].acc > 0 || rot[i].rej > 0) optimizeRot(rot[i], 5.0, 0.01);
+                }
+                for (int i = 0; i < 100; i++) {
+                    if (chainm[i].acc > 0 || chainm[i].rej > 0) optimizeStep(chainm[i], 1.5, 0.0);
+                    if (chainr[i].acc > 0 || chainr[i].rej > 0) optimizeRot(chainr[i], 5.0, 0.01);
+                }
+                optimizeStep(edge, 1.0, 0.0);
+                next_adjust += adjust_every;
+            }
             if (!(sweep % 100000)) for (int i = 0; i < conf->n; i++) conf->initParticle(i);
         }
         st.e_end = calc->allToAll();
         st.drift = st.e_end - st.e_start - edriftchanges;
     }
+
+    // main.cpp:270-297: equilibration (first half adapting the step sizes, second half at the adapted sizes), then production
+    void run(long nsweeps) {
+        bool again = false;
+        if (nequil) {
+            simulate(nequil / 2, adjust, false);
+            simulate(nequil / 2, 0, true);
+            again = true;
+        }
+        simulate(nsweeps, 0, again);
+    }
+    double transMx(int type) const { return trans[type].mx; }
 };
 
 }  // namespace schost
@@ -372,7 +448,7 @@ int schost_run_mc(void* sys, const char* options_text, int device, long nsweeps_
         TotalEGpu calc(s, device);
         SequentialMC mc(s, &calc, o);
         long ns = nsweeps_override > 0 ? nsweeps_override : (long)o.get("nsweeps");
-        mc.simulate(ns);
+        mc.run(ns);
         const McStats& t = mc.st;
         double v[13] = {(double)t.trans_acc, (double)t.trans_rej, (double)t.rot_acc, (double)t.rot_rej, (double)t.chainm_acc, (double)t.chainm_rej,
                         (double)t.chainr_acc, (double)t.chainr_rej, (double)t.edge_acc, (double)t.edge_rej, t.e_start, t.e_end, t.drift};

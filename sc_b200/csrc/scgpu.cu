@@ -1008,6 +1008,7 @@ constexpr int CHEAP_BUF = 256;    // patch-list entries buffered per warp betwee
 template <bool RODS, bool ONE>
 __global__ void __launch_bounds__(256, RODS ? CHEAP_MINB : 2)
 k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters, const __grid_constant__ scgpu_iaparam ia1) {
+    if (*fl.overflow) return;         // the gate could not finish its list (the host repeats the launch): spans may be missing or out of range
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     int total = *fl.total;
@@ -1146,6 +1147,7 @@ template <bool ONE>
 __global__ void __launch_bounds__(PF_THREADS, PATCH_MINB)
 k_patch_flat(DevSys s, FlatList fl, int any_two_patch, const __grid_constant__ scgpu_iaparam ia1) {
     const scgpu_iaparam* ia_one = ONE ? &ia1 : nullptr;
+    if (*fl.overflow) return;
     __shared__ PatchItem sh_a[PF_THREADS], sh_b[PF_THREADS];
     __shared__ int sh_warp[PF_THREADS / 32];
     __shared__ int sh_n1, sh_n2;
@@ -1206,6 +1208,7 @@ k_patch_flat(DevSys s, FlatList fl, int any_two_patch, const __grid_constant__ s
 // eight lanes per particle: each group reads its particle's span of the list 128 bytes at a time, lane k of the group sums
 // entries k, k+8, ... in order, then a fixed three-step shuffle tree -> the same bits on every run
 __global__ void __launch_bounds__(256) k_combine_flat(int n, FlatList fl, double* __restrict__ out) {
+    if (*fl.overflow) return;         // nothing valid to sum; the host resets the counters and repeats the launch
     const int sub = threadIdx.x & 7;
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     if (blockIdx.x == 0 && threadIdx.x == 0) { *fl.total = 0; *fl.chunk_count = 0; *fl.ptotal = 0; }   // lists consumed (stream order makes the reset safe)

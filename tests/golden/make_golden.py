@@ -238,6 +238,32 @@ def do_short():
         print("short:", name, ns)
 
 
+def do_equil():
+    """runs WITH an equilibration phase (nequil > 0, adjust > 0): the reference adapts its maximum step sizes every `adjust` sweeps
+    of the first half of the equilibration (Updater::optimizeStep / optimizeRot, mc/updater.cpp:238-253, 395-465), runs the second
+    half and the production at the adapted sizes. NVT rods, bonded chains with chain moves, and an NPT case (box-edge step)."""
+    import re
+    cases = [("test_01_normal_PSC", os.path.join(REF, "Tests", "test_01_normal_PSC", "new")),
+             ("test_20_chain_bond12", os.path.join(REF, "Tests", "test_20_chain_bond12", "new")),
+             ("volumeChange_0h", os.path.join(REF, "Tests", "volumeChange", "0h", "new"))]
+    for name, src in cases:
+        tmp = tempfile.mkdtemp(prefix="equil_")
+        for fn in os.listdir(src):
+            shutil.copy(os.path.join(src, fn), tmp)
+        opt = open(os.path.join(tmp, "options")).read()
+        opt = re.sub(r"(?m)^nsweeps\s*=\s*\d+", "nsweeps = 100", opt)
+        opt = re.sub(r"(?m)^nequil\s*=\s*\d+", "nequil = 120", opt)
+        opt = re.sub(r"(?m)^adjust\s*=\s*\d+", "adjust = 10", opt)
+        with open(os.path.join(tmp, "options"), "w") as f:
+            f.write(opt)
+        out = run([SC], tmp)
+        shutil.copy(os.path.join(tmp, "config.last"), os.path.join(HERE, "%s.equil.config.last" % name))
+        with open(os.path.join(HERE, "%s.equil.options" % name), "w") as f:
+            f.write(opt)
+        shutil.rmtree(tmp)
+        print("equil:", name)
+
+
 def do_membrane():
     """BASELINE.json configs[2]: the CPSC + SPN-SPA-SPA lipid membrane of Tests/SC_PSC_MEMBRANE_WANG (601 particles); the
     inputs are committed so that sc_b200.synth.membrane() can tile them to 265 k particles on the GPU box"""
@@ -267,6 +293,8 @@ def main():
         return do_extras()
     if "short" in sys.argv[1:]:
         return do_short()
+    if "equil" in sys.argv[1:]:
+        return do_equil()
     if not (os.path.exists(DRIVER) and os.path.exists(SC)):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
     tests = sorted(d for d in os.listdir(os.path.join(REF, "Tests")) if d.startswith("test_"))

@@ -52,3 +52,20 @@ def test_npt_trajectory_is_byte_identical(name):
     got, want, st = _run(name, name + ".short500.config.last", 500)
     assert st["edge_acc"] + st["edge_rej"] > 100
     assert got == want, (name, st)
+
+
+@pytest.mark.parametrize("name", ["test_01_normal_PSC", "test_20_chain_bond12", "volumeChange_0h"])
+def test_equilibration_with_step_size_adaptation_is_byte_identical(name):
+    """nequil = 120, adjust = 10, nsweeps = 100: Updater::optimizeStep / optimizeRot (mc/updater.cpp:238-253, 395-465) adapt the
+    per-type displacement, chain-displacement and box-edge steps during the first half of the equilibration; the run then
+    continues at the adapted sizes (main.cpp:270-297). Every later proposal depends on the adapted sizes, so a byte-identical
+    config.last pins the whole adaptation history."""
+    inputs = json.load(open(os.path.join(G, name + ".inputs.json")))
+    options = open(os.path.join(G, name + ".equil.options")).read()
+    assert re.search(r"(?m)^nequil\s*=\s*120", options) and re.search(r"(?m)^adjust\s*=\s*10", options)
+    hs = HostSystem(inputs["top.init"], inputs["config.init"])
+    st = hs.run_mc(options, 0, 0)
+    got = hs.config_last(True)
+    hs.close()
+    want = open(os.path.join(G, name + ".equil.config.last")).read()
+    assert got == want, (name, st)
