@@ -99,6 +99,22 @@ typedef struct scgpu_chainstats {
     int64_t noop;                                                      /* picks that landed on a one-particle molecule: no move */
 } scgpu_chainstats;
 
+/* One volume move (MoveCreator::pressureMove, scOOP/mc/movecreator.cpp:330-550, ptype 0-3) for callers that run the batched
+ * sweeps: positions are box-fractional, so only the box changes; both energies are full-system sums on the device. */
+typedef struct scgpu_pressureparams {
+    double temper, press;          /* Sim::temper, Sim::press */
+    double edge_mx;                /* stat.edge.mx (= 2*edge_mx of the options file, sim.h:364) */
+    int ptype;                     /* 0 anisotropic (one random edge), 1 isotropic, 2 isotropic in xy (z constant), 3 xy at constant volume */
+    int reserved;
+} scgpu_pressureparams;
+
+typedef struct scgpu_pressurestats {
+    int accepted, reserved;
+    double energy_old, energy_new; /* allToAll() before / allToAllTrial() at the proposed box */
+    double enthalpy_delta;         /* accepted moves: what the reference adds to its drift sum (dE + P dV - N T ln(V'/V)), else 0 */
+    double box[3];                 /* the box after the move */
+} scgpu_pressurestats;
+
 const char* scgpu_last_error(void);
 int scgpu_device_count(void);
 
@@ -167,6 +183,9 @@ int scgpu_sweep_checkerboard(scgpu_ctx* ctx, const scgpu_moveparams* mp, uint64_
 /* the same sweep with a share `chainprob` of its trials made chain moves (cm == NULL or chainprob == 0: identical to the call above) */
 int scgpu_sweep_checkerboard_chains(scgpu_ctx* ctx, const scgpu_moveparams* mp, const scgpu_chainmoves* cm, uint64_t seed, uint64_t sweep,
                                     scgpu_sweepstats* stats, scgpu_chainstats* chain_stats);
+
+/* volume move between sweeps; the random numbers are a pure function of (seed, step) */
+int scgpu_pressure_move(scgpu_ctx* ctx, const scgpu_pressureparams* pp, uint64_t seed, uint64_t step, scgpu_pressurestats* out);
 
 /* replica exchange helper (MoveCreator::replicaExchangeMove, scOOP/mc/movecreator.cpp:552-795): full energy stays on
  * the device; returns the device address of a packed double[8] record {E, V, N, 0...} for an NCCL all-gather */

@@ -2252,6 +2252,60 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     return SCGPU_OK;
 }
 
+extern "C" int scgpu_pressure_move(scgpu_ctx* c, const scgpu_pressureparams* pp, uint64_t seed, uint64_t step, scgpu_pressurestats* out) {
+    ARG(c && pp && out, "scgpu_pressure_move: NULL argument");
+    ARG(pp->temper > 0 && pp->ptype >= 0 && pp->ptype <= 3, "scgpu_pressure_move: temperature must be positive and ptype in 0..3");
+    ARG(c->n > 0 && c->box[0] > 0, "scgpu_pressure_move: particles and box must be set first");
+    unsigned long long st = seed * 0xA0761D6478BD642Full + step * 0xE7037ED1A0B428DBull + 0x8EBC6AF09C88C6E3ull;
+    auto u01h = [&]() { return (double)(splitmix64(st) >> 11) * (1.0 / 9007199254740992.0); };
+    double energy = 0.0, enermove = 0.0, etrial = 0.0;
+    if (int r = scgpu_all_to_all(c, &energy, nullptr)) return r;
+    const double old[3] = {c->box[0], c->box[1], c->box[2]};
+    double nb[3] = {old[0], old[1], old[2]};
+    const double N = (double)c->n;
+    bool positive = true;
+    if (pp->ptype == 0) {               // movecreator.cpp:345-396: one edge, chosen at random
+        const double rsave = u01h();
+        const int side = rsave < 1.0 / 3.0 ? 0 : (rsave < 2.0 / 3.0 ? 1 : 2);
+        const double area = old[(side + 1) % 3] * old[(side + 2) % 3];
+        nb[side] += pp->edge_mx * (u01h() - 0.5);
+        positive = nb[side] > 0.0;
+        if (positive) enermove = pp->press * area * (nb[side] - old[side]) - N * pp->temper * log(nb[side] / old[side]);
+    } else if (pp->ptype == 1) {        // :398-431 isotropic
+        const double psch = pp->edge_mx * (u01h() - 0.5);
+        nb[0] += psch; nb[1] += psch; nb[2] += psch;
+        positive = nb[0] > 0 && nb[1] > 0 && nb[2] > 0;
+        const double pvol = old[0] * old[1] * old[2], pvoln = nb[0] * nb[1] * nb[2];
+        if (positive) enermove = pp->press * (pvoln - pvol) - N * pp->temper * log(pvoln / pvol);
+    } else if (pp->ptype == 2) {        // :433-466 isotropic in xy, z constant
+        const double psch = pp->edge_mx * (u01h() - 0.5);
+        nb[0] += psch; nb[1] += psch;
+        positive = nb[0] > 0 && nb[1] > 0;
+        const double pvol = old[0] * old[1], pvoln = nb[0] * nb[1];
+        if (positive) enermove = pp->press * old[2] * (pvoln - pvol) - N * pp->temper * log(pvoln / pvol);
+    } else {                            // :468-503 xy at constant volume
+        const double psch = pp->edge_mx * (u01h() - 0.5);
+        nb[0] += psch; nb[1] += psch;
+        positive = nb[0] > 0 && nb[1] > 0;
+        if (positive) nb[2] = old[0] * old[1] * old[2] / nb[0] / nb[1];
+    }
+    bool accept = false;
+    if (positive) {
+        if (int r = scgpu_set_box(c, nb)) return r;
+        if (int r = scgpu_all_to_all(c, &etrial, nullptr)) return r;
+        enermove += etrial;
+        accept = (enermove <= energy) || (exp(-(enermove - energy) / pp->temper) > u01h());      // moveTry (movecreator.h:175-187)
+        if (!accept) { if (int r = scgpu_set_box(c, old)) return r; }
+    }
+    out->accepted = accept ? 1 : 0;
+    out->reserved = 0;
+    out->energy_old = energy;
+    out->energy_new = positive ? etrial : energy;
+    out->enthalpy_delta = accept ? enermove - energy : 0.0;
+    for (int d = 0; d < 3; d++) out->box[d] = c->box[d];
+    return SCGPU_OK;
+}
+
 extern "C" int scgpu_timer_start(scgpu_ctx* c) {
     ARG(c, "scgpu_timer_start: NULL context");
     CK(cudaSetDevice(c->device));

@@ -41,11 +41,20 @@ class ChainStats(C.Structure):
                 ("cell_rej", C.c_int64), ("energy_delta", C.c_double), ("noop", C.c_int64)]
 
 
+class PressureParams(C.Structure):
+    _fields_ = [("temper", C.c_double), ("press", C.c_double), ("edge_mx", C.c_double), ("ptype", C.c_int), ("reserved", C.c_int)]
+
+
+class PressureStats(C.Structure):
+    _fields_ = [("accepted", C.c_int), ("reserved", C.c_int), ("energy_old", C.c_double), ("energy_new", C.c_double),
+                ("enthalpy_delta", C.c_double), ("box", C.c_double * 3)]
+
+
 SYMBOLS = ["scgpu_last_error", "scgpu_device_count", "scgpu_create", "scgpu_destroy", "scgpu_set_topology",
            "scgpu_set_particles", "scgpu_set_particles_compact", "scgpu_set_box", "scgpu_update_particle", "scgpu_download_particles",
            "scgpu_build_cells", "scgpu_cell_assignment", "scgpu_cell_order", "scgpu_one_to_all",
            "scgpu_one_to_all_batch", "scgpu_one_to_all_everyone", "scgpu_submit_everyone", "scgpu_mol_to_others", "scgpu_all_to_all",
-           "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_sweep_checkerboard_chains", "scgpu_replica_record",
+           "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_sweep_checkerboard_chains", "scgpu_pressure_move", "scgpu_replica_record",
            "scgpu_timer_start", "scgpu_timer_stop", "scgpu_sync", "scgpu_fp64_peak", "scgpu_flush_l2",
            "scgpu_kernel_launches"]
 
@@ -82,6 +91,7 @@ def load_library(variant="fast"):
     L.scgpu_overlap_one.argtypes = [vp, C.c_int, _dp, C.c_int, _ip]
     L.scgpu_overlap_all.argtypes = [vp, C.c_int, _ip]
     L.scgpu_sweep_checkerboard.argtypes = [vp, C.POINTER(MoveParams), C.c_uint64, C.c_uint64, C.POINTER(SweepStats)]
+    L.scgpu_pressure_move.argtypes = [vp, C.POINTER(PressureParams), C.c_uint64, C.c_uint64, C.POINTER(PressureStats)]
     L.scgpu_sweep_checkerboard_chains.argtypes = [vp, C.POINTER(MoveParams), C.POINTER(ChainMoves), C.c_uint64, C.c_uint64,
                                                   C.POINTER(SweepStats), C.POINTER(ChainStats)]
     L.scgpu_replica_record.argtypes = [vp, C.POINTER(vp)]
@@ -266,6 +276,14 @@ class Engine:
         st, cst = SweepStats(), ChainStats()
         self._ck(self.L.scgpu_sweep_checkerboard_chains(self.h, C.byref(mp), C.byref(cm), int(seed), int(sweep), C.byref(st), C.byref(cst)))
         return st, cst
+
+    def pressure_move(self, ptype, press, temper, edge_mx, seed, step):
+        """one volume move (pressureMove, ptype 0-3); edge_mx as stat.edge.mx (= 2 * the options file's edge_mx) -> PressureStats"""
+        pp = PressureParams()
+        pp.temper, pp.press, pp.edge_mx, pp.ptype = float(temper), float(press), float(edge_mx), int(ptype)
+        st = PressureStats()
+        self._ck(self.L.scgpu_pressure_move(self.h, C.byref(pp), int(seed), int(step), C.byref(st)))
+        return st
 
     def replica_record_ptr(self):
         p = C.c_void_p()

@@ -33,6 +33,8 @@ def test_record_sizes_match_header():
     assert "#define SCGPU_STATE_DOUBLES 30" in txt and "#define SCGPU_IAPARAM_DOUBLES 48" in txt
     assert ctypes.sizeof(engine.MoveParams) == 8 + 40 * 8 * 2 + 8
     assert ctypes.sizeof(engine.SweepStats) == 6 * 8
+    assert ctypes.sizeof(engine.ChainMoves) == 8 + 32 * 8 * 2 and ctypes.sizeof(engine.ChainStats) == 7 * 8
+    assert ctypes.sizeof(engine.PressureParams) == 3 * 8 + 8 and ctypes.sizeof(engine.PressureStats) == 8 + 6 * 8
 
 
 def test_host_library_loads():

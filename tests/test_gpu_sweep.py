@@ -346,3 +346,93 @@ def test_membrane_lipids_chain_sweeps():
     e2 = eng.all_to_all()
     assert abs((e2 - e0) - tot) <= 1e-9 * max(abs(e0), abs(e2)), (e0, e2, tot)
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# volume moves between batched sweeps (MoveCreator::pressureMove, scOOP/mc/movecreator.cpp:330-550)
+# ------------------------------------------------------------------------------------------------
+def test_pressure_move_mechanics():
+    top, cfg = synth.small_case("psc_lattice")
+    hs = HostSystem(top, cfg)
+    eng = Engine(0, "fast").load(hs)
+    box = np.array(hs.box, dtype=np.float64)
+    n_acc = 0
+    for step in range(40):
+        ptype = step % 4
+        e_before = eng.all_to_all()
+        st = eng.pressure_move(ptype, 0.08, 0.5, 0.3, 2024, step)
+        assert st.energy_old == e_before
+        nb = np.array(list(st.box))
+        if st.accepted:
+            n_acc += 1
+            assert not np.array_equal(nb, box)
+            assert eng.all_to_all() == st.energy_new                       # the accepted box is the one the device now holds
+            if ptype == 0:
+                assert np.sum(nb != box) == 1                               # one edge
+            elif ptype == 1:
+                assert np.allclose(nb - box, (nb - box)[0], rtol=0, atol=1e-12)
+            elif ptype == 2:
+                assert nb[2] == box[2] and abs((nb[0] - box[0]) - (nb[1] - box[1])) < 1e-12
+            else:
+                assert abs(nb.prod() - box.prod()) < 1e-9 * box.prod()
+            dv = nb.prod() - box.prod()
+            de = st.energy_new - st.energy_old
+            if ptype == 1:
+                assert abs(st.enthalpy_delta - (de + 0.08 * dv - hs.n * 0.5 * math.log(nb.prod() / box.prod()))) < 1e-9 * max(1.0, abs(de))
+            box = nb
+        else:
+            assert np.array_equal(nb, box) and st.enthalpy_delta == 0.0
+            assert eng.all_to_all() == e_before                            # the old box is back, to the last bit
+    assert 0 < n_acc < 40
+    # a pure function of (seed, step, configuration)
+    a = eng.pressure_move(1, 0.08, 0.5, 0.3, 7, 7)
+    if a.accepted:
+        eng.set_box(box)
+    b = eng.pressure_move(1, 0.08, 0.5, 0.3, 7, 7)
+    assert (a.accepted, a.energy_new) == (b.accepted, b.energy_new)
+    eng.close()
+
+
+def test_npt_average_volume_matches_reference_sequential_sweeps():
+    """checkerboard sweeps + one volume move per sweep (the reference draws a volume move with probability shave/N per step, i.e.
+    `shave` per sweep on average) against the reference's own NPT run: <V> and <E> over the second half"""
+    gold = json.load(open(os.path.join(G, "sweep_npt_psc1280.json")))
+    P = gold["params"]
+    top, cfg = synth.small_case("psc_lattice")
+    hs = HostSystem(top, cfg)
+    skip = P["nsweeps"] // 2
+    ref_v, ref_e = [], []
+    for run in gold["runs"]:
+        sw, v = np.array(run["sweep"]), np.array(run["volume"])
+        ref_v.append(v[sw > skip].mean())
+        se, e = np.array(run["energy_sweep"]), np.array(run["energy"])
+        ref_e.append(e[se > skip].mean())
+    gpu_v, gpu_e = [], []
+    for seed in (101, 202, 303, 404, 505, 606, 707, 808):
+        eng = Engine(0, "fast").load(hs)
+        mp = move_params(P["temper"], P["transmx"], P["rotmx"])
+        vs, es = [], []
+        n_acc = 0
+        e = eng.all_to_all()
+        for sw in range(1, P["nsweeps"] + 1):
+            st = eng.sweep(mp, seed, sw)
+            e += st.energy_delta
+            pm = eng.pressure_move(P["ptype"], P["press"], P["temper"], 2.0 * P["edge_mx"], seed, sw)
+            if pm.accepted:
+                n_acc += 1
+                e = pm.energy_new
+            if sw > skip and sw % P["report"] == 0:
+                vs.append(float(np.prod(list(pm.box))))
+                es.append(e)
+        assert abs(eng.all_to_all() - e) <= 1e-7 * max(1.0, abs(e))
+        assert 0.2 < n_acc / P["nsweeps"] < 0.9
+        gpu_v.append(np.mean(vs))
+        gpu_e.append(np.mean(es))
+        eng.close()
+    rv, gv = float(np.mean(ref_v)), float(np.mean(gpu_v))
+    sv = math.sqrt(np.var(ref_v, ddof=1) / len(ref_v) + np.var(gpu_v, ddof=1) / len(gpu_v))
+    re_, ge = float(np.mean(ref_e)), float(np.mean(gpu_e))
+    se_ = math.sqrt(np.var(ref_e, ddof=1) / len(ref_e) + np.var(gpu_e, ddof=1) / len(gpu_e))
+    print("reference <V> = %.1f, checkerboard NPT <V> = %.1f (sigma %.1f); <E> %.2f vs %.2f (sigma %.2f)" % (rv, gv, sv, re_, ge, se_))
+    assert abs(gv - rv) <= 4.0 * sv + 5e-3 * rv, (gv, rv, sv)
+    assert abs(ge - re_) <= 4.0 * se_ + 2e-2 * abs(re_), (ge, re_, se_)
