@@ -758,7 +758,9 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                         if (pass && on) fl.pair[cur + __popc(m & lt_mask)] = make_int2(ti, s.slot_of[orig]);
                         cur += __popc(m);
                     }
+                    __syncwarp();        // every lane has read its cursor (racecheck: make the order of the lane-0 update explicit)
                     if (lane == 0) { if (pass) sh_pos[ti - bt] = cur; else sh_cnt[ti - bt] += cur; }
+                    __syncwarp();        // ... and the same warp reads this entry again on the next tile
                     if (!pass && count) {
                         n_cand = __reduce_add_sync(0xffffffffu, n_cand);
                         n_sure = __reduce_add_sync(0xffffffffu, n_sure);
