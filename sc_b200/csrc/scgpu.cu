@@ -504,6 +504,8 @@ struct FlatList {
     int4* chunks; int* chunk_count; int chunk_cap;
     int* plist; int* ptotal;     // indices into pair[] that owe a patch term
     int* overflow;
+    int* heavy;                  // bit t set by k_gate_rows_gen: a target of type t had more partners than its shared-memory buffer holds
+    unsigned heavy_types;        // types handled by k_gate_cells (targets of the other types by k_gate_rows_gen); 0 = no split
 };
 
 constexpr int GT_TILE = 1024;     // staged candidates per tile of a cell neighbourhood: 1024 x 20 B = 20 KB
@@ -538,6 +540,11 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
     const int c0 = blockIdx.x;
     const int tb = s.cell_start[c0], te = s.cell_start[c0 + 1];
     if (tb == te) return;
+    if (fl.heavy_types) {        // split launch: only the targets of the heavy types are this kernel's; most cells hold none
+        int any = 0;
+        for (int k = tb + (int)threadIdx.x; k < te; k += blockDim.x) any |= (fl.heavy_types >> w_type(s.posw[k].w)) & 1u;
+        if (!__syncthreads_or(any)) return;
+    }
     const int cx = c0 % s.nc[0], cy = (c0 / s.nc[0]) % s.nc[1], cz = c0 / (s.nc[0] * s.nc[1]);
     const int nx = s.nc[0] == 1 ? 1 : 3, ny = s.nc[1] == 1 ? 1 : 3, nz = s.nc[2] == 1 ? 1 : 3;
     const int ncell_nb = nx * ny * nz;
@@ -657,6 +664,7 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                         const double4 tpw = s.posw[ti];
                         target = w_orig(tpw.w);
                         ttype = w_type(tpw.w);
+                        if (fl.heavy_types && !((fl.heavy_types >> ttype) & 1u)) continue;      // warp-uniform: k_gate_rows_gen has listed this target
                         if (!RODS) {
                             ConList cl;
                             get_conlist(s.mol, w_moltype(tpw.w), target, cl);
@@ -789,8 +797,10 @@ k_gate_cells(DevSys s, FlatList fl, unsigned long long* counters) {
                     }
                     base = __shfl_sync(0xffffffffu, base, 0);
                     for (int k = lane; k < nb; k += 32) {
-                        const int target = w_orig(s.posw[bt + k].w);
+                        const double tw = s.posw[bt + k].w;
+                        const int target = w_orig(tw);
                         sh_pos[k] += base;
+                        if (fl.heavy_types && !((fl.heavy_types >> w_type(tw)) & 1u)) continue;
                         fl.chunks[target] = make_int4(sh_pos[k], sh_cnt[k], -1, 0);      // the particle's span of the list
                         fl.head[target] = target;
                     }
@@ -835,16 +845,19 @@ k_gate_rows(DevSys s, FlatList fl) {
     __shared__ int sh_cnt[GR_SL][GR_T];
     __shared__ int sh_off[GR_SL][GR_T];
     __shared__ int sh_sb[20], sh_soff[20];          // staged segments: first slot, offset in the tile
-    __shared__ int sh_cx[2];
+    __shared__ int sh_cx[3];
     __shared__ int sh_ok;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int row = blockIdx.y;
     const int nx = s.nc[0], ny = s.nc[1];
     const int cy = row % ny, cz = row / ny;
     const int rs = s.cell_start[row * nx], re = s.cell_start[(row + 1) * nx];
-    for (int first = rs + GR_T * blockIdx.x; first < re; first += GR_T * gridDim.x) {
-        const int count = min(GR_T, re - first);
-        const int last = first + count - 1;
+    // A unit is 32 consecutive slots of the row. Where the row is sparse such a unit would span many cells (and its neighbourhood
+    // the whole row): it is then processed in sub-units of at most kmax cells each (dense rows: one sub-unit, all lanes busy).
+    const int kmax = min(6, nx - 3);
+    for (int ufirst = rs + GR_T * blockIdx.x; ufirst < re; ufirst += GR_T * gridDim.x) {
+      const int ulast = min(ufirst + GR_T, re) - 1;
+      for (int first = ufirst; first <= ulast;) {
         __syncthreads();                 // previous unit fully written out
         // ---- cells of the first and the last target (warp 0: lanes over the cells of the row)
         if (wid == 0) {
@@ -854,10 +867,12 @@ k_gate_rows(DevSys s, FlatList fl) {
                 int b = 0, e = 0;
                 if (cxl < nx) { b = s.cell_start[row * nx + cxl]; e = s.cell_start[row * nx + cxl + 1]; }
                 const unsigned ma = __ballot_sync(0xffffffffu, cxl < nx && b <= first && first < e);
-                const unsigned mb = __ballot_sync(0xffffffffu, cxl < nx && b <= last && last < e);
+                const unsigned mb = __ballot_sync(0xffffffffu, cxl < nx && b <= ulast && ulast < e);
                 if (ma) cxa = c0 + __ffs(ma) - 1;
                 if (mb) cxb = c0 + __ffs(mb) - 1;
             }
+            int lastv = ulast;
+            if (cxb - cxa + 1 > kmax) { cxb = cxa + kmax - 1; lastv = s.cell_start[row * nx + cxb + 1] - 1; }
             // ---- the <= 18 contiguous slot ranges of the neighbourhood: 9 rows x (one range, or two when the x range wraps)
             const int k = cxb - cxa + 1;
             const bool fits = nx >= k + 3;
@@ -876,7 +891,7 @@ k_gate_rows(DevSys s, FlatList fl) {
             int x = len;
             for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
             if (lane < 19) { sh_sb[lane] = b; sh_soff[lane] = x - len; }
-            if (lane == 0) { sh_cx[0] = cxa; sh_cx[1] = cxb; }
+            if (lane == 0) { sh_cx[0] = cxa; sh_cx[1] = cxb; sh_cx[2] = lastv; }
             const int C = __shfl_sync(0xffffffffu, x, 18);
             if (lane == 0) {
                 sh_ok = (fits && C <= GR_TILE) ? 1 : 0;
@@ -885,6 +900,8 @@ k_gate_rows(DevSys s, FlatList fl) {
         }
         __syncthreads();
         if (!sh_ok) return;
+        const int last = sh_cx[2];
+        const int count = last - first + 1;
         const int C = sh_soff[18];
         const int Cpad = (C + 4 * GR_SL - 1) / (4 * GR_SL) * (4 * GR_SL);
         const double ccen[3] = {0.5 * (sh_cx[0] + sh_cx[1] + 1) / nx, (cy + 0.5) / ny, (cz + 0.5) / s.nc[2]};
@@ -998,6 +1015,219 @@ k_gate_rows(DevSys s, FlatList fl) {
             if (lane < nh) fl.pair[off + lane] = make_int2(first + t, t_slot[my_row[t]]);
             if (big && lane + 32 < nh) fl.pair[off + lane + 32] = make_int2(first + t, t_slot[my_row[32 * GR_STRIDE + t]]);
         }
+        first = last + 1;
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_gate_rows_gen: the same thread-per-target gate for systems with spheres, mixed types and bonded molecules (the lipid
+// membrane: ~80 particles per cell, 2 000 candidates per neighbourhood of which 2 % interact -- k_gate_cells spends 93 % of the
+// membrane's full-energy pass there). Differences from k_gate_rows:
+//   * the neighbourhood of a unit is processed in tiles of GR_TILE candidates; hits (sorted slots, 32 bit) stay in shared
+//     memory across the tiles
+//   * the reach depends on the (target type, candidate type) pair: per-lane row of a T x T table in shared memory (T <= 8)
+//   * chain neighbours: candidates whose original index is within +-2 of the target's are left out of the distance scan
+//     (one subtract and one unsigned compare per test, which also drops the target itself) and decided per target
+//     afterwards: a bonded partner (ParticleVector::getConlist, structures/Conf.h:90-147) is always listed -- the cutoff does
+//     not apply to it (mc/paire.h:1214) -- any other one by its exact FP64 minimum-image distance.
+// ------------------------------------------------------------------------------------------------
+constexpr int GG_CAP = 48;          // hits per (target, slice)
+constexpr int GG_TILE = 768;        // staged candidates per tile
+constexpr int GG_STRIDE = 33;       // words per buffer row
+constexpr int GG_MAXT = 8;          // particle types the shared reach table holds
+
+template <int MODE>
+__global__ void __launch_bounds__(GR_SL * 32, 4)
+k_gate_rows_gen(DevSys s, FlatList fl) {
+    __shared__ float4 t_pf[GG_TILE];                // x, y, z relative to the unit centre (length units), w = x^2 + y^2 + z^2
+    __shared__ __align__(16) int t_ot[GG_TILE];     // original index | type << 24
+    __shared__ __align__(16) int t_slot[GG_TILE];
+    __shared__ int sh_hit[GR_SL][GG_CAP * GG_STRIDE];
+    __shared__ int sh_cnt[GR_SL][GR_T];
+    __shared__ int sh_off[GR_SL][GR_T];
+    __shared__ float sh_reach[GG_MAXT * GG_MAXT];
+    __shared__ int sh_sb[20], sh_soff[20];
+    __shared__ int sh_cx[3];
+    __shared__ int sh_ok;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int row = blockIdx.y;
+    const int nx = s.nc[0], ny = s.nc[1];
+    const int cy = row % ny, cz = row / ny;
+    const int rs = s.cell_start[row * nx], re = s.cell_start[(row + 1) * nx];
+    const int T = s.ntypes;
+    for (int k = threadIdx.x; k < T * T; k += blockDim.x) sh_reach[k] = s.reach2[k];
+    // A unit is 32 consecutive slots of the row. Where the row is sparse such a unit would span many cells (and its neighbourhood
+    // the whole row): it is then processed in sub-units of at most kmax cells each (dense rows: one sub-unit, all lanes busy).
+    const int kmax = min(6, nx - 3);
+    for (int ufirst = rs + GR_T * blockIdx.x; ufirst < re; ufirst += GR_T * gridDim.x) {
+      const int ulast = min(ufirst + GR_T, re) - 1;
+      for (int first = ufirst; first <= ulast;) {
+        __syncthreads();
+        if (wid == 0) {
+            int cxa = 0, cxb = 0;
+            for (int c0 = 0; c0 < nx; c0 += 32) {
+                const int cxl = c0 + lane;
+                int b = 0, e = 0;
+                if (cxl < nx) { b = s.cell_start[row * nx + cxl]; e = s.cell_start[row * nx + cxl + 1]; }
+                const unsigned ma = __ballot_sync(0xffffffffu, cxl < nx && b <= first && first < e);
+                const unsigned mb = __ballot_sync(0xffffffffu, cxl < nx && b <= ulast && ulast < e);
+                if (ma) cxa = c0 + __ffs(ma) - 1;
+                if (mb) cxb = c0 + __ffs(mb) - 1;
+            }
+            int lastv = ulast;
+            if (cxb - cxa + 1 > kmax) { cxb = cxa + kmax - 1; lastv = s.cell_start[row * nx + cxb + 1] - 1; }
+            const int k = cxb - cxa + 1;
+            const bool fits = nx >= k + 3;
+            int b = 0, len = 0;
+            if (fits && lane < 18) {
+                const int rr = lane >> 1, part = lane & 1;
+                const int yy = (cy + rr % 3 - 1 + ny) % ny, zz = (cz + rr / 3 - 1 + s.nc[2]) % s.nc[2];
+                const int rbase = (zz * ny + yy) * nx;
+                const int lo = cxa - 1, hi = cxb + 1;
+                int a0, a1;
+                if (lo < 0) { if (part == 0) { a0 = 0; a1 = hi; } else { a0 = lo + nx; a1 = nx - 1; } }
+                else if (hi >= nx) { if (part == 0) { a0 = lo; a1 = nx - 1; } else { a0 = 0; a1 = hi - nx; } }
+                else { a0 = part == 0 ? lo : 1; a1 = part == 0 ? hi : 0; }
+                if (a0 <= a1) { b = s.cell_start[rbase + a0]; len = s.cell_start[rbase + a1 + 1] - b; }
+            }
+            int x = len;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane < 19) { sh_sb[lane] = b; sh_soff[lane] = x - len; }
+            if (lane == 0) { sh_cx[0] = cxa; sh_cx[1] = cxb; sh_cx[2] = lastv; sh_ok = fits ? 1 : 0; if (!fits) atomicOr(fl.overflow, 4); }
+        }
+        __syncthreads();
+        if (!sh_ok) return;
+        const int last = sh_cx[2];
+        const int count = last - first + 1;
+        const int C = sh_soff[18];
+        const double ccen[3] = {0.5 * (sh_cx[0] + sh_cx[1] + 1) / nx, (cy + 0.5) / ny, (cz + 0.5) / s.nc[2]};
+        auto staged = [&](const double4& pw) {
+            const float x = (float)(rel_frac(pw.x + s.shift[0], ccen[0]) * s.box[0]), y = (float)(rel_frac(pw.y + s.shift[1], ccen[1]) * s.box[1]),
+                        z = (float)(rel_frac(pw.z + s.shift[2], ccen[2]) * s.box[2]);
+            return make_float4(x, y, z, x * x + y * y + z * z);
+        };
+        // ---- this lane's target
+        float m2x = 0.f, m2y = 0.f, m2z = 0.f, tt2 = __int_as_float(0x7f800000);      // idle lanes: threshold -inf, never a hit
+        int target = -0x40000000, ttype = 0, tmol = 0;
+        double4 tpw = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (lane < count) {
+            tpw = s.posw[first + lane];
+            const float4 q = staged(tpw);
+            m2x = -2.f * q.x; m2y = -2.f * q.y; m2z = -2.f * q.z; tt2 = q.w;
+            target = w_orig(tpw.w); ttype = w_type(tpw.w); tmol = w_moltype(tpw.w);
+        }
+        // targets of the heavy types (a rod among lipid beads has hundreds of partners) are left to k_gate_cells, launched next
+        const bool mine = lane < count && !((fl.heavy_types >> ttype) & 1u);
+        if (!mine) { tt2 = __int_as_float(0x7f800000); target = -0x40000000; }
+        const float* reach_row = sh_reach + ttype * T;
+        int* buf = sh_hit[wid];
+        int cur = lane;
+        const int cur_max = lane + (GG_CAP - 4) * GG_STRIDE;
+        for (int t0 = 0; t0 < C; t0 += GG_TILE) {
+            const int TC = min(GG_TILE, C - t0);
+            const int TCpad = (TC + 4 * GR_SL - 1) / (4 * GR_SL) * (4 * GR_SL);
+            __syncthreads();            // previous tile consumed
+            for (int k = wid; k < 18; k += GR_SL) {
+                const int b = sh_sb[k], off = sh_soff[k], len = sh_soff[k + 1] - off;
+                const int lo = max(off, t0), hi = min(off + len, t0 + TC);
+                for (int p = lo + lane; p < hi; p += 32) {
+                    const double4 pw = s.posw[b + (p - off)];
+                    t_pf[p - t0] = staged(pw); t_ot[p - t0] = w_orig(pw.w) | (w_type(pw.w) << 24); t_slot[p - t0] = b + (p - off);
+                }
+            }
+            for (int p = TC + threadIdx.x; p < TCpad; p += blockDim.x) {
+                t_pf[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+                t_ot[p] = 0x00ffffff; t_slot[p] = 0;
+            }
+            __syncthreads();
+            {
+                for (int c0 = 4 * wid; c0 < TCpad; c0 += 4 * GR_SL) {
+                    const int4 ot4 = *reinterpret_cast<const int4*>(t_ot + c0);
+                    const int ot[4] = {ot4.x, ot4.y, ot4.z, ot4.w};
+                    bool hit[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const float4 q = t_pf[c0 + u];
+                        const float sq = fmaf(m2z, q.z, fmaf(m2y, q.y, fmaf(m2x, q.x, q.w)));
+                        const int ob = ot[u] & 0xffffff;
+                        const float thr = reach_row[ot[u] >> 24] - tt2;
+                        // the target itself and its chain neighbours (original index within +-2) are decided after the scan
+                        hit[u] = (sq <= thr) & ((unsigned)(ob - target + 2) > 4u) & (MODE == 2 ? ob < target : true);
+                    }
+                    if (hit[0] | hit[1] | hit[2] | hit[3]) {
+                        const int4 sl4 = *reinterpret_cast<const int4*>(t_slot + c0);
+                        const int sl[4] = {sl4.x, sl4.y, sl4.z, sl4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u++) { buf[cur] = sl[u]; cur += hit[u] ? GG_STRIDE : 0; }
+                        cur = min(cur, cur_max);
+                    }
+                }
+            }
+        }
+        // ---- chain neighbours and other particles whose original index is within +-2 (slice 0 only)
+        if (wid == 0 && mine) {
+            ConList cl;
+            get_conlist(s.mol, tmol, target, cl);
+            const v3 tp = mk(tpw.x, tpw.y, tpw.z);
+#pragma unroll
+            for (int dd = 0; dd < 4; dd++) {
+                const int partner = target + (dd == 0 ? -2 : dd == 1 ? -1 : dd == 2 ? 1 : 2);
+                if (partner < 0 || partner >= s.n) continue;
+                if (MODE == 2 && partner > target) continue;
+                const int ps = s.slot_of[partner];
+                bool list = (partner == cl.con[0]) | (partner == cl.con[1]) | (partner == cl.con[2]) | (partner == cl.con[3]);
+                if (!list) {
+                    const double4 pw = s.posw[ps];
+                    const v3 r = image(s.box, tp, mk(pw.x, pw.y, pw.z));
+                    list = dot(r, r) <= (double)reach_row[w_type(pw.w)];
+                }
+                if (list) { buf[cur] = ps; cur = min(cur + GG_STRIDE, cur_max); }
+            }
+        }
+        if (cur == cur_max) { atomicOr(fl.overflow, 4); atomicOr(fl.heavy, 1 << ttype); }       // rare: the host repeats with this type split off
+        const int cnt = (cur - lane) / GG_STRIDE;
+        sh_cnt[wid][lane] = cnt;
+        __syncthreads();
+        if (wid == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < GR_SL; w++) tot += sh_cnt[w][lane];
+            int x = tot;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            const int total = __shfl_sync(0xffffffffu, x, 31);
+            int base = 0;
+            if (lane == 0) {
+                base = atomicAdd(fl.total, total);
+                const bool ok = base + total <= fl.cap;
+                if (!ok) atomicOr(fl.overflow, 2);
+                sh_ok = ok ? 1 : 0;
+            }
+            base = __shfl_sync(0xffffffffu, base, 0) + x - tot;
+            {
+                int o = base;
+#pragma unroll
+                for (int w = 0; w < GR_SL; w++) { sh_off[w][lane] = o; o += sh_cnt[w][lane]; }
+            }
+            if (mine) {
+                fl.chunks[target] = make_int4(base, tot, -1, 0);
+                fl.head[target] = target;
+            }
+        }
+        __syncthreads();
+        if (!sh_ok) return;
+        const int my_off = sh_off[wid][lane];
+        const bool big = __any_sync(0xffffffffu, cnt > 32);
+        const int* my_row = buf + lane * GG_STRIDE;
+#pragma unroll
+        for (int t = 0; t < GR_T; t++) {
+            if (t >= count) break;
+            const int nh = __shfl_sync(0xffffffffu, cnt, t), off = __shfl_sync(0xffffffffu, my_off, t);
+            if (lane < nh) fl.pair[off + lane] = make_int2(first + t, my_row[t]);
+            if (big && lane + 32 < nh) fl.pair[off + lane + 32] = make_int2(first + t, my_row[32 * GG_STRIDE + t]);
+        }
+        first = last + 1;
+      }
     }
 }
 
@@ -1417,6 +1647,8 @@ struct scgpu_ctx {
     int* d_pl_overflow = nullptr;
     int pl_cap = 0;
     bool rods_only = false;          // every particle an un-bonded rod: the specialised kernels apply
+    int last_overflow = 0;
+    unsigned heavy_types = 0;        // particle types whose targets k_gate_rows_gen could not hold: they go to k_gate_cells
     int one_type = -1;               // >= 0: every particle present has this type (single table entry -> kernel parameter)
     bool use_rows = true;            // k_gate_rows until a launch reports a layout it cannot hold (then k_gate_cells for good)
     bool any_two_patch = false;      // some particle type present carries a second patch (TPSC/TCPSC/TCHPSC/TCHCPSC)
@@ -1714,6 +1946,7 @@ static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const 
     if (!same_types) {
         c->types_valid = true;
         c->use_rows = true;
+        c->heavy_types = 0;
         std::vector<char> tu(c->ntypes, 0), mu(c->nmol, 0);
         for (int i = 0; i < n; i++) { tu[type[i]] = 1; mu[moltype[i]] = 1; }
         bool rods = true;
@@ -1894,6 +2127,7 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
         fl.pair = c->d_fl_pair; fl.e = c->d_fl_e; fl.total = c->d_pl_total + 3; fl.cap = c->fl_cap; fl.head = c->d_fl_head;
         fl.chunks = c->d_fl_chunks; fl.chunk_count = c->d_pl_total + 4; fl.chunk_cap = c->fl_chunk_cap;
         fl.plist = c->d_fl_plist; fl.ptotal = c->d_pl_total + 5; fl.overflow = c->d_pl_overflow;
+        fl.heavy = c->d_pl_total + 6; fl.heavy_types = 0;
         const bool wrap = c->nc[0] < 5 || c->nc[1] < 5 || c->nc[2] < 5;
         const bool one = c->one_type >= 0 && c->rods_only;
         const scgpu_iaparam& ia1 = c->h_ia[one ? (size_t)c->one_type * c->ntypes + c->one_type : 0];
@@ -1903,6 +2137,18 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
             if (mode == 1) k_gate_rows<1><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
             else k_gate_rows<2><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
             if (one) k_cheap_flat<true, true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<true, false><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
+        } else if (!c->rods_only && c->use_rows && !wrap && !d_counters && nrows <= 65535 && c->ntypes <= GG_MAXT) {
+            const dim3 grid((unsigned)(c->n / nrows / GR_T + 2), (unsigned)nrows);
+            fl.heavy_types = c->heavy_types;
+            if (mode == 1) k_gate_rows_gen<1><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
+            else k_gate_rows_gen<2><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
+            if (c->heavy_types) {      // the few targets with very many partners: the cell gate, restricted to their types
+                if (mode == 1) k_gate_cells<1, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, nullptr);
+                else k_gate_cells<2, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, nullptr);
+                c->launches++;
+            }
+            fl.heavy_types = 0;
+            k_cheap_flat<false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         } else if (c->rods_only) {
             if (mode == 1) { if (wrap) k_gate_cells<1, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             else { if (wrap) k_gate_cells<2, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
@@ -1937,12 +2183,19 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
 // flag) the results of that launch are invalid: grow the list 4x and let the caller repeat the launch
 static int overflow_then_grow(scgpu_ctx* c, bool* repeat) {
     int* hflag = (int*)(c->h_small + 256 + 64);
-    CK(cudaMemcpyAsync(hflag, c->d_pl_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(hflag, c->d_pl_overflow, 6 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));      // [0] flags ... [5] heavy-type mask
     CK(cudaStreamSynchronize(c->stream));
     *repeat = false;
     if (!*hflag) return 0;
     const int which = *hflag;      // bit 0: patch work list, bit 1: flat pair list, bit 2: k_gate_rows cannot hold this configuration
-    if (which & 4) c->use_rows = false;
+    c->last_overflow = which;
+    if (which & 4) {
+        const unsigned heavy = (unsigned)hflag[5];       // d_pl_total[6]
+        unsigned present = 0;
+        for (int t = 0; t < c->ntypes && t < 32; t++) present |= 1u << t;
+        if (!c->rods_only && heavy && ((c->heavy_types | heavy) & present) != present) c->heavy_types |= heavy;     // split those types off and try again
+        else c->use_rows = false;
+    }
     if (which & 2) {
         if ((long long)c->fl_cap * 2 > (1ll << 30)) { g_err = "flat pair list overflow: more gated pairs than the list can ever hold"; return SCGPU_ERR_STATE; }
         cudaFree(c->d_fl_pair); cudaFree(c->d_fl_e); cudaFree(c->d_fl_plist); cudaFree(c->d_fl_chunks);
@@ -2327,7 +2580,11 @@ extern "C" int scgpu_sync(scgpu_ctx* c) {
     CK(cudaSetDevice(c->device));
     bool grew = false;
     if (int r = overflow_then_grow(c, &grew)) return r;
-    if (grew) { g_err = "scgpu_sync: an asynchronous energy launch overflowed the patch work list; its results are invalid (the list has been grown: repeat the call)"; return SCGPU_ERR_STATE; }
+    if (grew) {
+        g_err = "scgpu_sync: an asynchronous energy launch could not complete (a work list overflowed and has been grown, or the row-unit gate met a layout it cannot hold and has been switched off); its results are invalid: repeat the call [flags " +
+                std::to_string(c->last_overflow) + "]";
+        return SCGPU_ERR_STATE;
+    }
     return SCGPU_OK;
 }
 extern "C" int scgpu_kernel_launches(scgpu_ctx* c, int64_t* launches) {

@@ -169,6 +169,27 @@ E 160
             az = rnd.uniform(0.0, 2.0 * math.pi)
             lines.append(_fmt(c) + "   " + _fmt((0.0, 1.0, 0.0)) + "   " + _fmt((math.cos(az), 0.0, math.sin(az))) + " 0")
         return top, "\n".join(lines) + "\n"
+    if kind == "rods_in_spheres":
+        # 48 000 small attractive spheres and 40 long patchy rods on a 5 x 5 x 5 grid: a sphere has ~20 partners, a rod ~300 -- more
+        # than the per-target buffers of k_gate_rows_gen hold, so the rod type is split off to k_gate_cells (adaptive, per launch)
+        top = """[Types]
+S1 1 SPA    1.0  1.0  1.12246205  1.0
+R2 2 CPSC   1.0  1.0  1.12246205  1.0  120 5.0  6  0.0
+[Molecules]
+A: {
+particles: 1
+}
+B: {
+particles: 2
+}
+[System]
+A 48000
+B 40
+"""
+        box = (46.0, 46.0, 46.0)
+        lines = [_fmt(box)]
+        _gas(rnd, 48040, box, lines)
+        return top, "\n".join(lines) + "\n"
     if kind == "mix":
         top = """[Types]
 S1 1 SPA    1.333333  1.2  1.346954458  0.3

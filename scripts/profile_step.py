@@ -32,6 +32,8 @@ else:
 hs = HostSystem(top, cfg)
 eng = Engine(0, variant).load(hs)
 eng.build_cells()
+if what in ("everyone", "all_to_all", "membrane"):     # one synchronous call first: list sizes and the gate's kernel choice settle here
+    eng.all_to_all() if what != "everyone" else eng.one_to_all_everyone()
 for _ in range(reps):
     if what == "everyone":
         eng.one_to_all_everyone(fetch=False)
@@ -74,7 +76,7 @@ if what == "membrane_chainsweep":
         eng.sweep_chains(mp, cm, 4242, k)
     eng.sync()
     print("ms_per_sweep %.3f (N = %d, chainprob 0.5)" % ((time.perf_counter() - t0) / 3 * 1e3, n))
-if what in ("everyone", "all_to_all"):                # device time per pass (not under a profiler)
+if what in ("everyone", "all_to_all", "membrane"):    # device time per pass (not under a profiler)
     ms = []
     for k in range(20):
         eng.flush_l2()
