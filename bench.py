@@ -505,7 +505,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--with-membrane", action="store_true", help="also time the 265k-particle membrane full-energy pass (configs[2])")
+    ap.add_argument("--with-membrane", action="store_true", default=True, help="also time the 265k-particle membrane full-energy pass (configs[2]); on by default")
+    ap.add_argument("--no-membrane", dest="with_membrane", action="store_false", help="skip the membrane leg")
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: libraries that write to file descriptor 1 on their own (NCCL prints its version banner
     # there when NCCL_DEBUG is set) are sent to stderr for the duration of the run, the JSON line goes to the real stdout
