@@ -194,6 +194,10 @@ int scgpu_replica_record(scgpu_ctx* ctx, void** device_ptr_out);
 /* measurement helpers (CUDA events on the context's stream; FP64 FMA-chain peak microbenchmark) */
 int scgpu_timer_start(scgpu_ctx* ctx);
 int scgpu_timer_stop(scgpu_ctx* ctx, float* ms);
+/* waits for the context's stream. Returns SCGPU_ERR_STATE when an asynchronous energy launch (e_host == NULL forms,
+ * scgpu_submit_everyone) could not complete -- a work list overflowed and has been grown, or the thread-per-target gate met
+ * a layout it cannot hold and the library has switched those targets (or the whole pass) to the cell gate: the results of
+ * that launch are invalid, repeat the call (synchronous calls repeat internally and never report this). */
 int scgpu_sync(scgpu_ctx* ctx);
 int scgpu_fp64_peak(scgpu_ctx* ctx, double* tflops);
 int scgpu_flush_l2(scgpu_ctx* ctx);
