@@ -9,8 +9,9 @@ synthetic (sc_b200/synth.py, seed 12345). A STEP = one pass of the pair-energy p
 one-to-all trial energy of every particle against its 27-cell neighbourhood (N = 65 536 oneToAllTrial evaluations,
 one warp each, one kernel launch). Metric = gated pair-energy evaluations per second (pairs that pass the
 reference's sqmaxcut gate and reach a functor, PairE::operator(), scOOP/mc/paire.h:1209-1220).
-At N > 1 every rank holds its own replica (parallel tempering: one replica per GPU, weak scaling) and the ranks
-exchange their {E, V, N} records with one NCCL all-gather per step, as replicaExchangeMove does every nrepchange sweeps.
+At N > 1 every rank holds its own replica of the energy workload (weak scaling, no data-path collective); the parallel-tempering
+leg (secondary.parallel_tempering, BASELINE configs[4]) runs 8 replicas on the N GPUs with a replica exchange through the
+C ABI (scgpu_replica_exchange: device-side records, one ncclAllGather, device decision) every 10 sweeps, timed inside.
 """
 import argparse
 import json
@@ -216,10 +217,6 @@ def run_ours(args):
     _, ncand, ngate = eng.one_to_all_everyone(fetch=True, count=True)   # also builds the cell list
     peak = eng.fp64_peak()
     import torch
-    rec_t = None
-    if world > 1:
-        from sc_b200.replica import record_tensor
-        gathered = torch.zeros(world * 8, dtype=torch.float64, device="cuda")
 
     def step():
         eng.one_to_all_everyone(fetch=False)
@@ -239,9 +236,6 @@ def run_ours(args):
         eng.timer_start()
         step()
         kernel_ms.append(eng.timer_stop())
-        if world > 1:                         # replica exchange record: full energy -> NCCL all-gather (not in kernel_ms)
-            rec_t = record_tensor(eng)
-            dist.all_gather_into_tensor(gathered, rec_t)
     eng.sync()
     if world > 1:
         torch.cuda.synchronize()
@@ -399,27 +393,79 @@ def run_ours(args):
               "temper": 0.1, "transmx": 0.0212, "rotmx_deg": 7.5, "sweeps_timed": nsw,
               "note": "whole scgpu_sweep_checkerboard call: shifted cell build + 8 colour passes + statistics read-back"}
 
-    # several replicas on ONE GPU (the 8-replica parallel-tempering configuration on fewer than 8 GPUs): the sweeps of
-    # one 65k system are bound by the serial chain of trials inside a cell, so independent replicas on their own streams overlap
-    if world == 1:
-        R = 8
-        engines = [eng] + [Engine(local, "fast").load(hs) for _ in range(R - 1)]
-        for k in range(2):
-            for r, e in enumerate(engines):
-                e.sweep(mp, 777 + r, k, stats=False)
-        for e in engines:
-            e.sync()
-        t0 = time.perf_counter()
-        for k in range(nsw):
-            for r, e in enumerate(engines):
-                e.sweep(mp, 777 + r, 2 + k, stats=False)
-        for e in engines:
-            e.sync()
-        dt = time.perf_counter() - t0
-        sweeps["replicas_on_one_gpu"] = {"replicas": R, "aggregate_sweeps_per_s": R * nsw / dt, "ms_per_sweep_per_replica": dt / nsw * 1e3 / 1.0,
-                                          "trial_moves_per_s": R * nsw * n / dt}
-        for e in engines[1:]:
-            e.close()
+    # ---- BASELINE configs[4]: parallel tempering, 8 replicas x 65 536 PSC on `world` GPUs (8 / world replicas per GPU, each on its
+    # own stream), one scgpu_replica_exchange every nrepchange = 10 sweeps: allToAll() of every replica, records packed on the device,
+    # ONE ncclAllGather, device decision kernel (sc_b200/csrc/comm.cuh). Timed on the device: events on every replica's stream
+    # bracket the loop (all streams idle at the start), max over replicas and ranks.
+    from sc_b200 import replica as _rep
+    from sc_b200.engine import Comm
+    R_total = 8
+    nlocal = max(1, R_total // world)
+    engines = [eng] + [Engine(local, "fast").load(hs) for _ in range(nlocal - 1)]
+    for e in engines:
+        e.set_particles(hs.state, hs.type, hs.moltype)
+    if world > 1:
+        box = [Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, device=torch.device("cuda", local))
+        comm = Comm(local, world, rank, box[0])
+    else:
+        comm = Comm(local, 1, 0)
+    ptr = _rep.ParallelTempering(comm, engines, 0.1, 0.13, 0.0212, 7.5, nrepchange=10, seed=145658)
+    nsw_pt = 20 if args.steps >= 10 else 10
+    for k in range(1, 11):                   # warm-up: 10 sweeps and one exchange (also creates the NCCL channels)
+        ptr.sweep(k)
+    for e in engines:
+        e.sync()
+    ptr.exchange_us.clear()
+    acc0, rej0 = sum(ptr.acc), sum(ptr.rej)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+    for e in engines:
+        e.timer_start()
+    t0 = time.perf_counter()
+    t_exch = 0.0
+    for k in range(11, 11 + nsw_pt):
+        if k % 10 == 0:
+            te = time.perf_counter()
+            ptr.sweep(k)
+            t_exch += time.perf_counter() - te      # host view of a sweep submission + the whole exchange call
+        else:
+            ptr.sweep(k)
+    pt_ms = max(e.timer_stop() for e in engines)
+    pt_wall = time.perf_counter() - t0
+    acc1, rej1 = sum(ptr.acc) - acc0, sum(ptr.rej) - rej0
+    vals = [pt_ms, float(np.mean(ptr.exchange_us)) if ptr.exchange_us else 0.0, float(acc1), float(rej1)]
+    if world > 1:
+        t = torch.tensor(vals[:2], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c2 = torch.tensor(vals[2:], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c2, op=dist.ReduceOp.SUM)
+        vals = [float(t[0].item()), float(t[1].item()), float(c2[0].item()), float(c2[1].item())]
+    pt_ms, exch_us, acc1, rej1 = vals
+    n_exch = nsw_pt // 10
+    # the full energy of one replica alone (what every exchange needs first), for the share of the exchange that is energy
+    fe = []
+    for _ in range(3):
+        eng.timer_start()
+        eng.all_to_all(fetch=False)
+        fe.append(eng.timer_stop())
+    pt = {"workload": "BASELINE configs[4]: parallel tempering, %d replicas x %d PSC, T = 0.1 .. 0.13 (ladder of sim.h:389-393), exchange every 10 sweeps" % (ptr.R, n),
+          "replicas": ptr.R, "gpus": world, "replicas_per_gpu": nlocal, "sweeps_timed": nsw_pt, "exchanges_timed": n_exch,
+          "aggregate_sweeps_per_s": ptr.R * nsw_pt / (pt_ms * 1e-3), "ms_per_sweep_all_replicas": pt_ms / nsw_pt,
+          "trial_moves_per_s": ptr.R * nsw_pt * n / (pt_ms * 1e-3),
+          "exchange_us_after_energy": exch_us, "all_to_all_us_one_replica": float(np.mean(fe)) * 1e3,
+          "exchange_share_of_time": (exch_us + float(np.mean(fe)) * 1e3 * nlocal) * n_exch * 1e-3 / pt_ms,
+          "exchange_call_host_ms": t_exch / max(1, n_exch) * 1e3,
+          "pair_acceptance": acc1 / max(1.0, acc1 + rej1), "pairs_attempted": int((acc1 + rej1) // 2),
+          "analytic_estimate": _rep.switch_probability_estimate(n, ptr.dtemp),
+          "analytic_note": "exp(-0.5 N dT^2 / (1 + dT)) as the reference prints it (mc/inicializer.cpp:52-55); with N = 65 536 and 8 rungs between T = 0.1 and 0.13 it is ~0: the ladder of BASELINE configs[4] is far too coarse for this system size, exchanges are attempted and (correctly) rejected",
+          "timing": "CUDA events on every replica's stream around the whole loop (sweeps + exchanges), max over replicas and ranks; wall %.4f s" % pt_wall,
+          "path": "scgpu_replica_exchange (C ABI): device-side records, %s, device decision kernel; no host round trip of the energies" % ("one ncclAllGather of %d x 512 B" % ptr.R if world > 1 else "one process: device copy instead of NCCL")}
+    comm.close()
+    for e in engines[1:]:
+        e.close()
+    sweeps["parallel_tempering"] = pt
 
     if rank != 0:
         if world > 1:
@@ -430,16 +476,32 @@ def run_ours(args):
     try:
         from oracle import oracle as O
         s = O.system_from_text(top, cfg)
-        sample = list(range(0, n, 64))
+        sample = sorted(np.random.default_rng(2024).choice(n, 1024, replace=False).tolist())      # unbiased: random targets, not a lattice stride
         d = O.count_flops(s, sample)
         flops_sample = sum(FLOP_WEIGHTS[k] * d[k] for k in FLOP_WEIGHTS)
-        flops_step = flops_sample * (n / len(sample))
-        ach = flops_step / (np.mean(kernel_ms) * 1e-3) / 1e12
+        gate_sample = sum(FLOP_WEIGHTS[k] * d["gate"][k] for k in FLOP_WEIGHTS)
+        scale = n / len(sample)
+        flops_step, flops_gate = flops_sample * scale, gate_sample * scale
+        flops_functor = flops_step - flops_gate
+        kms = float(np.mean(kernel_ms))
+        ach = flops_step / (kms * 1e-3) / 1e12
+        us = eng.profile_everyone()           # one pass with events between the launches (warm L2; shares, not absolutes)
+        us_tot = sum(us)
+        fp64_us = us[1] + us[2]
         roof.update({"achieved": ach, "frac": ach / peak, "flops_per_launch": flops_step,
-                     "flops_per_gated_pair": flops_sample / max(1, d["gated"]),
+                     "flops_gate": flops_gate, "flops_functor": flops_functor,
+                     "flops_per_candidate_gate": gate_sample / max(1, d["candidates"]),
+                     "flops_per_gated_pair_functor": (flops_sample - gate_sample) / max(1, d["gated"]),
+                     "candidates_per_target_sampled": d["candidates"] / len(sample), "gated_per_target_sampled": d["gated"] / len(sample),
+                     "counting": "op-counting oracle over 1024 random targets: the cutoff gate of PairE::operator() (image + |r|^2, 17 flop) ONCE per candidate + the functor work of every gated pair; add/sub/mul/div/sqrt = 1, cos/acos = 20, pow = 3",
                      "peak_source": "DFMA-chain microbenchmark in this process (scgpu_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
-                     "kernel_ms": float(np.mean(kernel_ms)),
-                     "kernels": "one step = k_gate_cells + k_cheap_flat + k_patch_flat + k_combine_flat (shares in profiles/launches_r1_summary.txt)"})
+                     "kernel_ms": kms,
+                     "per_kernel_us": {"gate": us[0], "cheap": us[1], "patch": us[2], "combine": us[3]},
+                     "per_kernel_share": {"gate": us[0] / us_tot, "cheap": us[1] / us_tot, "patch": us[2] / us_tot, "combine": us[3] / us_tot},
+                     "functor_frac_over_fp64_kernels": flops_functor / (fp64_us * 1e-6) / 1e12 / peak,
+                     "functor_frac_over_step": flops_functor / (kms * 1e-3) / 1e12 / peak,
+                     "note": "the gate runs in FP32 (its 17 flop per candidate are algorithmic FP64 flops of the reference, executed as 3 FFMA + compare); the FP64 pipe sees the functor work only -- compare functor_frac_over_fp64_kernels with ncu sm__pipe_fp64_cycles_active of the cheap/patch kernels in profiles/",
+                     "kernels": "one step = gate (k_gate_rows) + cheap terms (k_cheap_flat) + patch terms (k_patch_flat) + k_combine_flat; per_kernel_us measured live by scgpu_profile_everyone"})
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             roof["traffic"] = json.load(open(prof)).get("pipeline_dram_bytes_per_step_total")

@@ -187,9 +187,80 @@ int scgpu_sweep_checkerboard_chains(scgpu_ctx* ctx, const scgpu_moveparams* mp, 
 /* volume move between sweeps; the random numbers are a pure function of (seed, step) */
 int scgpu_pressure_move(scgpu_ctx* ctx, const scgpu_pressureparams* pp, uint64_t seed, uint64_t step, scgpu_pressurestats* out);
 
-/* replica exchange helper (MoveCreator::replicaExchangeMove, scOOP/mc/movecreator.cpp:552-795): full energy stays on
- * the device; returns the device address of a packed double[8] record {E, V, N, 0...} for an NCCL all-gather */
-int scgpu_replica_record(scgpu_ctx* ctx, void** device_ptr_out);
+/* ---- multi-GPU: parallel-tempering replicas / Wang-Landau walkers, one process per GPU, NCCL over NVLink -------------------
+ * The reference's only parallel mode is one MPI rank per replica/walker (ENABLE_MPI): MoveCreator::replicaExchangeMove
+ * (scOOP/mc/movecreator.cpp:552-795) and the shared Wang-Landau arrays (scOOP/mc/wanglandau.cpp:190-212, wanglandau.h:66-123,
+ * 282-289). A communicator spans `nranks` processes, each holding `nlocal` replicas on its GPU (8 replicas on 1/2/4/8 GPUs =
+ * 8/4/2/1 per GPU). NCCL is loaded at run time (libnccl.so.2) and only when nranks > 1. */
+typedef struct scgpu_comm scgpu_comm;
+#define SCGPU_UNIQUE_ID_BYTES 128
+#define SCGPU_REPLICA_PAYLOAD 40
+#define SCGPU_REPLICA_MOLTYPES 8
+#define SCGPU_MAX_LOCAL_REPLICAS 16
+
+/* rank 0 draws the NCCL unique id (ncclGetUniqueId), the host program hands it to the other ranks (MPI_Bcast in the reference's
+ * own main(), a torch.distributed store in ours) and every rank creates the communicator (ncclCommInitRank; replaces MPI_Init +
+ * MPI_Comm_rank/size, scOOP/main.cpp:37-45). nranks == 1 needs no id and no NCCL. */
+int scgpu_comm_unique_id(char id[SCGPU_UNIQUE_ID_BYTES]);
+int scgpu_comm_create(scgpu_comm** out, int device, int nranks, int rank, const char id[SCGPU_UNIQUE_ID_BYTES]);
+/* the same around an ncclComm_t the caller already owns (it is not destroyed by scgpu_comm_destroy) */
+int scgpu_comm_attach(scgpu_comm** out, int device, void* nccl_comm, int nranks, int rank);
+int scgpu_comm_destroy(scgpu_comm* comm);
+
+/* What a replica owns and what travels on an accepted exchange: temperature, pressure, pseudo-rank and a payload (the reference
+ * swaps its whole Statistics block, i.e. the adapted step sizes and counters that belong to the temperature:
+ * movecreator.cpp:670-671, 766-767; the caller packs what it wants to travel -- per-type trans/rot maxima, edge maximum). */
+typedef struct scgpu_replica_state {
+    double temper, press;                       /* Sim::temper, Sim::press */
+    int pseudo_rank;                            /* Sim::pseudoRank: position on the temperature ladder */
+    int replica;                                /* out: global replica index = rank * nlocal + local index (MpiExchangeData::mpiRank) */
+    int64_t wl_order[2];                        /* wl.currorder (only read when Wang-Landau weights are passed) */
+    double part_num[SCGPU_REPLICA_MOLTYPES];    /* molecules per molecule type (grand-canonical term, movecreator.cpp:736-739) */
+    double payload[SCGPU_REPLICA_PAYLOAD];
+    /* results of the last call */
+    int attempted, accepted;                    /* this replica was part of a pair / the pair was swapped */
+    int partner;                                /* global replica index of the partner, -1 if none */
+    int reserved;
+    int64_t partner_wl_order[2];                /* the partner's wl.currorder (the lower replica adopts it on acceptance, :757-762) */
+    double change;                              /* the exponent of the acceptance rule (:722-745) */
+    double energy, volume;                      /* this replica's allToAll() and box volume as used in the rule */
+    double edrift;                              /* what the reference adds to its drift sum on acceptance (:676-684, 751-755) */
+} scgpu_replica_state;
+
+typedef struct scgpu_exchangeparams {
+    int nrepchange;                             /* Sim::nrepchange: decides which neighbours pair up on this sweep (:616-623) */
+    int wl_len;                                 /* 0, or length of every replica's Wang-Landau weight array (wl.length[0] * max(1, wl.length[1])) */
+    int64_t wl_len0;                            /* wl.length[0] (index = order[0] + order[1] * wl_len0) */
+    double dtemp, dpress;                       /* Sim::dtemp, Sim::dpress (sim.h:389-399) */
+    double chempot[SCGPU_REPLICA_MOLTYPES];     /* MoleculeParams::chemPot where activity != -1, else 0 */
+    uint64_t seed;
+} scgpu_exchangeparams;
+
+/* MoveCreator::replicaExchangeMove for the `nlocal` replicas of this process (ctxs[k] holds replica k's configuration, states[k]
+ * its thermodynamic state; in/out). Per call: allToAll() of every local replica on its own stream, a kernel packs the records
+ * {E, V, N, T, P, pseudoRank, wl order, particle numbers, payload} on the device (the energy never visits the host), ONE
+ * ncclAllGather (replaces MPI_Alltoall + 4 point-to-point messages per pair), a device kernel takes every pair's decision -- the
+ * reference's odd/even pairing and acceptance rule with a counter-based uniform keyed on (seed, sweep, lower pseudo-rank), hence
+ * identical on every rank -- and swaps {T, P, pseudoRank, payload}; the states of the local replicas come back in one small
+ * page-locked copy. wl_weights: NULL, or nlocal arrays of wl_len doubles (host) for the Wang-Landau term of the rule. */
+int scgpu_replica_exchange(scgpu_comm* comm, int nlocal, scgpu_ctx* const* ctxs, scgpu_replica_state* states,
+                           const scgpu_exchangeparams* params, uint64_t sweep, const double* const* wl_weights);
+/* device time of the last scgpu_replica_exchange after the energy kernels: pack + all-gather + decision + copy back */
+int scgpu_comm_last_exchange_us(scgpu_comm* comm, float* us);
+
+/* Multiple-walker Wang-Landau: the reference's walkers share weights/hist through an MPI-3 shared window and update them in
+ * place (WangLandau::accept, wanglandau.h:282-289); here every walker applies its accepts to its own copy and the walkers merge
+ * every K sweeps: delta = mine - base, ncclAllReduce(sum) of the deltas, base += sum, then WangLandau::update
+ * (wanglandau.h:66-123: flatness test, alpha /= 2, weights -= wmin, hist = 0) evaluated on the device -- identically on every
+ * rank -- and {alpha, min, wmin} broadcast from rank 0 as the reference's shared_A_min_wmin. */
+typedef struct scgpu_wlstate {
+    double alpha;                               /* in/out: wl.alpha */
+    double wmin;                                /* out */
+    int64_t min, max;                           /* out: histogram extremes */
+    int halved, converged;                      /* out: alpha was halved on this call / alpha < WL_ALPHATOL (update returns true) */
+} scgpu_wlstate;
+int scgpu_wl_merge(scgpu_comm* comm, int len, double* weights, int64_t* hist, double* weights_base, int64_t* hist_base,
+                   double temper, scgpu_wlstate* st);
 
 /* measurement helpers (CUDA events on the context's stream; FP64 FMA-chain peak microbenchmark) */
 int scgpu_timer_start(scgpu_ctx* ctx);
@@ -200,6 +271,8 @@ int scgpu_timer_stop(scgpu_ctx* ctx, float* ms);
  * that launch are invalid, repeat the call (synchronous calls repeat internally and never report this). */
 int scgpu_sync(scgpu_ctx* ctx);
 int scgpu_fp64_peak(scgpu_ctx* ctx, double* tflops);
+/* one scgpu_one_to_all_everyone pass with an event between its launches: microseconds of {gate, cheap terms, patch terms, combine} */
+int scgpu_profile_everyone(scgpu_ctx* ctx, float us[4]);
 int scgpu_flush_l2(scgpu_ctx* ctx);
 int scgpu_kernel_launches(scgpu_ctx* ctx, int64_t* launches);
 

@@ -9,6 +9,17 @@
 
 struct Counters { long long add, mul, div, sqrt_, cos_, acos_, pow_; };
 static Counters g_cnt = {0, 0, 0, 0, 0, 0, 0};
+// g_gate: the share spent in the cutoff gate of PairE::operator() (image + |r|^2, once per candidate); the rest of g_cnt is
+// functor work (only pairs that pass the gate). g_enter / g_saved: snapshots used by the hooks below.
+static Counters g_gate = {0, 0, 0, 0, 0, 0, 0}, g_enter, g_saved;
+static inline void cnt_add_diff(Counters* acc, const Counters* now, const Counters* then) {
+    acc->add += now->add - then->add; acc->mul += now->mul - then->mul; acc->div += now->div - then->div; acc->sqrt_ += now->sqrt_ - then->sqrt_;
+    acc->cos_ += now->cos_ - then->cos_; acc->acos_ += now->acos_ - then->acos_; acc->pow_ += now->pow_ - then->pow_;
+}
+#define SCO_COUNT_ENTER() (g_enter = g_cnt)
+#define SCO_COUNT_GATED() cnt_add_diff(&g_gate, &g_cnt, &g_enter)
+#define SCO_COUNT_PAUSE() (g_saved = g_cnt)
+#define SCO_COUNT_RESUME() (g_cnt = g_saved)
 
 struct CD {
     double v;
@@ -66,7 +77,11 @@ static inline CD modf(CD a, CD* ip) { double i; double f = std::modf(a.v, &i); i
 #include "sc_oracle.c"
 #undef double
 
-extern "C" void cnt_reset(void) { memset(&g_cnt, 0, sizeof g_cnt); }
+extern "C" void cnt_reset(void) { memset(&g_cnt, 0, sizeof g_cnt); memset(&g_gate, 0, sizeof g_gate); }
+extern "C" void cnt_get_gate(long long* out7) {
+    out7[0] = g_gate.add; out7[1] = g_gate.mul; out7[2] = g_gate.div; out7[3] = g_gate.sqrt_;
+    out7[4] = g_gate.cos_; out7[5] = g_gate.acos_; out7[6] = g_gate.pow_;
+}
 extern "C" void cnt_get(long long* out7) {
     out7[0] = g_cnt.add; out7[1] = g_cnt.mul; out7[2] = g_cnt.div; out7[3] = g_cnt.sqrt_;
     out7[4] = g_cnt.cos_; out7[5] = g_cnt.acos_; out7[6] = g_cnt.pow_;

@@ -185,7 +185,8 @@ _clib = None
 
 def count_flops(system, targets):
     """Algorithmic operation counts of the cell-path one-to-all over `targets` (oracle/flopcount.cpp):
-    returns dict(add, mul, div, sqrt, cos, acos, pow, candidates, gated)."""
+    returns dict(add, mul, div, sqrt, cos, acos, pow, candidates, gated, gate=dict(...)): the totals count the cutoff gate of
+    PairE::operator() (image + |r|^2) ONCE per candidate; `gate` is that share, the rest is functor work of the gated pairs."""
     global _clib
     if _clib is None:
         path = os.path.join(HERE, "libscoracle_count.so")
@@ -209,6 +210,8 @@ def count_flops(system, targets):
     names = ["add", "mul", "div", "sqrt", "cos", "acos", "pow"]
     d = {k: int(out[i]) for i, k in enumerate(names)}
     d["candidates"], d["gated"] = cand, gated
+    _clib.cnt_get_gate(out)
+    d["gate"] = {k: int(out[i]) for i, k in enumerate(names)}
     return d
 
 

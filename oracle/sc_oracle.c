@@ -700,15 +700,27 @@ static double mix_sp_sc_e(const sco_system* s, int kind, double dist, vec3 r_cm,
     return abE + repenergy + atrenergy;
 }
 
+/* Hooks of the op-counting build (oracle/flopcount.cpp); they expand to nothing in the oracle proper. */
+#ifndef SCO_COUNT_ENTER
+#define SCO_COUNT_ENTER()
+#define SCO_COUNT_GATED()
+#define SCO_COUNT_PAUSE()
+#define SCO_COUNT_RESUME()
+#endif
+
 /* PairE::operator(), mc/paire.h:1209-1220 */
 double sco_pair_energy(const sco_system* s, const double* s1, int type1, int moltype1, int i1,
                        const double* s2, int type2, int i2, const sco_conlist* cl) {
-    vec3 r_cm = image(s->box, ld(s1), ld(s2));
-    double dotrcm = dot(r_cm, r_cm);
+    vec3 r_cm;
+    double dotrcm;
     const sco_iaparam* ia = &s->ia[type1 * s->ntypes + type2];
     double dist;
     int kind;
     (void)i1;
+    SCO_COUNT_ENTER();
+    r_cm = image(s->box, ld(s1), ld(s2));
+    dotrcm = dot(r_cm, r_cm);
+    SCO_COUNT_GATED();          /* everything up to here is the cutoff gate: executed for EVERY candidate */
     if (dotrcm > s->sqmaxcut && cl->is_empty) return 0.0;
     dist = sqrt(dotrcm);
     kind = functor_kind((int)ia->geotype[0], (int)ia->geotype[1]);
@@ -1072,9 +1084,13 @@ double sco_one_to_all_cells(const sco_system* s, int target, const double* trial
     qsort(list, (size_t)nl, sizeof(int), cmp_int);
     for (k = 0; k < nl; k++) {
         int j = list[k];
-        vec3 r = image(s->box, ld(st), ld(s->state + (size_t)j * SCO_STATE));
-        /* work counter of the cell path: pairs that reach a functor there = inside sqmaxcut, or bonded */
+        vec3 r;
+        /* work counter of the cell path: pairs that reach a functor there = inside sqmaxcut, or bonded. The separation is
+         * computed again inside sco_pair_energy; the op-counting build must see it once (PairE::operator() does it once). */
+        SCO_COUNT_PAUSE();
+        r = image(s->box, ld(st), ld(s->state + (size_t)j * SCO_STATE));
         if (dot(r, r) <= s->sqmaxcut || j == cl.con[0] || j == cl.con[1] || j == cl.con[2] || j == cl.con[3]) gated++;
+        SCO_COUNT_RESUME();
         energy += sco_pair_energy(s, st, s->type[target], s->moltype[target], target,
                                   s->state + (size_t)j * SCO_STATE, s->type[j], j, &cl);
     }

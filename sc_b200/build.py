@@ -9,7 +9,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "scgpu.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "pair_energy.cuh"), os.path.join(HERE, "csrc", "sweep.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "pair_energy.cuh"), os.path.join(HERE, "csrc", "sweep.cuh"), os.path.join(HERE, "csrc", "comm.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "scgpu.h")]
 VARIANTS = {"fast": ("libscgpu.so", ["-fmad=true", "-DSCG_FAST_DIV"]), "strict": ("libscgpu_strict.so", ["-fmad=false"])}
 
@@ -28,16 +28,20 @@ def _stale(out):
 def build(variant=None, force=False, verbose=False):
     """Compile the CUDA library (both variants by default). nvcc cross-compiles without a GPU."""
     names = [variant] if variant else list(VARIANTS)
+    procs = []
     for v in names:
         out, flags = lib_path(v), VARIANTS[v][1]
         if not force and not _stale(out):
             continue
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-               "-diag-suppress", "177", "-shared", "-Xcompiler", "-fPIC"] + flags + ["-o", out, SRC]
+               "-diag-suppress", "177", "-shared", "-Xcompiler", "-fPIC"] + flags + ["-o", out, SRC, "-ldl"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
-        subprocess.check_call(cmd)
+        procs.append((cmd, subprocess.Popen(cmd)))      # the variants compile side by side
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
     return [lib_path(v) for v in names]
 
 

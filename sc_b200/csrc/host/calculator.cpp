@@ -66,16 +66,19 @@ double TotalEGpu::mol2othersTrial(const Molecule& mol) {
 double TotalEGpu::p2p(int part1, int part2) {
     scratch.assign(conf->n, 0.0);
     double e = 0.0;
+    pushBox();
     check(scgpu_one_to_all(ctx, part1, nullptr, &e, scratch.data()), "scgpu_one_to_all");
     return scratch[part2];
 }
 int TotalEGpu::overlapAll(int target, int variant) {
     int f = 0;
+    pushBox();
     check(scgpu_overlap_one(ctx, target, &conf->state[(size_t)target * 30], variant, &f), "scgpu_overlap_one");
     return f;
 }
 int TotalEGpu::checkall(int variant) {
     int f = 0;
+    pushBox();
     check(scgpu_overlap_all(ctx, variant, &f), "scgpu_overlap_all");
     return f;
 }

@@ -1619,6 +1619,7 @@ struct scgpu_ctx {
     scgpu_iaparam* d_ia = nullptr;
     scgpu_molparam* d_mol = nullptr;
     double sqmaxcut = 0, maxcut = 0;
+    double min_reach2 = 0;           // the smallest non-zero squared reach of the table (bounds the FP32 rounding the row-unit gates may carry)
     // particles
     int n = 0, cap = 0;
     double box[3] = {0, 0, 0};
@@ -1792,7 +1793,7 @@ static int functor_kind(int g, int o) {
 extern "C" int scgpu_set_topology(scgpu_ctx* c, int ntypes, const scgpu_iaparam* table, double sqmaxcut, double maxcut,
                                   int nmoltypes, const scgpu_molparam* mol) {
     ARG(c && table && mol, "scgpu_set_topology: NULL argument");
-    ARG(ntypes > 0 && ntypes <= 255 && nmoltypes > 0, "scgpu_set_topology: bad counts");
+    ARG(ntypes > 0 && ntypes <= 40 && nmoltypes > 0, "scgpu_set_topology: 1 .. 40 particle types (MAXT, scOOP/structures/macros.h:87) and at least one molecule type");
     ARG(maxcut > 0 && sqmaxcut > 0, "scgpu_set_topology: cutoff must be positive");
     CK(cudaSetDevice(c->device));
     c->types_valid = false;          // rods_only / any_two_patch are derived from (topology, types): the next upload must bring types
@@ -1831,6 +1832,8 @@ extern "C" int scgpu_set_topology(scgpu_ctx* c, int ntypes, const scgpu_iaparam*
             for (int b = 0; b < ntypes; b++) m = fmaxf(m, reach[(size_t)a * ntypes + b]);
             reach.push_back(m);
         }
+        c->min_reach2 = 0.0;
+        for (size_t k = 0; k < (size_t)ntypes * ntypes; k++) if (reach[k] > 0.f && (c->min_reach2 == 0.0 || reach[k] < c->min_reach2)) c->min_reach2 = reach[k];
         CK(cudaMalloc(&c->d_reach2, reach.size() * sizeof(float)));
         CK(cudaMemcpy(c->d_reach2, reach.data(), reach.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
@@ -2114,7 +2117,8 @@ static int ensure_trial(scgpu_ctx* c, int m) {
 
 // the three launches behind every energy entry point
 static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_targets, const double* d_trial, int excl_lo, int excl_hi,
-                         double* d_out, double* d_pairs, unsigned long long* d_counters) {
+                         double* d_out, double* d_pairs, unsigned long long* d_counters, cudaEvent_t* stage_ev = nullptr) {
+    // stage_ev (measurement only): 5 events recorded before / between / after the launches of the flat pipeline
     DevSys s = view(c);
     PatchList pl;
     pl.pair = c->d_pl_pair; pl.e = c->d_pl_e; pl.total = c->d_pl_total; pl.cap = c->pl_cap;
@@ -2132,12 +2136,28 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
         const bool one = c->one_type >= 0 && c->rods_only;
         const scgpu_iaparam& ia1 = c->h_ia[one ? (size_t)c->one_type * c->ntypes + c->one_type : 0];
         const int nrows = c->nc[1] * c->nc[2];
-        if (c->rods_only && c->use_rows && !wrap && !d_counters && nrows <= 65535) {
+        // The row-unit gates test |q|^2 - 2 t.q <= reach^2 - |t|^2 in FP32 coordinates relative to the unit centre: the rounding
+        // error of that form grows with R^2 (R = half-span of a unit's neighbourhood: up to (kmax + 2) / 2 cells along x, 1.5 along
+        // y and z), not with the reach. The reach carries a 0.1 % margin; where ~4 roundings of relative size 2^-24 on R^2 would
+        // eat more than half of it (long rods set the cells, short-reach beads are the pair) the cell gate is used instead -- its
+        // test is a plain |t - q|^2, whose error is relative to the distance itself.
+        bool rows_exact = true;
+        if (!wrap) {
+            const double kx = 0.5 * (double)((c->nc[0] - 3 < 6 ? c->nc[0] - 3 : 6) + 2);
+            const double hx = kx * c->box[0] / c->nc[0], hy = 1.5 * c->box[1] / c->nc[1], hz = 1.5 * c->box[2] / c->nc[2];
+            const double R2 = hx * hx + hy * hy + hz * hz;
+            rows_exact = R2 * 4.0 * 5.96e-8 <= 0.5 * 0.001 * c->min_reach2;
+        }
+        const bool rows_ok = rows_exact && c->use_rows && !wrap && !d_counters && nrows <= 65535;
+        auto mark = [&](int k) { if (stage_ev) cudaEventRecord(stage_ev[k], c->stream); };
+        mark(0);
+        if (c->rods_only && rows_ok) {
             const dim3 grid((unsigned)(c->n / nrows / GR_T + 2), (unsigned)nrows);
             if (mode == 1) k_gate_rows<1><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
             else k_gate_rows<2><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
+            mark(1);
             if (one) k_cheap_flat<true, true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<true, false><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
-        } else if (!c->rods_only && c->use_rows && !wrap && !d_counters && nrows <= 65535 && c->ntypes <= GG_MAXT) {
+        } else if (!c->rods_only && rows_ok && c->ntypes <= GG_MAXT) {
             const dim3 grid((unsigned)(c->n / nrows / GR_T + 2), (unsigned)nrows);
             fl.heavy_types = c->heavy_types;
             if (mode == 1) k_gate_rows_gen<1><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
@@ -2148,18 +2168,24 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
                 c->launches++;
             }
             fl.heavy_types = 0;
+            mark(1);
             k_cheap_flat<false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         } else if (c->rods_only) {
             if (mode == 1) { if (wrap) k_gate_cells<1, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             else { if (wrap) k_gate_cells<2, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
+            mark(1);
             if (one) k_cheap_flat<true, true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<true, false><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         } else {
             if (mode == 1) { if (wrap) k_gate_cells<1, false, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             else { if (wrap) k_gate_cells<2, false, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
+            mark(1);
             k_cheap_flat<false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         }
+        mark(2);
         if (one) k_patch_flat<true><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, ia1); else k_patch_flat<false><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, ia1);
+        mark(3);
         k_combine_flat<<<(c->n + 31) / 32, 256, 0, c->stream>>>(c->n, fl, d_out);
+        mark(4);
         c->launches += 4;
         CK(cudaGetLastError());
         return 0;
@@ -2291,6 +2317,22 @@ extern "C" int scgpu_one_to_all_everyone(scgpu_ctx* c, double* e_host, int64_t* 
     return SCGPU_OK;
 }
 
+// measurement: one every-particle pass with an event between its launches -> microseconds of gate, cheap, patch, combine
+extern "C" int scgpu_profile_everyone(scgpu_ctx* c, float* us4) {
+    ARG(c && us4, "scgpu_profile_everyone: NULL argument");
+    CK(cudaSetDevice(c->device));
+    if (int r = ensure_cells(c)) return r;
+    cudaEvent_t ev[5];
+    for (int k = 0; k < 5; k++) CK(cudaEventCreate(&ev[k]));
+    for (bool repeat = true; repeat;) {
+        if (launch_energy(c, 1, c->n, 1, nullptr, nullptr, 0, 0, c->d_out, nullptr, nullptr, ev)) return SCGPU_ERR_CUDA;
+        if (int r = overflow_then_grow(c, &repeat)) return r;
+    }
+    for (int k = 0; k < 4; k++) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); us4[k] = ms * 1000.f; }
+    for (int k = 0; k < 5; k++) cudaEventDestroy(ev[k]);
+    return SCGPU_OK;
+}
+
 extern "C" int scgpu_submit_everyone(scgpu_ctx* c, const double* state9, double* e_out) {
     ARG(c && state9 && e_out, "scgpu_submit_everyone: NULL argument");
     ARG(c->n > 0 && c->types_valid, "scgpu_submit_everyone: needs a previous upload that brought the particle types");
@@ -2348,23 +2390,6 @@ extern "C" int scgpu_all_to_all(scgpu_ctx* c, double* e_total, double* e_per_par
         repeat = false;
         if (e_total || e_per_particle) { if (int r = overflow_then_grow(c, &repeat)) return r; }
     }
-    return SCGPU_OK;
-}
-
-extern "C" int scgpu_replica_record(scgpu_ctx* c, void** device_ptr_out) {
-    ARG(c && device_ptr_out, "scgpu_replica_record: NULL argument");
-    CK(cudaSetDevice(c->device));
-    if (int r = ensure_cells(c)) return r;
-    for (bool repeat = true; repeat;) {
-        if (launch_all_to_all(c)) return SCGPU_ERR_CUDA;
-        if (int r = overflow_then_grow(c, &repeat)) return r;
-    }
-    double rec[7] = {c->box[0] * c->box[1] * c->box[2], (double)c->n, 0, 0, 0, 0, 0};
-    // record = {E (written by the reduction at d_scalar[0]), V, N, ...}: lay it out at d_scalar[8..15]
-    CK(cudaMemcpyAsync(c->d_scalar + 8, c->d_scalar, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_scalar + 9, rec, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    *device_ptr_out = (void*)(c->d_scalar + 8);
     return SCGPU_OK;
 }
 
@@ -2630,6 +2655,8 @@ extern "C" int scgpu_flush_l2(scgpu_ctx* c) {
     CK(cudaGetLastError());
     return SCGPU_OK;
 }
+
+#include "comm.cuh"
 
 #ifdef SW_PROFILE
 extern "C" int scgpu_sweep_profile(unsigned long long* out16, int reset) {

@@ -50,12 +50,32 @@ class PressureStats(C.Structure):
                 ("enthalpy_delta", C.c_double), ("box", C.c_double * 3)]
 
 
+class ReplicaState(C.Structure):
+    """scgpu_replica_state (include/scgpu.h): what a replica owns and what travels on an accepted exchange"""
+    _fields_ = [("temper", C.c_double), ("press", C.c_double), ("pseudo_rank", C.c_int), ("replica", C.c_int),
+                ("wl_order", C.c_int64 * 2), ("part_num", C.c_double * 8), ("payload", C.c_double * 40),
+                ("attempted", C.c_int), ("accepted", C.c_int), ("partner", C.c_int), ("reserved", C.c_int),
+                ("partner_wl_order", C.c_int64 * 2), ("change", C.c_double), ("energy", C.c_double), ("volume", C.c_double),
+                ("edrift", C.c_double)]
+
+
+class ExchangeParams(C.Structure):
+    _fields_ = [("nrepchange", C.c_int), ("wl_len", C.c_int), ("wl_len0", C.c_int64), ("dtemp", C.c_double), ("dpress", C.c_double),
+                ("chempot", C.c_double * 8), ("seed", C.c_uint64)]
+
+
+class WLState(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("wmin", C.c_double), ("min", C.c_int64), ("max", C.c_int64), ("halved", C.c_int), ("converged", C.c_int)]
+
+
 SYMBOLS = ["scgpu_last_error", "scgpu_device_count", "scgpu_create", "scgpu_destroy", "scgpu_set_topology",
            "scgpu_set_particles", "scgpu_set_particles_compact", "scgpu_set_box", "scgpu_update_particle", "scgpu_download_particles",
            "scgpu_build_cells", "scgpu_cell_assignment", "scgpu_cell_order", "scgpu_one_to_all",
            "scgpu_one_to_all_batch", "scgpu_one_to_all_everyone", "scgpu_submit_everyone", "scgpu_mol_to_others", "scgpu_all_to_all",
-           "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_sweep_checkerboard_chains", "scgpu_pressure_move", "scgpu_replica_record",
-           "scgpu_timer_start", "scgpu_timer_stop", "scgpu_sync", "scgpu_fp64_peak", "scgpu_flush_l2",
+           "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_sweep_checkerboard_chains", "scgpu_pressure_move",
+           "scgpu_comm_unique_id", "scgpu_comm_create", "scgpu_comm_attach", "scgpu_comm_destroy", "scgpu_replica_exchange",
+           "scgpu_comm_last_exchange_us", "scgpu_wl_merge",
+           "scgpu_timer_start", "scgpu_timer_stop", "scgpu_sync", "scgpu_fp64_peak", "scgpu_profile_everyone", "scgpu_flush_l2",
            "scgpu_kernel_launches"]
 
 _libs = {}
@@ -94,12 +114,19 @@ def load_library(variant="fast"):
     L.scgpu_pressure_move.argtypes = [vp, C.POINTER(PressureParams), C.c_uint64, C.c_uint64, C.POINTER(PressureStats)]
     L.scgpu_sweep_checkerboard_chains.argtypes = [vp, C.POINTER(MoveParams), C.POINTER(ChainMoves), C.c_uint64, C.c_uint64,
                                                   C.POINTER(SweepStats), C.POINTER(ChainStats)]
-    L.scgpu_replica_record.argtypes = [vp, C.POINTER(vp)]
+    L.scgpu_comm_unique_id.argtypes = [C.c_char_p]
+    L.scgpu_comm_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_char_p]
+    L.scgpu_comm_attach.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_int, C.c_int]
+    L.scgpu_comm_destroy.argtypes = [vp]
+    L.scgpu_replica_exchange.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(ReplicaState), C.POINTER(ExchangeParams), C.c_uint64, C.POINTER(_dp)]
+    L.scgpu_comm_last_exchange_us.argtypes = [vp, C.POINTER(C.c_float)]
+    L.scgpu_wl_merge.argtypes = [vp, C.c_int, _dp, _i64p, _dp, _i64p, C.c_double, C.POINTER(WLState)]
     L.scgpu_timer_start.argtypes = [vp]
     L.scgpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.scgpu_sync.argtypes = [vp]
     L.scgpu_fp64_peak.argtypes = [vp, _dp]
     L.scgpu_flush_l2.argtypes = [vp]
+    L.scgpu_profile_everyone.argtypes = [vp, C.POINTER(C.c_float)]
     L.scgpu_kernel_launches.argtypes = [vp, _i64p]
     _libs[variant] = L
     return L
@@ -285,11 +312,6 @@ class Engine:
         self._ck(self.L.scgpu_pressure_move(self.h, C.byref(pp), int(seed), int(step), C.byref(st)))
         return st
 
-    def replica_record_ptr(self):
-        p = C.c_void_p()
-        self._ck(self.L.scgpu_replica_record(self.h, C.byref(p)))
-        return p.value
-
     # ---- measurement
     def timer_start(self):
         self._ck(self.L.scgpu_timer_start(self.h))
@@ -307,6 +329,12 @@ class Engine:
         self._ck(self.L.scgpu_fp64_peak(self.h, C.byref(t)))
         return t.value
 
+    def profile_everyone(self):
+        """microseconds of the four launches of one every-particle pass: gate, cheap terms, patch terms, combine"""
+        us = (C.c_float * 4)()
+        self._ck(self.L.scgpu_profile_everyone(self.h, us))
+        return [float(x) for x in us]
+
     def flush_l2(self):
         self._ck(self.L.scgpu_flush_l2(self.h))
 
@@ -314,3 +342,67 @@ class Engine:
         v = C.c_int64(0)
         self._ck(self.L.scgpu_kernel_launches(self.h, C.byref(v)))
         return v.value
+
+
+class Comm:
+    """scgpu_comm: the replicas / walkers of `nranks` processes (one per GPU), NCCL underneath when nranks > 1.
+    unique_id: the 128 bytes of Comm.unique_id() drawn on rank 0 and handed to every rank by the host program."""
+
+    def __init__(self, device=0, nranks=1, rank=0, unique_id=None, variant="fast"):
+        self.L = load_library(variant)
+        self.h = C.c_void_p()
+        self.nranks, self.rank = int(nranks), int(rank)
+        rc = self.L.scgpu_comm_create(C.byref(self.h), int(device), self.nranks, self.rank, unique_id)
+        if rc != 0:
+            raise ScgpuError("scgpu error %d: %s" % (rc, self.L.scgpu_last_error().decode()))
+
+    @staticmethod
+    def unique_id(variant="fast"):
+        L = load_library(variant)
+        buf = C.create_string_buffer(128)
+        rc = L.scgpu_comm_unique_id(buf)
+        if rc != 0:
+            raise ScgpuError("scgpu error %d: %s" % (rc, L.scgpu_last_error().decode()))
+        return buf.raw
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise ScgpuError("scgpu error %d: %s" % (rc, self.L.scgpu_last_error().decode()))
+
+    def close(self):
+        if self.h:
+            self.L.scgpu_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def exchange(self, engines, states, params, sweep, wl_weights=None):
+        """MoveCreator::replicaExchangeMove for this process's replicas. engines: list of Engine, states: ctypes array of
+        ReplicaState (updated in place), params: ExchangeParams, wl_weights: None or a list of float64 arrays."""
+        n = len(engines)
+        hs = (C.c_void_p * n)(*[e.h for e in engines])
+        wl = None
+        if wl_weights is not None:
+            wl = (_dp * n)(*[_d(w) for w in wl_weights])
+        self._ck(self.L.scgpu_replica_exchange(self.h, n, hs, states, C.byref(params), int(sweep), wl))
+
+    def last_exchange_us(self):
+        v = C.c_float(0.0)
+        self._ck(self.L.scgpu_comm_last_exchange_us(self.h, C.byref(v)))
+        return v.value
+
+    def wl_merge(self, weights, hist, weights_base, hist_base, temper, alpha):
+        """merge this walker's Wang-Landau arrays with everybody's (all float64 / int64 numpy arrays, updated in place) -> WLState"""
+        st = WLState()
+        st.alpha = float(alpha)
+        for a in (weights, weights_base):
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+        for a in (hist, hist_base):
+            assert a.dtype == np.int64 and a.flags.c_contiguous
+        self._ck(self.L.scgpu_wl_merge(self.h, len(weights), _d(weights), hist.ctypes.data_as(_i64p), _d(weights_base),
+                                       hist_base.ctypes.data_as(_i64p), float(temper), C.byref(st)))
+        return st
