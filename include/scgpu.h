@@ -76,7 +76,8 @@ typedef struct scgpu_moveparams {
     double temper;                 /* Sim::temper */
     double trans_mx[40];           /* per particle type: stat.trans[type].mx  (= 2*transmx, sim.h:365) */
     double rot_angle[40];          /* per particle type: stat.rot[type].angle (radians, sim.h:360) */
-    int n_sub;                     /* trials per active cell per colour = ceil(n_sub * cell population) ; 1 = one sweep */
+    int n_sub;                     /* sweeps per call: n_sub * N trials in total; every non-empty cell of the checkerboard performs the same
+                                      number of them (n_sub * N / non-empty cells, stochastically rounded), whatever its population */
     int reserved;
 } scgpu_moveparams;
 

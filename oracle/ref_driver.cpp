@@ -30,6 +30,13 @@
 #include "mc/inicializer.h"
 #include "mc/totalenergycalculator.h"
 #include "mc/randomGenerator.h"
+#ifdef REF_FULL      // sc_ref_full: built from a scratch copy whose calculator typedef is TotalEFull (oracle/Makefile); the sweep mode calls the
+#include <iomanip>   // reference's own MoveCreator::partDisplace / partRotate on chosen targets (private members: opened for this one header,
+#include "mc/wanglandau.h"   // everything it includes has been included above)
+#define private public
+#include "mc/movecreator.h"
+#undef private
+#endif
 
 using namespace std;
 
@@ -251,7 +258,72 @@ static int do_time(int argc, char** argv) {
     return 0;
 }
 
+#ifdef REF_FULL
+// Measured sequential sweeps of the reference's own move code at sizes its default calculator cannot hold: MoveCreator::partDisplace /
+// partRotate (mc/movecreator.cpp:947-1028) over TotalEFull<PairE> (the reference's compile-time alternative calculator, :525-619)
+// with the reference's neighbour lists (cut-off rule of Updater::genSimplePairList, updater.cpp:484-552, main.cpp:117-126), on a
+// bounded sample: `ntargets` evenly spaced particles get their lists (the O(N) scan per target is reported, not charged -- the
+// reference amortises it over pairlist_update sweeps), then `ntrials` trial moves are drawn among them exactly as particleMove()
+// does (movecreator.cpp:11-33). One sweep = N such trials (updater.cpp:206).
+static int do_sweep(int argc, char** argv) {
+    long ntargets = argc > 2 ? atol(argv[2]) : 1024;
+    long ntrials = argc > 3 ? atol(argv[3]) : 8192;
+    vector<long> counts;
+    for (int a = 4; a < argc; a++) counts.push_back(atol(argv[a]));
+    FileNames files(0);
+    Conf conf;
+    Sim* sim = nullptr;
+    load(conf, sim, files, (long)counts.size(), counts.data());
+    long n = (long)conf.pvec.size();
+    for (int i = 0; i < MAXT; i++) for (int j = 0; j < MAXT; j++) {   // main.cpp:117-126
+        double m = AVER(sim->stat.trans[i].mx, sim->stat.trans[j].mx);
+        m *= (1 + sim->pairlist_update) * 2;
+        m += topo.maxcut;
+        sim->max_dist_squared[i][j] = m * m;
+    }
+    long stride = n / ntargets; if (stride < 1) stride = 1;
+    vector<int> targets;
+    for (long t = 0; t < n && (long)targets.size() < ntargets; t += stride) targets.push_back((int)t);
+    conf.neighborList.resize(n);
+    conf.pairlist_update = true;
+    auto l0 = chrono::steady_clock::now();
+    for (int t : targets) {
+        vector<long> nb;
+        ConList ct = conf.pvec.getConlist(t);
+        for (long i = 0; i < n; i++) if (i != t) {
+            Vector r = conf.geo.image(&conf.pvec[t].pos, &conf.pvec[i].pos);
+            bool bonded = false;
+            for (int q = 0; q < 4; q++) if (ct.conlist[q] == &conf.pvec[i]) bonded = true;
+            if (r.dot(r) <= sim->max_dist_squared[conf.pvec[t].type][conf.pvec[i].type] || bonded) nb.push_back(i);
+        }
+        conf.neighborList[t].neighborID = (long*)malloc(sizeof(long) * (nb.size() + 1));
+        memcpy(conf.neighborList[t].neighborID, nb.data(), sizeof(long) * nb.size());
+        conf.neighborList[t].neighborCount = (long)nb.size();
+    }
+    double list_s = chrono::duration<double>(chrono::steady_clock::now() - l0).count();
+    TotalEnergyCalculator calc(sim, &conf);      // = TotalEFull<PairE> in this build
+    calc.pairListUpdate = true;
+    MoveCreator move(sim, &conf, &calc);
+    auto t0 = chrono::steady_clock::now();
+    double edrift = 0.0;
+    for (long k = 0; k < ntrials; k++) {
+        long target = targets[(size_t)(ran2() * (double)targets.size())];
+        if ((ran2() < 0.5) || (topo.ia_params[conf.pvec[target].type][conf.pvec[target].type].geotype[0] >= SP)) edrift += move.partDisplace(target);
+        else edrift += move.partRotate(target);
+    }
+    double s = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
+    long acc = 0, rej = 0;
+    for (int t = 0; t < MAXT; t++) { acc += sim->stat.trans[t].acc + sim->stat.rot[t].acc; rej += sim->stat.trans[t].rej + sim->stat.rot[t].rej; }
+    printf("REFJSON {\"n\": %ld, \"targets\": %ld, \"trials\": %ld, \"trial_s\": %.6f, \"list_build_s\": %.6f, \"accepted\": %ld, \"rejected\": %ld, "
+           "\"sweeps_per_s_one_core\": %.6f, \"edrift\": %.17g}\n", n, (long)targets.size(), ntrials, s, list_s, acc, rej, (double)ntrials / s / (double)n, edrift);
+    return 0;
+}
+#endif
+
 int main(int argc, char** argv) {
+#ifdef REF_FULL
+    if (argc >= 2 && !strcmp(argv[1], "sweep")) return do_sweep(argc, argv);
+#endif
     if (argc >= 2 && !strcmp(argv[1], "dump")) return do_dump(argc > 2 ? argv[2] : "ref_dump.txt", false);
     if (argc >= 2 && !strcmp(argv[1], "dump0")) return do_dump(argc > 2 ? argv[2] : "ref_dump.txt", true);
     if (argc >= 2 && !strcmp(argv[1], "time")) return do_time(argc, argv);

@@ -15,7 +15,8 @@ VARIANTS = {"fast": ("libscgpu.so", ["-fmad=true", "-DSCG_FAST_DIV"]), "strict":
 
 
 def lib_path(variant="fast"):
-    return os.path.join(HERE, VARIANTS[variant][0])
+    # SCGPU_LIB_FAST / SCGPU_LIB_STRICT: measure an experimental build (scripts/sweep_variants.py) through the same bindings
+    return os.environ.get("SCGPU_LIB_" + variant.upper()) or os.path.join(HERE, VARIANTS[variant][0])
 
 
 def _stale(out):

@@ -64,7 +64,9 @@ struct DevSys {
     const int* moltype;
     const scgpu_iaparam* ia;
     const scgpu_molparam* mol;
-    const float* reach2;  // per ordered type pair: squared centre distance beyond which the pair energy is exactly 0 (x 1.001)
+    const float* reach2;  // per ordered type pair: squared centre distance beyond which the pair energy is exactly 0 (x 1.001);
+                          // [T*T .. T*T+T): the largest of each row; [T*T+T .. 2*T*T+T): cut2 = max(rcut, rcutwca)^2 x 1.001 of rod pairs
+                          // (0 for other kinds: no segment bound applies); [2*T*T+T .. 2*T*T+2*T): half length of each type (0 = sphere)
     double box[3];
     double shift[3];     // fractional grid shift used for the current cell assignment (0 for the energy API)
     double sqmaxcut;
@@ -836,11 +838,11 @@ constexpr int GR_CAP = GR_CAP_N;    // hits per (target, slice)
 constexpr int GR_STRIDE = 34;       // halfwords per buffer row: row k of target t at k * 34 + t -> the write-out (fixed t, k = lane) is conflict-free
 
 template <int MODE>
-__global__ void __launch_bounds__(GR_SL * 32, 6)
+__global__ void __launch_bounds__(GR_SL * 32, 5)
 k_gate_rows(DevSys s, FlatList fl) {
     __shared__ float4 t_pf[GR_TILE];                // x, y, z: FP32 coordinates relative to the unit centre, length units; w = x^2 + y^2 + z^2
     __shared__ __align__(16) int t_orig[GR_TILE];
-    __shared__ int t_slot[GR_TILE];
+    __shared__ float t_dx[GR_TILE], t_dy[GR_TILE], t_dz[GR_TILE];      // FP32 axis of every staged rod (segment lower bound, lb_beyond)
     __shared__ unsigned short sh_hit[GR_SL][GR_CAP * GR_STRIDE];
     __shared__ int sh_cnt[GR_SL][GR_T];
     __shared__ int sh_off[GR_SL][GR_T];
@@ -915,23 +917,31 @@ k_gate_rows(DevSys s, FlatList fl) {
             const int b = sh_sb[k], off = sh_soff[k], len = sh_soff[k + 1] - off;
             for (int idx = lane; idx < len; idx += 32) {
                 const double4 pw = s.posw[b + idx];
-                t_pf[off + idx] = staged(pw); t_orig[off + idx] = w_orig(pw.w); t_slot[off + idx] = b + idx;
+                const double4 dw = ldg256(s.rec + (size_t)(b + idx) * REC + R_DIR);
+                t_pf[off + idx] = staged(pw); t_orig[off + idx] = w_orig(pw.w);
+                t_dx[off + idx] = (float)dw.x; t_dy[off + idx] = (float)dw.y; t_dz[off + idx] = (float)dw.z;
             }
         }
         for (int p = C + threadIdx.x; p < Cpad; p += blockDim.x) {          // padding: an infinite |q|^2 fails the comparison
             t_pf[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
-            t_orig[p] = -1; t_slot[p] = 0;
+            t_orig[p] = -1;
         }
         // ---- this lane's target: |t - q|^2 <= reach  <=>  |q|^2 - 2 t.q <= reach - |t|^2 (three FMAs and a compare per test; the
         // rounding error, ~1e-6 relative at these magnitudes, is far inside the 0.1 % margin carried by reach)
         float m2x = 0.f, m2y = 0.f, m2z = 0.f, thr = __int_as_float(0xff800000);
+        float tdx = 0.f, tdy = 0.f, tdz = 1.f, hl = 0.f, cut2 = 0.f;
         int target = -2;
         if (lane < count) {
             const double4 pw = s.posw[first + lane];
+            const double4 dw = ldg256(s.rec + (size_t)(first + lane) * REC + R_DIR);
             const float4 q = staged(pw);
             m2x = -2.f * q.x; m2y = -2.f * q.y; m2z = -2.f * q.z;
+            tdx = (float)dw.x; tdy = (float)dw.y; tdz = (float)dw.z;
             target = w_orig(pw.w);
-            thr = s.reach2[s.ntypes * s.ntypes + w_type(pw.w)] - q.w;     // the largest reach of this type: conservative for mixed rod types
+            const int T = s.ntypes, tt = w_type(pw.w);
+            thr = s.reach2[T * T + tt] - q.w;     // the largest reach of this type: conservative for mixed rod types
+            hl = s.reach2[2 * T * T + T + tt];    // all rods of a system have one length (Topo::genParamPairs enforces it, topo.cpp:22-33)
+            for (int b = 0; b < T; b++) cut2 = fmaxf(cut2, s.reach2[T * T + T + tt * T + b]);      // the largest surface cutoff of this type's rod pairs
         }
         __syncthreads();
         // ---- scan: every lane tests its own target against the candidates of this warp's slice. Hits are appended through a
@@ -973,6 +983,20 @@ k_gate_rows(DevSys s, FlatList fl) {
             }
         }
         if (__any_sync(0xffffffffu, cur == cur_max) && lane == 0) atomicOr(fl.overflow, 4);
+        // ---- segment lower bound (lb_beyond, sweep.cuh): of the candidates within the centre-distance reach only those whose rods can
+        // come within the surface cutoff interact at all -- a sixth of them in a dense rod fluid. Every lane filters its own hits in place.
+        {
+            const int nk = (cur - lane) / GR_STRIDE;
+            const float tx = -0.5f * m2x, ty = -0.5f * m2y, tz = -0.5f * m2z;
+            int wr = lane;
+            for (int k = 0, rd = lane; k < nk; k++, rd += GR_STRIDE) {
+                const int c = buf[rd];
+                const float4 q = t_pf[c];
+                const float rx = tx - q.x, ry = ty - q.y, rz = tz - q.z;
+                if (!lb_beyond(rx, ry, rz, rx * rx + ry * ry + rz * rz, tdx, tdy, tdz, t_dx[c], t_dy[c], t_dz[c], hl, hl, cut2)) { buf[wr] = (unsigned short)c; wr += GR_STRIDE; }
+            }
+            cur = wr;
+        }
         const int cnt = (cur - lane) / GR_STRIDE;
         sh_cnt[wid][lane] = cnt;
         __syncthreads();
@@ -1008,12 +1032,18 @@ k_gate_rows(DevSys s, FlatList fl) {
         const int my_off = sh_off[wid][lane];       // lane t holds the sub-span of target t
         const bool big = __any_sync(0xffffffffu, cnt > 32);
         const unsigned short* my_row = buf + lane * GR_STRIDE;
+        auto slot_of_c = [&](int c) {         // tile index -> sorted slot: which of the 18 staged segments holds it
+            int k = 0;
+#pragma unroll
+            for (int j = 1; j < 18; j++) k += c >= sh_soff[j] ? 1 : 0;
+            return sh_sb[k] + (c - sh_soff[k]);
+        };
 #pragma unroll
         for (int t = 0; t < GR_T; t++) {      // fully unrolled: lane indices and buffer offsets become immediates
             if (t >= count) break;
             const int nh = __shfl_sync(0xffffffffu, cnt, t), off = __shfl_sync(0xffffffffu, my_off, t);
-            if (lane < nh) fl.pair[off + lane] = make_int2(first + t, t_slot[my_row[t]]);
-            if (big && lane + 32 < nh) fl.pair[off + lane + 32] = make_int2(first + t, t_slot[my_row[32 * GR_STRIDE + t]]);
+            if (lane < nh) fl.pair[off + lane] = make_int2(first + t, slot_of_c(my_row[t]));
+            if (big && lane + 32 < nh) fl.pair[off + lane + 32] = make_int2(first + t, slot_of_c(my_row[32 * GR_STRIDE + t]));
         }
         first = last + 1;
       }
@@ -1237,7 +1267,7 @@ k_gate_rows_gen(DevSys s, FlatList fl) {
 constexpr int CHEAP_BUF = 256;    // patch-list entries buffered per warp between global appends
 // ONE: every particle present has the same type, so there is a single interaction-table entry: it travels as a kernel parameter
 // (constant bank, read by LDC on the uniform path) instead of being fetched field by field through the load/store unit
-template <bool RODS, bool ONE>
+template <bool RODS, bool ONE, bool MIRROR>
 __global__ void __launch_bounds__(256, RODS ? CHEAP_MINB : 2)
 k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters, const __grid_constant__ scgpu_iaparam ia1) {
     if (*fl.overflow) return;         // the gate could not finish its list (the host repeats the launch): spans may be missing or out of range
@@ -1297,7 +1327,11 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters, const __grid_c
                                                   s.rec + (size_t)pr.y * REC, w_type(pj.w), oj, cl, np);
                 n_gate++;
             }
-            fl.e[p] = make_double2(e, 0.0);
+            // every-particle passes list a patch pair from both sides: the patch term is evaluated once, by the side whose first particle
+            // has the larger original index; the other side marks its entry (NaN) and k_combine_flat fetches the value from its mirror
+            double mark = 0.0;
+            if (MIRROR && np && oi < oj) { np = false; mark = __longlong_as_double(0x7ff8000000000000ll); }
+            fl.e[p] = make_double2(e, mark);
         }
         const unsigned m = __ballot_sync(0xffffffffu, np);
         if (np) wbuf[wn + __popc(m & lt_mask)] = p;
@@ -1439,7 +1473,7 @@ k_patch_flat(DevSys s, FlatList fl, int any_two_patch, const __grid_constant__ s
 
 // eight lanes per particle: each group reads its particle's span of the list 128 bytes at a time, lane k of the group sums
 // entries k, k+8, ... in order, then a fixed three-step shuffle tree -> the same bits on every run
-__global__ void __launch_bounds__(256) k_combine_flat(int n, FlatList fl, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_combine_flat(int n, FlatList fl, const double4* __restrict__ posw, double* __restrict__ out) {
     if (*fl.overflow) return;         // nothing valid to sum; the host resets the counters and repeats the launch
     const int sub = threadIdx.x & 7;
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -1448,7 +1482,18 @@ __global__ void __launch_bounds__(256) k_combine_flat(int n, FlatList fl, double
     if (t < n) {
         for (int cid = fl.head[t]; cid >= 0;) {
             const int4 ch = fl.chunks[cid];
-            for (int r = sub; r < ch.y; r += 8) { const double2 v = fl.e[ch.x + r]; e += v.x + v.y; }     // per pair (cheap + patch), then accumulate
+            for (int r = sub; r < ch.y; r += 8) {
+                double2 v = fl.e[ch.x + r];
+                if (v.y != v.y) {        // patch term evaluated by the partner's side (k_cheap_flat): find this pair in the partner's span
+                    const int2 pr = fl.pair[ch.x + r];
+                    const int4 cj = fl.chunks[w_orig(posw[pr.y].w)];
+                    v.y = 0.0;
+                    bool found = false;
+                    for (int q = 0; q < cj.y; q++) if (fl.pair[cj.x + q].y == pr.x) { v.y = fl.e[cj.x + q].y; found = true; break; }
+                    if (!found || v.y != v.y) atomicOr(fl.overflow, 8);      // cannot happen: a pair inside the patch range is listed by both sides
+                }
+                e += v.x + v.y;      // per pair (cheap + patch), then accumulate
+            }
             cid = ch.z;
         }
     }
@@ -1832,6 +1877,19 @@ extern "C" int scgpu_set_topology(scgpu_ctx* c, int ntypes, const scgpu_iaparam*
             for (int b = 0; b < ntypes; b++) m = fmaxf(m, reach[(size_t)a * ntypes + b]);
             reach.push_back(m);
         }
+        // segment lower-bound filter (sweep.cuh, lb_reject): squared surface cutoff of rod-rod pairs and the rods' half lengths
+        for (int a = 0; a < ntypes; a++) for (int b = 0; b < ntypes; b++) {
+            const scgpu_iaparam& q = c->h_ia[(size_t)a * ntypes + b];
+            const int k = (int)q.reserved[0];
+            double cut = sqrt(q.rcutSq > q.rcutwcaSq ? q.rcutSq : q.rcutwcaSq);
+            if (q.rcut > cut) cut = q.rcut;
+            if (q.rcutwca > cut) cut = q.rcutwca;
+            reach.push_back((k >= K_SC_PSCCPSC && k <= K_SC_SCA) ? (float)(cut * cut * 1.001) : 0.f);
+        }
+        for (int a = 0; a < ntypes; a++) {
+            const scgpu_iaparam& q = c->h_ia[(size_t)a * ntypes + a];
+            reach.push_back((int)q.geotype[0] < SCGPU_SPN ? (float)q.half_len[0] : 0.f);
+        }
         c->min_reach2 = 0.0;
         for (size_t k = 0; k < (size_t)ntypes * ntypes; k++) if (reach[k] > 0.f && (c->min_reach2 == 0.0 || reach[k] < c->min_reach2)) c->min_reach2 = reach[k];
         CK(cudaMalloc(&c->d_reach2, reach.size() * sizeof(float)));
@@ -2003,8 +2061,10 @@ static int sync_api_from_sorted(scgpu_ctx* c) {
     return 0;
 }
 
-// shift: fractional grid offset; even_grid: checkerboard sweeps need an even cell count (>= 4) per axis, else one cell
-static int build_cells_impl(scgpu_ctx* c, const double shift[3], bool even_grid) {
+// shift: fractional grid offset; sweep_k = 0: the energy grid (cells >= maxcut); sweep_k = K >= 1: the checkerboard grid of the
+// sweeps: cells of edge >= maxcut / K, a multiple of K + 1 cells per axis (>= 2 (K + 1), so that the 2K + 1 neighbour cells of an
+// axis are distinct), else that axis is one cell
+static int build_cells_impl(scgpu_ctx* c, const double shift[3], int sweep_k) {
     ARG(c, "scgpu_build_cells: NULL context");
     ARG(c->n > 0 && c->ntypes > 0 && c->box[0] > 0, "scgpu_build_cells: topology, particles and box must be set first");
     CK(cudaSetDevice(c->device));
@@ -2012,7 +2072,11 @@ static int build_cells_impl(scgpu_ctx* c, const double shift[3], bool even_grid)
     for (int d = 0; d < 3; d++) {
         int nc = (int)floor(c->box[d] / c->maxcut);
         if (nc < 3) nc = 1;      // fewer than 3 cells: the +-1 neighbours would alias through the periodic image
-        if (even_grid) nc = (nc >= 4) ? (nc & ~1) : 1;
+        if (sweep_k > 0) {
+            nc = (int)floor(c->box[d] * sweep_k / c->maxcut);
+            nc -= nc % (sweep_k + 1);
+            if (nc < 2 * (sweep_k + 1)) nc = 1;
+        }
         c->nc[d] = nc;
         c->shift[d] = shift[d];
     }
@@ -2042,7 +2106,7 @@ static int build_cells_impl(scgpu_ctx* c, const double shift[3], bool even_grid)
 
 extern "C" int scgpu_build_cells(scgpu_ctx* c) {
     const double zero[3] = {0.0, 0.0, 0.0};
-    return build_cells_impl(c, zero, false);
+    return build_cells_impl(c, zero, 0);
 }
 
 static int ensure_cells(scgpu_ctx* c) {
@@ -2150,13 +2214,18 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
         }
         const bool rows_ok = rows_exact && c->use_rows && !wrap && !d_counters && nrows <= 65535;
         auto mark = [&](int k) { if (stage_ev) cudaEventRecord(stage_ev[k], c->stream); };
+        auto launch_cheap_rods = [&]() {        // MIRROR (every-particle passes): a patch pair is evaluated by one of its two sides only
+            const int nb = c->sm_count * CHEAP_MINB * 2;
+            if (one) { if (mode == 1) k_cheap_flat<true, true, true><<<nb, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<true, true, false><<<nb, 256, 0, c->stream>>>(s, fl, d_counters, ia1); }
+            else { if (mode == 1) k_cheap_flat<true, false, true><<<nb, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<true, false, false><<<nb, 256, 0, c->stream>>>(s, fl, d_counters, ia1); }
+        };
         mark(0);
         if (c->rods_only && rows_ok) {
             const dim3 grid((unsigned)(c->n / nrows / GR_T + 2), (unsigned)nrows);
             if (mode == 1) k_gate_rows<1><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
             else k_gate_rows<2><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
             mark(1);
-            if (one) k_cheap_flat<true, true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<true, false><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
+            launch_cheap_rods();
         } else if (!c->rods_only && rows_ok && c->ntypes <= GG_MAXT) {
             const dim3 grid((unsigned)(c->n / nrows / GR_T + 2), (unsigned)nrows);
             fl.heavy_types = c->heavy_types;
@@ -2169,22 +2238,22 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
             }
             fl.heavy_types = 0;
             mark(1);
-            k_cheap_flat<false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
+            if (mode == 1) k_cheap_flat<false, false, true><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<false, false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         } else if (c->rods_only) {
             if (mode == 1) { if (wrap) k_gate_cells<1, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             else { if (wrap) k_gate_cells<2, true, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, true, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             mark(1);
-            if (one) k_cheap_flat<true, true><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<true, false><<<c->sm_count * CHEAP_MINB * 2, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
+            launch_cheap_rods();
         } else {
             if (mode == 1) { if (wrap) k_gate_cells<1, false, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<1, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             else { if (wrap) k_gate_cells<2, false, true><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); else k_gate_cells<2, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, d_counters); }
             mark(1);
-            k_cheap_flat<false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
+            if (mode == 1) k_cheap_flat<false, false, true><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<false, false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         }
         mark(2);
         if (one) k_patch_flat<true><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, ia1); else k_patch_flat<false><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, ia1);
         mark(3);
-        k_combine_flat<<<(c->n + 31) / 32, 256, 0, c->stream>>>(c->n, fl, d_out);
+        k_combine_flat<<<(c->n + 31) / 32, 256, 0, c->stream>>>(c->n, fl, c->d_posw, d_out);
         mark(4);
         c->launches += 4;
         CK(cudaGetLastError());
@@ -2215,6 +2284,11 @@ static int overflow_then_grow(scgpu_ctx* c, bool* repeat) {
     if (!*hflag) return 0;
     const int which = *hflag;      // bit 0: patch work list, bit 1: flat pair list, bit 2: k_gate_rows cannot hold this configuration
     c->last_overflow = which;
+    if (which & 8) {
+        CK(cudaMemsetAsync(c->d_pl_total, 0, 8 * sizeof(int), c->stream));
+        g_err = "internal error: a patch pair was listed by one side of an every-particle pass only";
+        return SCGPU_ERR_STATE;
+    }
     if (which & 4) {
         const unsigned heavy = (unsigned)hflag[5];       // d_pl_total[6]
         unsigned present = 0;
@@ -2457,10 +2531,32 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     unsigned long long st = seed * 0xD1342543DE82EF95ull + sweep * 0x9E3779B97F4A7C15ull + 0x2545F4914F6CDD1Dull;
     double shift[3];
     for (int d = 0; d < 3; d++) shift[d] = (double)(splitmix64(st) >> 11) * (1.0 / 9007199254740992.0);
-    if (int r = build_cells_impl(c, shift, true)) return r;
-    int3 ncol = make_int3(c->nc[0] >= 4 ? 2 : 1, c->nc[1] >= 4 ? 2 : 1, c->nc[2] >= 4 ? 2 : 1);
+    // Fineness of the checkerboard: the serial chain of trials inside a cell is what a sweep costs, (K+1)^3 N / cells(K) trials long;
+    // the largest K <= 3 that still leaves about two particles per cell. Chain moves need every member of a molecule in one cell and
+    // the 27-cell neighbourhood of their kernel: sweeps with chain moves stay on the coarse grid.
+    int K = 1;
+    if (!chains) {
+        for (int k = 3; k >= 2; k--) {
+            double cells = 1.0;
+            bool fits = true;
+            for (int d = 0; d < 3; d++) {
+                int nc = (int)floor(c->box[d] * k / c->maxcut);
+                nc -= nc % (k + 1);
+                if (nc < 2 * (k + 1)) { fits = false; nc = 1; }
+                cells *= nc;
+            }
+            if (fits && (double)c->n / cells >= 2.0) { K = k; break; }
+        }
+    }
+#ifdef SW_FORCE_K
+    if (!chains) K = SW_FORCE_K;
+#endif
+    if (int r = build_cells_impl(c, shift, K)) return r;
+    SweepGrid grid;
+    for (int d = 0; d < 3; d++) { grid.k[d] = c->nc[d] > 1 ? K : 0; grid.ncol[d] = c->nc[d] > 1 ? K + 1 : 1; }
+    int3 ncol = make_int3(grid.ncol[0], grid.ncol[1], grid.ncol[2]);
     int ncolours = ncol.x * ncol.y * ncol.z;
-    int order[8];
+    int order[64];
     for (int k = 0; k < ncolours; k++) order[k] = k;
     for (int k = ncolours - 1; k > 0; k--) { int j = (int)(splitmix64(st) % (unsigned long long)(k + 1)); int t = order[k]; order[k] = order[j]; order[j] = t; }
     SweepParams sp;
@@ -2487,15 +2583,14 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     }
     CK(cudaMemsetAsync(c->d_sweep_acc, 0, (size_t)2 * c->ncells * sizeof(SweepAcc), c->stream));
     SweepAcc* d_chain_acc = (SweepAcc*)c->d_sweep_acc + c->sweep_acc_cap;
-    if (stats || cstats) CK(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
     DevSys s = view(c);
     int nactive = (c->nc[0] / ncol.x) * (c->nc[1] / ncol.y) * (c->nc[2] / ncol.z);
     const bool one = c->one_type >= 0 && c->rods_only;
     const scgpu_iaparam& ia1 = c->h_ia[one ? (size_t)c->one_type * c->ntypes + c->one_type : 0];
     for (int k = 0; k < ncolours; k++) {
-        if (c->rods_only && one) k_sweep_colour<true, true><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags, ia1);
-        else if (c->rods_only) k_sweep_colour<true, false><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags, ia1);
-        else k_sweep_colour<false, false><<<nactive, SW_WARPS * 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, c->d_flags, ia1);
+        if (c->rods_only && one) k_sweep_cells<true, true><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
+        else if (c->rods_only) k_sweep_cells<true, false><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
+        else k_sweep_cells<false, false><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
         c->launches++;
         if (chains) {
             k_sweep_chain_colour<<<nactive, CH_THREADS, 0, c->stream>>>(s, cp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, d_chain_acc);
@@ -2505,10 +2600,9 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     CK(cudaGetLastError());
     c->api_stale = true;           // the cell-sorted arrays are now the newest copy of the configuration
     c->h_cell_of.clear();
-    if (!stats && !cstats) return SCGPU_OK;       // asynchronous form: nothing is read back; a too-dense cell is reported by the next call with stats / scgpu_sync
-    int* hfail = (int*)(c->h_small + 256 + 128);
+    if (K > 1) c->cells_valid = false;      // the energy kernels need cells of edge >= maxcut: the next energy call re-sorts
+    if (!stats && !cstats) return SCGPU_OK;       // asynchronous form: nothing is read back
     std::vector<SweepAcc> acc(c->ncells), cacc(chains ? c->ncells : 0);
-    CK(cudaMemcpyAsync(hfail, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(acc.data(), c->d_sweep_acc, (size_t)c->ncells * sizeof(SweepAcc), cudaMemcpyDeviceToHost, c->stream));
     if (chains) CK(cudaMemcpyAsync(cacc.data(), d_chain_acc, (size_t)c->ncells * sizeof(SweepAcc), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -2520,7 +2614,6 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
             cstats->cell_rej += cacc[i].cell_rej; cstats->energy_delta += cacc[i].de; cstats->noop += cacc[i].pad;
         }
     }
-    if (*hfail) { g_err = "scgpu_sweep_checkerboard: a cell neighbourhood holds more particles than the staged tile (SW_TILE); configuration too dense for this build"; return SCGPU_ERR_STATE; }
     if (stats) {
         memset(stats, 0, sizeof *stats);
         for (int i = 0; i < c->ncells; i++) {       // fixed order

@@ -78,15 +78,21 @@ __device__ inline void rotate_record(double* r, int geotype, double angle, const
     for (int v = 0; v < 9; v++) if (record_vector_rotates(geotype, v)) rotate_vector(r + 3 * v, d);
 }
 
-#ifndef SW_WARPS_N
-#define SW_WARPS_N 2
-#endif
-constexpr int SW_WARPS = SW_WARPS_N;
 #ifndef SW_MINBLOCKS
-#define SW_MINBLOCKS 1
+#define SW_MINBLOCKS 8
 #endif
-constexpr int SW_TILE = 1280;     // staged neighbourhood (FP32 relative coordinates + slot): 1280 x 20 B = 25 KB
-constexpr int SW_BATCH = 32;      // trials whose random numbers and proposal geometry are prepared together, one thread each
+constexpr int SW_WARPS = 1;       // one warp per active cell: no block barrier anywhere in a trial
+constexpr int SW_TILE = 576;      // staged neighbourhood: FP32 position + direction + slot, 32 B per candidate = 18 KB (8 warps per SM resident)
+constexpr int SW_BATCH = 32;      // trials whose random numbers and proposal geometry are prepared together, one lane each
+constexpr int SW_MAXROWS = 49;    // (2K+1)^2 rows of neighbour cells, K <= 3
+constexpr int SW_MAXT = 8;        // particle types whose reach / cutoff tables are kept in shared memory
+constexpr int SW_VLP = 8;         // particles of the active cell that get a partner list of their own ...
+constexpr int SW_VLC = 96;        // ... of at most this many candidates (anything beyond falls back to the full scan)
+
+struct SweepGrid {                // fine checkerboard: cells of edge >= maxcut / K, K + 1 colours per axis, active cells K cells apart
+    int k[3];                     // per axis: half-width of the neighbourhood in cells (K, or 0 where the axis is a single cell)
+    int ncol[3];                  // per axis: colours (K + 1, or 1)
+};
 
 struct SweepProposal {            // everything of a trial that does not depend on the outcome of earlier trials
     int slot, displace;
@@ -94,107 +100,192 @@ struct SweepProposal {            // everything of a trial that does not depend 
     double m[9];                  // displacement (m[0..2], box-fractional) or the rotation coefficients d1..d9 of pscRotate
 };
 
-#ifdef SW_PROFILE      // debug build only: cycles per phase of a trial, summed over blocks (thread 0's view)
+#ifdef SW_PROFILE      // debug build only: cycles per phase of a trial, summed over blocks (lane 0's view)
 __device__ unsigned long long sw_prof[16];
 #define SWP_MARK(k) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&sw_prof[k], (unsigned long long)(t_ - swp_t)); swp_t = t_; } } while (0)
 #else
 #define SWP_MARK(k) do { } while (0)
 #endif
 
-// one block per ACTIVE cell of the current colour
-// ONE (with RODS): a single particle type is present -> its interaction-table entry is a kernel parameter (constant bank); in this
-// latency-bound kernel every field fetched through the load/store unit sits on the serial path of a trial
+// the never-taken overflow path of the patch list: out of line, so that it does not bloat the kernel's instruction footprint
+__device__ __noinline__ double pair_energy_patch_outofline(const scgpu_iaparam& ia, const v3& r_cm, const double* s1, const double* s2) {
+    return pair_energy_patch(ia, r_cm, s1, s2);
+}
+
+// One WARP per ACTIVE cell of the current colour, sequential trials inside it, no block barrier anywhere.
+// The grid is FINE: cells of edge >= maxcut / K (K = 1, 2, 3, chosen by the host from the mean cell population), K + 1 colours
+// per axis, so that two active cells are K cells (>= maxcut) apart and the (2K+1)^3 cells around an active cell hold every
+// partner of its particles. Compared with the coarse grid (K = 1) a pass has (2K/(K+1))^3 times more independent cells in
+// flight and a sweep (K+1)^3 N / cells serial trials per cell instead of 8 N / cells -- the length of that serial chain is what
+// a sweep costs, because a single trial is bound by the latency of its own FP64 dependency chain.
+// Per trial: the staged neighbourhood (FP32 position and direction of every candidate) is scanned by the 32 lanes for the old AND
+// the new state: centre distance against the exact reach of the type pair, then the segment lower bound above; the few
+// survivors are evaluated in FP64 on different lanes (old and new state side by side), patch terms with two lanes per term.
+// ONE (with RODS): a single particle type is present -> its interaction-table entry is a kernel parameter (constant bank).
 template <bool RODS, bool ONE>
-__global__ void __launch_bounds__(SW_WARPS * 32, SW_MINBLOCKS)
-k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long long sweep, int colour, int3 ncol,
-               double4* posw, double* rec, SweepAcc* acc_out, int* fail_flag, const __grid_constant__ scgpu_iaparam ia1) {
-    __shared__ float4 t_pf[SW_TILE];
-    __shared__ int t_slot[SW_TILE];
+__global__ void __launch_bounds__(32, SW_MINBLOCKS)
+k_sweep_cells(DevSys s, SweepParams sp, unsigned long long seed, unsigned long long sweep, int colour, SweepGrid g,
+              double4* posw, double* rec, SweepAcc* acc_out, const __grid_constant__ scgpu_iaparam ia1) {
+    __shared__ float4 t_pf[SW_TILE];          // x, y, z: box-fractional position relative to the cell centre; w: original index | type << 24
+    __shared__ float4 t_df[SW_TILE];          // direction; w: slot
     __shared__ double sh_old[REC], sh_new[REC];
-    __shared__ int sh_queue[SW_WARPS][96];
-    __shared__ int sh_pl[SW_WARPS][32];       // per-warp lists of (slot, state) entries that owe a patch evaluation
-    __shared__ double sh_eo[SW_WARPS], sh_en[SW_WARPS];
-    __shared__ int sh_b[28], sh_off[28];
+    __shared__ int sh_queue[128];
+    __shared__ int sh_pl[32];                 // (tile entry, state) pairs that owe a patch evaluation
+    __shared__ int sh_b[2 * SW_MAXROWS + 2], sh_off[2 * SW_MAXROWS + 2];
     __shared__ SweepProposal sh_prop[SW_BATCH];
-    static_assert(SW_WARPS * 32 >= SW_BATCH && SW_WARPS * 32 >= REC + 1, "block too small");
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ float sh_tab[2 * SW_MAXT * SW_MAXT + SW_MAXT];
+    __shared__ unsigned short sh_vl[SW_VLP][SW_VLC];
+    __shared__ int sh_vn[SW_VLP];
+    const int lane = threadIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
-    // active cell of this block
-    const int ax = s.nc[0] / ncol.x, ay = s.nc[1] / ncol.y;
+    // active cell of this warp
+    const int ax = s.nc[0] / g.ncol[0], ay = s.nc[1] / g.ncol[1];
     const int bx = blockIdx.x % ax, by = (blockIdx.x / ax) % ay, bz = blockIdx.x / (ax * ay);
-    const int cx = bx * ncol.x + (colour % ncol.x), cy = by * ncol.y + ((colour / ncol.x) % ncol.y), cz = bz * ncol.z + (colour / (ncol.x * ncol.y));
+    const int cx = bx * g.ncol[0] + (colour % g.ncol[0]), cy = by * g.ncol[1] + ((colour / g.ncol[0]) % g.ncol[1]), cz = bz * g.ncol[2] + (colour / (g.ncol[0] * g.ncol[1]));
     const int c0 = (cz * s.nc[1] + cy) * s.nc[0] + cx;
     const int tb = s.cell_start[c0], te = s.cell_start[c0 + 1];
     const int npart = te - tb;
     SweepAcc acc = {0, 0, 0, 0, 0, 0, 0.0};
-    if (npart == 0) { if (threadIdx.x == 0) acc_out[c0] = acc; return; }
-    const int nx = s.nc[0] == 1 ? 1 : 3, ny = s.nc[1] == 1 ? 1 : 3, nz = s.nc[2] == 1 ? 1 : 3;
-    const int ncell_nb = nx * ny * nz;
-    if (wid == 0) {
-        int len = 0, b = 0;
-        if (lane < ncell_nb) {
-            int dx = lane % nx, dy = (lane / nx) % ny, dz = lane / (nx * ny);
-            int ccx = nx == 1 ? 0 : (cx + dx - 1 + s.nc[0]) % s.nc[0];
-            int ccy = ny == 1 ? 0 : (cy + dy - 1 + s.nc[1]) % s.nc[1];
-            int ccz = nz == 1 ? 0 : (cz + dz - 1 + s.nc[2]) % s.nc[2];
-            int c = (ccz * s.nc[1] + ccy) * s.nc[0] + ccx;
-            b = s.cell_start[c];
-            len = s.cell_start[c + 1] - b;
+    if (npart == 0) { if (lane == 0) acc_out[c0] = acc; return; }
+#ifdef SW_PROFILE
+    const long long swp_t0 = clock64();
+#endif
+    // ---- the neighbourhood: (2ky+1)(2kz+1) rows of cells, each row one contiguous slot range [cx-kx, cx+kx] or two where it wraps
+    const int wy = 2 * g.k[1] + 1, wz = 2 * g.k[2] + 1, nrows = wy * wz;
+    const int T = s.ntypes;
+    for (int part = 0; part < 2; part++) {
+        int b = 0, len = 0;
+        for (int r0 = 0; r0 < nrows; r0 += 32) {
+            const int r = r0 + lane;
+            b = 0; len = 0;
+            if (r < nrows) {
+                const int yy = (cy + r % wy - g.k[1] + s.nc[1]) % s.nc[1], zz = (cz + r / wy - g.k[2] + s.nc[2]) % s.nc[2];
+                const int rbase = (zz * s.nc[1] + yy) * s.nc[0];
+                const int lo = cx - g.k[0], hi = cx + g.k[0];
+                int a0, a1;
+                if (lo < 0) { if (part == 0) { a0 = 0; a1 = hi; } else { a0 = lo + s.nc[0]; a1 = s.nc[0] - 1; } }
+                else if (hi >= s.nc[0]) { if (part == 0) { a0 = lo; a1 = s.nc[0] - 1; } else { a0 = 0; a1 = hi - s.nc[0]; } }
+                else { a0 = part == 0 ? lo : 1; a1 = part == 0 ? hi : 0; }
+                if (a0 <= a1) { b = s.cell_start[rbase + a0]; len = s.cell_start[rbase + a1 + 1] - b; }
+                sh_b[2 * r + part] = b; sh_off[2 * r + part] = len;      // lengths first, offsets below
+            }
         }
-        int x = len;
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane < 28) { sh_b[lane] = b; sh_off[lane] = x - len; }
     }
-    __syncthreads();
-    const int C = sh_off[ncell_nb];
+    __syncwarp();
+    int C = 0;
+    {   // exclusive scan of the 2 * nrows segment lengths (at most 98: four per lane)
+        int v[4], tot = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int k = 4 * lane + u; v[u] = k < 2 * nrows ? sh_off[k] : 0; tot += v[u]; }
+        int x = tot;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        C = __shfl_sync(0xffffffffu, x, 31);
+        int run = x - tot;
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int k = 4 * lane + u; if (k < 2 * nrows) sh_off[k] = run; run += v[u]; }
+        if (lane == 0) sh_off[2 * nrows] = C;
+    }
+    const bool tabs = !(RODS && ONE) && T <= SW_MAXT;       // reach / cutoff / half-length tables in shared memory
+    if (tabs) for (int k = lane; k < 2 * T * T + T; k += 32) sh_tab[k] = k < T * T ? s.reach2[k] : s.reach2[k + T];
+    __syncwarp();
+    const int nseg = 2 * nrows;
     const bool tiled = C <= SW_TILE;        // denser neighbourhoods are scanned from global memory (slower, same results)
-    (void)fail_flag;
     const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
     const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
-    const float pre_cut = (float)(s.sqmaxcut * 1.001);
     auto slot_of_p = [&](int p) {
         int k = 0;
-        while (k + 1 < ncell_nb && sh_off[k + 1] <= p) k++;
+        while (k + 1 < nseg && sh_off[k + 1] <= p) k++;
         return sh_b[k] + (p - sh_off[k]);
     };
-    auto staged = [&](int slot) {
-        double4 pw = posw[slot];
+    auto staged_pos = [&](const double4& pw) {
         return make_float4((float)rel_frac(pw.x + s.shift[0], ccen[0]), (float)rel_frac(pw.y + s.shift[1], ccen[1]),
-                           (float)rel_frac(pw.z + s.shift[2], ccen[2]), 0.f);
+                           (float)rel_frac(pw.z + s.shift[2], ccen[2]), __int_as_float(w_orig(pw.w) | (w_type(pw.w) << 24)));
+    };
+    auto staged_dir = [&](int slot) {
+        const double4 d = ldg256(rec + (size_t)slot * REC + R_DIR);
+        return make_float4((float)d.x, (float)d.y, (float)d.z, __int_as_float(slot));
     };
     if (tiled) {
-        for (int k = wid; k < ncell_nb; k += SW_WARPS) {
+        // slots first (shared memory only), then one flat pass with every lane busy and two candidates in flight per lane: the
+        // segments are short (a few cells each), a pass per segment would expose one L2 round trip per segment
+        for (int k = 0; k < nseg; k++) {
             const int b = sh_b[k], off = sh_off[k], len = sh_off[k + 1] - off;
-            for (int idx = lane; idx < len; idx += 32) { t_pf[off + idx] = staged(b + idx); t_slot[off + idx] = b + idx; }
+            for (int idx = lane; idx < len; idx += 32) t_df[off + idx].w = __int_as_float(b + idx);
+        }
+        __syncwarp();
+        for (int p0 = 0; p0 < C; p0 += 64) {
+            const int pa = p0 + lane, pb = p0 + 32 + lane;
+            const int sa = pa < C ? __float_as_int(t_df[pa].w) : tb, sb = pb < C ? __float_as_int(t_df[pb].w) : tb;
+            const double4 wa = posw[sa], wb = posw[sb];
+            const float4 da = staged_dir(sa), db = staged_dir(sb);
+            if (pa < C) { t_pf[pa] = staged_pos(wa); t_df[pa] = da; }
+            if (pb < C) { t_pf[pb] = staged_pos(wb); t_df[pb] = db; }
         }
     }
     // the active cell is the centre of its own neighbourhood: where its particles sit in the staged tile
-    const int k_centre = (nz == 1 ? 0 : nx * ny) + (ny == 1 ? 0 : nx) + (nx == 1 ? 0 : 1);
-    const int centre_off = sh_off[k_centre];
+    const int centre_seg = 2 * (g.k[2] * wy + g.k[1]);
+    const int centre_off = sh_off[centre_seg] + (tb - sh_b[centre_seg]);
     // every non-empty cell performs the same number of trials (n_sub * N / non-empty cells, stochastically rounded): the count
     // does not depend on anything a trial can change (particles never leave their cell within a pass), so detailed balance
-    // holds, and all blocks of a pass finish together instead of waiting for the fullest cell
+    // holds, and all cells of a pass finish together instead of waiting for the fullest one
     int ntrial;
     {
         const double avg = sp.trial_scale * (double)sp.n_sub * (double)s.n / (double)s.cell_start[s.ncells + 1];
-        const uint4 r = philox4x32((uint32_t)sweep, (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 28), (uint32_t)c0, 0xffffffffu, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint4 r = philox4x32((uint32_t)sweep, (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 24), (uint32_t)c0, 0xffffffffu, (uint32_t)seed, (uint32_t)(seed >> 32));
         const double fl = floor(avg);
         ntrial = (int)fl + (u01(r.x, r.y) < avg - fl ? 1 : 0);
     }
+    // ---- partner lists of the cell's own particles, built once per pass: a candidate can only become a partner during the pass if
+    // it is within reach + skin now, skin = the farthest the particle itself can travel (ntrial displacements of fixed length;
+    // candidates outside the cell do not move during the pass, those inside are few and the same skin covers them twice over:
+    // 2 * skin). A trial then scans its particle's list (a few dozen entries) instead of the whole neighbourhood.
+    if (tiled) {
+        for (int a = 0; a < SW_VLP && a < npart; a++) {
+            const int ia = centre_off + a;
+            const float4 me = t_pf[ia];
+            const int mytype = __float_as_int(me.w) >> 24;
+            float tmax = 0.f;
+            for (int t = 0; t < T; t++) tmax = fmaxf(tmax, (float)sp.trans_mx[t]);
+            const float skin = 2.f * tmax * (float)ntrial * 1.0001f + 1e-3f;
+            const float* rrow = (RODS && ONE) ? nullptr : (tabs ? sh_tab + mytype * T : s.reach2 + mytype * T);
+            const float r_one = (RODS && ONE) ? (float)(ia1.reserved[1] * 1.001) : 0.f;
+            int cnt = 0;
+            for (int base = 0; base < C; base += 32) {
+                const int p = base + lane;
+                bool keep = false;
+                if (p < C && p != ia) {
+                    const float4 q = t_pf[p];
+                    float dx = me.x - q.x, dy = me.y - q.y, dz = me.z - q.z;
+                    dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
+                    const float rr = (RODS && ONE) ? r_one : rrow[__float_as_int(q.w) >> 24];
+                    const float lim = sqrtf(rr) + skin;
+                    keep = dx * dx + dy * dy + dz * dz <= lim * lim;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const int at = cnt + __popc(m & lt_mask);
+                if (keep && at < SW_VLC) sh_vl[a][at] = (unsigned short)p;
+                cnt += __popc(m);
+            }
+            if (lane == 0) sh_vn[a] = cnt <= SW_VLC ? cnt : -1;
+        }
+    }
+    __syncwarp();
 #ifdef SW_PROFILE
+    if (lane == 0) { atomicAdd(&sw_prof[15], (unsigned long long)ntrial); atomicAdd(&sw_prof[14], 1ull); atomicAdd(&sw_prof[8], (unsigned long long)(clock64() - swp_t0)); }
     long long swp_t = clock64();
-    if (threadIdx.x == 0) atomicAdd(&sw_prof[15], (unsigned long long)ntrial);
 #endif
+    __syncwarp();
     for (int trial = 0; trial < ntrial; trial++) {
         const int bi = trial % SW_BATCH;
         if (bi == 0) {
-            // ---- random numbers and proposal geometry of the next SW_BATCH trials, one thread per trial.
+            // ---- random numbers and proposal geometry of the next SW_BATCH trials, one lane per trial.
             // Philox counter = (sweep, colour, cell, 3*trial + k); nothing here depends on earlier acceptances.
-            __syncthreads();
-            const int tr = trial + (int)threadIdx.x;
-            if (threadIdx.x < SW_BATCH && tr < ntrial) {
+            __syncwarp();
+            const int tr = trial + lane;
+            if (tr < ntrial) {
                 double u[6];
-                const uint32_t c1 = (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 28);
+                const uint32_t c1 = (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 24);
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
                     uint4 r = philox4x32((uint32_t)sweep, c1, (uint32_t)c0, (uint32_t)(3 * tr + k), (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -204,12 +295,12 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                 int pick = tb + (int)(u[0] * npart);          // uniformly chosen particle of this cell, with replacement
                 if (pick >= te) pick = te - 1;
                 const int ty = w_type(posw[pick].w);
-                const int g = sp.geotype_of_type[ty];
-                const bool displace = (g >= SCGPU_SPN) || (u[1] < 0.5);                 // particleMove (movecreator.cpp:11-33)
+                const int gt = sp.geotype_of_type[ty];
+                const bool displace = (gt >= SCGPU_SPN) || (u[1] < 0.5);                 // particleMove (movecreator.cpp:11-33)
                 const double z = 1.0 - 2.0 * u[2], phi = 6.283185307179586476925 * u[3];
                 const double rr = sqrt(fmax(0.0, 1.0 - z * z));
                 const v3 ax3 = mk(rr * cos(phi), rr * sin(phi), z);                     // uniform on the unit sphere
-                SweepProposal& P = sh_prop[threadIdx.x];
+                SweepProposal& P = sh_prop[lane];
                 P.slot = pick;
                 P.displace = displace ? 1 : 0;
                 P.u_acc = u[1] < 0.5 ? 2.0 * u[1] : 2.0 * u[1] - 1.0;   // the move-type bit is used up; the rest is still uniform
@@ -220,55 +311,74 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                     rotation_coefficients(P.m, sp.rot_angle[ty] * u[4], ax3, u[5] < 0.5);
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
         SWP_MARK(0);
         const int tslot = sh_prop[bi].slot;
         const bool displace = sh_prop[bi].displace != 0;
         const double u_acc = sh_prop[bi].u_acc;
-        if (threadIdx.x < REC) { double v = rec[(size_t)tslot * REC + threadIdx.x]; sh_old[threadIdx.x] = v; sh_new[threadIdx.x] = v; }
+        { const double v = rec[(size_t)tslot * REC + lane]; sh_old[lane] = v; sh_new[lane] = v; }       // REC == 32 == the warp
         const double4 tpw = posw[tslot];
         const int target = w_orig(tpw.w), type1 = w_type(tpw.w), moltype1 = w_moltype(tpw.w);
-        __syncthreads();
-        SWP_MARK(1);
+        __syncwarp();
         if (displace) {
-            if (threadIdx.x < 3) sh_new[R_POS + threadIdx.x] += sh_prop[bi].m[threadIdx.x];
-        } else if (threadIdx.x < 9) {      // one thread per vector of the record
-            const int g = sp.geotype_of_type[type1];
-            const int off = 3 * threadIdx.x;                   // R_DIR, R_PD0, R_S0, R_S1, R_PD1, R_S2, R_S3, R_CH0, R_CH1
-            if (record_vector_rotates(g, threadIdx.x)) rotate_vector(sh_new + off, sh_prop[bi].m);
+            if (lane < 3) sh_new[R_POS + lane] += sh_prop[bi].m[lane];
+        } else if (lane < 9) {      // one lane per vector of the record
+            const int gt = sp.geotype_of_type[type1];
+            if (record_vector_rotates(gt, lane)) rotate_vector(sh_new + 3 * lane, sh_prop[bi].m);      // R_DIR, R_PD0, R_S0, R_S1, R_PD1, R_S2, R_S3, R_CH0, R_CH1
         }
-        __syncthreads();
-        SWP_MARK(2);
+        __syncwarp();
+        SWP_MARK(1);
         // a move that leaves the cell would break the independence of the active cells: reject it
-        const bool in_cell = cell_index(sh_new + R_POS, s.shift, s.nc) == c0;
+        bool in_cell = cell_index(sh_new + R_POS, s.shift, s.nc) == c0;
+        ConList cl;
+        if (RODS) { cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0; }
+        else {
+            get_conlist(s.mol, moltype1, target, cl);
+            // a bonded partner is evaluated wherever it is; if it sits in ANOTHER active cell it may be moving right now: reject
+            // (the test depends only on the partner's position, which this trial does not change: detailed balance holds)
+            if (!cl.is_empty && in_cell) {
+                bool clash = false;
+                if (lane < 4 && cl.con[lane] >= 0) {
+                    const double4 pw = posw[s.slot_of[cl.con[lane]]];
+                    const int px = cell_coord(pw.x + s.shift[0], s.nc[0]), py = cell_coord(pw.y + s.shift[1], s.nc[1]), pz = cell_coord(pw.z + s.shift[2], s.nc[2]);
+                    const bool active = px % g.ncol[0] == colour % g.ncol[0] && py % g.ncol[1] == (colour / g.ncol[0]) % g.ncol[1] && pz % g.ncol[2] == colour / (g.ncol[0] * g.ncol[1]);
+                    clash = active && !(px == cx && py == cy && pz == cz);
+                }
+                if (__any_sync(0xffffffffu, clash)) in_cell = false;
+            }
+        }
         double e_old = 0.0, e_new = 0.0;
         if (in_cell) {
-            ConList cl;
-            if (RODS) { cl.is_empty = 1; cl.con[0] = cl.con[1] = cl.con[2] = cl.con[3] = -1; cl.sp = cl.mod0 = cl.mod1 = cl.c0 = cl.c1 = cl.eq0 = cl.eq1 = 0.0; }
-            else get_conlist(s.mol, moltype1, target, cl);
             const v3 po = ld3(sh_old + R_POS), pn = ld3(sh_new + R_POS);
             const float ox = (float)rel_frac(po.x + s.shift[0], ccen[0]), oy = (float)rel_frac(po.y + s.shift[1], ccen[1]), oz = (float)rel_frac(po.z + s.shift[2], ccen[2]);
             const float nxf = (float)rel_frac(pn.x + s.shift[0], ccen[0]), nyf = (float)rel_frac(pn.y + s.shift[1], ccen[1]), nzf = (float)rel_frac(pn.z + s.shift[2], ccen[2]);
-            int* queue = sh_queue[wid];
+            const float dox = (float)sh_old[R_DIR], doy = (float)sh_old[R_DIR + 1], doz = (float)sh_old[R_DIR + 2];
+            const float dnx = (float)sh_new[R_DIR], dny = (float)sh_new[R_DIR + 1], dnz = (float)sh_new[R_DIR + 2];
+            const float* reach_row = tabs ? sh_tab + type1 * T : s.reach2 + type1 * T;
+            const float* cut_row = tabs ? sh_tab + T * T + type1 * T : s.reach2 + T * T + T + type1 * T;
+            const float* hl_tab = tabs ? sh_tab + 2 * T * T : s.reach2 + 2 * T * T + T;
+            const float h1 = (RODS && ONE) ? (float)ia1.half_len[0] : hl_tab[type1];
+            const float reach_one = (float)(ia1.reserved[1] * 1.001), cut_one = (float)(fmax(ia1.rcutSq, ia1.rcutwcaSq) * 1.001);
             int qn = 0;
             double lo = 0.0, ln = 0.0;
-            // one queue entry = (partner slot, which state): the old and the new state of a trial are evaluated on DIFFERENT
-            // lanes. Phase A: exact gate + everything but the rod-rod patch term; entries that owe a patch term are collected
-            // per warp. Phase B: each warp evaluates its own patch terms, two lanes per term.
+            // one queue entry = (candidate, which state): the old and the new state of a trial are evaluated on DIFFERENT lanes.
+            // Phase A: exact gate + everything but the rod-rod patch term; entries that owe a patch term are collected.
+            // Phase B: the patch terms, two lanes per term.
             int pc = 0;
+            auto entry_slot = [&](int entry) { const int p = entry >> 1; return (tiled && p >= 0) ? __float_as_int(t_df[p].w) : (p >= 0 ? slot_of_p(p) : -1 - p); };
             auto patch_entry = [&](int entry) {
-                const int slot = entry >> 1;
+                const int slot = entry_slot(entry);
                 const bool is_new = entry & 1;
                 double4 pw = posw[slot];
                 v3 r = image(s.box, is_new ? pn : po, mk(pw.x, pw.y, pw.z));
-                double e = pair_energy_patch(ONE ? ia1 : s.ia[type1 * s.ntypes + w_type(pw.w)], r, is_new ? sh_new : sh_old, rec + (size_t)slot * REC);
+                double e = pair_energy_patch_outofline(ONE ? ia1 : s.ia[type1 * s.ntypes + w_type(pw.w)], r, is_new ? sh_new : sh_old, rec + (size_t)slot * REC);
                 if (is_new) ln += e; else lo += e;
             };
             auto eval = [&](int entry, bool on) {
                 bool np = false;
                 if (on) {
-                    const int slot = entry >> 1;
+                    const int slot = entry_slot(entry);
                     const bool is_new = entry & 1;
                     double4 pw = posw[slot];
                     int orig = w_orig(pw.w);
@@ -289,61 +399,74 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
                     if (pc + c > 32) {                 // list full (never in physical configurations): evaluate in place
                         if (np) patch_entry(entry);
                     } else {
-                        if (np) sh_pl[wid][pc + __popc(m & lt_mask)] = entry;
+                        if (np) sh_pl[pc + __popc(m & lt_mask)] = entry;
                         pc += c;
                     }
                     __syncwarp();
                 }
             };
-            for (int base = wid * 32; base < C; base += SW_WARPS * 32) {
+            const int va = tslot - tb;
+            const int vn = (tiled && va < SW_VLP) ? sh_vn[va] : -1;
+            const int nscan = vn >= 0 ? vn : C;
+            for (int base = 0; base < nscan; base += 32) {
                 int p = base + lane;
                 bool pass_o = false, pass_n = false;
-                int slot = 0;
-                if (p < C) {
-                    slot = tiled ? t_slot[p] : slot_of_p(p);
-                    if (slot != tslot) {
-                        float4 q = tiled ? t_pf[p] : staged(slot);
+                if (p < nscan) {
+                    if (vn >= 0) p = sh_vl[va][p];
+                    float4 q, qd;
+                    if (tiled) { q = t_pf[p]; qd = t_df[p]; }
+                    else { const int sl = slot_of_p(p); q = staged_pos(posw[sl]); qd = staged_dir(sl); }
+                    const int wbits = __float_as_int(q.w);
+                    const int orig = wbits & 0xffffff, ctype = wbits >> 24;
+                    if (orig != target) {
                         float dx = ox - q.x, dy = oy - q.y, dz = oz - q.z;
                         dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
                         float ex = nxf - q.x, ey = nyf - q.y, ez = nzf - q.z;
                         ex = (ex - rintf(ex)) * boxf[0]; ey = (ey - rintf(ey)) * boxf[1]; ez = (ez - rintf(ez)) * boxf[2];
-                        pass_o = (dx * dx + dy * dy + dz * dz <= pre_cut);
-                        pass_n = (ex * ex + ey * ey + ez * ez <= pre_cut);
+                        const float d2o = dx * dx + dy * dy + dz * dz, d2n = ex * ex + ey * ey + ez * ez;
+                        const float reach = (RODS && ONE) ? reach_one : reach_row[ctype];
+                        pass_o = d2o <= reach;
+                        pass_n = d2n <= reach;
+                        const float cut2 = (RODS && ONE) ? cut_one : cut_row[ctype];
+                        if (cut2 > 0.f && (pass_o || pass_n)) {     // rod pair: the segment bound
+                            const float h2 = (RODS && ONE) ? h1 : hl_tab[ctype];
+                            if (pass_o && lb_beyond(dx, dy, dz, d2o, dox, doy, doz, qd.x, qd.y, qd.z, h1, h2, cut2)) pass_o = false;
+                            if (pass_n && lb_beyond(ex, ey, ez, d2n, dnx, dny, dnz, qd.x, qd.y, qd.z, h1, h2, cut2)) pass_n = false;
+                        }
                         if (!RODS && !cl.is_empty) {       // bonded partners are evaluated by index below
-                            int orig = w_orig(posw[slot].w);
                             if (orig == cl.con[0] || orig == cl.con[1] || orig == cl.con[2] || orig == cl.con[3]) { pass_o = false; pass_n = false; }
                         }
                     }
                 }
                 unsigned mo = __ballot_sync(0xffffffffu, pass_o), mn = __ballot_sync(0xffffffffu, pass_n);
                 int no = __popc(mo);
-                if (pass_o) queue[qn + __popc(mo & lt_mask)] = slot * 2;
-                if (pass_n) queue[qn + no + __popc(mn & lt_mask)] = slot * 2 + 1;
+                if (pass_o) sh_queue[qn + __popc(mo & lt_mask)] = p * 2;
+                if (pass_n) sh_queue[qn + no + __popc(mn & lt_mask)] = p * 2 + 1;
                 qn += no + __popc(mn);
                 __syncwarp();
                 while (qn >= 32) {
-                    eval(queue[lane], true);
+                    eval(sh_queue[lane], true);
                     int rest = qn - 32;
-                    int mv0 = (lane < rest) ? queue[32 + lane] : 0;
-                    int mv1 = (lane + 32 < rest) ? queue[64 + lane] : 0;
+                    int mv0 = (lane < rest) ? sh_queue[32 + lane] : 0;
+                    int mv1 = (lane + 32 < rest) ? sh_queue[64 + lane] : 0;
                     __syncwarp();
-                    if (lane < rest) queue[lane] = mv0;
-                    if (lane + 32 < rest) queue[32 + lane] = mv1;
+                    if (lane < rest) sh_queue[lane] = mv0;
+                    if (lane + 32 < rest) sh_queue[32 + lane] = mv1;
                     qn = rest;
                     __syncwarp();
                 }
             }
-            if (qn > 0) eval(lane < qn ? queue[lane] : 0, lane < qn);
-            if (!RODS && wid == 0 && !cl.is_empty) {
+            if (qn > 0) eval(lane < qn ? sh_queue[lane] : 0, lane < qn);
+            if (!RODS && !cl.is_empty) {      // bonded partners by index, both states: entry = (-1 - slot) * 2 + state
                 bool on = lane < 8 && cl.con[lane >> 1] >= 0;
-                eval(on ? s.slot_of[cl.con[lane >> 1]] * 2 + (lane & 1) : 0, on);
+                eval(on ? (-1 - s.slot_of[cl.con[lane >> 1]]) * 2 + (lane & 1) : 0, on);
             }
             SWP_MARK(3);
-            for (int base = 0; base < 2 * pc; base += 32) {      // phase B: this warp's patch terms, two lanes per term, in list order
+            for (int base = 0; base < 2 * pc; base += 32) {      // phase B: the patch terms, two lanes per term, in list order
                 const int idx = (base + lane) >> 1;
                 const bool act = idx < pc;
-                const int entry = act ? sh_pl[wid][idx] : 0;
-                const int slot = entry >> 1;
+                const int entry = act ? sh_pl[idx] : 0;
+                const int slot = act ? entry_slot(entry) : tslot;
                 const bool is_new = entry & 1;
                 double4 pw = posw[slot];
                 v3 r = image(s.box, is_new ? pn : po, mk(pw.x, pw.y, pw.z));
@@ -354,38 +477,34 @@ k_sweep_colour(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
             e_old = warp_sum(lo);
             e_new = warp_sum(ln);
         }
-        if (lane == 0) { sh_eo[wid] = e_old; sh_en[wid] = e_new; }
-        __syncthreads();
         SWP_MARK(6);
         bool accept = false;
-        if (in_cell) {
-            double de = 0.0;
-            if (lane == 0) {          // every warp takes the same decision from the same numbers (no broadcast barrier)
-                double eo = 0.0, en = 0.0;
-                for (int k = 0; k < SW_WARPS; k++) { eo += sh_eo[k]; en += sh_en[k]; }     // fixed order
-                de = en - eo;
-                accept = (de <= 0.0) || (exp(-de / sp.temper) > u_acc);                    // moveTry (movecreator.h:175-187)
-            }
-            accept = __shfl_sync(0xffffffffu, accept ? 1 : 0, 0) != 0;
-            if (threadIdx.x == 0 && accept) acc.de += de;
+        double de = 0.0;
+        if (in_cell) {        // every lane takes the same decision from the same numbers
+            de = e_new - e_old;
+            accept = (de <= 0.0) || (exp(-de / sp.temper) > u_acc);                    // moveTry (movecreator.h:175-187)
         }
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
+            if (accept) acc.de += de;
             if (!in_cell) acc.cell_rej++;
             if (displace) { if (accept) acc.trans_acc++; else acc.trans_rej++; }
             else { if (accept) acc.rot_acc++; else acc.rot_rej++; }
         }
-        if (accept) {          // commit in place: sorted record, position word, staged FP32 copy
-            if (threadIdx.x < REC) rec[(size_t)tslot * REC + threadIdx.x] = sh_new[threadIdx.x];
-            if (threadIdx.x == REC) {
-                posw[tslot] = make_double4(sh_new[R_POS], sh_new[R_POS + 1], sh_new[R_POS + 2], tpw.w);
-                if (tiled) t_pf[centre_off + (tslot - tb)] = make_float4((float)rel_frac(sh_new[R_POS] + s.shift[0], ccen[0]), (float)rel_frac(sh_new[R_POS + 1] + s.shift[1], ccen[1]),
-                                                                         (float)rel_frac(sh_new[R_POS + 2] + s.shift[2], ccen[2]), 0.f);
+        if (accept) {          // commit in place: sorted record, position word, staged FP32 copies
+            rec[(size_t)tslot * REC + lane] = sh_new[lane];
+            if (lane == 0) {
+                const double4 npw = make_double4(sh_new[R_POS], sh_new[R_POS + 1], sh_new[R_POS + 2], tpw.w);
+                posw[tslot] = npw;
+                if (tiled) {
+                    t_pf[centre_off + (tslot - tb)] = staged_pos(npw);
+                    t_df[centre_off + (tslot - tb)] = make_float4((float)sh_new[R_DIR], (float)sh_new[R_DIR + 1], (float)sh_new[R_DIR + 2], __int_as_float(tslot));
+                }
             }
         }
-        __syncthreads();
+        __syncwarp();
         SWP_MARK(7);
     }
-    if (threadIdx.x == 0) acc_out[c0] = acc;
+    if (lane == 0) acc_out[c0] = acc;
 }
 
 

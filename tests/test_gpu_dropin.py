@@ -1,0 +1,61 @@
+"""GPU: the drop-in, literally. oracle/_ref/SC_scgpu is the reference's OWN program -- its main.cpp, parsers, move code, random
+stream -- with two lines changed by sed on a scratch copy (oracle/Makefile, target scgpu_ref):
+    #include "totalegpu.h"
+    typedef TotalEGpu<PairE> TotalEnergyCalculator;            (scOOP/mc/totalenergycalculator.h:1226-1228)
+i.e. the calculator class of integration/totalegpu.h forwarding every virtual of TotalE<> to the C ABI.
+It is run on the reference's own regression inputs (Tests/test_*, Tests/volumeChange/*; committed as tests/golden/*.inputs.json)
+and its config.last must be BYTE-IDENTICAL to the one the unmodified reference program wrote (tests/golden/*.config.last) -- the
+reference's own regression method (Tests/test: diff config.last config.last2). The binary is built where /root/reference exists
+and travels to the GPU box; nothing here reads /root/reference."""
+import json
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+SC = os.path.join(ROOT, "oracle", "_ref", "SC_scgpu")
+
+NVT = ["test_01_normal_PSC", "test_02_normal_CPSC", "test_03_normal_CHPSC", "test_04_normal_CHCPSC", "test_05_normal_TPSC",
+       "test_06_normal_TCPSC", "test_07_normal_TCHPSC", "test_08_normal_TCHCPSC", "test_09_normal_SPN", "test_10_normal_SPA",
+       "test_11_normal_PSC_CPSC", "test_12_normal_SPA_CPSC", "test_13_normal_SPA_PSC", "test_14_normal_SPA_PSC_CPSC",
+       "test_20_chain_bond12", "test_21_chain_bondd2"]
+NPT = ["volumeChange_%d%s" % (k, hl) for k in range(4) for hl in "hl"]
+
+
+def run_reference_program(name, nsweeps):
+    if not os.path.exists(SC):
+        pytest.skip("oracle/_ref/SC_scgpu was not built (make -C oracle scgpu_ref needs /root/reference)")
+    inputs = json.load(open(os.path.join(G, name + ".inputs.json")))
+    with tempfile.TemporaryDirectory(prefix="dropin_") as tmp:
+        opt = inputs["options"]
+        if nsweeps:
+            opt = re.sub(r"(?m)^nsweeps\s*=\s*\d+", "nsweeps = %d" % nsweeps, opt)
+        for fn, text in (("options", opt), ("top.init", inputs["top.init"]), ("config.init", inputs["config.init"])):
+            with open(os.path.join(tmp, fn), "w") as f:
+                f.write(text)
+        r = subprocess.run([SC], cwd=tmp, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        return open(os.path.join(tmp, "config.last")).read(), r.stdout
+
+
+@pytest.mark.parametrize("name", NVT)
+def test_reference_main_on_gpu_calculator_nvt(name):
+    got, out = run_reference_program(name, 300)
+    assert got == open(os.path.join(G, name + ".short300.config.last")).read(), out[-800:]
+
+
+@pytest.mark.parametrize("name", NPT)
+def test_reference_main_on_gpu_calculator_npt(name):
+    got, out = run_reference_program(name, 500)
+    assert got == open(os.path.join(G, name + ".short500.config.last")).read(), out[-800:]
+
+
+def test_reference_main_full_length_test_01():
+    """Tests/test_01_normal_PSC exactly as Tests/test runs it (BASELINE configs[0])"""
+    got, out = run_reference_program("test_01_normal_PSC", 0)
+    assert got == open(os.path.join(G, "test_01_normal_PSC.config.last")).read(), out[-800:]
