@@ -110,6 +110,38 @@ def cpu_reference(ntargets, reps, nproc):
             "seconds": tmax, "gated_pairs": gated}
 
 
+def cpu_reference_sweeps(ntargets, ntrials, nproc):
+    """Measured sequential sweeps of the reference's own move code (MoveCreator::partDisplace / partRotate over TotalEFull<PairE> and the
+    reference's neighbour lists; oracle/_ref/sc_ref_full, see oracle/ref_driver.cpp do_sweep): `nproc` independent processes (the
+    reference is single-threaded; independent replicas are its parallel model), each `ntrials` trial moves among `ntargets` particles."""
+    top, cfg, n = workload_texts()
+    drv = os.path.join(ROOT, "oracle", "_ref", "sc_ref_full")
+    if not os.path.exists(drv):
+        return None
+    tmp = tempfile.mkdtemp(prefix="scsweep_")
+    try:
+        with open(os.path.join(tmp, "top.init"), "w") as f:
+            f.write(top.replace("A %d" % n, "A 1"))
+        with open(os.path.join(tmp, "config.init"), "w") as f:
+            f.write(cfg)
+        with open(os.path.join(tmp, "options"), "w") as f:
+            f.write(options_text())
+        procs = [subprocess.Popen([drv, "sweep", str(ntargets), str(ntrials), str(n)], cwd=tmp, stdout=subprocess.PIPE,
+                                  stderr=subprocess.DEVNULL, text=True) for _ in range(nproc)]
+        outs = [p.communicate()[0] for p in procs]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    recs = [json.loads(line[8:]) for o in outs for line in o.splitlines() if line.startswith("REFJSON ")]
+    if len(recs) != nproc:
+        return None
+    tmax = max(r["trial_s"] for r in recs)
+    return {"sweeps_per_s": nproc * ntrials / tmax / n, "sweeps_per_s_one_core": float(np.mean([r["sweeps_per_s_one_core"] for r in recs])), "cores": nproc,
+            "us_per_trial_one_core": tmax / ntrials * 1e6, "acceptance": recs[0]["accepted"] / max(1, recs[0]["accepted"] + recs[0]["rejected"]),
+            "kind": "reference", "sample": "%d trial moves among %d particles per process, %d independent processes; MoveCreator::partDisplace/partRotate over "
+            "TotalEFull<PairE> (old AND trial energy evaluated per move: the reference's default TotalEMatrix caches the old one but needs 34 GB at this size) "
+            "and the reference's neighbour lists, -Ofast; list construction (%.2f s per process for the sample) not charged" % (ntrials, ntargets, nproc, recs[0]["list_build_s"])}
+
+
 def cpu_port_fallback(ntargets):
     """oracle port, 1 core -- only if oracle/_ref did not travel"""
     from oracle import oracle as O
@@ -322,6 +354,22 @@ def run_ours(args):
     h2d = state_host.nbytes
     d2h = e_host.nbytes
 
+    # ---- latency of ONE calculator call: what the literal drop-in pays per virtual (integration/totalegpu.h issues one scgpu_one_to_all
+    # per oneToAll / oneToAllTrial: upload of the trial record, three launches, read-back, one synchronisation)
+    eng.set_particles(hs.state, hs.type, hs.moltype)
+    eng.build_cells()
+    trial = hs.state[1234].copy()
+    trial[0:3] += 1e-4
+    for k in range(50):
+        eng.one_to_all(1234, trial)
+    t0 = time.perf_counter()
+    ncall = 400
+    for k in range(ncall):
+        eng.one_to_all(1234 + 97 * k, trial if (k & 1) else None)
+    single_call = {"us_per_call": (time.perf_counter() - t0) / ncall * 1e6, "calls": ncall,
+                   "what": "scgpu_one_to_all on the 65 536-particle system through ctypes (trial state every other call): the cost of one oneToAll()/oneToAllTrial() "
+                           "virtual of the drop-in class; a sequential trial move costs two of them plus update() on acceptance"}
+
     # ---- cell-list build (counting sort by cell + SoA permute): the HBM-bound kernel group of the path
     cb_ms = []
     for _ in range(max(3, min(args.steps, 10))):
@@ -462,6 +510,18 @@ def run_ours(args):
           "analytic_note": "exp(-0.5 N dT^2 / (1 + dT)) as the reference prints it (mc/inicializer.cpp:52-55); with N = 65 536 and 8 rungs between T = 0.1 and 0.13 it is ~0: the ladder of BASELINE configs[4] is far too coarse for this system size, exchanges are attempted and (correctly) rejected",
           "timing": "CUDA events on every replica's stream around the whole loop (sweeps + exchanges), max over replicas and ranks; wall %.4f s" % pt_wall,
           "path": "scgpu_replica_exchange (C ABI): device-side records, %s, device decision kernel; no host round trip of the energies" % ("one ncclAllGather of %d x 512 B" % ptr.R if world > 1 else "one process: device copy instead of NCCL")}
+    # the same loop on a ladder the system size allows (the reference's estimate exp(-0.5 N dT^2 / (1 + dT)) ~ 0.3): exchanges do happen
+    ptt = _rep.ParallelTempering(comm, engines, 0.1, 0.100426, 0.0212, 7.5, nrepchange=10, seed=145658)
+    for k in range(1001, 1041):
+        ptt.sweep(k)
+    tv = [float(sum(ptt.acc)), float(sum(ptt.rej))]
+    if world > 1:
+        c3 = torch.tensor(tv, dtype=torch.float64, device="cuda")
+        dist.all_reduce(c3, op=dist.ReduceOp.SUM)
+        tv = [float(c3[0].item()), float(c3[1].item())]
+    pt["tight_ladder"] = {"T": [0.1, 0.100426], "sweeps": 40, "pairs_attempted": int((tv[0] + tv[1]) // 2), "pair_acceptance": tv[0] / max(1.0, tv[0] + tv[1]),
+                          "analytic_estimate": _rep.switch_probability_estimate(n, ptt.dtemp),
+                          "note": "all replicas start from the same lattice and have not equilibrated at their rungs: a plausibility check of the exchange rule, not a converged ratio"}
     comm.close()
     for e in engines[1:]:
         e.close()
@@ -521,11 +581,12 @@ def run_ours(args):
                    "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
                    "mode": "scgpu_submit_everyone, two contexts alternating (copies of one configuration overlap the kernels of the other)",
                    "one_at_a_time": {"value": float(ngate) * e2e_steps * world / e2e_serial_s, "ms_per_step": e2e_serial_s / e2e_steps * 1e3}},
-           "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall, "secondary": sweeps, "cell_build": cell_build, "full_energy": full_energy}
-    if cpu:
-        # the reference's sweep = N trials, each one trial-energy evaluation over its neighbour list (old energies are cached in its
-        # energy matrix): derived from the measured pair rate, labelled as such
-        out["secondary"]["cpu_reference_derived_sweeps_per_s"] = cpu["value"] / (float(ngate))
+           "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall, "secondary": sweeps, "cell_build": cell_build, "full_energy": full_energy, "single_call": single_call}
+    if world == 1 and not args.no_cpu:
+        cs = cpu_reference_sweeps(2048, 32768, os.cpu_count() or 1)
+        if cs:
+            out["secondary"]["cpu_reference_sweeps"] = cs
+            out["single_call"]["cpu_us_per_trial_one_core"] = cs["us_per_trial_one_core"]
     print(json.dumps(out), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

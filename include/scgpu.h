@@ -100,12 +100,13 @@ typedef struct scgpu_chainstats {
     int64_t noop;                                                      /* picks that landed on a one-particle molecule: no move */
 } scgpu_chainstats;
 
-/* One volume move (MoveCreator::pressureMove, scOOP/mc/movecreator.cpp:330-550, ptype 0-3) for callers that run the batched
+/* One volume move (MoveCreator::pressureMove, scOOP/mc/movecreator.cpp:330-550, ptype 0-5) for callers that run the batched
  * sweeps: positions are box-fractional, so only the box changes; both energies are full-system sums on the device. */
 typedef struct scgpu_pressureparams {
     double temper, press;          /* Sim::temper, Sim::press */
     double edge_mx;                /* stat.edge.mx (= 2*edge_mx of the options file, sim.h:364) */
-    int ptype;                     /* 0 anisotropic (one random edge), 1 isotropic, 2 isotropic in xy (z constant), 3 xy at constant volume */
+    int ptype;                     /* 0 anisotropic (one random edge), 1 isotropic, 2 isotropic in xy (z constant), 3 xy at constant volume,
+                                      4 "anisotropic in xy" (as written in the reference: the x edge only), 5 the y edge only */
     int reserved;
 } scgpu_pressureparams;
 

@@ -5,7 +5,7 @@
 //   Updater::simulate           scOOP/mc/updater.cpp:45-389             (step loop; production run only)
 //   MoveCreator::particleMove / partDisplace / partRotate       scOOP/mc/movecreator.cpp:11-33, 947-1028
 //   MoveCreator::chainMove / chainDisplace / chainRotate / clusterRotate   :304-328, 1075-1392
-//   MoveCreator::pressureMove (ptype 0-3) / moveTry             :330-485, movecreator.h:175-187
+//   MoveCreator::pressureMove (ptype 0-5) / moveTry             :330-550, movecreator.h:175-187
 //   Particle::pscRotate, Vector::randomUnitSphere               scOOP/structures/particle.h:182-272, Vector.h:190-205
 // Not mirrored (outside the hot path's callers this round): Wang-Landau, muVT, cluster and switch moves, the wall
 // potential, step-size adaptation (adjust/nequil must be 0, as in every Tests/test_* input).
@@ -302,7 +302,7 @@ public:
         return chainRotate(target);
     }
 
-    double pressureMove() {                    // movecreator.cpp:330-550, ptype 0-3
+    double pressureMove() {                    // movecreator.cpp:330-550, ptype 0-5
         double energy = calc->allToAll();
         double enermove = 0.0;
         auto& box = conf->box;
@@ -347,7 +347,27 @@ public:
             enermove += calc->allToAllTrial();
             reject = moveTry(energy, enermove);
             if (reject) { box[0] -= psch; box[1] -= psch; box[2] = pvol / box[0] / box[1]; }
-        } else throw Error("sequential driver: ptype 4/5 are not mirrored");
+        } else if (ptype == 4) {           // :480-514 "anisotropic in xy, z const". As written `if (ran2() - 0.5)` tests a non-zero double: always
+            double pvol = box[0] * box[1];       // true, so only the x edge ever changes -- two random numbers are drawn all the same
+            double psx = 0.0, psy = 0.0;
+            if (ran2() - 0.5) psx = edge.mx * (ran2() - 0.5);
+            else psy = edge.mx * (ran2() - 0.5);
+            box[0] += psx; box[1] += psy;
+            double pvoln = box[0] * box[1];
+            enermove = press * box[2] * (pvoln - pvol) - N * temper * log(pvoln / pvol);
+            enermove += calc->allToAllTrial();
+            reject = moveTry(energy, enermove);
+            if (reject) { box[0] -= psx; box[1] -= psy; }
+        } else if (ptype == 5) {           // :515-541 box change along y only
+            double pvol = box[1];
+            double psy = edge.mx * (ran2() - 0.5);
+            box[1] += psy;
+            double pvoln = box[1];
+            enermove = press * box[2] * box[0] * (pvoln - pvol) - N * temper * log(pvoln / pvol);
+            enermove += calc->allToAllTrial();
+            reject = moveTry(energy, enermove);
+            if (reject) box[1] -= psy;
+        } else throw Error("sequential driver: unknown type of pressure coupling");
         if (reject) { st.edge_rej++; edge.rej++; return 0.0; }     // the calculator re-reads the restored box on its next call
         st.edge_acc++; edge.acc++;
         calc->update();

@@ -57,6 +57,8 @@ struct DevSys {
     const double* api;
     const double4* posw;
     const double* rec;
+    const float4* p32;    // cell-sorted FP32 copy for the gates: x, y, z = position wrapped into [0, 1) (box fractions), w = original index | type << 24
+    const float4* d32;    // cell-sorted FP32 axis (dir); w unused
     const int* cell_start;
     const int* order;
     const int* slot_of;
@@ -154,8 +156,22 @@ __global__ void k_cell_fill(int n, const int* __restrict__ cell_of, int* __restr
 }
 
 // stable placement: slot = cell_start[c] + #{members of c with a smaller original index}; permute the records
+__device__ __forceinline__ float4 make_p32(double x, double y, double z, int orig, int type) {
+    return make_float4((float)(x - floor(x)), (float)(y - floor(y)), (float)(z - floor(z)), __int_as_float(orig | (type << 24)));
+}
+// FP32 copies of the sorted positions / axes (the gates stage these: 16 contiguous bytes per candidate, no FP64 arithmetic)
+__global__ void k_make_f32(int n, const double4* __restrict__ posw, const double* __restrict__ rec, float4* __restrict__ p32, float4* __restrict__ d32) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const double4 pw = posw[slot];
+    const double4 dw = ldg256(rec + (size_t)slot * REC + R_DIR);
+    p32[slot] = make_p32(pw.x, pw.y, pw.z, w_orig(pw.w), w_type(pw.w));
+    d32[slot] = make_float4((float)dw.x, (float)dw.y, (float)dw.z, 0.f);
+}
+
 __global__ void k_cell_place(DevSys s, const int* __restrict__ cell_of, const int* __restrict__ tmp,
-                             int* __restrict__ order, int* __restrict__ slot_of, double4* __restrict__ posw, double* __restrict__ rec) {
+                             int* __restrict__ order, int* __restrict__ slot_of, double4* __restrict__ posw, double* __restrict__ rec,
+                             float4* __restrict__ p32, float4* __restrict__ d32) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < s.n;
     int slot = 0;
@@ -188,7 +204,13 @@ __global__ void k_cell_place(DevSys s, const int* __restrict__ cell_of, const in
             rec[(size_t)dst[u] * REC + lane] = v[u];
             if (lane == 31) {
                 const double* a = s.api + (size_t)srcs[u] * 30;
-                posw[dst[u]] = make_double4(a[0], a[1], a[2], pack_w(s.type[srcs[u]], s.moltype[srcs[u]], srcs[u]));
+                const int ty = s.type[srcs[u]];
+                posw[dst[u]] = make_double4(a[0], a[1], a[2], pack_w(ty, s.moltype[srcs[u]], srcs[u]));
+                p32[dst[u]] = make_p32(a[0], a[1], a[2], srcs[u], ty);
+            }
+            if (lane == 30) {
+                const double* a = s.api + (size_t)srcs[u] * 30;
+                d32[dst[u]] = make_float4((float)a[3], (float)a[4], (float)a[5], 0.f);
             }
         }
     }
@@ -261,12 +283,13 @@ __global__ void k_particle_init(int n, int ntypes, const double* __restrict__ co
 }
 
 // rewrite one particle's sorted record in place (update(int target) when it stayed in its cell)
-__global__ void k_update_one(DevSys s, int idx, double4* __restrict__ posw, double* __restrict__ rec) {
+__global__ void k_update_one(DevSys s, int idx, double4* __restrict__ posw, double* __restrict__ rec, float4* __restrict__ p32, float4* __restrict__ d32) {
     int k = threadIdx.x;
     int slot = s.slot_of[idx];
     const double* a = s.api + (size_t)idx * 30;
     if (k < 30) rec[(size_t)slot * REC + k] = a[c_api_of[k]];
-    if (k == 31) posw[slot] = make_double4(a[0], a[1], a[2], pack_w(s.type[idx], s.moltype[idx], idx));
+    if (k == 31) { posw[slot] = make_double4(a[0], a[1], a[2], pack_w(s.type[idx], s.moltype[idx], idx)); p32[slot] = make_p32(a[0], a[1], a[2], idx, s.type[idx]); }
+    if (k == 30) d32[slot] = make_float4((float)a[3], (float)a[4], (float)a[5], 0.f);
 }
 
 // sorted -> original order (after device-side sweeps changed the sorted arrays)
@@ -838,11 +861,11 @@ constexpr int GR_CAP = GR_CAP_N;    // hits per (target, slice)
 constexpr int GR_STRIDE = 34;       // halfwords per buffer row: row k of target t at k * 34 + t -> the write-out (fixed t, k = lane) is conflict-free
 
 template <int MODE>
-__global__ void __launch_bounds__(GR_SL * 32, 5)
+__global__ void __launch_bounds__(GR_SL * 32, 6)
 k_gate_rows(DevSys s, FlatList fl) {
     __shared__ float4 t_pf[GR_TILE];                // x, y, z: FP32 coordinates relative to the unit centre, length units; w = x^2 + y^2 + z^2
-    __shared__ __align__(16) int t_orig[GR_TILE];
-    __shared__ float t_dx[GR_TILE], t_dy[GR_TILE], t_dz[GR_TILE];      // FP32 axis of every staged rod (segment lower bound, lb_beyond)
+    __shared__ __align__(16) int t_orig[MODE == 2 ? GR_TILE : 4];      // allToAll rows compare original indices; every-particle passes only need "not myself"
+    __shared__ uint2 t_dq[GR_TILE];                 // axis of every staged rod, 3 x snorm16 (segment lower bound; its margin covers the quantisation)
     __shared__ unsigned short sh_hit[GR_SL][GR_CAP * GR_STRIDE];
     __shared__ int sh_cnt[GR_SL][GR_T];
     __shared__ int sh_off[GR_SL][GR_T];
@@ -854,6 +877,7 @@ k_gate_rows(DevSys s, FlatList fl) {
     const int nx = s.nc[0], ny = s.nc[1];
     const int cy = row % ny, cz = row / ny;
     const int rs = s.cell_start[row * nx], re = s.cell_start[(row + 1) * nx];
+    const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
     // A unit is 32 consecutive slots of the row. Where the row is sparse such a unit would span many cells (and its neighbourhood
     // the whole row): it is then processed in sub-units of at most kmax cells each (dense rows: one sub-unit, all lanes busy).
     const int kmax = min(6, nx - 3);
@@ -906,39 +930,46 @@ k_gate_rows(DevSys s, FlatList fl) {
         const int count = last - first + 1;
         const int C = sh_soff[18];
         const int Cpad = (C + 4 * GR_SL - 1) / (4 * GR_SL) * (4 * GR_SL);
-        const double ccen[3] = {0.5 * (sh_cx[0] + sh_cx[1] + 1) / nx, (cy + 0.5) / ny, (cz + 0.5) / s.nc[2]};
-        auto staged = [&](const double4& pw) {
-            const float x = (float)(rel_frac(pw.x + s.shift[0], ccen[0]) * s.box[0]), y = (float)(rel_frac(pw.y + s.shift[1], ccen[1]) * s.box[1]),
-                        z = (float)(rel_frac(pw.z + s.shift[2], ccen[2]) * s.box[2]);
+        // unit centre in box fractions (the staged FP32 positions are wrapped into [0, 1): the difference is folded once)
+        const float cen[3] = {(float)(0.5 * (sh_cx[0] + sh_cx[1] + 1) / nx - s.shift[0]), (float)((cy + 0.5) / ny - s.shift[1]), (float)((cz + 0.5) / s.nc[2] - s.shift[2])};
+        auto staged = [&](const float4& f) {
+            float x = f.x - cen[0], y = f.y - cen[1], z = f.z - cen[2];
+            x = (x - rintf(x)) * boxf[0]; y = (y - rintf(y)) * boxf[1]; z = (z - rintf(z)) * boxf[2];
             return make_float4(x, y, z, x * x + y * y + z * z);
         };
-        // ---- stage: a warp per segment, contiguous 32-byte loads
+        auto quant = [](const float4& d) {          // 3 x snorm16
+            const int qx = __float2int_rn(d.x * 32767.f), qy = __float2int_rn(d.y * 32767.f), qz = __float2int_rn(d.z * 32767.f);
+            return make_uint2((unsigned)(qx & 0xffff) | ((unsigned)qy << 16), (unsigned)(qz & 0xffff));
+        };
+        // ---- stage: a warp per segment, contiguous 16-byte loads of the FP32 copies
         for (int k = wid; k < 18; k += GR_SL) {
             const int b = sh_sb[k], off = sh_soff[k], len = sh_soff[k + 1] - off;
             for (int idx = lane; idx < len; idx += 32) {
-                const double4 pw = s.posw[b + idx];
-                const double4 dw = ldg256(s.rec + (size_t)(b + idx) * REC + R_DIR);
-                t_pf[off + idx] = staged(pw); t_orig[off + idx] = w_orig(pw.w);
-                t_dx[off + idx] = (float)dw.x; t_dy[off + idx] = (float)dw.y; t_dz[off + idx] = (float)dw.z;
+                const float4 f = s.p32[b + idx], d = s.d32[b + idx];
+                t_pf[off + idx] = staged(f);
+                t_dq[off + idx] = quant(d);
+                if (MODE == 2) t_orig[off + idx] = __float_as_int(f.w) & 0xffffff;
             }
         }
         for (int p = C + threadIdx.x; p < Cpad; p += blockDim.x) {          // padding: an infinite |q|^2 fails the comparison
             t_pf[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
-            t_orig[p] = -1;
+            t_dq[p] = make_uint2(0u, 0u);
+            if (MODE == 2) t_orig[p] = -1;
         }
         // ---- this lane's target: |t - q|^2 <= reach  <=>  |q|^2 - 2 t.q <= reach - |t|^2 (three FMAs and a compare per test; the
         // rounding error, ~1e-6 relative at these magnitudes, is far inside the 0.1 % margin carried by reach)
         float m2x = 0.f, m2y = 0.f, m2z = 0.f, thr = __int_as_float(0xff800000);
         float tdx = 0.f, tdy = 0.f, tdz = 1.f, hl = 0.f, cut2 = 0.f;
-        int target = -2;
+        int target = -2, c_self = -1;
         if (lane < count) {
-            const double4 pw = s.posw[first + lane];
-            const double4 dw = ldg256(s.rec + (size_t)(first + lane) * REC + R_DIR);
-            const float4 q = staged(pw);
+            const float4 f = s.p32[first + lane], d = s.d32[first + lane];
+            const float4 q = staged(f);
             m2x = -2.f * q.x; m2y = -2.f * q.y; m2z = -2.f * q.z;
-            tdx = (float)dw.x; tdy = (float)dw.y; tdz = (float)dw.z;
-            target = w_orig(pw.w);
-            const int T = s.ntypes, tt = w_type(pw.w);
+            tdx = d.x; tdy = d.y; tdz = d.z;
+            const int wb = __float_as_int(f.w);
+            target = wb & 0xffffff;
+            c_self = sh_soff[8] + (first + lane - sh_sb[8]);      // the targets sit in the centre row of their own neighbourhood (segment 8)
+            const int T = s.ntypes, tt = wb >> 24;
             thr = s.reach2[T * T + tt] - q.w;     // the largest reach of this type: conservative for mixed rod types
             hl = s.reach2[2 * T * T + T + tt];    // all rods of a system have one length (Topo::genParamPairs enforces it, topo.cpp:22-33)
             for (int b = 0; b < T; b++) cut2 = fmaxf(cut2, s.reach2[T * T + T + tt * T + b]);      // the largest surface cutoff of this type's rod pairs
@@ -949,15 +980,15 @@ k_gate_rows(DevSys s, FlatList fl) {
         unsigned short* buf = sh_hit[wid];
         int cur = lane;
         const int cur_max = lane + (GR_CAP - 4) * GR_STRIDE;
-        // warp w takes the candidates 16 i + 4 w .. 16 i + 4 w + 3: four float4 reads and ONE int4 read of the original indices,
-        // fetched one trip ahead so that the shared-memory latency hides behind the arithmetic of the current trip
+        // warp w takes the candidates 16 i + 4 w .. 16 i + 4 w + 3: four float4 reads (and, for allToAll rows, ONE int4 read of the
+        // original indices), fetched one trip ahead so that the shared-memory latency hides behind the arithmetic of the current trip
         float4 qn[4];
         int4 on = make_int4(-1, -1, -1, -1);
         {
             const int c0 = 4 * wid;       // Cpad >= 16: always inside the padded tile
 #pragma unroll
             for (int u = 0; u < 4; u++) qn[u] = t_pf[c0 + u];
-            on = *reinterpret_cast<const int4*>(t_orig + c0);
+            if (MODE == 2) on = *reinterpret_cast<const int4*>(t_orig + c0);
         }
         for (int c0 = 4 * wid; c0 < Cpad; c0 += 4 * GR_SL) {
             float4 q[4];
@@ -968,13 +999,13 @@ k_gate_rows(DevSys s, FlatList fl) {
                 const int cn = min(c0 + 4 * GR_SL, Cpad - 4 * GR_SL + 4 * wid);      // the last trip re-reads its own entries
 #pragma unroll
                 for (int u = 0; u < 4; u++) qn[u] = t_pf[cn + u];
-                on = *reinterpret_cast<const int4*>(t_orig + cn);
+                if (MODE == 2) on = *reinterpret_cast<const int4*>(t_orig + cn);
             }
             bool hit[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {        // four independent tests first (instruction-level parallelism), appends afterwards
                 const float sq = fmaf(m2z, q[u].z, fmaf(m2y, q[u].y, fmaf(m2x, q[u].x, q[u].w)));
-                hit[u] = (sq <= thr) & (MODE == 2 ? ob[u] < target : ob[u] != target);
+                hit[u] = (sq <= thr) & (MODE == 2 ? ob[u] < target : (c0 + u) != c_self);
             }
             if (hit[0] | hit[1] | hit[2] | hit[3]) {
 #pragma unroll
@@ -983,8 +1014,9 @@ k_gate_rows(DevSys s, FlatList fl) {
             }
         }
         if (__any_sync(0xffffffffu, cur == cur_max) && lane == 0) atomicOr(fl.overflow, 4);
-        // ---- segment lower bound (lb_beyond, sweep.cuh): of the candidates within the centre-distance reach only those whose rods can
-        // come within the surface cutoff interact at all -- a sixth of them in a dense rod fluid. Every lane filters its own hits in place.
+        // ---- segment lower bound (lb_beyond_one, pair_energy.cuh): of the candidates within the centre-distance reach only those whose
+        // rods can come within the surface cutoff interact at all -- a sixth of them in a dense rod fluid. Every lane filters its own
+        // hits in place.
         {
             const int nk = (cur - lane) / GR_STRIDE;
             const float tx = -0.5f * m2x, ty = -0.5f * m2y, tz = -0.5f * m2z;
@@ -992,8 +1024,11 @@ k_gate_rows(DevSys s, FlatList fl) {
             for (int k = 0, rd = lane; k < nk; k++, rd += GR_STRIDE) {
                 const int c = buf[rd];
                 const float4 q = t_pf[c];
+                const uint2 dq = t_dq[c];
+                const float bx = (float)(short)(dq.x & 0xffff) * (1.f / 32767.f), by = (float)(short)(dq.x >> 16) * (1.f / 32767.f), bz = (float)(short)(dq.y & 0xffff) * (1.f / 32767.f);
                 const float rx = tx - q.x, ry = ty - q.y, rz = tz - q.z;
-                if (!lb_beyond(rx, ry, rz, rx * rx + ry * ry + rz * rz, tdx, tdy, tdz, t_dx[c], t_dy[c], t_dz[c], hl, hl, cut2)) { buf[wr] = (unsigned short)c; wr += GR_STRIDE; }
+                // 7.5e-3: |sin| of the angle between the axes can be that much larger than computed from a 16-bit quantised axis
+                if (!lb_beyond_one(rx, ry, rz, rx * rx + ry * ry + rz * rz, tdx, tdy, tdz, bx, by, bz, hl, hl, cut2, 7.5e-3f)) { buf[wr] = (unsigned short)c; wr += GR_STRIDE; }
             }
             cur = wr;
         }
@@ -1038,9 +1073,7 @@ k_gate_rows(DevSys s, FlatList fl) {
             for (int j = 1; j < 18; j++) k += c >= sh_soff[j] ? 1 : 0;
             return sh_sb[k] + (c - sh_soff[k]);
         };
-#pragma unroll
-        for (int t = 0; t < GR_T; t++) {      // fully unrolled: lane indices and buffer offsets become immediates
-            if (t >= count) break;
+        for (int t = 0; t < count; t++) {
             const int nh = __shfl_sync(0xffffffffu, cnt, t), off = __shfl_sync(0xffffffffu, my_off, t);
             if (lane < nh) fl.pair[off + lane] = make_int2(first + t, slot_of_c(my_row[t]));
             if (big && lane + 32 < nh) fl.pair[off + lane + 32] = make_int2(first + t, slot_of_c(my_row[32 * GR_STRIDE + t]));
@@ -1675,6 +1708,8 @@ struct scgpu_ctx {
     double* d_compact = nullptr;     // staging of 9-double records (scgpu_set_particles_compact)
     double4* d_posw = nullptr;
     double* d_rec = nullptr;
+    float4 *d_p32 = nullptr, *d_d32 = nullptr;      // FP32 copies of position / axis for the gates (k_cell_place, k_make_f32)
+    bool f32_valid = false;
     int *d_type = nullptr, *d_moltype = nullptr, *d_cell_of = nullptr, *d_order = nullptr, *d_slot_of = nullptr, *d_tmp = nullptr;
     int *d_counts = nullptr, *d_cell_start = nullptr, *d_cursor = nullptr;
     int cells_cap = 0;
@@ -1742,7 +1777,7 @@ static DevSys view(const scgpu_ctx* c) {
     s.n = c->n; s.ntypes = c->ntypes; s.nmol = c->nmol;
     for (int d = 0; d < 3; d++) { s.nc[d] = c->nc[d]; s.box[d] = c->box[d]; s.shift[d] = c->shift[d]; }
     s.ncells = c->ncells;
-    s.api = c->d_api; s.posw = c->d_posw; s.rec = c->d_rec; s.cell_start = c->d_cell_start; s.order = c->d_order;
+    s.api = c->d_api; s.posw = c->d_posw; s.rec = c->d_rec; s.p32 = c->d_p32; s.d32 = c->d_d32; s.cell_start = c->d_cell_start; s.order = c->d_order;
     s.slot_of = c->d_slot_of; s.type = c->d_type; s.moltype = c->d_moltype; s.ia = c->d_ia; s.mol = c->d_mol; s.reach2 = c->d_reach2;
     s.sqmaxcut = c->sqmaxcut;
     return s;
@@ -1787,6 +1822,7 @@ extern "C" int scgpu_create(scgpu_ctx** out, int device) {
 
 static void free_particles(scgpu_ctx* c) {
     cudaFree(c->d_api); cudaFree(c->d_compact); cudaFree(c->d_posw); cudaFree(c->d_rec); cudaFree(c->d_type); cudaFree(c->d_moltype);
+    cudaFree(c->d_p32); cudaFree(c->d_d32); c->d_p32 = c->d_d32 = nullptr;
     cudaFree(c->d_cell_of); cudaFree(c->d_order); cudaFree(c->d_slot_of); cudaFree(c->d_tmp); cudaFree(c->d_out);
     cudaFree(c->d_pairs); cudaFree(c->d_flags);
     cudaFree(c->d_fl_pair); cudaFree(c->d_fl_e); cudaFree(c->d_fl_plist); cudaFree(c->d_fl_head); cudaFree(c->d_fl_chunks);
@@ -1939,6 +1975,8 @@ static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const 
         CK(cudaMalloc(&c->d_api, N * 30 * sizeof(double)));
         CK(cudaMalloc(&c->d_compact, N * 9 * sizeof(double)));
         CK(cudaMalloc(&c->d_posw, N * sizeof(double4)));
+        CK(cudaMalloc(&c->d_p32, N * sizeof(float4)));
+        CK(cudaMalloc(&c->d_d32, N * sizeof(float4)));
         CK(cudaMalloc(&c->d_rec, N * REC * sizeof(double)));
         CK(cudaMalloc(&c->d_type, N * sizeof(int)));
         CK(cudaMalloc(&c->d_moltype, N * sizeof(int)));
@@ -2096,7 +2134,8 @@ static int build_cells_impl(scgpu_ctx* c, const double shift[3], int sweep_k) {
     k_cell_count<<<nb, 256, 0, c->stream>>>(s, c->d_cell_of, c->d_counts);
     k_cell_scan<<<1, 1024, 0, c->stream>>>(c->ncells, c->d_counts, c->d_cell_start, c->d_cursor);
     k_cell_fill<<<nb, 256, 0, c->stream>>>(c->n, c->d_cell_of, c->d_cursor, c->d_tmp);
-    k_cell_place<<<nb, 256, 0, c->stream>>>(s, c->d_cell_of, c->d_tmp, c->d_order, c->d_slot_of, c->d_posw, c->d_rec);
+    k_cell_place<<<nb, 256, 0, c->stream>>>(s, c->d_cell_of, c->d_tmp, c->d_order, c->d_slot_of, c->d_posw, c->d_rec, c->d_p32, c->d_d32);
+    c->f32_valid = true;
     c->launches += 4;
     CK(cudaGetLastError());
     c->cells_valid = true;
@@ -2151,7 +2190,7 @@ extern "C" int scgpu_update_particle(scgpu_ctx* c, int idx, const double* state3
             c->cells_valid = false;      // left its cell: the next energy call re-sorts
         } else {
             DevSys s = view(c);
-            k_update_one<<<1, 32, 0, c->stream>>>(s, idx, c->d_posw, c->d_rec);
+            k_update_one<<<1, 32, 0, c->stream>>>(s, idx, c->d_posw, c->d_rec, c->d_p32, c->d_d32);
             c->launches++;
             CK(cudaGetLastError());
         }
@@ -2210,9 +2249,16 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
             const double kx = 0.5 * (double)((c->nc[0] - 3 < 6 ? c->nc[0] - 3 : 6) + 2);
             const double hx = kx * c->box[0] / c->nc[0], hy = 1.5 * c->box[1] / c->nc[1], hz = 1.5 * c->box[2] / c->nc[2];
             const double R2 = hx * hx + hy * hy + hz * hz;
-            rows_exact = R2 * 4.0 * 5.96e-8 <= 0.5 * 0.001 * c->min_reach2;
+            const double bmax = fmax(c->box[0], fmax(c->box[1], c->box[2]));
+            // + the staged positions are FP32 box fractions: 2^-24 of the box per coordinate, entering d^2 as 2 sqrt(reach2) sqrt(3) times that
+            rows_exact = R2 * 4.0 * 5.96e-8 + 2.0 * sqrt(c->min_reach2) * 1.74 * bmax * 1.2e-7 <= 0.5 * 0.001 * c->min_reach2;
         }
         const bool rows_ok = rows_exact && c->use_rows && !wrap && !d_counters && nrows <= 65535;
+        if (!c->f32_valid) {
+            k_make_f32<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->d_posw, c->d_rec, c->d_p32, c->d_d32);
+            c->launches++;
+            c->f32_valid = true;
+        }
         auto mark = [&](int k) { if (stage_ev) cudaEventRecord(stage_ev[k], c->stream); };
         auto launch_cheap_rods = [&]() {        // MIRROR (every-particle passes): a patch pair is evaluated by one of its two sides only
             const int nb = c->sm_count * CHEAP_MINB * 2;
@@ -2398,10 +2444,11 @@ extern "C" int scgpu_profile_everyone(scgpu_ctx* c, float* us4) {
     if (int r = ensure_cells(c)) return r;
     cudaEvent_t ev[5];
     for (int k = 0; k < 5; k++) CK(cudaEventCreate(&ev[k]));
-    for (bool repeat = true; repeat;) {
-        if (launch_energy(c, 1, c->n, 1, nullptr, nullptr, 0, 0, c->d_out, nullptr, nullptr, ev)) return SCGPU_ERR_CUDA;
-        if (int r = overflow_then_grow(c, &repeat)) return r;
-    }
+    for (int pass = 0; pass < 4; pass++)       // the first passes bring the clocks up after an idle period; the last one is reported
+        for (bool repeat = true; repeat;) {
+            if (launch_energy(c, 1, c->n, 1, nullptr, nullptr, 0, 0, c->d_out, nullptr, nullptr, ev)) return SCGPU_ERR_CUDA;
+            if (int r = overflow_then_grow(c, &repeat)) return r;
+        }
     for (int k = 0; k < 4; k++) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); us4[k] = ms * 1000.f; }
     for (int k = 0; k < 5; k++) cudaEventDestroy(ev[k]);
     return SCGPU_OK;
@@ -2599,6 +2646,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     }
     CK(cudaGetLastError());
     c->api_stale = true;           // the cell-sorted arrays are now the newest copy of the configuration
+    c->f32_valid = false;          // ... and their FP32 copies are out of date
     c->h_cell_of.clear();
     if (K > 1) c->cells_valid = false;      // the energy kernels need cells of edge >= maxcut: the next energy call re-sorts
     if (!stats && !cstats) return SCGPU_OK;       // asynchronous form: nothing is read back
@@ -2627,7 +2675,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
 
 extern "C" int scgpu_pressure_move(scgpu_ctx* c, const scgpu_pressureparams* pp, uint64_t seed, uint64_t step, scgpu_pressurestats* out) {
     ARG(c && pp && out, "scgpu_pressure_move: NULL argument");
-    ARG(pp->temper > 0 && pp->ptype >= 0 && pp->ptype <= 3, "scgpu_pressure_move: temperature must be positive and ptype in 0..3");
+    ARG(pp->temper > 0 && pp->ptype >= 0 && pp->ptype <= 5, "scgpu_pressure_move: temperature must be positive and ptype in 0..5");
     ARG(c->n > 0 && c->box[0] > 0, "scgpu_pressure_move: particles and box must be set first");
     unsigned long long st = seed * 0xA0761D6478BD642Full + step * 0xE7037ED1A0B428DBull + 0x8EBC6AF09C88C6E3ull;
     auto u01h = [&]() { return (double)(splitmix64(st) >> 11) * (1.0 / 9007199254740992.0); };
@@ -2656,11 +2704,21 @@ extern "C" int scgpu_pressure_move(scgpu_ctx* c, const scgpu_pressureparams* pp,
         positive = nb[0] > 0 && nb[1] > 0;
         const double pvol = old[0] * old[1], pvoln = nb[0] * nb[1];
         if (positive) enermove = pp->press * old[2] * (pvoln - pvol) - N * pp->temper * log(pvoln / pvol);
-    } else {                            // :468-503 xy at constant volume
+    } else if (pp->ptype == 3) {        // :468-503 xy at constant volume
         const double psch = pp->edge_mx * (u01h() - 0.5);
         nb[0] += psch; nb[1] += psch;
         positive = nb[0] > 0 && nb[1] > 0;
         if (positive) nb[2] = old[0] * old[1] * old[2] / nb[0] / nb[1];
+    } else if (pp->ptype == 4) {        // :480-514 "anisotropic in xy, z constant": as written only the x edge ever changes (the branch
+        u01h();                         // `if (ran2() - 0.5)` tests a non-zero double), two random numbers are drawn all the same
+        nb[0] += pp->edge_mx * (u01h() - 0.5);
+        positive = nb[0] > 0;
+        const double pvol = old[0] * old[1], pvoln = nb[0] * nb[1];
+        if (positive) enermove = pp->press * old[2] * (pvoln - pvol) - N * pp->temper * log(pvoln / pvol);
+    } else {                            // :515-541 the y edge only
+        nb[1] += pp->edge_mx * (u01h() - 0.5);
+        positive = nb[1] > 0;
+        if (positive) enermove = pp->press * old[2] * old[0] * (nb[1] - old[1]) - N * pp->temper * log(nb[1] / old[1]);
     }
     bool accept = false;
     if (positive) {

@@ -286,7 +286,35 @@ def do_membrane():
     print("membrane601 done")
 
 
+def do_ptype45():
+    """pressureMove ptype 4 and 5 (mc/movecreator.cpp:480-550): the reference ships volumeChange inputs for ptype 0-3 only; these
+    are Tests/volumeChange/0h and 0l with the coupling type switched, 500 sweeps by the unmodified reference program"""
+    import re
+    for pt in (4, 5):
+        for hl in "hl":
+            src = os.path.join(REF, "Tests", "volumeChange", "0" + hl, "new")
+            name = "volumeChange_%d%s" % (pt, hl)
+            tmp = tempfile.mkdtemp(prefix="pt45_")
+            inputs = {}
+            for fn in ("options", "top.init", "config.init"):
+                with open(os.path.join(src, fn)) as f:
+                    inputs[fn] = f.read()
+            inputs["options"] = re.sub(r"(?m)^ptype\s*=\s*\d+", "ptype = %d" % pt, inputs["options"])
+            with open(os.path.join(HERE, name + ".inputs.json"), "w") as f:
+                json.dump(inputs, f)
+            opt = re.sub(r"(?m)^nsweeps\s*=\s*\d+", "nsweeps = 500", inputs["options"])
+            for fn, txt in (("options", opt), ("top.init", inputs["top.init"]), ("config.init", inputs["config.init"])):
+                with open(os.path.join(tmp, fn), "w") as f:
+                    f.write(txt)
+            run([SC], tmp)
+            shutil.copy(os.path.join(tmp, "config.last"), os.path.join(HERE, "%s.short500.config.last" % name))
+            shutil.rmtree(tmp)
+            print("ptype45:", name)
+
+
 def main():
+    if "ptype45" in sys.argv[1:]:
+        return do_ptype45()
     if "membrane" in sys.argv[1:]:
         return do_membrane()
     if "extras" in sys.argv[1:]:

@@ -24,7 +24,7 @@ NVT = ["test_01_normal_PSC", "test_02_normal_CPSC", "test_03_normal_CHPSC", "tes
        "test_06_normal_TCPSC", "test_07_normal_TCHPSC", "test_08_normal_TCHCPSC", "test_09_normal_SPN", "test_10_normal_SPA",
        "test_11_normal_PSC_CPSC", "test_12_normal_SPA_CPSC", "test_13_normal_SPA_PSC", "test_14_normal_SPA_PSC_CPSC",
        "test_20_chain_bond12", "test_21_chain_bondd2"]
-NPT = ["volumeChange_%d%s" % (k, hl) for k in range(4) for hl in "hl"]
+NPT = ["volumeChange_%d%s" % (k, hl) for k in range(6) for hl in "hl"]      # 4, 5: tests/golden/make_golden.py ptype45
 
 
 def run_reference_program(name, nsweeps):

@@ -436,3 +436,67 @@ def test_npt_average_volume_matches_reference_sequential_sweeps():
     print("reference <V> = %.1f, checkerboard NPT <V> = %.1f (sigma %.1f); <E> %.2f vs %.2f (sigma %.2f)" % (rv, gv, sv, re_, ge, se_))
     assert abs(gv - rv) <= 4.0 * sv + 5e-3 * rv, (gv, rv, sv)
     assert abs(ge - re_) <= 4.0 * se_ + 2e-2 * abs(re_), (ge, re_, se_)
+
+
+# ---- the reference's own "comprehensive" inputs: Tests/System_averages_tests/CPSC/various_temp --------------
+def _cpsc_golden():
+    import gzip
+    return json.loads(gzip.open(os.path.join(G, "sweep_cpsc_temps.json.gz"), "rt").read())
+
+
+def _window_stats(sweeps, energy, lo, hi):
+    e = np.array([v for s_, v in zip(sweeps, energy) if lo < s_ <= hi])
+    return float(e.mean()), _block_stderr(e, 4) if len(e) >= 8 else float(e.std() / math.sqrt(max(1, len(e))))
+
+
+@pytest.mark.parametrize("system", ["cpsc100", "cpsc800"])
+def test_cpsc_system_averages_three_temperatures(system):
+    """<E> AND the per-move acceptance ratios at T = 0.1, 0.16, 0.22 against sequential runs of the unmodified reference program
+    (8 seeds each; tests/golden/make_sweep_cpsc_golden.py). cpsc100 is the input as shipped (one cell: the proposal / acceptance logic
+    alone); cpsc800 is the same configuration tiled 2 x 2 x 2 (4 cells per axis: the checkerboard decomposition, where a bias would
+    show first at the lowest temperature). Both sides start from the same configuration and are compared over the same window of
+    sweeps, (W/3, W], W = 20 000: low-temperature runs are still relaxing, equal windows compare equal stages."""
+    from concurrent.futures import ThreadPoolExecutor
+    gold = _cpsc_golden()
+    W = 20000
+    top = gold["top"][system]
+    cfg = next(r["config"] for r in gold["runs"] if r["system"] == system and r["config"])
+    temps = [0.1, 0.16, 0.22]
+    seeds = [5, 6]
+    chunk = 50
+
+    def run(job):
+        temper, seed = job
+        hs = HostSystem(top, cfg)
+        eng = Engine(0, "fast").load(hs)
+        mp = move_params(temper, 0.03, 15.0, n_sub=chunk)
+        sw, en = [], []
+        ta = tr = ra = rr = 0
+        for k in range(W // chunk):
+            st = eng.sweep(mp, 1000 + seed, k)
+            ta += st.trans_acc; tr += st.trans_rej; ra += st.rot_acc; rr += st.rot_rej
+            sw.append((k + 1) * chunk)
+            en.append(eng.all_to_all())
+        eng.close()
+        hs.close()
+        return temper, sw, en, ta / max(1, ta + tr), ra / max(1, ra + rr)
+
+    with ThreadPoolExecutor(len(temps) * len(seeds)) as ex:
+        results = list(ex.map(run, [(t, s_) for t in temps for s_ in seeds]))
+    for temper in temps:
+        ref = [r for r in gold["runs"] if r["system"] == system and abs(r["temper"] - temper) < 1e-9]
+        assert len(ref) == 8
+        rm = [_window_stats(r["sweep"], r["energy"], W // 3, W)[0] for r in ref]
+        ref_mean, ref_se = float(np.mean(rm)), float(np.std(rm, ddof=1) / math.sqrt(len(rm)))
+        mine = [r for r in results if r[0] == temper]
+        gm = [_window_stats(r[1], r[2], W // 3, W) for r in mine]
+        g_mean = float(np.mean([m for m, _ in gm]))
+        g_se = math.sqrt(sum(e * e for _, e in gm)) / len(gm)
+        tol = 4.0 * math.sqrt(ref_se ** 2 + g_se ** 2) + 0.005 * abs(ref_mean)
+        assert abs(g_mean - ref_mean) <= tol, (system, temper, g_mean, ref_mean, tol)
+        # acceptance ratios: the reference prints whole per cent of the full run (Statistics::print)
+        ref_t = float(np.mean([r["acceptance"]["trans_acc_pct"] for r in ref])) / 100.0
+        ref_r = float(np.mean([r["acceptance"]["rot_acc_pct"] for r in ref])) / 100.0
+        g_t, g_r = float(np.mean([r[3] for r in mine])), float(np.mean([r[4] for r in mine]))
+        slack = 0.03 if system == "cpsc100" else 0.04          # + moves rejected for leaving their cell on the tiled system
+        assert abs(g_t - ref_t) <= slack and abs(g_r - ref_r) <= slack, (system, temper, g_t, ref_t, g_r, ref_r)

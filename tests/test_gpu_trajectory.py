@@ -18,7 +18,7 @@ NVT = ["test_01_normal_PSC", "test_02_normal_CPSC", "test_03_normal_CHPSC", "tes
        "test_06_normal_TCPSC", "test_07_normal_TCHPSC", "test_08_normal_TCHCPSC", "test_09_normal_SPN", "test_10_normal_SPA",
        "test_11_normal_PSC_CPSC", "test_12_normal_SPA_CPSC", "test_13_normal_SPA_PSC", "test_14_normal_SPA_PSC_CPSC",
        "test_20_chain_bond12", "test_21_chain_bondd2"]
-NPT = ["volumeChange_%d%s" % (k, hl) for k in range(4) for hl in "hl"]
+NPT = ["volumeChange_%d%s" % (k, hl) for k in range(6) for hl in "hl"]      # 4, 5: tests/golden/make_golden.py ptype45
 
 
 def _run(name, golden_file, nsweeps=0):
@@ -48,7 +48,7 @@ def test_full_length_run_is_byte_identical(name):
 
 @pytest.mark.parametrize("name", NPT)
 def test_npt_trajectory_is_byte_identical(name):
-    """pressure moves (ptype 0-3, high and low pressure): allToAll / allToAllTrial / update() through the GPU path"""
+    """pressure moves (ptype 0-5, high and low pressure): allToAll / allToAllTrial / update() through the GPU path"""
     got, want, st = _run(name, name + ".short500.config.last", 500)
     assert st["edge_acc"] + st["edge_rej"] > 100
     assert got == want, (name, st)
