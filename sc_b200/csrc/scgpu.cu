@@ -855,7 +855,7 @@ constexpr int GR_T = 32;            // targets per unit (= lanes)
 constexpr int GR_SL = 4;            // candidate slices (= warps per block)
 constexpr int GR_TILE = 1024;       // staged candidates per unit
 #ifndef GR_CAP_N
-#define GR_CAP_N 40
+#define GR_CAP_N 39
 #endif
 constexpr int GR_CAP = GR_CAP_N;    // hits per (target, slice)
 constexpr int GR_STRIDE = 34;       // halfwords per buffer row: row k of target t at k * 34 + t -> the write-out (fixed t, k = lane) is conflict-free
@@ -869,7 +869,7 @@ k_gate_rows(DevSys s, FlatList fl) {
     __shared__ unsigned short sh_hit[GR_SL][GR_CAP * GR_STRIDE];
     __shared__ int sh_cnt[GR_SL][GR_T];
     __shared__ int sh_off[GR_SL][GR_T];
-    __shared__ int sh_sb[20], sh_soff[20];          // staged segments: first slot, offset in the tile
+    __shared__ int sh_sb[20], sh_soff[40];          // staged segments: first slot, offset in the tile ([19..39]: INT_MAX, the slot search reads past 18)
     __shared__ int sh_cx[3];
     __shared__ int sh_ok;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -877,6 +877,7 @@ k_gate_rows(DevSys s, FlatList fl) {
     const int nx = s.nc[0], ny = s.nc[1];
     const int cy = row % ny, cz = row / ny;
     const int rs = s.cell_start[row * nx], re = s.cell_start[(row + 1) * nx];
+    if (threadIdx.x >= 19 && threadIdx.x < 40) sh_soff[threadIdx.x] = 0x7fffffff;
     const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
     // A unit is 32 consecutive slots of the row. Where the row is sparse such a unit would span many cells (and its neighbourhood
     // the whole row): it is then processed in sub-units of at most kmax cells each (dense rows: one sub-unit, all lanes busy).
@@ -1063,20 +1064,20 @@ k_gate_rows(DevSys s, FlatList fl) {
         }
         __syncthreads();
         if (!sh_ok) return;
-        // ---- write-out: warp w appends its slice's hits of every target behind those of the warps before it
-        const int my_off = sh_off[wid][lane];       // lane t holds the sub-span of target t
-        const bool big = __any_sync(0xffffffffu, cnt > 32);
-        const unsigned short* my_row = buf + lane * GR_STRIDE;
-        auto slot_of_c = [&](int c) {         // tile index -> sorted slot: which of the 18 staged segments holds it
-            int k = 0;
-#pragma unroll
-            for (int j = 1; j < 18; j++) k += c >= sh_soff[j] ? 1 : 0;
-            return sh_sb[k] + (c - sh_soff[k]);
-        };
-        for (int t = 0; t < count; t++) {
-            const int nh = __shfl_sync(0xffffffffu, cnt, t), off = __shfl_sync(0xffffffffu, my_off, t);
-            if (lane < nh) fl.pair[off + lane] = make_int2(first + t, slot_of_c(my_row[t]));
-            if (big && lane + 32 < nh) fl.pair[off + lane + 32] = make_int2(first + t, slot_of_c(my_row[32 * GR_STRIDE + t]));
+        // ---- write-out: after the segment bound a (target, slice) keeps one or two partners, so every lane writes its own target's
+        // hits (behind those of the slices before it: a fixed order, the combine step stays bit-reproducible)
+        {
+            const int my_off = sh_off[wid][lane];
+            for (int k = 0, rd = lane; k < cnt; k++, rd += GR_STRIDE) {
+                const int c = buf[rd];
+                int sg = 0;                    // tile index -> sorted slot: which of the 18 staged segments holds it (sh_soff is padded with INT_MAX)
+                sg += c >= sh_soff[sg + 16] ? 16 : 0;
+                sg += c >= sh_soff[sg + 8] ? 8 : 0;
+                sg += c >= sh_soff[sg + 4] ? 4 : 0;
+                sg += c >= sh_soff[sg + 2] ? 2 : 0;
+                sg += c >= sh_soff[sg + 1] ? 1 : 0;
+                fl.pair[my_off + k] = make_int2(first + lane, sh_sb[sg] + (c - sh_soff[sg]));
+            }
         }
         first = last + 1;
       }
@@ -1361,10 +1362,9 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters, const __grid_c
                 n_gate++;
             }
             // every-particle passes list a patch pair from both sides: the patch term is evaluated once, by the side whose first particle
-            // has the larger original index; the other side marks its entry (NaN) and k_combine_flat fetches the value from its mirror
-            double mark = 0.0;
-            if (MIRROR && np && oi < oj) { np = false; mark = __longlong_as_double(0x7ff8000000000000ll); }
-            fl.e[p] = make_double2(e, mark);
+            // has the larger original index; k_patch_flat writes a non-zero result into the mirror entry as well
+            if (MIRROR && np && oi < oj) np = false;
+            fl.e[p] = make_double2(e, 0.0);
         }
         const unsigned m = __ballot_sync(0xffffffffu, np);
         if (np) wbuf[wn + __popc(m & lt_mask)] = p;
@@ -1426,81 +1426,139 @@ __device__ __forceinline__ void patch_setup(const DevSys& s, const FlatList& fl,
     load_patch_args(s2, pn2, secondCH, P2);
 }
 
-// block-wide stable compaction: returns this thread's rank among the threads with flag set, total in *count (shared)
-__device__ __forceinline__ int block_rank(bool flag, int* sh_warp, int* count) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned m = __ballot_sync(0xffffffffu, flag);
-    if (lane == 0) sh_warp[wid] = __popc(m);
-    __syncthreads();
-    int off = 0, tot = 0;
-    for (int w = 0; w < PF_THREADS / 32; w++) { int c = sh_warp[w]; if (w < wid) off += c; tot += c; }
-    if (threadIdx.x == 0) *count = tot;
-    __syncthreads();
-    return off + __popc(m & ((1u << lane) - 1u));
+#ifndef PATCH_MINB
+#define PATCH_MINB 6
+#endif
+// Patch terms, every warp on its own: no block barrier. A warp takes 32 listed pairs per trip and runs patch_intersect #1 on them;
+// the survivors (the partner is inside the patch wedge: about a quarter) go to a per-warp queue in shared memory together with what
+// the later phases need (slots, separation vector, T1, T2). Whenever a queue holds 32 entries the warp runs the next phase on a FULL
+// set of lanes: intersect #2 -> second queue (+ S1, S2) -> atr_e. The expensive later phases therefore always run densely packed,
+// and nothing is re-derived: the first version of this kernel compacted per block behind three barriers and re-loaded and
+// re-imaged every pair in each phase (barrier stall 8.2 and long-scoreboard 6.0 per issue, profiles/r2e_pipeline.txt).
+struct PQItem { int p, si, sj, pad; double rx, ry, rz, T1, T2, S1, S2; };      // 72 bytes
+constexpr int PQ_CAP = 64;
+
+struct PatchKind { const scgpu_iaparam* ia; bool first_psc, second_psc, firstCH, secondCH, firstT, secondT; };
+__device__ __forceinline__ PatchKind patch_kind(const DevSys& s, int si, int sj, const scgpu_iaparam* ia_one) {
+    PatchKind k;
+    k.ia = ia_one ? ia_one : &s.ia[w_type(s.posw[si].w) * s.ntypes + w_type(s.posw[sj].w)];
+    const int kind = (int)k.ia->reserved[0], g0 = (int)k.ia->geotype[0], g1 = (int)k.ia->geotype[1];
+    k.firstCH = is_chiral(g0); k.secondCH = is_chiral(g1); k.firstT = is_two_patch(g0); k.secondT = is_two_patch(g1);
+    k.first_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && is_psc_family(g0));
+    k.second_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && !is_psc_family(g0));
+    return k;
 }
 
-#ifndef PATCH_MINB
-#define PATCH_MINB 7
-#endif
 template <bool ONE>
 __global__ void __launch_bounds__(PF_THREADS, PATCH_MINB)
-k_patch_flat(DevSys s, FlatList fl, int any_two_patch, const __grid_constant__ scgpu_iaparam ia1) {
+k_patch_flat(DevSys s, FlatList fl, int any_two_patch, int mirror, const __grid_constant__ scgpu_iaparam ia1) {
     const scgpu_iaparam* ia_one = ONE ? &ia1 : nullptr;
     if (*fl.overflow) return;
-    __shared__ PatchItem sh_a[PF_THREADS], sh_b[PF_THREADS];
-    __shared__ int sh_warp[PF_THREADS / 32];
-    __shared__ int sh_n1, sh_n2;
+    __shared__ PQItem sh_qa[PF_THREADS / 32][PQ_CAP], sh_qb[PF_THREADS / 32][PQ_CAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    PQItem* qa = sh_qa[wid];
+    PQItem* qb = sh_qb[wid];
     const int total = *fl.ptotal;
     const int ncombo = any_two_patch ? 4 : 1;
-    for (int base = blockIdx.x * PF_THREADS; base < total; base += gridDim.x * PF_THREADS) {       // block-uniform trip count
-        const int q = base + threadIdx.x;
-        const int p = q < total ? fl.plist[q] : -1;
-        for (int combo = 0; combo < ncombo; combo++) {
-            // ---- phase 1: rod 2 against the patch of rod 1 (T1, T2)
-            bool keep = false;
-            double a = 0.0, b = 0.0;
-            if (p >= 0) {
-                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
-                patch_setup(s, fl, p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
-                if (ok) {
-                    const int pn1 = combo & 1;
-                    int n = fp ? patch_intersect<false>(P1.dir, P2.dir, P1, r_cm, a, b, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1])
-                               : patch_intersect<true>(P1.dir, P2.dir, P1, r_cm, a, b, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1]);
-                    keep = n >= 2;
+    const int nwarps = gridDim.x * (PF_THREADS / 32), gw = blockIdx.x * (PF_THREADS / 32) + wid;
+    for (int combo = 0; combo < ncombo; combo++) {
+        const int pn1 = combo & 1, pn2 = combo >> 1;
+        int na = 0, nb = 0;
+        auto consume = [&](PQItem* q, int& n, int used) {        // drop the first `used` entries of a queue
+            const int rest = n - used;
+            PQItem t;
+            if (lane < rest) t = q[used + lane];
+            __syncwarp();
+            if (lane < rest) q[lane] = t;
+            n = rest;
+            __syncwarp();
+        };
+        // one loop, each phase body once (three inlined copies of the intersection code would triple the kernel's instruction footprint):
+        // a trip feeds 32 listed pairs to phase 1 while there is input, then runs phase 2 / phase 3 if their queue is full (or, once
+        // the input is exhausted, as long as anything is left)
+        for (int base = gw * 32;; base += nwarps * 32) {
+            const bool input = base < total;
+            if (input) {
+                // ---- phase 1: rod 2 against the patch of rod 1 (T1, T2)
+                const int q = base + lane;
+                const int p = q < total ? fl.plist[q] : -1;
+                bool keep = false;
+                PQItem it;
+                it.p = p; it.pad = 0; it.S1 = it.S2 = 0.0;
+                if (p >= 0) {
+                    const int2 pr = fl.pair[p];
+                    it.si = pr.x; it.sj = pr.y;
+                    const double4 pi = ldg256(s.posw + pr.x), pj = ldg256(s.posw + pr.y);
+                    const v3 r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
+                    it.rx = r_cm.x; it.ry = r_cm.y; it.rz = r_cm.z;
+                    const scgpu_iaparam* ia = ia_one ? ia_one : &s.ia[w_type(pi.w) * s.ntypes + w_type(pj.w)];
+                    const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
+                    const bool firstT = is_two_patch(g0), secondT = is_two_patch(g1);
+                    const bool ok = (combo == 0) || (combo == 1 && firstT) || (combo == 2 && secondT) || (combo == 3 && firstT && secondT);
+                    if (ok) {
+                        const bool first_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && is_psc_family(g0));
+                        PatchArgs P1, P2;
+                        load_patch_args(s.rec + (size_t)pr.x * REC, pn1, is_chiral(g0), P1);
+                        load_patch_args(s.rec + (size_t)pr.y * REC, pn2, is_chiral(g1), P2);
+                        const int nn = first_psc ? patch_intersect<false>(P1.dir, P2.dir, P1, r_cm, it.T1, it.T2, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1])
+                                                 : patch_intersect<true>(P1.dir, P2.dir, P1, r_cm, it.T1, it.T2, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1]);
+                        keep = nn >= 2;
+                    }
                 }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) qa[na + __popc(m & lt_mask)] = it;
+                na += __popc(m);
+                __syncwarp();
             }
-            int r = block_rank(keep, sh_warp, &sh_n1);
-            if (keep) { sh_a[r].p = p; sh_a[r].T1 = a; sh_a[r].T2 = b; }
-            __syncthreads();
-            const int n1 = sh_n1;
-            // ---- phase 2: rod 1 against the patch of rod 2 (S1, S2), survivors only
-            keep = false;
-            PatchItem it;
-            it.p = -1; it.T1 = it.T2 = it.S1 = it.S2 = 0.0;
-            if ((int)threadIdx.x < n1) {
-                it = sh_a[threadIdx.x];
-                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
-                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
-                const int pn2 = combo >> 1;
-                v3 vec1 = neg(r_cm);
-                int n = sp ? patch_intersect<false>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0])
-                           : patch_intersect<true>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0]);
-                keep = n >= 2;
+            const bool more_input = base + nwarps * 32 < total;
+            if (na >= 32 || (!more_input && na > 0)) {
+                // ---- phase 2: rod 1 against the patch of rod 2 (S1, S2)
+                const int n = na < 32 ? na : 32;
+                bool keep = false;
+                PQItem it;
+                if (lane < n) {
+                    it = qa[lane];
+                    const PatchKind k = patch_kind(s, it.si, it.sj, ia_one);
+                    PatchArgs P1, P2;
+                    load_patch_args(s.rec + (size_t)it.si * REC, pn1, k.firstCH, P1);
+                    load_patch_args(s.rec + (size_t)it.sj * REC, pn2, k.secondCH, P2);
+                    const v3 vec1 = neg(mk(it.rx, it.ry, it.rz));
+                    const scgpu_iaparam* ia = k.ia;
+                    const int nn = k.second_psc ? patch_intersect<false>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0])
+                                                : patch_intersect<true>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0]);
+                    keep = nn >= 2;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) qb[nb + __popc(m & lt_mask)] = it;
+                nb += __popc(m);
+                __syncwarp();
+                consume(qa, na, n);
             }
-            r = block_rank(keep, sh_warp, &sh_n2);
-            if (keep) sh_b[r] = it;
-            __syncthreads();
-            const int n2 = sh_n2;
-            // ---- phase 3: attraction of the survivors
-            if ((int)threadIdx.x < n2) {
-                it = sh_b[threadIdx.x];
-                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
-                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
-                double e = atr_e(*ia, P1.dir, P2.dir, P1.pdir, P2.pdir, r_cm, combo & 1, combo >> 1, it.S1, it.S2, it.T1, it.T2);
-                fl.e[it.p].y += e;        // one writer per pair and phase; the combinations run one after another
+            if (nb >= 32 || (!more_input && na == 0 && nb > 0)) {
+                // ---- phase 3: attraction of the survivors
+                const int n = nb < 32 ? nb : 32;
+                if (lane < n) {
+                    const PQItem it = qb[lane];
+                    const PatchKind k = patch_kind(s, it.si, it.sj, ia_one);
+                    PatchArgs P1, P2;
+                    load_patch_args(s.rec + (size_t)it.si * REC, pn1, k.firstCH, P1);
+                    load_patch_args(s.rec + (size_t)it.sj * REC, pn2, k.secondCH, P2);
+                    const double e = atr_e(*k.ia, P1.dir, P2.dir, P1.pdir, P2.pdir, mk(it.rx, it.ry, it.rz), pn1, pn2, it.S1, it.S2, it.T1, it.T2);
+                    fl.e[it.p].y += e;        // one writer per pair; the combinations run one after another in the same warp
+                    if (mirror && e != 0.0) {      // every-particle pass: the partner lists this pair too -- find it in the partner's span (a few entries)
+                        const int4 cj = fl.chunks[w_orig(s.posw[it.sj].w)];
+                        bool found = false;
+                        for (int q = 0; q < cj.y; q++) if (fl.pair[cj.x + q].y == it.si) { fl.e[cj.x + q].y += e; found = true; break; }
+                        if (!found) atomicOr(fl.overflow, 8);      // cannot happen: a pair inside the patch range is listed by both sides
+                    }
+                }
+                __syncwarp();
+                consume(qb, nb, n);
             }
-            __syncthreads();
+            if (!more_input && na == 0 && nb == 0) break;
         }
+        __syncwarp();
     }
 }
 
@@ -1516,15 +1574,7 @@ __global__ void __launch_bounds__(256) k_combine_flat(int n, FlatList fl, const 
         for (int cid = fl.head[t]; cid >= 0;) {
             const int4 ch = fl.chunks[cid];
             for (int r = sub; r < ch.y; r += 8) {
-                double2 v = fl.e[ch.x + r];
-                if (v.y != v.y) {        // patch term evaluated by the partner's side (k_cheap_flat): find this pair in the partner's span
-                    const int2 pr = fl.pair[ch.x + r];
-                    const int4 cj = fl.chunks[w_orig(posw[pr.y].w)];
-                    v.y = 0.0;
-                    bool found = false;
-                    for (int q = 0; q < cj.y; q++) if (fl.pair[cj.x + q].y == pr.x) { v.y = fl.e[cj.x + q].y; found = true; break; }
-                    if (!found || v.y != v.y) atomicOr(fl.overflow, 8);      // cannot happen: a pair inside the patch range is listed by both sides
-                }
+                const double2 v = fl.e[ch.x + r];
                 e += v.x + v.y;      // per pair (cheap + patch), then accumulate
             }
             cid = ch.z;
@@ -2297,7 +2347,7 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
             if (mode == 1) k_cheap_flat<false, false, true><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<false, false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         }
         mark(2);
-        if (one) k_patch_flat<true><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, ia1); else k_patch_flat<false><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, ia1);
+        if (one) k_patch_flat<true><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, mode == 1 ? 1 : 0, ia1); else k_patch_flat<false><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, mode == 1 ? 1 : 0, ia1);
         mark(3);
         k_combine_flat<<<(c->n + 31) / 32, 256, 0, c->stream>>>(c->n, fl, c->d_posw, d_out);
         mark(4);
