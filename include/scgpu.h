@@ -78,7 +78,9 @@ typedef struct scgpu_moveparams {
     double rot_angle[40];          /* per particle type: stat.rot[type].angle (radians, sim.h:360) */
     int n_sub;                     /* sweeps per call: n_sub * N trials in total; every non-empty cell of the checkerboard performs the same
                                       number of them (n_sub * N / non-empty cells, stochastically rounded), whatever its population */
-    int reserved;
+    int grid_k;                    /* fineness of the checkerboard: 0 = chosen by the library (the finest grid that leaves ~2 particles per
+                                      cell: shortest serial chain, best for ONE system on the GPU); 1, 2, 3 = cells of edge >= maxcut / k.
+                                      Many replicas sharing a GPU are throughput-bound and run best on the coarse grid (1) */
 } scgpu_moveparams;
 
 typedef struct scgpu_sweepstats {

@@ -23,6 +23,7 @@
 #include <string>
 #include <type_traits>
 #include <vector>
+#include <algorithm>
 
 #include "pair_energy.cuh"
 
@@ -60,6 +61,8 @@ struct DevSys {
     const float4* p32;    // cell-sorted FP32 copy for the gates: x, y, z = position wrapped into [0, 1) (box fractions), w = original index | type << 24
     const float4* d32;    // cell-sorted FP32 axis (dir); w unused
     const int* cell_start;
+    const int* fine_start;   // sub > 1: every cell is cut into sub^3 sub-cells and sorted by them; [cell * sub^3 + (sz * sub + sy) * sub + sx] -> first slot
+    int sub;                 // (== cell_start when sub == 1)
     const int* order;
     const int* slot_of;
     const int* type;
@@ -88,6 +91,27 @@ __host__ __device__ __forceinline__ int cell_coord(double u, int nc) {
     if (c == nc) c = 0;
     return c;
 }
+// the same with the sub-cell (0 .. S-1) the particle sits in along this axis
+__host__ __device__ __forceinline__ int cell_coord_sub(double u, int nc, int S, int& sx) {
+    double ip;
+    double f = (u > 0) ? modf(u, &ip) : modf(u, &ip) + 1;
+    const double t = f * nc;
+    int c = (int)t;
+    sx = (int)((t - (double)c) * S);
+    if (sx >= S) sx = S - 1;
+    if (sx < 0) sx = 0;
+    if (c == nc) { c = 0; sx = 0; }
+    return c;
+}
+__host__ __device__ __forceinline__ int fine_index(const double* pos, const double* shift, const int* nc, int S, int* coarse) {
+    int sx, sy, sz;
+    const int cx = cell_coord_sub(pos[0] + shift[0], nc[0], S, sx);
+    const int cy = cell_coord_sub(pos[1] + shift[1], nc[1], S, sy);
+    const int cz = cell_coord_sub(pos[2] + shift[2], nc[2], S, sz);
+    const int c = (cz * nc[1] + cy) * nc[0] + cx;
+    if (coarse) *coarse = c;
+    return c * (S * S * S) + (sz * S + sy) * S + sx;
+}
 __host__ __device__ __forceinline__ int cell_index(const double* pos, const double* shift, const int* nc) {
     int cx = cell_coord(pos[0] + shift[0], nc[0]);
     int cy = cell_coord(pos[1] + shift[1], nc[1]);
@@ -102,12 +126,20 @@ static const int h_api_of[30] = {3, 4, 5, 6, 7, 8, 12, 13, 14, 15, 16, 17, 9, 10
 // ------------------------------------------------------------------------------------------------
 // cell list: counting sort by cell, stable in the original index
 // ------------------------------------------------------------------------------------------------
-__global__ void k_cell_count(DevSys s, int* __restrict__ cell_of, int* __restrict__ counts) {
+__global__ void k_cell_count(DevSys s, int* __restrict__ cell_of, int* __restrict__ fine_of, int* __restrict__ counts) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
-    int c = cell_index(s.api + (size_t)i * 30, s.shift, s.nc);
+    int c;
+    const int f = s.sub > 1 ? fine_index(s.api + (size_t)i * 30, s.shift, s.nc, s.sub, &c) : (c = cell_index(s.api + (size_t)i * 30, s.shift, s.nc));
     cell_of[i] = c;
-    atomicAdd(&counts[c], 1);
+    if (s.sub > 1) fine_of[i] = f;
+    atomicAdd(&counts[f], 1);
+}
+// sub > 1: the start of every (coarse) cell out of the sub-cell starts
+__global__ void k_coarse_start(int ncells, int s3, const int* __restrict__ fine_start, int* __restrict__ cell_start) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= ncells) cell_start[c] = fine_start[c * s3];
+    if (c == ncells + 1) cell_start[c] = 0;
 }
 
 // single-block exclusive scan of counts[0..ncells) -> cell_start[0..ncells]; cursor := cell_start
@@ -147,6 +179,32 @@ __global__ void k_cell_scan(int ncells, const int* __restrict__ counts, int* __r
     if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += warp_tot[w]; cell_start[ncells + 1] = t; }
 }
 
+constexpr int HV_MAX = 4096;      // heavy-type particles the sorted list holds (beyond that the sub-cell gate is not used)
+__global__ void k_heavy_collect(int n, const double4* __restrict__ posw, unsigned heavy, int* __restrict__ list, int* __restrict__ count) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    if ((heavy >> (__double2hiint(posw[slot].w) & 0xff)) & 1u) { const int p = atomicAdd(count, 1); if (p < HV_MAX) list[p] = slot; }
+}
+// one block: ascending slots (bitonic, padded with INT_MAX) -> the list does not depend on the order the atomics came in
+__global__ void __launch_bounds__(1024) k_heavy_sort(int* __restrict__ list, int* __restrict__ count) {
+    __shared__ int v[HV_MAX];
+    const int n = min(count[0], HV_MAX);
+    for (int k = threadIdx.x; k < HV_MAX; k += blockDim.x) v[k] = k < n ? list[k] : 0x7fffffff;
+    __syncthreads();
+    for (int size = 2; size <= HV_MAX; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int k = threadIdx.x; k < HV_MAX / 2; k += blockDim.x) {
+                const int i = 2 * k - (k & (stride - 1)), j = i + stride;
+                const bool up = (i & size) == 0;
+                const int a = v[i], b = v[j];
+                if ((a > b) == up) { v[i] = b; v[j] = a; }
+            }
+            __syncthreads();
+        }
+    for (int k = threadIdx.x; k < n; k += blockDim.x) list[k] = v[k];
+    if (threadIdx.x == 0) count[1] = count[0] > HV_MAX ? 1 : 0;      // overflow: the host falls back to the cell gate
+}
+
 // unordered fill of each cell's segment with original indices (order fixed afterwards by k_cell_place)
 __global__ void k_cell_fill(int n, const int* __restrict__ cell_of, int* __restrict__ cursor, int* __restrict__ tmp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,8 +234,8 @@ __global__ void k_cell_place(DevSys s, const int* __restrict__ cell_of, const in
     const bool valid = i < s.n;
     int slot = 0;
     if (valid) {
-        int c = cell_of[i];
-        int b = s.cell_start[c], e = s.cell_start[c + 1];
+        int c = cell_of[i];          // (the caller passes the sub-cell index of every particle when sub > 1)
+        int b = s.fine_start[c], e = s.fine_start[c + 1];
         int r = 0;
         for (int k = b; k < e; k++) r += (tmp[k] < i);
         slot = b + r;
@@ -1295,6 +1353,358 @@ k_gate_rows_gen(DevSys s, FlatList fl) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_gate_fine: the thread-per-target gate on the SUB-CELL level (build_cells_impl: cells cut into sub^3 sub-cells, particles sorted by
+// (cell, sub-cell, index)) for systems whose cell edge is set by a few long particles while most have short interactions -- the
+// lipid membrane: 265 041 beads with reaches of 1.1 - 2.7 in cells 9.9 wide, k_gate_rows_gen tested ~7 000 candidates per bead for
+// ~40 partners. A unit is 32 consecutive slots of ONE cell; its neighbourhood is the bounding box of its sub-cells grown by one
+// sub-cell: rows of sub-cells, each row up to three contiguous slot ranges (one per cell it crosses). Only pairs of LIGHT types
+// (reach <= sub-cell edge, chosen by the host) are found here; a light target finds its few HEAVY partners in the sorted list of
+// heavy particles (binary search for the 27 surrounding cells), heavy targets are listed by k_gate_cells as before.
+// ------------------------------------------------------------------------------------------------
+constexpr int GF_SEG = 112;         // staged slot ranges per unit: <= 36 rows x 3 runs (sub <= 4)
+
+template <int MODE>
+__global__ void __launch_bounds__(GR_SL * 32, 4)
+k_gate_fine(DevSys s, FlatList fl, const int* __restrict__ heavy_list, const int* __restrict__ heavy_count, unsigned heavy_mask, unsigned skip_mask) {
+    // heavy_mask: types whose pairs are not looked for among the sub-cells (their particles are in heavy_list); skip_mask: types whose
+    // TARGETS other gates list (the heavy ones and any type whose targets overflowed a buffer of this kernel)
+    __shared__ float4 t_pf[GG_TILE];                // x, y, z relative to the cell centre (length units), w = x^2 + y^2 + z^2
+    __shared__ __align__(16) int t_ot[GG_TILE];     // original index | type << 24
+    __shared__ __align__(16) int t_slot[GG_TILE];
+    __shared__ int sh_hit[GR_SL][GG_CAP * GG_STRIDE];
+    __shared__ int sh_cnt[GR_SL][GR_T];
+    __shared__ int sh_off[GR_SL][GR_T];
+    __shared__ float sh_reach[GG_MAXT * GG_MAXT];
+    __shared__ int sh_sb[GF_SEG + 16], sh_soff[GF_SEG + 16];
+    __shared__ int sh_hr[27][2];                    // per surrounding cell: its run in the heavy list
+    __shared__ int sh_ok;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c0 = blockIdx.y;
+    const int nx = s.nc[0], ny = s.nc[1], nz = s.nc[2];
+    const int S = s.sub, S3 = S * S * S;
+    const int cx = c0 % nx, cy = (c0 / nx) % ny, cz = c0 / (nx * ny);
+    const int cs = s.cell_start[c0], ce = s.cell_start[c0 + 1];
+    if (cs == ce) return;
+    const int T = s.ntypes;
+    // reach table of the scan: pairs with a heavy partner are not looked for among the sub-cells
+    for (int k = threadIdx.x; k < T * T; k += blockDim.x) sh_reach[k] = ((heavy_mask >> (k % T)) & 1u) ? -1.f : s.reach2[k];
+    const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
+    const float cen[3] = {(float)((cx + 0.5) / nx - s.shift[0]), (float)((cy + 0.5) / ny - s.shift[1]), (float)((cz + 0.5) / nz - s.shift[2])};
+    auto staged = [&](const float4& f) {
+        float x = f.x - cen[0], y = f.y - cen[1], z = f.z - cen[2];
+        x = (x - rintf(x)) * boxf[0]; y = (y - rintf(y)) * boxf[1]; z = (z - rintf(z)) * boxf[2];
+        return make_float4(x, y, z, x * x + y * y + z * z);
+    };
+    if (heavy_mask && wid == 1) {       // the heavy particles of the 27 surrounding cells: runs of the sorted heavy list
+        const int nh = min(heavy_count[0], HV_MAX);
+        int lo = 0, hi = 0;
+        if (lane < 27) {
+            const int ccx = (cx + lane % 3 - 1 + nx) % nx, ccy = (cy + (lane / 3) % 3 - 1 + ny) % ny, ccz = (cz + lane / 9 - 1 + nz) % nz;
+            const int cc = (ccz * ny + ccy) * nx + ccx;
+            const int b = s.cell_start[cc], e = s.cell_start[cc + 1];
+            int a0 = 0, a1 = nh;      // first entry >= b
+            while (a0 < a1) { const int m = (a0 + a1) >> 1; if (heavy_list[m] < b) a0 = m + 1; else a1 = m; }
+            lo = a0; a1 = nh;         // first entry >= e
+            while (a0 < a1) { const int m = (a0 + a1) >> 1; if (heavy_list[m] < e) a0 = m + 1; else a1 = m; }
+            hi = a0;
+            sh_hr[lane][0] = lo; sh_hr[lane][1] = hi;
+        }
+    }
+    for (int ufirst = cs + GR_T * blockIdx.x; ufirst < ce; ufirst += GR_T * gridDim.x) {
+        const int first = ufirst, last = min(ufirst + GR_T, ce) - 1;
+        const int count = last - first + 1;
+        __syncthreads();
+        if (wid == 0) {
+            // ---- sub-cells of the first and the last target, bounding box of everything between them
+            const int fb = c0 * S3;
+            int sa = 0, sb = 0;
+            for (int f0 = 0; f0 < S3; f0 += 32) {
+                const int f = f0 + lane;
+                int b = 0, e = 0;
+                if (f < S3) { b = s.fine_start[fb + f]; e = s.fine_start[fb + f + 1]; }
+                const unsigned ma = __ballot_sync(0xffffffffu, f < S3 && b <= first && first < e);
+                const unsigned mb = __ballot_sync(0xffffffffu, f < S3 && b <= last && last < e);
+                if (ma) sa = f0 + __ffs(ma) - 1;
+                if (mb) sb = f0 + __ffs(mb) - 1;
+            }
+            int x0 = S, x1 = -1, y0 = S, y1 = -1, z0 = S, z1 = -1;
+            for (int f = sa + lane; f <= sb; f += 32) {
+                const int sx = f % S, sy = (f / S) % S, sz = f / (S * S);
+                x0 = min(x0, sx); x1 = max(x1, sx); y0 = min(y0, sy); y1 = max(y1, sy); z0 = min(z0, sz); z1 = max(z1, sz);
+            }
+            x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+            y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
+            z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
+            const int gx0 = cx * S + x0 - 1, gx1 = cx * S + x1 + 1, gy0 = cy * S + y0 - 1, gz0 = cz * S + z0 - 1;
+            const int wy = y1 - y0 + 3, wz = z1 - z0 + 3;
+            const int nq = wy * wz * 3;                              // (row, run) pairs: a row crosses at most three cells
+            const int cxa = gx0 >= 0 ? gx0 / S : -1;                  // the (unwrapped) cell the row starts in
+            int carry = 0;
+            for (int q0 = 0; q0 < nq; q0 += 32) {
+                const int q = q0 + lane;
+                int b = 0, len = 0;
+                if (q < nq) {
+                    const int r = q / 3, u = q % 3;
+                    int gy = gy0 + r % wy, gz = gz0 + r / wy;
+                    gy = (gy + ny * S) % (ny * S); gz = (gz + nz * S) % (nz * S);
+                    const int ccy = gy / S, sy = gy % S, ccz = gz / S, sz = gz % S;
+                    const int cr = cxa + u;                           // unwrapped cell of this run
+                    const int lo = max(gx0, cr * S), hi = min(gx1, cr * S + S - 1);
+                    if (lo <= hi) {
+                        const int ccx = (cr + nx) % nx;
+                        const int base = ((ccz * ny + ccy) * nx + ccx) * S3 + (sz * S + sy) * S;
+                        b = s.fine_start[base + (lo - cr * S)];
+                        len = s.fine_start[base + (hi - cr * S) + 1] - b;
+                    }
+                }
+                int x = len;
+                for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                if (q < nq) { sh_sb[q] = b; sh_soff[q] = carry + x - len; }
+                carry += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (lane == 0) { sh_soff[nq] = carry; sh_sb[GF_SEG + 8] = nq; sh_ok = nq <= GF_SEG ? 1 : 0; if (!sh_ok) atomicOr(fl.overflow, 4); }
+        }
+        __syncthreads();
+        if (!sh_ok) return;
+        const int nq = sh_sb[GF_SEG + 8];
+        const int C = sh_soff[nq];
+        // ---- this lane's target
+        float m2x = 0.f, m2y = 0.f, m2z = 0.f, tt2 = __int_as_float(0x7f800000);      // idle lanes: threshold -inf, never a hit
+        int target = -0x40000000, ttype = 0, tmol = 0;
+        double4 tpw = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (lane < count) {
+            tpw = s.posw[first + lane];
+            const float4 q = staged(s.p32[first + lane]);
+            m2x = -2.f * q.x; m2y = -2.f * q.y; m2z = -2.f * q.z; tt2 = q.w;
+            target = w_orig(tpw.w); ttype = w_type(tpw.w); tmol = w_moltype(tpw.w);
+        }
+        // targets of the heavy types are left to k_gate_heavy / k_gate_cells, launched next
+        const bool mine = lane < count && !((skip_mask >> ttype) & 1u);
+        if (!mine) { tt2 = __int_as_float(0x7f800000); target = -0x40000000; }
+        const float* reach_row = sh_reach + ttype * T;
+        int* buf = sh_hit[wid];
+        int cur = lane;
+        const int cur_max = lane + (GG_CAP - 4) * GG_STRIDE;
+        for (int t0 = 0; t0 < C; t0 += GG_TILE) {
+            const int TC = min(GG_TILE, C - t0);
+            const int TCpad = (TC + 4 * GR_SL - 1) / (4 * GR_SL) * (4 * GR_SL);
+            __syncthreads();            // previous tile consumed
+            for (int k = wid; k < nq; k += GR_SL) {
+                const int b = sh_sb[k], off = sh_soff[k], len = sh_soff[k + 1] - off;
+                const int lo = max(off, t0), hi = min(off + len, t0 + TC);
+                for (int p = lo + lane; p < hi; p += 32) {
+                    const float4 f = s.p32[b + (p - off)];
+                    t_pf[p - t0] = staged(f); t_ot[p - t0] = __float_as_int(f.w); t_slot[p - t0] = b + (p - off);
+                }
+            }
+            for (int p = TC + threadIdx.x; p < TCpad; p += blockDim.x) {
+                t_pf[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+                t_ot[p] = 0x00ffffff; t_slot[p] = 0;
+            }
+            __syncthreads();
+            for (int c4 = 4 * wid; c4 < TCpad; c4 += 4 * GR_SL) {
+                const int4 ot4 = *reinterpret_cast<const int4*>(t_ot + c4);
+                const int ot[4] = {ot4.x, ot4.y, ot4.z, ot4.w};
+                bool hit[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float4 q = t_pf[c4 + u];
+                    const float sq = fmaf(m2z, q.z, fmaf(m2y, q.y, fmaf(m2x, q.x, q.w)));
+                    const int ob = ot[u] & 0xffffff;
+                    const float thr = reach_row[ot[u] >> 24] - tt2;
+                    // the target itself and its chain neighbours (original index within +-2) are decided after the scan
+                    hit[u] = (sq <= thr) & ((unsigned)(ob - target + 2) > 4u) & (MODE == 2 ? ob < target : true);
+                }
+                if (hit[0] | hit[1] | hit[2] | hit[3]) {
+                    const int4 sl4 = *reinterpret_cast<const int4*>(t_slot + c4);
+                    const int sl[4] = {sl4.x, sl4.y, sl4.z, sl4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { buf[cur] = sl[u]; cur += hit[u] ? GG_STRIDE : 0; }
+                    cur = min(cur, cur_max);
+                }
+            }
+        }
+        // ---- chain neighbours and other particles whose original index is within +-2 (slice 0 only): exact, whatever their type
+        if (wid == 0 && mine) {
+            ConList cl;
+            get_conlist(s.mol, tmol, target, cl);
+            const v3 tp = mk(tpw.x, tpw.y, tpw.z);
+#pragma unroll
+            for (int dd = 0; dd < 4; dd++) {
+                const int partner = target + (dd == 0 ? -2 : dd == 1 ? -1 : dd == 2 ? 1 : 2);
+                if (partner < 0 || partner >= s.n) continue;
+                if (MODE == 2 && partner > target) continue;
+                const int ps = s.slot_of[partner];
+                bool list = (partner == cl.con[0]) | (partner == cl.con[1]) | (partner == cl.con[2]) | (partner == cl.con[3]);
+                if (!list) {
+                    const double4 pw = s.posw[ps];
+                    const v3 r = image(s.box, tp, mk(pw.x, pw.y, pw.z));
+                    list = dot(r, r) <= (double)s.reach2[ttype * T + w_type(pw.w)];
+                }
+                if (list) { buf[cur] = ps; cur = min(cur + GG_STRIDE, cur_max); }
+            }
+        }
+        // ---- heavy partners of a light target (slice 1): the heavy particles of the 27 surrounding cells, exact distance
+        if (wid == 1 && mine && heavy_mask) {
+            const v3 tp = mk(tpw.x, tpw.y, tpw.z);
+            for (int k = 0; k < 27; k++) {
+                for (int h = sh_hr[k][0]; h < sh_hr[k][1]; h++) {
+                    const int hs = heavy_list[h];
+                    const double4 pw = s.posw[hs];
+                    const int ob = w_orig(pw.w);
+                    if ((unsigned)(ob - target + 2) <= 4u) continue;                 // decided above
+                    if (MODE == 2 && ob > target) continue;
+                    const v3 r = image(s.box, tp, mk(pw.x, pw.y, pw.z));
+                    if (dot(r, r) <= (double)s.reach2[ttype * T + w_type(pw.w)]) { buf[cur] = hs; cur = min(cur + GG_STRIDE, cur_max); }
+                }
+            }
+        }
+        if (cur == cur_max) { atomicOr(fl.overflow, 4); atomicOr(fl.heavy, 1 << ttype); }       // rare: the host repeats with this type split off
+        const int cnt = (cur - lane) / GG_STRIDE;
+        sh_cnt[wid][lane] = cnt;
+        __syncthreads();
+        if (wid == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < GR_SL; w++) tot += sh_cnt[w][lane];
+            int x = tot;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            const int total = __shfl_sync(0xffffffffu, x, 31);
+            int base = 0;
+            if (lane == 0) {
+                base = atomicAdd(fl.total, total);
+                const bool ok = base + total <= fl.cap;
+                if (!ok) atomicOr(fl.overflow, 2);
+                sh_ok = ok ? 1 : 0;
+            }
+            base = __shfl_sync(0xffffffffu, base, 0) + x - tot;
+            {
+                int o = base;
+#pragma unroll
+                for (int w = 0; w < GR_SL; w++) { sh_off[w][lane] = o; o += sh_cnt[w][lane]; }
+            }
+            if (mine) {
+                fl.chunks[target] = make_int4(base, tot, -1, 0);
+                fl.head[target] = target;
+            }
+        }
+        __syncthreads();
+        if (!sh_ok) return;
+        {
+            const int my_off = sh_off[wid][lane];
+            for (int k = 0, rd = lane; k < cnt; k++, rd += GG_STRIDE) fl.pair[my_off + k] = make_int2(first + lane, buf[rd]);
+        }
+    }
+}
+
+// k_gate_heavy: the partner list of ONE heavy-type particle per block (sub-cell mode; the heavy particles are the few long rods of a
+// system of short-range beads). All 256 threads walk the 27 cells around it -- thousands of candidates, read as contiguous 16-byte
+// FP32 records -- each warp over its own contiguous share, hits compacted by ballot in candidate order; the shares are counted
+// first, the block reserves the span, a second walk writes it: the list is in candidate order, whatever the timing.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_gate_heavy(DevSys s, FlatList fl, const int* __restrict__ heavy_list, int nheavy) {
+    __shared__ int sh_b[32], sh_off[64];
+    __shared__ int sh_wcnt[8], sh_woff[8];
+    __shared__ int sh_extra[4];
+    __shared__ int sh_nextra, sh_base, sh_ok;
+    if ((int)blockIdx.x >= nheavy) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int hs = heavy_list[blockIdx.x];
+    const double4 tpw = s.posw[hs];
+    const int target = w_orig(tpw.w), ttype = w_type(tpw.w), tmol = w_moltype(tpw.w);
+    const int nx = s.nc[0], ny = s.nc[1], nz = s.nc[2], T = s.ntypes;
+    const int cx = cell_coord(tpw.x + s.shift[0], nx), cy = cell_coord(tpw.y + s.shift[1], ny), cz = cell_coord(tpw.z + s.shift[2], nz);
+    if (threadIdx.x >= 28 && threadIdx.x < 64) sh_off[threadIdx.x] = 0x7fffffff;
+    if (wid == 0) {
+        int b = 0, len = 0;
+        if (lane < 27) {
+            const int ccx = (cx + lane % 3 - 1 + nx) % nx, ccy = (cy + (lane / 3) % 3 - 1 + ny) % ny, ccz = (cz + lane / 9 - 1 + nz) % nz;
+            const int cc = (ccz * ny + ccy) * nx + ccx;
+            b = s.cell_start[cc];
+            len = s.cell_start[cc + 1] - b;
+        }
+        int x = len;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane < 28) { sh_b[lane] = b; sh_off[lane] = x - len; }       // [27] = total
+    }
+    if (threadIdx.x == 32) {        // chain neighbours / original index within +-2: decided exactly, wherever they are
+        ConList cl;
+        get_conlist(s.mol, tmol, target, cl);
+        const v3 tp = mk(tpw.x, tpw.y, tpw.z);
+        int ne = 0;
+        for (int dd = 0; dd < 4; dd++) {
+            const int partner = target + (dd == 0 ? -2 : dd == 1 ? -1 : dd == 2 ? 1 : 2);
+            if (partner < 0 || partner >= s.n) continue;
+            if (MODE == 2 && partner > target) continue;
+            const int ps = s.slot_of[partner];
+            bool list = (partner == cl.con[0]) | (partner == cl.con[1]) | (partner == cl.con[2]) | (partner == cl.con[3]);
+            if (!list) {
+                const double4 pw = s.posw[ps];
+                const v3 r = image(s.box, tp, mk(pw.x, pw.y, pw.z));
+                list = dot(r, r) <= (double)s.reach2[ttype * T + w_type(pw.w)];
+            }
+            if (list) sh_extra[ne++] = ps;
+        }
+        sh_nextra = ne;
+    }
+    __syncthreads();
+    const int C = sh_off[27];
+    const int per_warp = ((C + 7) / 8 + 31) & ~31;
+    const int wlo = wid * per_warp, whi = min(C, wlo + per_warp);
+    const float4 tf = s.p32[hs];
+    const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
+    const float* reach_row = s.reach2 + ttype * T;
+    for (int pass = 0; pass < 2; pass++) {
+        int cnt = 0;
+        const int out0 = pass ? sh_base + sh_nextra + sh_woff[wid] : 0;
+        for (int p0 = wlo; p0 < whi; p0 += 32) {
+            const int p = p0 + lane;
+            bool hit = false;
+            int slot = 0;
+            if (p < whi) {
+                int sg = 0;
+                sg += p >= sh_off[sg + 16] ? 16 : 0;
+                sg += p >= sh_off[sg + 8] ? 8 : 0;
+                sg += p >= sh_off[sg + 4] ? 4 : 0;
+                sg += p >= sh_off[sg + 2] ? 2 : 0;
+                sg += p >= sh_off[sg + 1] ? 1 : 0;
+                slot = sh_b[sg] + (p - sh_off[sg]);
+                const float4 f = s.p32[slot];
+                const int wb = __float_as_int(f.w), ob = wb & 0xffffff;
+                float dx = tf.x - f.x, dy = tf.y - f.y, dz = tf.z - f.z;
+                dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
+                hit = (dx * dx + dy * dy + dz * dz <= reach_row[wb >> 24]) & ((unsigned)(ob - target + 2) > 4u) & (MODE == 2 ? ob < target : true);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (pass && hit) fl.pair[out0 + cnt + __popc(m & lt_mask)] = make_int2(hs, slot);
+            cnt += __popc(m);
+        }
+        if (pass == 0) {
+            if (lane == 0) sh_wcnt[wid] = cnt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int tot = sh_nextra;
+                for (int w = 0; w < 8; w++) { sh_woff[w] = tot - sh_nextra; tot += sh_wcnt[w]; }
+                const int base = atomicAdd(fl.total, tot);
+                const bool ok = base + tot <= fl.cap;
+                if (!ok) atomicOr(fl.overflow, 2);
+                sh_ok = ok ? 1 : 0;
+                sh_base = base;
+                if (ok) {
+                    for (int k = 0; k < sh_nextra; k++) fl.pair[base + k] = make_int2(hs, sh_extra[k]);
+                    fl.chunks[target] = make_int4(base, tot, -1, 0);
+                    fl.head[target] = target;
+                }
+            }
+            __syncthreads();
+            if (!sh_ok) return;
+        }
+    }
+}
+
 #ifndef CHEAP_MINB
 #define CHEAP_MINB 3
 #endif
@@ -1426,139 +1836,88 @@ __device__ __forceinline__ void patch_setup(const DevSys& s, const FlatList& fl,
     load_patch_args(s2, pn2, secondCH, P2);
 }
 
-#ifndef PATCH_MINB
-#define PATCH_MINB 6
-#endif
-// Patch terms, every warp on its own: no block barrier. A warp takes 32 listed pairs per trip and runs patch_intersect #1 on them;
-// the survivors (the partner is inside the patch wedge: about a quarter) go to a per-warp queue in shared memory together with what
-// the later phases need (slots, separation vector, T1, T2). Whenever a queue holds 32 entries the warp runs the next phase on a FULL
-// set of lanes: intersect #2 -> second queue (+ S1, S2) -> atr_e. The expensive later phases therefore always run densely packed,
-// and nothing is re-derived: the first version of this kernel compacted per block behind three barriers and re-loaded and
-// re-imaged every pair in each phase (barrier stall 8.2 and long-scoreboard 6.0 per issue, profiles/r2e_pipeline.txt).
-struct PQItem { int p, si, sj, pad; double rx, ry, rz, T1, T2, S1, S2; };      // 72 bytes
-constexpr int PQ_CAP = 64;
-
-struct PatchKind { const scgpu_iaparam* ia; bool first_psc, second_psc, firstCH, secondCH, firstT, secondT; };
-__device__ __forceinline__ PatchKind patch_kind(const DevSys& s, int si, int sj, const scgpu_iaparam* ia_one) {
-    PatchKind k;
-    k.ia = ia_one ? ia_one : &s.ia[w_type(s.posw[si].w) * s.ntypes + w_type(s.posw[sj].w)];
-    const int kind = (int)k.ia->reserved[0], g0 = (int)k.ia->geotype[0], g1 = (int)k.ia->geotype[1];
-    k.firstCH = is_chiral(g0); k.secondCH = is_chiral(g1); k.firstT = is_two_patch(g0); k.secondT = is_two_patch(g1);
-    k.first_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && is_psc_family(g0));
-    k.second_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && !is_psc_family(g0));
-    return k;
+// block-wide stable compaction: returns this thread's rank among the threads with flag set, total in *count (shared)
+__device__ __forceinline__ int block_rank(bool flag, int* sh_warp, int* count) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) sh_warp[wid] = __popc(m);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < PF_THREADS / 32; w++) { int c = sh_warp[w]; if (w < wid) off += c; tot += c; }
+    if (threadIdx.x == 0) *count = tot;
+    __syncthreads();
+    return off + __popc(m & ((1u << lane) - 1u));
 }
 
+#ifndef PATCH_MINB
+#define PATCH_MINB 7
+#endif
 template <bool ONE>
 __global__ void __launch_bounds__(PF_THREADS, PATCH_MINB)
 k_patch_flat(DevSys s, FlatList fl, int any_two_patch, int mirror, const __grid_constant__ scgpu_iaparam ia1) {
     const scgpu_iaparam* ia_one = ONE ? &ia1 : nullptr;
     if (*fl.overflow) return;
-    __shared__ PQItem sh_qa[PF_THREADS / 32][PQ_CAP], sh_qb[PF_THREADS / 32][PQ_CAP];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    PQItem* qa = sh_qa[wid];
-    PQItem* qb = sh_qb[wid];
+    __shared__ PatchItem sh_a[PF_THREADS], sh_b[PF_THREADS];
+    __shared__ int sh_warp[PF_THREADS / 32];
+    __shared__ int sh_n1, sh_n2;
     const int total = *fl.ptotal;
     const int ncombo = any_two_patch ? 4 : 1;
-    const int nwarps = gridDim.x * (PF_THREADS / 32), gw = blockIdx.x * (PF_THREADS / 32) + wid;
-    for (int combo = 0; combo < ncombo; combo++) {
-        const int pn1 = combo & 1, pn2 = combo >> 1;
-        int na = 0, nb = 0;
-        auto consume = [&](PQItem* q, int& n, int used) {        // drop the first `used` entries of a queue
-            const int rest = n - used;
-            PQItem t;
-            if (lane < rest) t = q[used + lane];
-            __syncwarp();
-            if (lane < rest) q[lane] = t;
-            n = rest;
-            __syncwarp();
-        };
-        // one loop, each phase body once (three inlined copies of the intersection code would triple the kernel's instruction footprint):
-        // a trip feeds 32 listed pairs to phase 1 while there is input, then runs phase 2 / phase 3 if their queue is full (or, once
-        // the input is exhausted, as long as anything is left)
-        for (int base = gw * 32;; base += nwarps * 32) {
-            const bool input = base < total;
-            if (input) {
-                // ---- phase 1: rod 2 against the patch of rod 1 (T1, T2)
-                const int q = base + lane;
-                const int p = q < total ? fl.plist[q] : -1;
-                bool keep = false;
-                PQItem it;
-                it.p = p; it.pad = 0; it.S1 = it.S2 = 0.0;
-                if (p >= 0) {
-                    const int2 pr = fl.pair[p];
-                    it.si = pr.x; it.sj = pr.y;
-                    const double4 pi = ldg256(s.posw + pr.x), pj = ldg256(s.posw + pr.y);
-                    const v3 r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
-                    it.rx = r_cm.x; it.ry = r_cm.y; it.rz = r_cm.z;
-                    const scgpu_iaparam* ia = ia_one ? ia_one : &s.ia[w_type(pi.w) * s.ntypes + w_type(pj.w)];
-                    const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
-                    const bool firstT = is_two_patch(g0), secondT = is_two_patch(g1);
-                    const bool ok = (combo == 0) || (combo == 1 && firstT) || (combo == 2 && secondT) || (combo == 3 && firstT && secondT);
-                    if (ok) {
-                        const bool first_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && is_psc_family(g0));
-                        PatchArgs P1, P2;
-                        load_patch_args(s.rec + (size_t)pr.x * REC, pn1, is_chiral(g0), P1);
-                        load_patch_args(s.rec + (size_t)pr.y * REC, pn2, is_chiral(g1), P2);
-                        const int nn = first_psc ? patch_intersect<false>(P1.dir, P2.dir, P1, r_cm, it.T1, it.T2, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1])
-                                                 : patch_intersect<true>(P1.dir, P2.dir, P1, r_cm, it.T1, it.T2, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1]);
-                        keep = nn >= 2;
-                    }
+    for (int base = blockIdx.x * PF_THREADS; base < total; base += gridDim.x * PF_THREADS) {       // block-uniform trip count
+        const int q = base + threadIdx.x;
+        const int p = q < total ? fl.plist[q] : -1;
+        for (int combo = 0; combo < ncombo; combo++) {
+            // ---- phase 1: rod 2 against the patch of rod 1 (T1, T2)
+            bool keep = false;
+            double a = 0.0, b = 0.0;
+            if (p >= 0) {
+                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
+                patch_setup(s, fl, p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
+                if (ok) {
+                    const int pn1 = combo & 1;
+                    int n = fp ? patch_intersect<false>(P1.dir, P2.dir, P1, r_cm, a, b, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1])
+                               : patch_intersect<true>(P1.dir, P2.dir, P1, r_cm, a, b, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1]);
+                    keep = n >= 2;
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (keep) qa[na + __popc(m & lt_mask)] = it;
-                na += __popc(m);
-                __syncwarp();
             }
-            const bool more_input = base + nwarps * 32 < total;
-            if (na >= 32 || (!more_input && na > 0)) {
-                // ---- phase 2: rod 1 against the patch of rod 2 (S1, S2)
-                const int n = na < 32 ? na : 32;
-                bool keep = false;
-                PQItem it;
-                if (lane < n) {
-                    it = qa[lane];
-                    const PatchKind k = patch_kind(s, it.si, it.sj, ia_one);
-                    PatchArgs P1, P2;
-                    load_patch_args(s.rec + (size_t)it.si * REC, pn1, k.firstCH, P1);
-                    load_patch_args(s.rec + (size_t)it.sj * REC, pn2, k.secondCH, P2);
-                    const v3 vec1 = neg(mk(it.rx, it.ry, it.rz));
-                    const scgpu_iaparam* ia = k.ia;
-                    const int nn = k.second_psc ? patch_intersect<false>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0])
-                                                : patch_intersect<true>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0]);
-                    keep = nn >= 2;
+            int r = block_rank(keep, sh_warp, &sh_n1);
+            if (keep) { sh_a[r].p = p; sh_a[r].T1 = a; sh_a[r].T2 = b; }
+            __syncthreads();
+            const int n1 = sh_n1;
+            // ---- phase 2: rod 1 against the patch of rod 2 (S1, S2), survivors only
+            keep = false;
+            PatchItem it;
+            it.p = -1; it.T1 = it.T2 = it.S1 = it.S2 = 0.0;
+            if ((int)threadIdx.x < n1) {
+                it = sh_a[threadIdx.x];
+                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
+                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
+                const int pn2 = combo >> 1;
+                v3 vec1 = neg(r_cm);
+                int n = sp ? patch_intersect<false>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0])
+                           : patch_intersect<true>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0]);
+                keep = n >= 2;
+            }
+            r = block_rank(keep, sh_warp, &sh_n2);
+            if (keep) sh_b[r] = it;
+            __syncthreads();
+            const int n2 = sh_n2;
+            // ---- phase 3: attraction of the survivors
+            if ((int)threadIdx.x < n2) {
+                it = sh_b[threadIdx.x];
+                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
+                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
+                double e = atr_e(*ia, P1.dir, P2.dir, P1.pdir, P2.pdir, r_cm, combo & 1, combo >> 1, it.S1, it.S2, it.T1, it.T2);
+                fl.e[it.p].y += e;        // one writer per pair and phase; the combinations run one after another
+                if (mirror && e != 0.0) {      // every-particle pass: the partner lists this pair too -- find it in the partner's span (a few entries)
+                    const int2 pr = fl.pair[it.p];
+                    const int4 cj = fl.chunks[w_orig(s.posw[pr.y].w)];
+                    bool found = false;
+                    for (int q = 0; q < cj.y; q++) if (fl.pair[cj.x + q].y == pr.x) { fl.e[cj.x + q].y += e; found = true; break; }
+                    if (!found) atomicOr(fl.overflow, 8);      // cannot happen: a pair inside the patch range is listed by both sides
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (keep) qb[nb + __popc(m & lt_mask)] = it;
-                nb += __popc(m);
-                __syncwarp();
-                consume(qa, na, n);
             }
-            if (nb >= 32 || (!more_input && na == 0 && nb > 0)) {
-                // ---- phase 3: attraction of the survivors
-                const int n = nb < 32 ? nb : 32;
-                if (lane < n) {
-                    const PQItem it = qb[lane];
-                    const PatchKind k = patch_kind(s, it.si, it.sj, ia_one);
-                    PatchArgs P1, P2;
-                    load_patch_args(s.rec + (size_t)it.si * REC, pn1, k.firstCH, P1);
-                    load_patch_args(s.rec + (size_t)it.sj * REC, pn2, k.secondCH, P2);
-                    const double e = atr_e(*k.ia, P1.dir, P2.dir, P1.pdir, P2.pdir, mk(it.rx, it.ry, it.rz), pn1, pn2, it.S1, it.S2, it.T1, it.T2);
-                    fl.e[it.p].y += e;        // one writer per pair; the combinations run one after another in the same warp
-                    if (mirror && e != 0.0) {      // every-particle pass: the partner lists this pair too -- find it in the partner's span (a few entries)
-                        const int4 cj = fl.chunks[w_orig(s.posw[it.sj].w)];
-                        bool found = false;
-                        for (int q = 0; q < cj.y; q++) if (fl.pair[cj.x + q].y == it.si) { fl.e[cj.x + q].y += e; found = true; break; }
-                        if (!found) atomicOr(fl.overflow, 8);      // cannot happen: a pair inside the patch range is listed by both sides
-                    }
-                }
-                __syncwarp();
-                consume(qb, nb, n);
-            }
-            if (!more_input && na == 0 && nb == 0) break;
+            __syncthreads();
         }
-        __syncwarp();
     }
 }
 
@@ -1763,6 +2122,14 @@ struct scgpu_ctx {
     int *d_type = nullptr, *d_moltype = nullptr, *d_cell_of = nullptr, *d_order = nullptr, *d_slot_of = nullptr, *d_tmp = nullptr;
     int *d_counts = nullptr, *d_cell_start = nullptr, *d_cursor = nullptr;
     int cells_cap = 0;
+    int *d_fine_of = nullptr, *d_fine_start = nullptr;      // sub-cell sort (sub > 1): per particle, per sub-cell
+    int fine_cap = 0;
+    int sub = 1;                     // sub-cells per cell and axis of the current cell list
+    unsigned present_mask = 0;       // particle types present (bit per type, types < 32)
+    long long type_count[40] = {0};
+    unsigned fine_heavy = 0;         // types whose reach exceeds a sub-cell: their pairs stay on the coarse grid
+    int *d_heavy = nullptr, *d_nheavy = nullptr;             // sorted slots of the heavy-type particles
+    int heavy_cap = 0;
     int nc[3] = {1, 1, 1};
     int ncells = 1;
     bool cells_valid = false;
@@ -1828,6 +2195,7 @@ static DevSys view(const scgpu_ctx* c) {
     for (int d = 0; d < 3; d++) { s.nc[d] = c->nc[d]; s.box[d] = c->box[d]; s.shift[d] = c->shift[d]; }
     s.ncells = c->ncells;
     s.api = c->d_api; s.posw = c->d_posw; s.rec = c->d_rec; s.p32 = c->d_p32; s.d32 = c->d_d32; s.cell_start = c->d_cell_start; s.order = c->d_order;
+    s.fine_start = c->sub > 1 ? c->d_fine_start : c->d_cell_start; s.sub = c->sub;
     s.slot_of = c->d_slot_of; s.type = c->d_type; s.moltype = c->d_moltype; s.ia = c->d_ia; s.mol = c->d_mol; s.reach2 = c->d_reach2;
     s.sqmaxcut = c->sqmaxcut;
     return s;
@@ -1890,6 +2258,7 @@ extern "C" int scgpu_destroy(scgpu_ctx* c) {
     cudaStreamSynchronize(c->stream);
     free_particles(c);
     cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_reach2); cudaFree(c->d_counts); cudaFree(c->d_cell_start); cudaFree(c->d_cursor);
+    cudaFree(c->d_fine_of); cudaFree(c->d_fine_start); cudaFree(c->d_heavy); cudaFree(c->d_nheavy);
     cudaFree(c->d_sweep_acc);
     cudaFree(c->d_trial); cudaFree(c->d_trial_rec); cudaFree(c->d_pl_total); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_reduce); cudaFree(c->d_counters); cudaFree(c->d_flush);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -2098,6 +2467,10 @@ static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const 
         c->heavy_types = 0;
         std::vector<char> tu(c->ntypes, 0), mu(c->nmol, 0);
         for (int i = 0; i < n; i++) { tu[type[i]] = 1; mu[moltype[i]] = 1; }
+        c->present_mask = 0;
+        for (int t = 0; t < 40; t++) c->type_count[t] = 0;
+        for (int i = 0; i < n; i++) c->type_count[type[i]]++;
+        for (int t = 0; t < c->ntypes && t < 32; t++) if (tu[t]) c->present_mask |= 1u << t;
         bool rods = true;
         for (int a = 0; a < c->ntypes && rods; a++) for (int b = 0; b < c->ntypes && rods; b++) {
             if (!tu[a] || !tu[b]) continue;
@@ -2171,20 +2544,83 @@ static int build_cells_impl(scgpu_ctx* c, const double shift[3], int sweep_k) {
     long long ncells = (long long)c->nc[0] * c->nc[1] * c->nc[2];
     ARG(ncells < (1ll << 30), "scgpu_build_cells: too many cells");
     c->ncells = (int)ncells;
-    if (c->ncells + 2 > c->cells_cap) {
-        cudaFree(c->d_counts); cudaFree(c->d_cell_start); cudaFree(c->d_cursor);
-        c->cells_cap = c->ncells + 2;
-        CK(cudaMalloc(&c->d_counts, (size_t)c->cells_cap * sizeof(int)));
-        CK(cudaMalloc(&c->d_cell_start, (size_t)c->cells_cap * sizeof(int)));
-        CK(cudaMalloc(&c->d_cursor, (size_t)c->cells_cap * sizeof(int)));
+    // ---- sub-cells. The cell edge is set by the LONGEST interaction of the system (maxcut); where most particles only have short
+    // ones -- lipid beads among a few long rods: cells 9.6 wide, bead reach 2.7 -- a particle would test thousands of candidates for
+    // a few dozen partners. The cells are then cut into sub^3 sub-cells, particles sorted by (cell, sub-cell, index), and the
+    // every-particle gate of the "light" types scans the 27 sub-cells around a target (k_gate_fine); pairs that involve a "heavy" type
+    // (reach beyond a sub-cell) stay on the cell level. The cell assignment itself (definition C1) is unchanged.
+    c->sub = 1;
+    c->fine_heavy = 0;
+    if (sweep_k == 0 && c->types_valid && !c->rods_only && c->ntypes <= GG_MAXT && c->n >= 8192 && c->nc[0] >= 3 && c->nc[1] >= 3 && c->nc[2] >= 3
+        && c->use_rows && getenv("SCGPU_NO_SUBCELLS") == nullptr) {
+        double edge = c->box[0] / c->nc[0];
+        for (int d = 1; d < 3; d++) edge = fmin(edge, c->box[d] / c->nc[d]);
+        unsigned light = c->present_mask;
+        const int T = c->ntypes;
+        auto pair_reach = [&](int a, int b) {
+            const scgpu_iaparam& q = c->h_ia[(size_t)a * T + b];
+            const int k = (int)q.reserved[0];
+            double cut = sqrt(q.rcutSq > q.rcutwcaSq ? q.rcutSq : q.rcutwcaSq);
+            if (q.rcut > cut) cut = q.rcut;
+            if (q.rcutwca > cut) cut = q.rcutwca;
+            if (k == K_EBASIC) return 0.0;
+            return cut + q.half_len[0] + q.half_len[1];
+        };
+        int best = 1;
+        while (light) {
+            double rmax = 0.0;
+            int worst = -1;
+            for (int a = 0; a < T; a++) for (int b = 0; b < T; b++)
+                if (((light >> a) & 1u) && ((light >> b) & 1u)) { const double r = pair_reach(a, b); if (r > rmax) { rmax = r; worst = a; } }
+            const int S = rmax > 0 ? (int)floor(edge / (1.02 * rmax)) : 1;
+            if (S >= 2) { best = S > 4 ? 4 : S; break; }
+            if (worst < 0) break;
+            light &= ~(1u << worst);
+        }
+        // worth it only if the light types are the bulk of the system
+        if (best >= 2 && light) {
+            long long nlight = 0;
+            for (int t = 0; t < T; t++) if ((light >> t) & 1u) nlight += c->type_count[t];
+            if (nlight * 4 >= (long long)c->n * 3 && (long long)c->n - nlight <= HV_MAX) { c->sub = best; c->fine_heavy = c->present_mask & ~light; }
+        }
     }
+    const int s3 = c->sub * c->sub * c->sub;
+    const long long nfine = ncells * s3;
+    ARG(nfine < (1ll << 30), "scgpu_build_cells: too many sub-cells");
+    if (c->ncells + 2 > c->cells_cap) {
+        cudaFree(c->d_cell_start);
+        c->cells_cap = c->ncells + 2;
+        CK(cudaMalloc(&c->d_cell_start, (size_t)c->cells_cap * sizeof(int)));
+    }
+    if ((int)nfine + 2 > c->fine_cap) {
+        cudaFree(c->d_counts); cudaFree(c->d_cursor); cudaFree(c->d_fine_start);
+        c->fine_cap = (int)nfine + 2;
+        CK(cudaMalloc(&c->d_counts, (size_t)c->fine_cap * sizeof(int)));
+        CK(cudaMalloc(&c->d_cursor, (size_t)c->fine_cap * sizeof(int)));
+        CK(cudaMalloc(&c->d_fine_start, (size_t)c->fine_cap * sizeof(int)));
+    }
+    if (c->sub > 1 && !c->d_fine_of) CK(cudaMalloc(&c->d_fine_of, (size_t)c->cap * sizeof(int)));
     DevSys s = view(c);
     int nb = (c->n + 255) / 256;
-    CK(cudaMemsetAsync(c->d_counts, 0, (size_t)c->ncells * sizeof(int), c->stream));
-    k_cell_count<<<nb, 256, 0, c->stream>>>(s, c->d_cell_of, c->d_counts);
-    k_cell_scan<<<1, 1024, 0, c->stream>>>(c->ncells, c->d_counts, c->d_cell_start, c->d_cursor);
-    k_cell_fill<<<nb, 256, 0, c->stream>>>(c->n, c->d_cell_of, c->d_cursor, c->d_tmp);
-    k_cell_place<<<nb, 256, 0, c->stream>>>(s, c->d_cell_of, c->d_tmp, c->d_order, c->d_slot_of, c->d_posw, c->d_rec, c->d_p32, c->d_d32);
+    CK(cudaMemsetAsync(c->d_counts, 0, (size_t)nfine * sizeof(int), c->stream));
+    k_cell_count<<<nb, 256, 0, c->stream>>>(s, c->d_cell_of, c->d_fine_of, c->d_counts);
+    if (c->sub > 1) {
+        k_cell_scan<<<1, 1024, 0, c->stream>>>((int)nfine, c->d_counts, c->d_fine_start, c->d_cursor);
+        k_coarse_start<<<(c->ncells + 2 + 255) / 256, 256, 0, c->stream>>>(c->ncells, s3, c->d_fine_start, c->d_cell_start);
+        k_cell_fill<<<nb, 256, 0, c->stream>>>(c->n, c->d_fine_of, c->d_cursor, c->d_tmp);
+        k_cell_place<<<nb, 256, 0, c->stream>>>(s, c->d_fine_of, c->d_tmp, c->d_order, c->d_slot_of, c->d_posw, c->d_rec, c->d_p32, c->d_d32);
+        // the heavy-type particles, as a sorted list of slots (a few hundred among hundreds of thousands)
+        if (!c->d_nheavy) CK(cudaMalloc(&c->d_nheavy, 4 * sizeof(int)));
+        if (c->heavy_cap < HV_MAX) { cudaFree(c->d_heavy); CK(cudaMalloc(&c->d_heavy, HV_MAX * sizeof(int))); c->heavy_cap = HV_MAX; }
+        CK(cudaMemsetAsync(c->d_nheavy, 0, 4 * sizeof(int), c->stream));
+        k_heavy_collect<<<nb, 256, 0, c->stream>>>(c->n, c->d_posw, c->fine_heavy, c->d_heavy, c->d_nheavy);
+        k_heavy_sort<<<1, 1024, 0, c->stream>>>(c->d_heavy, c->d_nheavy);
+        c->launches += 3;
+    } else {
+        k_cell_scan<<<1, 1024, 0, c->stream>>>(c->ncells, c->d_counts, c->d_cell_start, c->d_cursor);
+        k_cell_fill<<<nb, 256, 0, c->stream>>>(c->n, c->d_cell_of, c->d_cursor, c->d_tmp);
+        k_cell_place<<<nb, 256, 0, c->stream>>>(s, c->d_cell_of, c->d_tmp, c->d_order, c->d_slot_of, c->d_posw, c->d_rec, c->d_p32, c->d_d32);
+    }
     c->f32_valid = true;
     c->launches += 4;
     CK(cudaGetLastError());
@@ -2218,6 +2654,8 @@ extern "C" int scgpu_cell_order(scgpu_ctx* c, int* order, int* cell_start) {
     CK(cudaMemcpyAsync(order, c->d_order, (size_t)c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(cell_start, c->d_cell_start, (size_t)(c->ncells + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    // definition C1: ascending original index inside a cell. With sub-cells the internal order is (sub-cell, index): re-sort per cell
+    if (c->sub > 1) for (int k = 0; k < c->ncells; k++) std::sort(order + cell_start[k], order + cell_start[k + 1]);
     return SCGPU_OK;
 }
 
@@ -2230,12 +2668,12 @@ extern "C" int scgpu_update_particle(scgpu_ctx* c, int idx, const double* state3
     memcpy(c->h_small + 512, state30, 30 * sizeof(double));
     CK(cudaMemcpyAsync(c->d_api + (size_t)idx * 30, c->h_small + 512, 30 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (c->cells_valid) {
-        if (c->h_cell_of.empty()) {
+        if (c->h_cell_of.empty()) {          // (sub-cells: the mirror holds the sub-cell index -- a particle must stay in its sub-cell to be updated in place)
             c->h_cell_of.resize(c->n);
-            CK(cudaMemcpyAsync(c->h_cell_of.data(), c->d_cell_of, (size_t)c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(c->h_cell_of.data(), c->sub > 1 ? c->d_fine_of : c->d_cell_of, (size_t)c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
         }
-        int newc = cell_index(state30, c->shift, c->nc);
+        int newc = c->sub > 1 ? fine_index(state30, c->shift, c->nc, c->sub, nullptr) : cell_index(state30, c->shift, c->nc);
         if (newc != c->h_cell_of[idx]) {
             c->cells_valid = false;      // left its cell: the next energy call re-sorts
         } else {
@@ -2296,10 +2734,16 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
         // test is a plain |t - q|^2, whose error is relative to the distance itself.
         bool rows_exact = true;
         if (!wrap) {
-            const double kx = 0.5 * (double)((c->nc[0] - 3 < 6 ? c->nc[0] - 3 : 6) + 2);
-            const double hx = kx * c->box[0] / c->nc[0], hy = 1.5 * c->box[1] / c->nc[1], hz = 1.5 * c->box[2] / c->nc[2];
-            const double R2 = hx * hx + hy * hy + hz * hz;
             const double bmax = fmax(c->box[0], fmax(c->box[1], c->box[2]));
+            double hx, hy, hz;
+            if (c->sub > 1 && !c->rods_only) {      // k_gate_fine: coordinates relative to the cell centre, candidates at most one sub-cell outside the cell
+                const double f = 0.5 + 1.0 / c->sub;
+                hx = f * c->box[0] / c->nc[0]; hy = f * c->box[1] / c->nc[1]; hz = f * c->box[2] / c->nc[2];
+            } else {
+                const double kx = 0.5 * (double)((c->nc[0] - 3 < 6 ? c->nc[0] - 3 : 6) + 2);
+                hx = kx * c->box[0] / c->nc[0]; hy = 1.5 * c->box[1] / c->nc[1]; hz = 1.5 * c->box[2] / c->nc[2];
+            }
+            const double R2 = hx * hx + hy * hy + hz * hz;
             // + the staged positions are FP32 box fractions: 2^-24 of the box per coordinate, entering d^2 as 2 sqrt(reach2) sqrt(3) times that
             rows_exact = R2 * 4.0 * 5.96e-8 + 2.0 * sqrt(c->min_reach2) * 1.74 * bmax * 1.2e-7 <= 0.5 * 0.001 * c->min_reach2;
         }
@@ -2322,6 +2766,28 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
             else k_gate_rows<2><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl);
             mark(1);
             launch_cheap_rods();
+        } else if (!c->rods_only && rows_ok && c->sub > 1 && c->ncells <= 65535) {
+            // sub-cell gate for the light types, cell gate for the targets of the heavy ones (and of any type whose targets overflowed a buffer)
+            const dim3 grid(4, (unsigned)c->ncells);
+            const unsigned skip = c->fine_heavy | c->heavy_types;
+            if (mode == 1) k_gate_fine<1><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl, c->d_heavy, c->d_nheavy, c->fine_heavy, skip);
+            else k_gate_fine<2><<<grid, GR_SL * 32, 0, c->stream>>>(s, fl, c->d_heavy, c->d_nheavy, c->fine_heavy, skip);
+            if (c->fine_heavy) {        // the heavy particles themselves: a block each
+                int nheavy = 0;
+                for (int t = 0; t < c->ntypes && t < 32; t++) if ((c->fine_heavy >> t) & 1u) nheavy += (int)c->type_count[t];
+                if (mode == 1) k_gate_heavy<1><<<nheavy, 256, 0, c->stream>>>(s, fl, c->d_heavy, nheavy);
+                else k_gate_heavy<2><<<nheavy, 256, 0, c->stream>>>(s, fl, c->d_heavy, nheavy);
+                c->launches++;
+            }
+            if (c->heavy_types & ~c->fine_heavy) {      // types whose targets overflowed k_gate_fine's buffers: the cell gate
+                fl.heavy_types = c->heavy_types & ~c->fine_heavy;
+                if (mode == 1) k_gate_cells<1, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, nullptr);
+                else k_gate_cells<2, false, false><<<c->ncells, GT_WARPS * 32, 0, c->stream>>>(s, fl, nullptr);
+                c->launches++;
+            }
+            fl.heavy_types = 0;
+            mark(1);
+            if (mode == 1) k_cheap_flat<false, false, true><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<false, false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         } else if (!c->rods_only && rows_ok && c->ntypes <= GG_MAXT) {
             const dim3 grid((unsigned)(c->n / nrows / GR_T + 2), (unsigned)nrows);
             fl.heavy_types = c->heavy_types;
@@ -2622,6 +3088,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     ARG(!chains || (cm->chainprob <= 1.0 && c->nmol <= CH_MAXMT), "scgpu_sweep_checkerboard_chains: chainprob must be in [0, 1] and at most 32 molecule types");
     if (chains) for (int t = 0; t < c->nmol; t++) ARG(c->h_mol[t].mol_size <= CH_MAX, "scgpu_sweep_checkerboard_chains: a molecule is longer than MAXCHL = 20");
     ARG(mp->temper > 0 && mp->n_sub >= 1, "scgpu_sweep_checkerboard: temperature and n_sub must be positive");
+    ARG(mp->grid_k >= 0 && mp->grid_k <= 3, "scgpu_sweep_checkerboard: grid_k must be 0 (automatic), 1, 2 or 3");
     ARG(c->n > 0 && c->ntypes > 0 && c->ntypes <= 40, "scgpu_sweep_checkerboard: set topology (<= 40 types) and particles first");
     CK(cudaSetDevice(c->device));
     // random grid shift and colour order for this sweep: a pure function of (seed, sweep)
@@ -2645,6 +3112,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
             if (fits && (double)c->n / cells >= 2.0) { K = k; break; }
         }
     }
+    if (!chains && mp->grid_k >= 1 && mp->grid_k <= 3) K = mp->grid_k;       // the caller's choice (a grid that does not fit falls back to one cell per axis)
 #ifdef SW_FORCE_K
     if (!chains) K = SW_FORCE_K;
 #endif

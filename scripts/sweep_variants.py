@@ -87,7 +87,19 @@ def run_one(name):
     for e in engines:
         e.sync()
     dt8 = time.perf_counter() - t0
-    print(json.dumps({"variant": name, "sweeps_per_s_1": nsw / dt1, "sweeps_per_s_1_async": nsw / dt1a, "sweeps_per_s_8": R * nsw / dt8, "acceptance": acc / max(1, tot),
+    mp.grid_k = 1
+    for r, e in enumerate(engines):
+        e.sweep(mp, 777 + r, 100, stats=False)
+    for e in engines:
+        e.sync()
+    t0 = time.perf_counter()
+    for k in range(nsw):
+        for r, e in enumerate(engines):
+            e.sweep(mp, 777 + r, 101 + k, stats=False)
+    for e in engines:
+        e.sync()
+    dt8k1 = time.perf_counter() - t0
+    print(json.dumps({"variant": name, "sweeps_per_s_8_grid_k1": R * nsw / dt8k1, "sweeps_per_s_1": nsw / dt1, "sweeps_per_s_1_async": nsw / dt1a, "sweeps_per_s_8": R * nsw / dt8, "acceptance": acc / max(1, tot),
                       "trials_per_sweep": tot / nsw, "bookkeeping_rel_err": drift, "e0": e0, "e1": e1}), flush=True)
 
 

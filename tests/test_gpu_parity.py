@@ -244,9 +244,10 @@ def test_row_unit_gate_falls_back_when_the_layout_does_not_fit(engine):
 
 
 def test_row_unit_gate_splits_off_targets_with_very_many_partners(engine):
-    """spheres with ~20 partners and a few long rods with ~300: the general row-unit gate lists the spheres, notices that the rods
-    overflow its per-target buffers, and the launch is repeated with the rod type handed to the cell gate (one extra launch from
-    then on). Same results as the cell gate alone (counting pass) and the oracle, bit-reproducible."""
+    """spheres with ~20 partners and a few long rods with ~300: the rods' targets go to their own gate. With sub-cells (the host sees
+    that the spheres' reach fits a third of a cell) the split is known before the first launch; without them (SCGPU_NO_SUBCELLS) the
+    general row-unit gate notices that the rods overflow its per-target buffers and the launch is repeated with the rod type split
+    off. Either way: five launches once settled, same results as the cell gate alone (counting pass) and the oracle, bit-reproducible."""
     top, cfg = synth.small_case("rods_in_spheres")
     s = O.system_from_text(top, cfg)
     engine.load(s)
@@ -259,7 +260,7 @@ def test_row_unit_gate_splits_off_targets_with_very_many_partners(engine):
     l1 = engine.launches()
     ev2 = engine.one_to_all_everyone()
     l2 = engine.launches()
-    assert l2 - l1 == 5 and l1 - l0 > 5               # settled: rows gate + cell gate for the rods + cheap + patch + combine
+    assert l2 - l1 == 5 and l1 - l0 >= 5              # settled: light-type gate + gate of the rods + cheap + patch + combine
     assert np.array_equal(ev, ev2)
     assert close(ev, ev_cells, sc * 10), worst(ev, ev_cells)
     rods = np.where(s.type == s.type[-1])[0]

@@ -462,7 +462,7 @@ def test_cpsc_system_averages_three_temperatures(system):
     top = gold["top"][system]
     cfg = next(r["config"] for r in gold["runs"] if r["system"] == system and r["config"])
     temps = [0.1, 0.16, 0.22]
-    seeds = [5, 6]
+    seeds = [5, 6, 7, 8, 9, 10, 11, 12]       # as many as the reference: a run is a single warp (cpsc100) or a few (cpsc800), they overlap on the GPU
     chunk = 50
 
     def run(job):
@@ -489,10 +489,12 @@ def test_cpsc_system_averages_three_temperatures(system):
         rm = [_window_stats(r["sweep"], r["energy"], W // 3, W)[0] for r in ref]
         ref_mean, ref_se = float(np.mean(rm)), float(np.std(rm, ddof=1) / math.sqrt(len(rm)))
         mine = [r for r in results if r[0] == temper]
-        gm = [_window_stats(r[1], r[2], W // 3, W) for r in mine]
-        g_mean = float(np.mean([m for m, _ in gm]))
-        g_se = math.sqrt(sum(e * e for _, e in gm)) / len(gm)
-        tol = 4.0 * math.sqrt(ref_se ** 2 + g_se ** 2) + 0.005 * abs(ref_mean)
+        gm = [_window_stats(r[1], r[2], W // 3, W)[0] for r in mine]
+        g_mean = float(np.mean(gm))
+        # seed-to-seed scatter is the honest error bar here (near T = 0.16 the window means of the REFERENCE's own seeds differ by 4 %:
+        # the correlation time is a good part of the window); both sides are means over 8 seeds
+        sd = max(float(np.std(rm, ddof=1)), float(np.std(gm, ddof=1)))
+        tol = 4.0 * sd * math.sqrt(1.0 / len(rm) + 1.0 / len(gm)) + 0.005 * abs(ref_mean)
         assert abs(g_mean - ref_mean) <= tol, (system, temper, g_mean, ref_mean, tol)
         # acceptance ratios: the reference prints whole per cent of the full run (Statistics::print)
         ref_t = float(np.mean([r["acceptance"]["trans_acc_pct"] for r in ref])) / 100.0
