@@ -130,6 +130,12 @@ int scgpu_destroy(scgpu_ctx* ctx);
  * row-major by (type of first particle, type of second particle) */
 int scgpu_set_topology(scgpu_ctx* ctx, int ntypes, const scgpu_iaparam* table, double sqmaxcut, double maxcut,
                        int nmoltypes, const scgpu_molparam* mol);
+/* the [EXTER] wall potential of the topology (topo.exter, scOOP/structures/structures.h:259-275; Topo::genParamPairs / genTopoParams,
+ * structures/topo.cpp:120-130, 151-152): a structureless wall in the plane z = 0 of the periodic box. Once set, every energy entry point
+ * adds ExternalEnergyCalculator::extere2 (scOOP/mc/externalenergycalculator.cpp:5-105) of the particles it sums over, exactly where
+ * the reference's calculators add it (mc/totalenergycalculator.h:348-350, 377-378, 410-411, 435-449), and the batched sweeps include
+ * it in both energies of a trial. Call after scgpu_set_topology (the wall parameters derive from the table); exist = 0 removes it. */
+int scgpu_set_exter(scgpu_ctx* ctx, int exist, double thickness, double epsilon, double attraction);
 /* conf->pvec (scOOP/structures/Conf.h:305); also what initEM() / update(EMResize) need after a particle-count change.
  * type == moltype == NULL: n and every particle's type are those of the previous upload (only coordinates travel).
  * Page-locked host buffers are read by DMA directly; pageable ones are staged through the library's own pinned buffer. */

@@ -67,12 +67,9 @@ class TotalEGpu : public TotalE<pairEFce> {
             r.mol_size = q.molSize(); r.first = conf->pvec.first[m];
         }
         if (scgpu_set_topology(ctx, T, tab.data(), topo.sqmaxcut, topo.maxcut, M, mol.data())) fail("set_topology");
+        // the [EXTER] wall: the library derives topo.exter.interactions[] from the table and adds extere2 wherever the reference's calculators do
+        if (scgpu_set_exter(ctx, topo.exter.exist ? 1 : 0, topo.exter.thickness, topo.exter.epsilon, topo.exter.attraction)) fail("set_exter");
     }
-    // the wall potential ([EXTER]) stays the reference's own host code: O(N) per call, outside the pair path
-    double exter() { double e = 0; if (topo.exter.exist) for (unsigned i = 0; i < conf->pvec.size(); i++) e += this->exterE.extere2(&conf->pvec[i]); return e; }
-    double exter(int t) { return topo.exter.exist ? this->exterE.extere2(&conf->pvec[t]) : 0.0; }
-    double exter(Molecule& m) { double e = 0; if (topo.exter.exist) for (unsigned k = 0; k < m.size(); k++) e += this->exterE.extere2(&conf->pvec[m[k]]); return e; }
-
 public:
     // the non-virtual helpers of the base class that muVT / cluster / analysis code calls stay visible (and stay host code)
     using TotalE<pairEFce>::mol2others;
@@ -94,25 +91,25 @@ public:
     void update(int t) override { double s[30]; pack(conf->pvec[t], s); if (scgpu_update_particle(ctx, t, s)) fail("update"); }
     void update(Molecule m) override { for (unsigned k = 0; k < m.size(); k++) update(m[k]); }
 
-    double allToAll() override { double e; pushBox(); if (scgpu_all_to_all(ctx, &e, NULL)) fail("all_to_all"); return e + exter(); }
+    double allToAll() override { double e; pushBox(); if (scgpu_all_to_all(ctx, &e, NULL)) fail("all_to_all"); return e; }
     double allToAllTrial() override { return allToAll(); }      // the caller has already changed conf->geo.box
     // NB the reference restores conf->geo.box behind the calculator's back on a rejected volume move: the box is re-sent on every call
-    double oneToAll(int t) override { double e; pushBox(); if (scgpu_one_to_all(ctx, t, NULL, &e, NULL)) fail("one_to_all"); return e + exter(t); }
+    double oneToAll(int t) override { double e; pushBox(); if (scgpu_one_to_all(ctx, t, NULL, &e, NULL)) fail("one_to_all"); return e; }
     double oneToAllTrial(int t) override {                      // the caller has already mutated conf->pvec[t]
         double s[30], e;
         pack(conf->pvec[t], s);
         pushBox();
         if (scgpu_one_to_all(ctx, t, s, &e, NULL)) fail("one_to_all");
-        return e + exter(t);
+        return e;
     }
-    double mol2others(Molecule& m) override { double e; pushBox(); if (scgpu_mol_to_others(ctx, m[0], (int)m.size(), NULL, &e)) fail("mol2others"); return e + exter(m); }
+    double mol2others(Molecule& m) override { double e; pushBox(); if (scgpu_mol_to_others(ctx, m[0], (int)m.size(), NULL, &e)) fail("mol2others"); return e; }
     double mol2othersTrial(Molecule& m) override {
         std::vector<double> s(m.size() * 30);
         for (size_t k = 0; k < m.size(); k++) pack(conf->pvec[m[k]], &s[k * 30]);
         double e;
         pushBox();
         if (scgpu_mol_to_others(ctx, m[0], (int)m.size(), s.data(), &e)) fail("mol2others");
-        return e + exter(m);
+        return e;
     }
 };
 

@@ -27,6 +27,7 @@ struct CD {
     template <typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>
     CD(T x) : v((double)x) {}
     explicit operator int() const { return (int)v; }
+    explicit operator long long() const { return (long long)v; }
     explicit operator double() const { return v; }
     explicit operator bool() const { return v != 0.0; }
 };

@@ -45,6 +45,9 @@ def lib():
         if not os.path.exists(LIB_PATH):
             build()
         L = C.CDLL(LIB_PATH)
+        L.sco_extere2.restype = C.c_double
+        L.sco_extere2.argtypes = [_dp, C.c_int, _dp, C.c_double, C.c_double]
+        L.sco_exter_params.argtypes = [_dp, C.c_double, C.c_double, C.c_double, _dp]
         L.sco_pair_energy.restype = C.c_double
         L.sco_pair_energy.argtypes = [C.POINTER(_SysC), _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.POINTER(_ConC)]
         L.sco_one_to_all.restype = C.c_double
@@ -106,6 +109,39 @@ class System:
         s.box[0], s.box[1], s.box[2] = self.box
         s.sqmaxcut, s.maxcut = self.sqmaxcut, self.maxcut
         return s
+
+    # ---- [EXTER] wall potential (ExternalEnergyCalculator::extere2, scOOP/mc/externalenergycalculator.cpp:5-500)
+    exter = None          # (thickness, epsilon, attraction switch) of the topology's [EXTER] section, or None
+
+    def exter_setup(self):
+        """topo.exter as Topo::genParamPairs / genTopoParams build it (structures/topo.cpp:120-130, 151-152):
+        -> (params[ntypes, 8], exter_sqmaxcut)"""
+        T = self.ntypes
+        par = np.zeros((T, 8))
+        sq = 0.0
+        maxlength = 0.0
+        L = lib()
+        for i in range(T):
+            q = self.ia[i, i]
+            maxlength = max(maxlength, q[41])                 # len[0]
+            if int(q[0]) == 0:
+                continue
+            L.sco_exter_params(_d(np.ascontiguousarray(q)), float(self.exter[0]), float(self.exter[1]), float(self.exter[2]), _d(par[i]))
+            if par[i, 3] > sq:
+                sq = par[i, 3]
+        sq += maxlength
+        sq *= sq * 1.1
+        return par, sq
+
+    def extere2(self, i, state=None):
+        if self.exter is None:
+            return 0.0
+        if not hasattr(self, "_exter_cache"):
+            self._exter_cache = self.exter_setup()
+        par, sq = self._exter_cache
+        st = np.ascontiguousarray(self.state[i] if state is None else state, dtype=np.float64)
+        t = int(self.type[i])
+        return lib().sco_extere2(_d(st), int(self.ia[t, t, 0]), _d(par[t]), float(sq), float(self.box[2]))
 
     # ---- oracle calls
     def conlist(self, i):
@@ -231,6 +267,7 @@ def system_from_text(top_text, config_text, counts=None):
     ia = otopo.pack_tables(t, types)
     mol = otopo.pack_mols(t, first)
     s = System(state, types, moltypes, ia, mol, box, t.sqmaxcut, t.maxcut)
+    s.exter = t.exter
     s.init_particles()
     return s
 
@@ -241,6 +278,33 @@ def system_from_dir(path, counts=None):
     with open(os.path.join(path, "config.init")) as f:
         cfg = f.read()
     return system_from_text(top, cfg, counts)
+
+
+def load_exter_dump(path):
+    """oracle/ref_driver.cpp `exter` dump -> dict(exter=(exist, thickness, epsilon, attraction, sqmaxcut), params={type: [geotype, 8 values]},
+    ext=array of extere2 per particle, state[n,30], type[n])"""
+    op = gzip.open if path.endswith(".gz") else open
+    out = {"params": {}, "ext": {}, "parts": []}
+    with op(path, "rt") as f:
+        for line in f:
+            t = line.split()
+            if not t:
+                continue
+            if t[0] == "EXTP":
+                out["exter"] = (int(t[1]),) + tuple(_hx(x) for x in t[2:6])
+            elif t[0] == "EXTI":
+                out["params"][int(t[1])] = [int(t[2])] + [_hx(x) for x in t[3:11]]
+            elif t[0] == "EXT":
+                out["ext"][int(t[1])] = _hx(t[2])
+            elif t[0] == "P":
+                out["parts"].append((int(t[2]), [_hx(x) for x in t[4:34]]))
+            elif t[0] == "BOX":
+                out["box"] = np.array([_hx(x) for x in t[1:4]])
+    n = len(out["parts"])
+    out["type"] = np.array([p[0] for p in out["parts"]], dtype=np.int32)
+    out["state"] = np.array([p[1] for p in out["parts"]], dtype=np.float64).reshape(n, STATE)
+    out["ext"] = np.array([out["ext"][i] for i in range(n)])
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -193,6 +193,38 @@ static int do_dump(const char* outname, bool only0) {
     return 0;
 }
 
+// [EXTER] wall potential: the parameters the reference derives (topo.exter, structures/topo.cpp:120-130, 151-152) and
+// ExternalEnergyCalculator::extere2 of every particle of the configuration in the current directory
+static int do_exter(const char* outname) {
+    FileNames files(0);
+    Conf conf;
+    Sim* sim = nullptr;
+    load(conf, sim, files, 0, nullptr);
+    FILE* f = fopen(outname, "w");
+    int n = (int)conf.pvec.size();
+    fprintf(f, "N %d\n", n);
+    fprintf(f, "BOX %a %a %a\n", conf.geo.box.x, conf.geo.box.y, conf.geo.box.z);
+    fprintf(f, "EXTP %d %a %a %a %a\n", (int)topo.exter.exist, topo.exter.thickness, topo.exter.epsilon, topo.exter.attraction, topo.exter.sqmaxcut);
+    bool used[MAXT] = {false};
+    for (int i = 0; i < n; i++) used[conf.pvec[i].type] = true;
+    for (int t = 0; t < MAXT; t++) if (used[t]) {
+        const Ia_param& p = topo.exter.interactions[t];
+        fprintf(f, "EXTI %d %d %a %a %a %a %a %a %a %a\n", t, p.geotype[0], p.sigma, p.epsilon, p.rcutwca, p.rcut, p.pdis, p.pswitch, p.len[0], p.half_len[0]);
+    }
+    ExternalEnergyCalculator ex(&conf.geo.box);
+    for (int i = 0; i < n; i++) {
+        Particle& p = conf.pvec[i];
+        fprintf(f, "P %d %d %d", i, p.type, p.molType);
+        pv(f, p.pos); pv(f, p.dir); pv(f, p.patchdir[0]); pv(f, p.patchdir[1]);
+        for (int k = 0; k < 4; k++) pv(f, p.patchsides[k]);
+        pv(f, p.chdir[0]); pv(f, p.chdir[1]);
+        fprintf(f, "\n");
+        fprintf(f, "EXT %d %a\n", i, ex.extere2(&conf.pvec[i]));
+    }
+    fclose(f);
+    return 0;
+}
+
 // Timing arm: the reference's own TotalEFull<PairE> (the compile-time alternative calculator,
 // totalenergycalculator.h:525-619; the default TotalEMatrix needs 2 x N^2/2 doubles and cannot hold 65k particles)
 // looping over the reference's neighbour lists (conf.neighborList, filled here for the sampled targets with the
@@ -326,6 +358,7 @@ int main(int argc, char** argv) {
 #endif
     if (argc >= 2 && !strcmp(argv[1], "dump")) return do_dump(argc > 2 ? argv[2] : "ref_dump.txt", false);
     if (argc >= 2 && !strcmp(argv[1], "dump0")) return do_dump(argc > 2 ? argv[2] : "ref_dump.txt", true);
+    if (argc >= 2 && !strcmp(argv[1], "exter")) return do_exter(argc > 2 ? argv[2] : "ref_exter.txt");
     if (argc >= 2 && !strcmp(argv[1], "time")) return do_time(argc, argv);
     fprintf(stderr, "usage: sc_ref_driver dump|dump0 [out] | time <ntargets> <reps> [count_per_moltype ...]\n");
     return 2;

@@ -700,6 +700,330 @@ static double mix_sp_sc_e(const sco_system* s, int kind, double dist, vec3 r_cm,
     return abE + repenergy + atrenergy;
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * External wall potential ([EXTER]): ExternalEnergyCalculator::extere2 and its helpers, scOOP/mc/externalenergycalculator.cpp:5-500
+ * (externalenergycalculator.h:21-115); parameters topo.exter.interactions[], scOOP/structures/topo.cpp:120-130, 151-152.
+ * The reference keeps intermediate values in members of the calculator object; they are the fields of wall_state here.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { double sigma, epsilon, rcutwca, rcut, pdis, pswitch, len0, half_len0; int geotype, pad; } wall_param;
+typedef struct { double dist, orient, rcmz, interendz; int positive, orientin; vec3 project; vec3 dir; } wall_state;
+#define false 0
+#define true 1
+static vec3 wall_v3zero(void) { vec3 v; v.x = 0; v.y = 0; v.z = 0; return v; }
+#define wall_project_in_z(v, pd, out) wall_project_in_z_((v), (pd), &(out))
+static void wall_project_in_z_(vec3 vec1, vec3 projectdir, vec3* projection) {
+    projection->x = vec1.x - vec1.z * projectdir.x / projectdir.z;
+    projection->y = vec1.y - vec1.z * projectdir.y / projectdir.z;
+    projection->z = 0;
+}
+
+/* ExternalEnergyCalculator::exter2ClosestDist (:107-145) */
+static void wall_closest_dist(wall_state* w, const wall_param* param) {
+    if (w->rcmz < 0) { w->dist = -(w->rcmz); w->positive = false; w->interendz = -1.0; w->project.z = 1.0; }
+    else { w->dist = (w->rcmz); w->positive = true; w->interendz = 1.0; w->project.z = -1.0; }
+    if (param->geotype < SCO_SPN) {        /* psc closest is always the end closer to the wall */
+        if (w->dir.z > 0) {
+            if (w->positive) { w->orientin = false; w->orient = -1.0; w->dist = w->rcmz - w->dir.z * param->half_len0; }
+            else { w->orientin = true; w->orient = 1.0; w->dist = -(w->rcmz + w->dir.z * param->half_len0); }
+        } else {
+            if (w->positive) { w->orientin = true; w->orient = 1.0; w->dist = w->rcmz + w->dir.z * param->half_len0; }
+            else { w->orientin = false; w->orient = -1.0; w->dist = -(w->rcmz - w->dir.z * param->half_len0); }
+        }
+    }
+}
+
+/* ExternalEnergyCalculator::pscWall (:263-458) */
+#define pbeg (*pbeg_)
+#define pend (*pend_)
+static int wall_psc_(const wall_state* w, vec3* pbeg_, vec3* pend_, vec3 projectdir, vec3 partdir, double cutdist,
+                                        vec3 partbeg, vec3 partend) {
+    vec3 vec1;
+    double k, x1, x2, y1, y2, a, b, c, e, d;
+    if (((w->positive) && (projectdir.z > 0)) || ((!(w->positive)) && (projectdir.z < 0))) return 0;
+    if (fabs(partbeg.z) > cutdist) return 0;
+    x2 = 0.0;
+    y2 = 0.0;
+    if (fabs(partdir.z) > 1.0e-8) { wall_project_in_z(partbeg, partdir, pbeg); a = 0; }
+    else {
+        vec1.x = 2.0 * partbeg.x - partend.x;
+        vec1.y = 2.0 * partbeg.y - partend.y;
+        vec1.z = 2.0 * partbeg.z - partend.z;
+        wall_project_in_z(vec1, projectdir, pbeg);
+        a = 1;
+    }
+    if (partdir.z != 0) b = fabs(partbeg.z / partdir.z);
+    else b = cutdist + 1.0;
+    if ((b > cutdist) || (a == 1)) {
+        if (fabs(projectdir.z) > 1.0e-8) wall_project_in_z(partbeg, projectdir, pend);
+        else { pend.x = pbeg.x + projectdir.x; pend.y = pbeg.y + projectdir.y; }
+        if (pend.y == pbeg.y) {
+            y1 = pbeg.y;
+            y2 = pbeg.y;
+            a = sqrt(cutdist * cutdist - partbeg.z * partbeg.z - (pbeg.y - partbeg.y) * (pbeg.y - partbeg.y));
+            x1 = partbeg.x + a;
+            x2 = partbeg.x - a;
+            if (pend.x > pbeg.x) { pbeg.x = x2; x2 = x1; }
+            else pbeg.x = x1;
+            pbeg.y = y1;
+        } else {
+            k = (pend.x - pbeg.x) / (pend.y - pbeg.y);
+            a = k * k + 1;
+            b = partbeg.y + k * k * pbeg.y - k * pbeg.x + k * partbeg.x;
+            c = partbeg.y * partbeg.y + partbeg.z * partbeg.z - cutdist * cutdist + (k * pbeg.y - pbeg.x + partbeg.x) * (k * pbeg.y - pbeg.x + partbeg.x);
+            e = b * b - a * c;
+            if (e < 0) return 0;
+            d = sqrt(e);
+            if (pend.y > pbeg.y) { y1 = (b - d) / a; y2 = (b + d) / a; }
+            else { y1 = (b + d) / a; y2 = (b - d) / a; }
+            x1 = k * (y1 - pbeg.y) + pbeg.x;
+            x2 = k * (y2 - pbeg.y) + pbeg.x;
+            pbeg.x = x1;
+            pbeg.y = y1;
+            pbeg.z = 0.0;
+        }
+    }
+    /* end point */
+    a = -cutdist * projectdir.z;      /* z coordinate of the point where the projection is at the cut distance */
+    if (((partend.z < a) && (w->positive)) || ((a < partend.z) && (!(w->positive)))) {
+        if (projectdir.z != 0) wall_project_in_z(partend, projectdir, pend);
+        else { pend.x = pbeg.x + projectdir.x; pend.y = pbeg.y + projectdir.y; }
+        if (pend.y == pbeg.y) {
+            y1 = pend.y;
+            y2 = pend.y;
+            a = sqrt(cutdist * cutdist - partend.z * partend.z - (pend.y - partend.y) * (pend.y - partend.y));
+            x1 = partend.x + a;
+            x2 = partend.x - a;
+            if (pbeg.x > pend.x) pend.x = x2;
+            else pend.x = x1;
+            pend.y = y1;
+        } else {
+            k = (pbeg.x - pend.x) / (pbeg.y - pend.y);
+            a = k * k + 1;
+            b = partend.y + k * k * pend.y - k * pend.x + k * partend.x;
+            c = partend.y * partend.y + partend.z * partend.z - cutdist * cutdist + (k * pend.y - pend.x + partend.x) * (k * pend.y - pend.x + partend.x);
+            e = b * b - a * c;
+            if (e < 0) return 0;
+            d = sqrt(e);
+            if (pbeg.y > pend.y) { y1 = (b - d) / a; y2 = (b + d) / a; }
+            else { y1 = (b + d) / a; y2 = (b - d) / a; }
+            x1 = k * (y1 - pend.y) + pend.x;
+            x2 = k * (y2 - pend.y) + pend.x;
+            pend.x = x1;
+            pend.y = y1;
+            pend.z = 0.0;
+        }
+    } else {
+        if (((partbeg.z < a) && (w->positive)) || ((a < partbeg.z) && (!(w->positive)))) {
+            /* the end is at the cutoff, going through the cylindrical part */
+            b = (a - partbeg.z) / partdir.z;
+            vec1.x = partbeg.x + b * partdir.x;
+            vec1.y = partbeg.y + b * partdir.y;
+            vec1.z = a;
+            wall_project_in_z(vec1, projectdir, pend);
+        } else {
+            /* the projected end is within the same sphere as the beginning: no contribution from the cylinder */
+            if (x2 == 0.0) {
+                if (projectdir.z != 0) wall_project_in_z(partbeg, projectdir, pend);
+                else { pend.x = pbeg.x + projectdir.x; pend.y = pbeg.y + projectdir.y; }
+                if (pend.y == pbeg.y) {
+                    y1 = pbeg.y;
+                    y2 = pbeg.y;
+                    a = sqrt(cutdist * cutdist - partbeg.z * partbeg.z - (pbeg.y - partbeg.y) * (pbeg.y - partbeg.y));
+                    x1 = partbeg.x + a;
+                    x2 = partbeg.x - a;
+                    if (pend.x > pbeg.x) pend.x = x1;
+                    else pend.x = x2;
+                    pend.y = y1;
+                } else {
+                    k = (pend.x - pbeg.x) / (pend.y - pbeg.y);
+                    a = k * k + 1;
+                    b = partbeg.y + k * k * pbeg.y - k * pbeg.x + k * partbeg.x;
+                    c = partbeg.y * partbeg.y + partbeg.z * partbeg.z - cutdist * cutdist + (k * pbeg.y - pbeg.x + partbeg.x) * (k * pbeg.y - pbeg.x + partbeg.x);
+                    e = b * b - a * c;
+                    if (e < 0) return 0;
+                    d = sqrt(e);
+                    if (pend.y > pbeg.y) { y1 = (b - d) / a; y2 = (b + d) / a; }
+                    else { y1 = (b + d) / a; y2 = (b - d) / a; }
+                    x1 = k * (y1 - pbeg.y) + pbeg.x;
+                    x2 = k * (y2 - pbeg.y) + pbeg.x;
+                    pend.x = x1;
+                    pend.y = y1;
+                    pend.z = 0.0;
+                }
+            } else {
+                pend.x = x2;
+                pend.y = y2;
+                pend.z = 0.0;
+            }
+            return 2;
+        }
+    }
+    return 1;
+}
+
+/* ExternalEnergyCalculator::cpscWall (:460-500) */
+static int wall_cpsc_(const wall_state* w, vec3* pbeg_, vec3* pend_, vec3 projectdir, vec3 partdir, double halfl,
+                                         double cutdist, vec3 partbeg, vec3 partend) {
+    vec3 vec1;
+    double a;
+    if (((w->positive) && (projectdir.z >= 0)) || ((!(w->positive)) && (projectdir.z <= 0))) return 0;
+    vec1.x = partbeg.x;
+    vec1.y = partbeg.y;
+    vec1.z = partbeg.z;
+    if (-vec1.z / projectdir.z < cutdist) wall_project_in_z(vec1, projectdir, pbeg);
+    else return 0;
+    if (-partend.z / projectdir.z < cutdist) vec1.z = partend.z;
+    else vec1.z = -cutdist * projectdir.z;
+    if (partdir.z != 0.0) a = (vec1.z - (w->rcmz)) / partdir.z;
+    else { if (w->orientin) a = -halfl; else a = halfl; }
+    vec1.x = partdir.x * a;
+    vec1.y = partdir.y * a;
+    wall_project_in_z(vec1, projectdir, pend);
+    return 1;
+}
+
+#undef pbeg
+#undef pend
+#define wall_psc(w, pb, pe, a, b, c, d, e) wall_psc_((w), &(pb), &(pe), (a), (b), (c), (d), (e))
+#define wall_cpsc(w, pb, pe, a, b, c, d, e, f) wall_cpsc_((w), &(pb), &(pe), (a), (b), (c), (d), (e), (f))
+/* ExternalEnergyCalculator::exter2Atre (:147-261) */
+static double wall_atre(wall_state* w, const wall_param* param, double* ndist, vec3 patchdir, double halfl) {
+    vec3 pbeg, pend;
+    double a, length1, length2, f0, f1;
+    vec3 cm1, cm2;
+    int line;
+    vec3 partbeg, partend;
+    vec3 inters;
+    double atrenergy = 0.0;
+    pbeg = wall_v3zero(); pend = wall_v3zero();
+    if ((param->geotype < SCO_SPN) && (param->geotype > SCO_SCA)) {
+        a = ((w->orientin ? 1.0 : 0.0) - 0.5) * 2;
+        partbeg.x = a * w->dir.x * halfl;
+        partbeg.y = a * w->dir.y * halfl;
+        partbeg.z = w->rcmz + a * w->dir.z * halfl;
+        partend.x = -a * w->dir.x * halfl;
+        partend.y = -a * w->dir.y * halfl;
+        partend.z = w->rcmz - a * w->dir.z * halfl;
+        if ((param->rcut - w->dist) / fabs(w->dir.z) < 2.0 * halfl) w->interendz *= param->rcut;
+        else w->interendz = partend.z;
+        if (w->positive) cm1.z = ((w->interendz + w->dist) * 0.5);
+        else cm1.z = ((w->interendz + -w->dist) * 0.5);
+        if (w->dir.z != 0.0) {
+            a = (w->interendz - cm1.z) / w->dir.z;
+            length1 = -w->orient * 2.0 * a;
+            a = a + w->orient * halfl;
+        } else {
+            a = 0.0;
+            length1 = 2.0 * halfl;
+        }
+        cm1.x = w->dir.x * a;
+        cm1.y = w->dir.y * a;
+        if ((param->geotype == SCO_CPSC) || (param->geotype == SCO_CHCPSC)) {
+            if (((w->interendz >= w->dist) && (w->positive)) || ((w->interendz <= -w->dist) && (!(w->positive))))
+                line = wall_cpsc(w, pbeg, pend, w->project, w->dir, param->half_len0, param->rcut, partbeg, partend);
+            else line = 0;
+        } else {
+            line = wall_psc(w, pbeg, pend, w->project, w->dir, param->rcut, partbeg, partend);
+        }
+        if (line > 0) {
+            cm2.x = ((pbeg.x + pend.x) * 0.5);
+            cm2.y = ((pbeg.y + pend.y) * 0.5);
+            cm2.z = 0.0;
+            length2 = sqrt((pend.x - pbeg.x) * (pend.x - pbeg.x) + (pend.y - pbeg.y) * (pend.y - pbeg.y));
+            inters.x = cm2.x - cm1.x;
+            inters.y = cm2.y - cm1.y;
+            inters.z = cm2.z - cm1.z;
+            *ndist = sqrt(inters.x * inters.x + inters.y * inters.y + inters.z * inters.z);
+            if (*ndist < param->pdis) atrenergy = -param->epsilon;
+            else {
+                atrenergy = cos(PIH * (*ndist - param->pdis) / param->pswitch);
+                atrenergy *= -atrenergy * param->epsilon;
+            }
+            f0 = (length1 + length2) * 0.5;
+            f1 = fabs(patchdir.z);
+            atrenergy *= f0 * f1;
+        } else atrenergy = 0.0;
+    } else {
+        if (*ndist < param->pdis) atrenergy = -param->epsilon;
+        else {
+            atrenergy = cos(PIH * (*ndist - param->pdis) / param->pswitch);
+            atrenergy *= -atrenergy * param->epsilon;
+        }
+        atrenergy *= (param->rcut * param->rcut - (*ndist) * (*ndist)) / (param->sigma * param->sigma);
+    }
+    return atrenergy;
+}
+
+/* ExternalEnergyCalculator::extere2 (:5-105). pos_z: box-fractional z; dir, patchdir[2], chdir[2]: the particle's vectors. */
+static double wall_energy(const wall_param* param, double exter_sqmaxcut, double box_z, double pos_z, vec3 dir,
+                                              vec3 patchdir0, vec3 patchdir1, vec3 chdir0, vec3 chdir1) {
+    double repenergy = 0.0, atrenergy = 0.0;
+    double ndist, halfl;
+    wall_state w_;
+    wall_state* w = &w_;
+    if (pos_z < 0) w->rcmz = box_z * (pos_z - (double)((long long)(pos_z - 0.5)));
+    else w->rcmz = box_z * (pos_z - (double)((long long)(pos_z + 0.5)));
+    w->project = wall_v3zero();
+    if (w->rcmz < 0) { w->dist = -w->rcmz; w->positive = false; w->interendz = -1.0; w->project.z = 1.0; }
+    else { w->dist = w->rcmz; w->positive = true; w->interendz = 1.0; w->project.z = -1.0; }
+    if (w->rcmz * w->rcmz > exter_sqmaxcut) return 0.0;
+    halfl = 0.5 * param->len0;
+    ndist = w->dist;
+    w->orientin = true;
+    w->orient = 0.0;
+    w->dir = dir;
+    wall_closest_dist(w, param);
+    if (w->dist > param->rcutwca) repenergy = 0.0;
+    else {
+        const double en6 = pow((param->sigma / w->dist), 6);
+        repenergy = 4 * en6 * (en6 - 1) + 1.0;
+    }
+    if ((param->geotype == SCO_CHCPSC) || (param->geotype == SCO_CHPSC)) {
+        w->dir = chdir0;
+        wall_closest_dist(w, param);
+    }
+    if ((w->dist > param->rcut) || (param->epsilon == 0.0) || ((patchdir0.z > 0) && (w->positive)) || ((patchdir0.z < 0) && (!w->positive))) atrenergy = 0.0;
+    else atrenergy = wall_atre(w, param, &ndist, patchdir0, halfl);
+    if ((param->geotype == SCO_TCPSC) || (param->geotype == SCO_TPSC) || (param->geotype == SCO_TCHCPSC) || (param->geotype == SCO_TCHPSC)) {
+        if ((param->geotype == SCO_TCHCPSC) || (param->geotype == SCO_TCHPSC)) {
+            w->dir = chdir1;
+            wall_closest_dist(w, param);
+        }
+        wall_closest_dist(w, param);
+        if ((w->dist > param->rcut) || (param->epsilon == 0.0) || ((patchdir1.z > 0) && (w->positive)) || ((patchdir1.z < 0) && (!(w->positive)))) atrenergy += 0.0;
+        else atrenergy += wall_atre(w, param, &ndist, patchdir1, halfl);
+    }
+    return repenergy + atrenergy;
+}
+
+
+#undef wall_psc
+#undef wall_cpsc
+#undef wall_project_in_z
+#undef false
+#undef true
+
+/* topo.exter.interactions[type] out of the type's own table entry (structures/topo.cpp:120-130); out8 = sigma, epsilon, rcutwca, rcut,
+ * pdis, pswitch, len0, half_len0 */
+void sco_exter_params(const sco_iaparam* self, double thickness, double epsilon, double attraction, double* out8) {
+    double sigma = (self->sigma + thickness) * 0.5;
+    double rcutwca = (sigma) * pow(2.0, 1.0 / 6.0);
+    double eps = sqrt(self->epsilon * epsilon);
+    double pswitch = (self->pswitch + attraction) * 0.5;
+    double pdis = (self->pdis - self->rcutwca + 0.0) * 0.5 + rcutwca;
+    out8[0] = sigma; out8[1] = eps; out8[2] = rcutwca; out8[3] = pswitch + pdis; out8[4] = pdis; out8[5] = pswitch;
+    out8[6] = self->len[0]; out8[7] = self->half_len[0];
+}
+
+/* extere2 of one particle (30-double state record); p8 as above */
+double sco_extere2(const double* st, int geotype, const double* p8, double exter_sqmaxcut, double box_z) {
+    wall_param pr;
+    pr.sigma = p8[0]; pr.epsilon = p8[1]; pr.rcutwca = p8[2]; pr.rcut = p8[3]; pr.pdis = p8[4]; pr.pswitch = p8[5];
+    pr.len0 = p8[6]; pr.half_len0 = p8[7]; pr.geotype = geotype; pr.pad = 0;
+    return wall_energy(&pr, exter_sqmaxcut, box_z, st[2], ld(st + 3), ld(st + 6), ld(st + 9), ld(st + 24), ld(st + 27));
+}
+
 /* Hooks of the op-counting build (oracle/flopcount.cpp); they expand to nothing in the oracle proper. */
 #ifndef SCO_COUNT_ENTER
 #define SCO_COUNT_ENTER()

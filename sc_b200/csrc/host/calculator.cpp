@@ -19,6 +19,7 @@ void TotalEGpu::pushBox() { check(scgpu_set_box(ctx, conf->box.data()), "scgpu_s
 void TotalEGpu::initEM() {
     check(scgpu_set_topology(ctx, conf->ntypes, conf->iaTable.data(), conf->topo.sqmaxcut, conf->topo.maxcut,
                              (int)conf->molTable.size(), conf->molTable.data()), "scgpu_set_topology");
+    check(scgpu_set_exter(ctx, conf->topo.exterExist ? 1 : 0, conf->topo.exter[0], conf->topo.exter[1], conf->topo.exter[2]), "scgpu_set_exter");
     pushBox();
     check(scgpu_set_particles(ctx, conf->n, conf->state.data(), conf->type.data(), conf->moltype.data()), "scgpu_set_particles");
     check(scgpu_build_cells(ctx), "scgpu_build_cells");

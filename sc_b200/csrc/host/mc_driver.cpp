@@ -112,9 +112,9 @@ public:
     SequentialMC(System* c, TotalEGpu* calc_, const Options& o)
         : conf(c), calc(calc_), ran2((long)o.get("seed")) {
         nequil = (long)o.get("nequil"); adjust = (long)o.get("adjust");
-        if (o.get("wlm") != 0 || o.get("nGrandCanon") != 0 || o.get("nClustMove") != 0 || o.get("switchprob") != 0 || o.get("nrepchange") != 0)
-            throw Error("sequential driver: Wang-Landau / muVT / cluster / switch / replica moves are outside the mirrored callers");
-        if (conf->topo.exterExist) throw Error("sequential driver: the [EXTER] wall potential is outside the hot path");
+        // (nrepchange is not an obstacle: without MPI the reference's replicaExchangeMove is an empty function, movecreator.cpp:552-795)
+        if (o.get("wlm") != 0 || o.get("nGrandCanon") != 0 || o.get("nClustMove") != 0 || o.get("switchprob") != 0)
+            throw Error("sequential driver: Wang-Landau / muVT / cluster / switch moves are outside the mirrored callers");
         temper = o.get("temper"); press = o.get("press"); ptype = (int)o.get("ptype");
         for (int i = 0; i < 40; i++) {                          // sim.h:358-374
             trans[i].mx = 2.0 * o.get("transmx");

@@ -44,6 +44,12 @@ int schost_export(void* sys, double* state30, int* type, int* moltype, double* i
     return 0;
 }
 
+// [EXTER] section: {exists, thickness, epsilon, attraction switch}
+int schost_exter(void* sys, double* out4) {
+    System* s = (System*)sys;
+    out4[0] = s->topo.exterExist ? 1.0 : 0.0; out4[1] = s->topo.exter[0]; out4[2] = s->topo.exter[1]; out4[3] = s->topo.exter[2];
+    return 0;
+}
 int schost_set_state(void* sys, int idx, const double* state30) {
     System* s = (System*)sys;
     if (idx < 0 || idx >= s->n) { g_err = "schost_set_state: index out of range"; return -1; }

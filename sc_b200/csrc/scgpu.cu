@@ -9,7 +9,7 @@
 // the FP64 pipe, the cell build by HBM/L2 bandwidth and launch latency.
 //
 // Kernels:
-//   k_cell_count / k_cell_scan / k_cell_fill / k_cell_place   counting sort by cell, stable (row C1)
+//   k_cell_count (+ scan by its last block) / k_cell_fill / k_cell_place   counting sort by cell, stable (row C1)
 //   k_gate_cheap<MODE> / k_patch / k_combine                    one-to-all energies in three dense phases (rows A1-A11, A13)
 //   k_reduce_fixed                                             fixed-order total for allToAll
 //   k_overlap                                                  warp-vote early exit (row A12)
@@ -26,6 +26,7 @@
 #include <algorithm>
 
 #include "pair_energy.cuh"
+#include "wall.cuh"
 
 using namespace scg;
 
@@ -75,6 +76,8 @@ struct DevSys {
     double box[3];
     double shift[3];     // fractional grid shift used for the current cell assignment (0 for the energy API)
     double sqmaxcut;
+    const WallParam* wall;   // [EXTER] wall: per particle type, or nullptr when the topology has none
+    double exter_sqmaxcut;
 };
 
 __device__ __forceinline__ double pack_w(int type, int moltype, int orig) { return __hiloint2double(type | (moltype << 8), orig); }
@@ -126,14 +129,29 @@ static const int h_api_of[30] = {3, 4, 5, 6, 7, 8, 12, 13, 14, 15, 16, 17, 9, 10
 // ------------------------------------------------------------------------------------------------
 // cell list: counting sort by cell, stable in the original index
 // ------------------------------------------------------------------------------------------------
-__global__ void k_cell_count(DevSys s, int* __restrict__ cell_of, int* __restrict__ fine_of, int* __restrict__ counts) {
+__device__ void cell_scan_block(int ncells, int* __restrict__ counts, int* __restrict__ cell_start, int* __restrict__ cursor);
+// one thread per particle: cell (and sub-cell) index, histogram. The block that finishes last turns the histogram into the exclusive
+// scan (one launch instead of memset + count + scan; ticket: one unsigned the last block leaves at zero again).
+__global__ void __launch_bounds__(1024)
+k_cell_count(DevSys s, int nsort, int* __restrict__ cell_of, int* __restrict__ fine_of, int* __restrict__ counts,
+             int* __restrict__ sort_start, int* __restrict__ cursor, unsigned* __restrict__ ticket) {
+    __shared__ bool last;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.n) return;
-    int c;
-    const int f = s.sub > 1 ? fine_index(s.api + (size_t)i * 30, s.shift, s.nc, s.sub, &c) : (c = cell_index(s.api + (size_t)i * 30, s.shift, s.nc));
-    cell_of[i] = c;
-    if (s.sub > 1) fine_of[i] = f;
-    atomicAdd(&counts[f], 1);
+    if (i < s.n) {
+        int c;
+        const int f = s.sub > 1 ? fine_index(s.api + (size_t)i * 30, s.shift, s.nc, s.sub, &c) : (c = cell_index(s.api + (size_t)i * 30, s.shift, s.nc));
+        cell_of[i] = c;
+        if (s.sub > 1) fine_of[i] = f;
+        atomicAdd(&counts[f], 1);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    cell_scan_block(nsort, counts, sort_start, cursor);
+    if (threadIdx.x == 0) *ticket = 0u;
 }
 // sub > 1: the start of every (coarse) cell out of the sub-cell starts
 __global__ void k_coarse_start(int ncells, int s3, const int* __restrict__ fine_start, int* __restrict__ cell_start) {
@@ -143,7 +161,7 @@ __global__ void k_coarse_start(int ncells, int s3, const int* __restrict__ fine_
 }
 
 // single-block exclusive scan of counts[0..ncells) -> cell_start[0..ncells]; cursor := cell_start
-__global__ void k_cell_scan(int ncells, const int* __restrict__ counts, int* __restrict__ cell_start, int* __restrict__ cursor) {
+__device__ void cell_scan_block(int ncells, int* __restrict__ counts, int* __restrict__ cell_start, int* __restrict__ cursor) {
     __shared__ int warp_tot[32];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -151,7 +169,7 @@ __global__ void k_cell_scan(int ncells, const int* __restrict__ counts, int* __r
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int base = 0; base < ncells; base += blockDim.x) {
         int i = base + threadIdx.x;
-        int v = (i < ncells) ? counts[i] : 0;
+        int v = (i < ncells) ? __ldcg(counts + i) : 0;        // written by other blocks' atomics: read at L2
         int x = v;
         for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
         if (lane == 31) warp_tot[wid] = x;
@@ -169,10 +187,11 @@ __global__ void k_cell_scan(int ncells, const int* __restrict__ counts, int* __r
         __syncthreads();
     }
     if (threadIdx.x == 0) cell_start[ncells] = carry;
-    // [ncells + 1]: number of non-empty cells (the sweep kernel spreads its trials over them)
+    // [ncells + 1]: number of non-empty cells (the sweep kernel spreads its trials over them); the counts are consumed here and left at
+    // zero for the next build (no memset launch)
     __syncthreads();
     int ne = 0;
-    for (int i = threadIdx.x; i < ncells; i += blockDim.x) ne += counts[i] > 0;
+    for (int i = threadIdx.x; i < ncells; i += blockDim.x) { ne += __ldcg(counts + i) > 0; counts[i] = 0; }
     ne = __reduce_add_sync(0xffffffffu, ne);
     if (lane == 0) warp_tot[wid] = ne;
     __syncthreads();
@@ -1857,62 +1876,99 @@ __global__ void __launch_bounds__(PF_THREADS, PATCH_MINB)
 k_patch_flat(DevSys s, FlatList fl, int any_two_patch, int mirror, const __grid_constant__ scgpu_iaparam ia1) {
     const scgpu_iaparam* ia_one = ONE ? &ia1 : nullptr;
     if (*fl.overflow) return;
-    __shared__ PatchItem sh_a[PF_THREADS], sh_b[PF_THREADS];
-    __shared__ int sh_warp[PF_THREADS / 32];
-    __shared__ int sh_n1, sh_n2;
+    // survivors of a phase are appended with one shared-memory atomic per warp: their order inside the block's list is arbitrary, but
+    // nothing depends on it (every item is a pair of its own, its result goes to that pair's slot) -- ONE barrier per phase instead
+    // of the three a ranked compaction needs. An item carries the slots and the separation vector, so that the later phases do not
+    // re-load the pair, both positions and re-image them.
+    struct Item { int p, si, sj, pad; double rx, ry, rz, T1, T2, S1, S2; };
+    __shared__ Item sh_a[PF_THREADS], sh_b[PF_THREADS];
+    __shared__ int sh_n[2];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int total = *fl.ptotal;
     const int ncombo = any_two_patch ? 4 : 1;
+    auto append = [&](Item* list, int* counter, bool keep, const Item& it) {
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(counter, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) list[base + __popc(m & lt_mask)] = it;
+    };
     for (int base = blockIdx.x * PF_THREADS; base < total; base += gridDim.x * PF_THREADS) {       // block-uniform trip count
         const int q = base + threadIdx.x;
         const int p = q < total ? fl.plist[q] : -1;
+        int2 pr = make_int2(0, 0);
+        v3 r_cm = mk(0.0, 0.0, 0.0);
+        int tbits = 0;
+        if (p >= 0) {
+            pr = fl.pair[p];
+            const double4 pi = ldg256(s.posw + pr.x), pj = ldg256(s.posw + pr.y);
+            r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
+            tbits = w_type(pi.w) * s.ntypes + w_type(pj.w);
+        }
         for (int combo = 0; combo < ncombo; combo++) {
+            const int pn1 = combo & 1, pn2 = combo >> 1;
+            if (threadIdx.x < 2) sh_n[threadIdx.x] = 0;
+            __syncthreads();
             // ---- phase 1: rod 2 against the patch of rod 1 (T1, T2)
-            bool keep = false;
-            double a = 0.0, b = 0.0;
-            if (p >= 0) {
-                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
-                patch_setup(s, fl, p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
-                if (ok) {
-                    const int pn1 = combo & 1;
-                    int n = fp ? patch_intersect<false>(P1.dir, P2.dir, P1, r_cm, a, b, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1])
-                               : patch_intersect<true>(P1.dir, P2.dir, P1, r_cm, a, b, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1]);
-                    keep = n >= 2;
+            {
+                bool keep = false;
+                Item it;
+                it.p = p; it.si = pr.x; it.sj = pr.y; it.pad = tbits; it.rx = r_cm.x; it.ry = r_cm.y; it.rz = r_cm.z; it.T1 = it.T2 = it.S1 = it.S2 = 0.0;
+                if (p >= 0) {
+                    const scgpu_iaparam* ia = ia_one ? ia_one : &s.ia[tbits];
+                    const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
+                    const bool firstT = is_two_patch(g0), secondT = is_two_patch(g1);
+                    const bool ok = (combo == 0) || (combo == 1 && firstT) || (combo == 2 && secondT) || (combo == 3 && firstT && secondT);
+                    if (ok) {
+                        const bool first_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && is_psc_family(g0));
+                        PatchArgs P1, P2;
+                        load_patch_args(s.rec + (size_t)pr.x * REC, pn1, is_chiral(g0), P1);
+                        load_patch_args(s.rec + (size_t)pr.y * REC, pn2, is_chiral(g1), P2);
+                        const int nn = first_psc ? patch_intersect<false>(P1.dir, P2.dir, P1, r_cm, it.T1, it.T2, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1])
+                                                 : patch_intersect<true>(P1.dir, P2.dir, P1, r_cm, it.T1, it.T2, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1]);
+                        keep = nn >= 2;
+                    }
                 }
+                append(sh_a, &sh_n[0], keep, it);
             }
-            int r = block_rank(keep, sh_warp, &sh_n1);
-            if (keep) { sh_a[r].p = p; sh_a[r].T1 = a; sh_a[r].T2 = b; }
             __syncthreads();
-            const int n1 = sh_n1;
+            const int n1 = sh_n[0];
             // ---- phase 2: rod 1 against the patch of rod 2 (S1, S2), survivors only
-            keep = false;
-            PatchItem it;
-            it.p = -1; it.T1 = it.T2 = it.S1 = it.S2 = 0.0;
-            if ((int)threadIdx.x < n1) {
-                it = sh_a[threadIdx.x];
-                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
-                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
-                const int pn2 = combo >> 1;
-                v3 vec1 = neg(r_cm);
-                int n = sp ? patch_intersect<false>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0])
-                           : patch_intersect<true>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0]);
-                keep = n >= 2;
+            {
+                bool keep = false;
+                Item it;
+                if ((int)threadIdx.x < n1) {
+                    it = sh_a[threadIdx.x];
+                    const scgpu_iaparam* ia = ia_one ? ia_one : &s.ia[it.pad];
+                    const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
+                    const bool second_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && !is_psc_family(g0));
+                    PatchArgs P1, P2;
+                    load_patch_args(s.rec + (size_t)it.si * REC, pn1, is_chiral(g0), P1);
+                    load_patch_args(s.rec + (size_t)it.sj * REC, pn2, is_chiral(g1), P2);
+                    const v3 vec1 = neg(mk(it.rx, it.ry, it.rz));
+                    const int nn = second_psc ? patch_intersect<false>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0])
+                                              : patch_intersect<true>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0]);
+                    keep = nn >= 2;
+                }
+                append(sh_b, &sh_n[1], keep, it);
             }
-            r = block_rank(keep, sh_warp, &sh_n2);
-            if (keep) sh_b[r] = it;
             __syncthreads();
-            const int n2 = sh_n2;
+            const int n2 = sh_n[1];
             // ---- phase 3: attraction of the survivors
             if ((int)threadIdx.x < n2) {
-                it = sh_b[threadIdx.x];
-                const scgpu_iaparam* ia; v3 r_cm; PatchArgs P1, P2; bool fp, sp, ok;
-                patch_setup(s, fl, it.p, combo, ia, r_cm, P1, P2, fp, sp, ok, ia_one);
-                double e = atr_e(*ia, P1.dir, P2.dir, P1.pdir, P2.pdir, r_cm, combo & 1, combo >> 1, it.S1, it.S2, it.T1, it.T2);
+                const Item it = sh_b[threadIdx.x];
+                const scgpu_iaparam* ia = ia_one ? ia_one : &s.ia[it.pad];
+                const int g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
+                PatchArgs P1, P2;
+                load_patch_args(s.rec + (size_t)it.si * REC, pn1, is_chiral(g0), P1);
+                load_patch_args(s.rec + (size_t)it.sj * REC, pn2, is_chiral(g1), P2);
+                const double e = atr_e(*ia, P1.dir, P2.dir, P1.pdir, P2.pdir, mk(it.rx, it.ry, it.rz), pn1, pn2, it.S1, it.S2, it.T1, it.T2);
                 fl.e[it.p].y += e;        // one writer per pair and phase; the combinations run one after another
                 if (mirror && e != 0.0) {      // every-particle pass: the partner lists this pair too -- find it in the partner's span (a few entries)
-                    const int2 pr = fl.pair[it.p];
-                    const int4 cj = fl.chunks[w_orig(s.posw[pr.y].w)];
+                    const int4 cj = fl.chunks[w_orig(s.posw[it.sj].w)];
                     bool found = false;
-                    for (int q = 0; q < cj.y; q++) if (fl.pair[cj.x + q].y == pr.x) { fl.e[cj.x + q].y += e; found = true; break; }
+                    for (int k = 0; k < cj.y; k++) if (fl.pair[cj.x + k].y == it.si) { fl.e[cj.x + k].y += e; found = true; break; }
                     if (!found) atomicOr(fl.overflow, 8);      // cannot happen: a pair inside the patch range is listed by both sides
                 }
             }
@@ -1930,17 +1986,18 @@ __global__ void __launch_bounds__(256) k_combine_flat(int n, FlatList fl, const 
     if (blockIdx.x == 0 && threadIdx.x == 0) { *fl.total = 0; *fl.chunk_count = 0; *fl.ptotal = 0; }   // lists consumed (stream order makes the reset safe)
     double e = 0.0;
     if (t < n) {
-        for (int cid = fl.head[t]; cid >= 0;) {
-            const int4 ch = fl.chunks[cid];
-            for (int r = sub; r < ch.y; r += 8) {
-                const double2 v = fl.e[ch.x + r];
-                e += v.x + v.y;      // per pair (cheap + patch), then accumulate
-            }
-            cid = ch.z;
+        const int4 ch = fl.chunks[t];        // every gate of the flat pipeline hands a particle ONE span of the list
+        for (int r = sub; r < ch.y; r += 8) {
+            const double2 v = fl.e[ch.x + r];
+            e += v.x + v.y;      // per pair (cheap + patch), then accumulate
         }
     }
     for (int o = 4; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if (t < n && sub == 0) out[t] = e;
+}
+
+__device__ __noinline__ double wall_energy_rec(const DevSys& s, const double* r, int type) {        // r: internal record (pair_energy.cuh layout)
+    return wall_energy(s.wall[type], s.exter_sqmaxcut, s.box[2], r[R_POS + 2], ld3(r + R_DIR), ld3(r + R_PD0), ld3(r + R_PD1), ld3(r + R_CH0), ld3(r + R_CH1));
 }
 
 #include "sweep.cuh"
@@ -2021,6 +2078,29 @@ __global__ void __launch_bounds__(RF_THREADS) k_reduce_fixed(int n, const double
         __syncthreads();
     }
     if (threadIdx.x == 0) { out[0] = sh[0]; *counter = 0u; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// external wall ([EXTER]): O(N) per-particle term the reference's calculators add to every sum when topo.exter.exist
+// (mc/totalenergycalculator.h:348-350, 377-378, 410-411, 435-449, 476-495, 516-518)
+// ------------------------------------------------------------------------------------------------
+// out[t] += extere2(particle of result t). mode 0: targets[] (+ trial states in C-ABI layout); 1 / 2: every particle, out indexed by
+// original index; 3: molecule members first .. first + m (+ trial states)
+__global__ void k_add_exter(DevSys s, int mode, int m, const int* __restrict__ targets, const double* __restrict__ trial_states, int first,
+                            double* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const int target = mode == 0 ? targets[t] : (mode == 3 ? first + t : t);
+    double r[REC];
+    if ((mode == 0 || mode == 3) && trial_states) {
+#pragma unroll
+        for (int k = 0; k < 30; k++) r[k] = trial_states[(size_t)t * 30 + c_api_of[k]];
+    } else {
+        const double* g = s.rec + (size_t)s.slot_of[target] * REC;
+#pragma unroll
+        for (int k = 0; k < 30; k++) r[k] = g[k];
+    }
+    out[t] += wall_energy_rec(s, r, s.type[target]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2106,6 +2186,9 @@ struct scgpu_ctx {
     scgpu_iaparam* d_ia = nullptr;
     scgpu_molparam* d_mol = nullptr;
     double sqmaxcut = 0, maxcut = 0;
+    bool exter = false;              // [EXTER] wall potential present (scgpu_set_exter)
+    double exter_sqmaxcut = 0;
+    WallParam* d_wall = nullptr;
     double min_reach2 = 0;           // the smallest non-zero squared reach of the table (bounds the FP32 rounding the row-unit gates may carry)
     // particles
     int n = 0, cap = 0;
@@ -2122,6 +2205,7 @@ struct scgpu_ctx {
     int *d_type = nullptr, *d_moltype = nullptr, *d_cell_of = nullptr, *d_order = nullptr, *d_slot_of = nullptr, *d_tmp = nullptr;
     int *d_counts = nullptr, *d_cell_start = nullptr, *d_cursor = nullptr;
     int cells_cap = 0;
+    unsigned* d_ticket = nullptr;    // last-block ticket of k_cell_count
     int *d_fine_of = nullptr, *d_fine_start = nullptr;      // sub-cell sort (sub > 1): per particle, per sub-cell
     int fine_cap = 0;
     int sub = 1;                     // sub-cells per cell and axis of the current cell list
@@ -2198,6 +2282,8 @@ static DevSys view(const scgpu_ctx* c) {
     s.fine_start = c->sub > 1 ? c->d_fine_start : c->d_cell_start; s.sub = c->sub;
     s.slot_of = c->d_slot_of; s.type = c->d_type; s.moltype = c->d_moltype; s.ia = c->d_ia; s.mol = c->d_mol; s.reach2 = c->d_reach2;
     s.sqmaxcut = c->sqmaxcut;
+    s.wall = c->exter ? c->d_wall : nullptr;
+    s.exter_sqmaxcut = c->exter_sqmaxcut;
     return s;
 }
 
@@ -2230,6 +2316,8 @@ extern "C" int scgpu_create(scgpu_ctx** out, int device) {
     CK(cudaMalloc(&c->d_reduce, (RF_BLOCKS + 2) * sizeof(double)));
     CK(cudaMemset(c->d_reduce, 0, (RF_BLOCKS + 2) * sizeof(double)));
     CK(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&c->d_ticket, 2 * sizeof(unsigned)));
+    CK(cudaMemset(c->d_ticket, 0, 2 * sizeof(unsigned)));
     CK(cudaMalloc(&c->d_pl_total, 8 * sizeof(int)));     // [0] patch pairs, [1] overflow flag, [2] patch chunks, [3] flat pairs, [4] flat chunks, [5] flat patch pairs
     CK(cudaMemset(c->d_pl_total, 0, 8 * sizeof(int)));
     c->d_pl_overflow = c->d_pl_total + 1;
@@ -2258,7 +2346,7 @@ extern "C" int scgpu_destroy(scgpu_ctx* c) {
     cudaStreamSynchronize(c->stream);
     free_particles(c);
     cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_reach2); cudaFree(c->d_counts); cudaFree(c->d_cell_start); cudaFree(c->d_cursor);
-    cudaFree(c->d_fine_of); cudaFree(c->d_fine_start); cudaFree(c->d_heavy); cudaFree(c->d_nheavy);
+    cudaFree(c->d_ticket); cudaFree(c->d_fine_of); cudaFree(c->d_fine_start); cudaFree(c->d_heavy); cudaFree(c->d_nheavy); cudaFree(c->d_wall);
     cudaFree(c->d_sweep_acc);
     cudaFree(c->d_trial); cudaFree(c->d_trial_rec); cudaFree(c->d_pl_total); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_reduce); cudaFree(c->d_counters); cudaFree(c->d_flush);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -2357,6 +2445,42 @@ extern "C" int scgpu_set_topology(scgpu_ctx* c, int ntypes, const scgpu_iaparam*
     CK(cudaStreamSynchronize(c->stream));
     c->ntypes = ntypes; c->nmol = nmoltypes; c->sqmaxcut = sqmaxcut; c->maxcut = maxcut;
     c->cells_valid = false;
+    c->exter = false;                // the wall parameters derive from this table: scgpu_set_exter comes after scgpu_set_topology
+    return SCGPU_OK;
+}
+
+// topo.exter (scOOP/structures/structures.h:259-275), filled by Topo::genParamPairs / genTopoParams (structures/topo.cpp:120-130, 151-152):
+// every particle type interacts with the wall through its own Ia_param with the wall's mixing rules
+extern "C" int scgpu_set_exter(scgpu_ctx* c, int exist, double thickness, double epsilon, double attraction) {
+    ARG(c, "scgpu_set_exter: NULL context");
+    ARG(c->ntypes > 0, "scgpu_set_exter: call scgpu_set_topology first");
+    CK(cudaSetDevice(c->device));
+    c->exter = false;
+    if (!exist) return SCGPU_OK;
+    std::vector<WallParam> w(c->ntypes);
+    double sq = 0.0, maxlength = 0.0;
+    for (int i = 0; i < c->ntypes; i++) {
+        const scgpu_iaparam& q = c->h_ia[(size_t)i * c->ntypes + i];
+        memset(&w[i], 0, sizeof(WallParam));
+        if (maxlength < q.len[0]) maxlength = q.len[0];
+        if ((int)q.geotype[0] == 0) continue;
+        w[i].geotype = (int)q.geotype[0];
+        w[i].len0 = q.len[0]; w[i].half_len0 = q.half_len[0];
+        w[i].sigma = (q.sigma + thickness) * 0.5;
+        w[i].rcutwca = (w[i].sigma) * pow(2.0, 1.0 / 6.0);
+        w[i].epsilon = sqrt(q.epsilon * epsilon);
+        w[i].pswitch = (q.pswitch + attraction) * 0.5;
+        w[i].pdis = (q.pdis - q.rcutwca + 0.0) * 0.5 + w[i].rcutwca;
+        w[i].rcut = w[i].pswitch + w[i].pdis;
+        if (w[i].rcut > sq) sq = w[i].rcut;
+    }
+    sq += maxlength;
+    sq *= sq * 1.1;
+    c->exter_sqmaxcut = sq;
+    if (!c->d_wall) CK(cudaMalloc(&c->d_wall, 40 * sizeof(WallParam)));
+    CK(cudaMemcpyAsync(c->d_wall, w.data(), (size_t)c->ntypes * sizeof(WallParam), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->exter = true;
     return SCGPU_OK;
 }
 
@@ -2596,16 +2720,17 @@ static int build_cells_impl(scgpu_ctx* c, const double shift[3], int sweep_k) {
         cudaFree(c->d_counts); cudaFree(c->d_cursor); cudaFree(c->d_fine_start);
         c->fine_cap = (int)nfine + 2;
         CK(cudaMalloc(&c->d_counts, (size_t)c->fine_cap * sizeof(int)));
+        CK(cudaMemsetAsync(c->d_counts, 0, (size_t)c->fine_cap * sizeof(int), c->stream));
         CK(cudaMalloc(&c->d_cursor, (size_t)c->fine_cap * sizeof(int)));
         CK(cudaMalloc(&c->d_fine_start, (size_t)c->fine_cap * sizeof(int)));
     }
     if (c->sub > 1 && !c->d_fine_of) CK(cudaMalloc(&c->d_fine_of, (size_t)c->cap * sizeof(int)));
     DevSys s = view(c);
     int nb = (c->n + 255) / 256;
-    CK(cudaMemsetAsync(c->d_counts, 0, (size_t)nfine * sizeof(int), c->stream));
-    k_cell_count<<<nb, 256, 0, c->stream>>>(s, c->d_cell_of, c->d_fine_of, c->d_counts);
+    // (the histogram array is zero here: cleared when allocated and again by every scan)
+    const int nb1 = (c->n + 1023) / 1024;
     if (c->sub > 1) {
-        k_cell_scan<<<1, 1024, 0, c->stream>>>((int)nfine, c->d_counts, c->d_fine_start, c->d_cursor);
+        k_cell_count<<<nb1, 1024, 0, c->stream>>>(s, (int)nfine, c->d_cell_of, c->d_fine_of, c->d_counts, c->d_fine_start, c->d_cursor, c->d_ticket);
         k_coarse_start<<<(c->ncells + 2 + 255) / 256, 256, 0, c->stream>>>(c->ncells, s3, c->d_fine_start, c->d_cell_start);
         k_cell_fill<<<nb, 256, 0, c->stream>>>(c->n, c->d_fine_of, c->d_cursor, c->d_tmp);
         k_cell_place<<<nb, 256, 0, c->stream>>>(s, c->d_fine_of, c->d_tmp, c->d_order, c->d_slot_of, c->d_posw, c->d_rec, c->d_p32, c->d_d32);
@@ -2617,12 +2742,12 @@ static int build_cells_impl(scgpu_ctx* c, const double shift[3], int sweep_k) {
         k_heavy_sort<<<1, 1024, 0, c->stream>>>(c->d_heavy, c->d_nheavy);
         c->launches += 3;
     } else {
-        k_cell_scan<<<1, 1024, 0, c->stream>>>(c->ncells, c->d_counts, c->d_cell_start, c->d_cursor);
+        k_cell_count<<<nb1, 1024, 0, c->stream>>>(s, c->ncells, c->d_cell_of, c->d_fine_of, c->d_counts, c->d_cell_start, c->d_cursor, c->d_ticket);
         k_cell_fill<<<nb, 256, 0, c->stream>>>(c->n, c->d_cell_of, c->d_cursor, c->d_tmp);
         k_cell_place<<<nb, 256, 0, c->stream>>>(s, c->d_cell_of, c->d_tmp, c->d_order, c->d_slot_of, c->d_posw, c->d_rec, c->d_p32, c->d_d32);
     }
     c->f32_valid = true;
-    c->launches += 4;
+    c->launches += 3;
     CK(cudaGetLastError());
     c->cells_valid = true;
     c->h_cell_of.clear();   // host mirror fetched lazily by scgpu_update_particle
@@ -2818,6 +2943,7 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
         k_combine_flat<<<(c->n + 31) / 32, 256, 0, c->stream>>>(c->n, fl, c->d_posw, d_out);
         mark(4);
         c->launches += 4;
+        if (c->exter) { k_add_exter<<<(c->n + 127) / 128, 128, 0, c->stream>>>(s, mode, c->n, nullptr, nullptr, 0, d_out); c->launches++; }
         CK(cudaGetLastError());
         return 0;
     }
@@ -2832,6 +2958,7 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
     k_patch<<<pblocks, 128, 0, c->stream>>>(s, pl, d_targets, mode, excl_lo, d_pairs);
     k_combine<<<(m + 255) / 256, 256, 0, c->stream>>>(m, gw, pl, c->d_warp_partial, d_out);
     c->launches += 3;
+    if (c->exter) { k_add_exter<<<(m + 127) / 128, 128, 0, c->stream>>>(s, mode, m, d_targets, d_trial, excl_lo, d_out); c->launches++; }
     CK(cudaGetLastError());
     return 0;
 }

@@ -82,7 +82,10 @@ __device__ inline void rotate_record(double* r, int geotype, double angle, const
 #define SW_MINBLOCKS 8
 #endif
 constexpr int SW_WARPS = 1;       // one warp per active cell: no block barrier anywhere in a trial
-constexpr int SW_TILE = 576;      // staged neighbourhood: FP32 position + direction + slot, 32 B per candidate = 18 KB (8 warps per SM resident)
+#ifndef SW_TILE_N
+#define SW_TILE_N 576
+#endif
+constexpr int SW_TILE = SW_TILE_N;      // staged neighbourhood: FP32 position + direction + slot, 32 B per candidate = 18 KB (8 warps per SM resident)
 constexpr int SW_BATCH = 32;      // trials whose random numbers and proposal geometry are prepared together, one lane each
 constexpr int SW_MAXROWS = 49;    // (2K+1)^2 rows of neighbour cells, K <= 3
 constexpr int SW_MAXT = 8;        // particle types whose reach / cutoff tables are kept in shared memory
@@ -476,6 +479,12 @@ k_sweep_cells(DevSys s, SweepParams sp, unsigned long long seed, unsigned long l
             SWP_MARK(5);
             e_old = warp_sum(lo);
             e_new = warp_sum(ln);
+            if (s.wall != nullptr) {       // [EXTER] wall: added to both energies of the trial, as oneToAll / oneToAllTrial do (totalenergycalculator.h:377-378, 410-411)
+                double wv = 0.0;
+                if (lane < 2) wv = wall_energy_rec(s, lane ? sh_new : sh_old, type1);
+                e_old += __shfl_sync(0xffffffffu, wv, 0);
+                e_new += __shfl_sync(0xffffffffu, wv, 1);
+            }
         }
         SWP_MARK(6);
         bool accept = false;
@@ -688,6 +697,8 @@ k_sweep_chain_colour(DevSys s, ChainParams cp, unsigned long long seed, unsigned
             if (in_cell) {
                 double a = 0.0, b2 = 0.0;
                 for (int k = 0; k < CH_THREADS / 32; k++) { a += sh_red[0][k]; b2 += sh_red[1][k]; }      // fixed order
+                if (s.wall != nullptr)       // [EXTER] wall term of every member (mol2others / mol2othersTrial, totalenergycalculator.h:435-449)
+                    for (int k = 0; k < m; k++) { a += wall_energy_rec(s, sh_old[k], sh_mtype[k]); b2 += wall_energy_rec(s, sh_new[k], sh_mtype[k]); }
                 de = b2 - a;
                 accept = (de <= 0.0) || (exp(-de / cp.temper) > u_acc);       // moveTry (movecreator.h:175-187)
             } else acc.cell_rej++;

@@ -69,7 +69,7 @@ class WLState(C.Structure):
 
 
 SYMBOLS = ["scgpu_last_error", "scgpu_device_count", "scgpu_create", "scgpu_destroy", "scgpu_set_topology",
-           "scgpu_set_particles", "scgpu_set_particles_compact", "scgpu_set_box", "scgpu_update_particle", "scgpu_download_particles",
+           "scgpu_set_particles", "scgpu_set_particles_compact", "scgpu_set_exter", "scgpu_set_box", "scgpu_update_particle", "scgpu_download_particles",
            "scgpu_build_cells", "scgpu_cell_assignment", "scgpu_cell_order", "scgpu_one_to_all",
            "scgpu_one_to_all_batch", "scgpu_one_to_all_everyone", "scgpu_submit_everyone", "scgpu_mol_to_others", "scgpu_all_to_all",
            "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_sweep_checkerboard_chains", "scgpu_pressure_move",
@@ -97,6 +97,7 @@ def load_library(variant="fast"):
     L.scgpu_set_particles.argtypes = [vp, C.c_int, _dp, _ip, _ip]
     L.scgpu_set_particles_compact.argtypes = [vp, C.c_int, _dp, _ip, _ip]
     L.scgpu_set_box.argtypes = [vp, _dp]
+    L.scgpu_set_exter.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double]
     L.scgpu_update_particle.argtypes = [vp, C.c_int, _dp]
     L.scgpu_download_particles.argtypes = [vp, _dp]
     L.scgpu_build_cells.argtypes = [vp]
@@ -195,9 +196,17 @@ class Engine:
         box = np.ascontiguousarray(box, dtype=np.float64)
         self._ck(self.L.scgpu_set_box(self.h, _d(box)))
 
+    def set_exter(self, exter):
+        """exter: None, or (thickness, epsilon, attraction switch) of the [EXTER] wall; after set_topology"""
+        if exter is None:
+            self._ck(self.L.scgpu_set_exter(self.h, 0, 0.0, 0.0, 0.0))
+        else:
+            self._ck(self.L.scgpu_set_exter(self.h, 1, float(exter[0]), float(exter[1]), float(exter[2])))
+
     def load(self, sysobj):
-        """sysobj: anything with .ia .mol .sqmaxcut .maxcut .state .type .moltype .box"""
+        """sysobj: anything with .ia .mol .sqmaxcut .maxcut .state .type .moltype .box (and optionally .exter)"""
         self.set_topology(sysobj.ia, sysobj.mol, sysobj.sqmaxcut, sysobj.maxcut)
+        self.set_exter(getattr(sysobj, "exter", None))
         self.set_box(sysobj.box)
         self.set_particles(sysobj.state, sysobj.type, sysobj.moltype)
         return self

@@ -29,6 +29,7 @@ def _load():
         L.schost_dims.argtypes = [vp, _ip, _ip, _ip]
         L.schost_export.argtypes = [vp, _dp, _ip, _ip, _dp, _dp, _dp, _dp]
         L.schost_set_state.argtypes = [vp, C.c_int, _dp]
+        L.schost_exter.argtypes = [vp, _dp]
         L.schost_set_box.argtypes = [vp, _dp]
         L.schost_calc_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
         L.schost_calc_free.argtypes = [vp]
@@ -79,6 +80,9 @@ class HostSystem:
         L.schost_export(self.h, self.state.ctypes.data_as(_dp), self.type.ctypes.data_as(_ip), self.moltype.ctypes.data_as(_ip),
                         self.ia.ctypes.data_as(_dp), self.mol.ctypes.data_as(_dp), self.box.ctypes.data_as(_dp), cut.ctypes.data_as(_dp))
         self.sqmaxcut, self.maxcut = float(cut[0]), float(cut[1])
+        ex = np.zeros(4)
+        L.schost_exter(self.h, ex.ctypes.data_as(_dp))
+        self.exter = [float(ex[1]), float(ex[2]), float(ex[3])] if ex[0] else None      # [EXTER]: thickness, epsilon, attraction switch
 
     def set_state(self, idx, state):
         st = np.ascontiguousarray(state, dtype=np.float64)

@@ -15,12 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "build_variants")
 VARIANTS = {
-    "k2_mb8": ["-DSW_FORCE_K=2", "-DSW_MINBLOCKS=8"],
-    "k2_mb12": ["-DSW_FORCE_K=2", "-DSW_MINBLOCKS=12"],
-    "k2_mb16": ["-DSW_FORCE_K=2", "-DSW_MINBLOCKS=16"],
-    "k1_mb8": ["-DSW_FORCE_K=1", "-DSW_MINBLOCKS=8"],
-    "k3_mb8": ["-DSW_FORCE_K=3", "-DSW_MINBLOCKS=8"],
-    "k3_mb16": ["-DSW_FORCE_K=3", "-DSW_MINBLOCKS=16"],
+    "t320_mb12": ["-DSW_MINBLOCKS=12", "-DSW_TILE_N=320"],
+    "t320_mb10": ["-DSW_MINBLOCKS=10", "-DSW_TILE_N=320"],
+    "t320_mb16": ["-DSW_MINBLOCKS=16", "-DSW_TILE_N=224"],
 }
 
 

@@ -312,7 +312,87 @@ def do_ptype45():
             print("ptype45:", name)
 
 
+WALL_TYPES = """[Types]
+PSC     1   PSC      1.0  1.2  1.346954458  0.5  80.0  5.0  3.0  0.0
+CPSC    2   CPSC     1.4  1.0  1.12246205   1.0  80.0  5.0  3.0  0.0
+CHPSC   3   CHPSC    1.0  1.2  1.346954458  0.5  90.0  5.0  3.0  0.0  10.0
+CHCPSC  4   CHCPSC   3.5  1.0  1.12246205   1.0 170.0  5.0  3.0  0.0  10.0
+TPSC    5   TPSC     1.0  1.2  1.346954458  0.5  80.0  5.0  3.0  0.0  180.0  60.0  5.0
+TCPSC   6   TCPSC    1.0  1.2  1.346954458  0.5  80.0  5.0  3.0  0.0  90.0   60.0  5.0
+TCHPSC  7   TCHPSC   1.0  1.2  1.346954458  0.5  80.0  5.0  3.0  0.0  180.0  60.0  5.0  10.0
+TCHCPSC 8   TCHCPSC  1.0  1.2  1.346954458  0.5  80.0  5.0  3.0  0.0  90.0   60.0  5.0  10.0
+SPN     9   SPN      1.0  1.2
+SPA     10  SPA      1.0  1.2  1.346954458  0.5
+[Molecules]
+"""
+
+
+def do_wall():
+    """[EXTER] wall potential: ExternalEnergyCalculator::extere2 of every particle (oracle/ref_driver.cpp `exter`) on (a) the initial
+    configuration of Tests/test_wallfibril and (b) a synthetic slab with every geotype at random heights and orientations around the
+    wall (the wall is the plane z = 0 of the periodic box), plus a 300-sweep trajectory of test_wallfibril by the reference program"""
+    import random
+    import re
+    rnd = random.Random(4711)
+    names = ["PSC", "CPSC", "CHPSC", "CHCPSC", "TPSC", "TCPSC", "TCHPSC", "TCHCPSC", "SPN", "SPA"]
+    per = 48
+    top = WALL_TYPES
+    for k, nm in enumerate(names):
+        top += "%s: {\nparticles: %d\n}\n" % (nm, k + 1)
+    top += "[System]\n" + "".join("%s %d\n" % (nm, per) for nm in names) + "[EXTER]\n5.0 4.00 1.0\n"
+    box = (30.0, 30.0, 24.0)
+    lines = ["%.8e %.8e %.8e" % box]
+    for nm in names:
+        for _ in range(per):
+            z = rnd.uniform(-7.0, 7.0)
+            pos = (rnd.uniform(-15, 15), rnd.uniform(-15, 15), z)
+            while True:
+                d = [rnd.gauss(0, 1) for _ in range(3)]
+                n = math.sqrt(sum(x * x for x in d))
+                if n > 1e-3:
+                    break
+            d = [x / n for x in d]
+            if rnd.random() < 0.08:
+                d = [1.0, 0.0, 0.0] if rnd.random() < 0.5 else [0.0, 0.0, 1.0]        # rods exactly parallel / perpendicular to the wall
+            while True:
+                p = [rnd.gauss(0, 1) for _ in range(3)]
+                dp = sum(a * b for a, b in zip(p, d))
+                p = [a - dp * b for a, b in zip(p, d)]
+                n = math.sqrt(sum(x * x for x in p))
+                if n > 1e-3:
+                    break
+            p = [x / n for x in p]
+            lines.append(" ".join("%.8e" % x for x in list(pos) + d + p) + " 0")
+    cfg = "\n".join(lines) + "\n"
+    with open(os.path.join(REF, "Tests", "Interactions_tests", "options")) as f:
+        opts = f.read()
+    cases = {"wall_mix": {"options": opts, "top.init": top, "config.init": cfg}}
+    src = os.path.join(REF, "Tests", "test_wallfibril", "new")
+    cases["wall_fibril"] = {fn: open(os.path.join(src, fn)).read() for fn in ("options", "top.init", "config.init")}
+    for name, inp in cases.items():
+        tmp = tempfile.mkdtemp(prefix="wall_")
+        for fn, txt in inp.items():
+            with open(os.path.join(tmp, fn), "w") as f:
+                f.write(txt)
+        run([DRIVER, "exter", "ref_exter.txt"], tmp)
+        gz_copy(os.path.join(tmp, "ref_exter.txt"), os.path.join(HERE, name + ".exter.gz"))
+        run([DRIVER, "dump", "ref_dump.txt"], tmp)
+        gz_copy(os.path.join(tmp, "ref_dump.txt"), os.path.join(HERE, name + "_init.ref.gz"))
+        with gzip.GzipFile(os.path.join(HERE, name + ".inputs.json.gz"), "wb", mtime=0) as g:
+            g.write(json.dumps(inp).encode())
+        if name == "wall_fibril":
+            opt = re.sub(r"(?m)^nsweeps\s*=\s*\d+", "nsweeps = 300", inp["options"])
+            with open(os.path.join(tmp, "options"), "w") as f:
+                f.write(opt)
+            run([SC], tmp)
+            shutil.copy(os.path.join(tmp, "config.last"), os.path.join(HERE, "test_wallfibril.short300.config.last"))
+        shutil.rmtree(tmp)
+        print("wall:", name)
+
+
 def main():
+    if "wall" in sys.argv[1:]:
+        return do_wall()
     if "ptype45" in sys.argv[1:]:
         return do_ptype45()
     if "membrane" in sys.argv[1:]:
