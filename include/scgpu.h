@@ -76,11 +76,20 @@ typedef struct scgpu_moveparams {
     double temper;                 /* Sim::temper */
     double trans_mx[40];           /* per particle type: stat.trans[type].mx  (= 2*transmx, sim.h:365) */
     double rot_angle[40];          /* per particle type: stat.rot[type].angle (radians, sim.h:360) */
-    int n_sub;                     /* sweeps per call: n_sub * N trials in total; every non-empty cell of the checkerboard performs the same
-                                      number of them (n_sub * N / non-empty cells, stochastically rounded), whatever its population */
+    int n_sub;                     /* sweeps per call: n_sub * N trials in total, shared among the cells by trial_rule */
     int grid_k;                    /* fineness of the checkerboard: 0 = chosen by the library (the finest grid that leaves ~2 particles per
                                       cell: shortest serial chain, best for ONE system on the GPU); 1, 2, 3 = cells of edge >= maxcut / k.
                                       Many replicas sharing a GPU are throughput-bound and run best on the coarse grid (1) */
+    int trial_rule;                /* how the n_sub * N trials are shared among the cells of the checkerboard.
+                                      0: every non-empty cell performs the same number, n_sub * N / (non-empty cells) -- all cells of a pass
+                                      finish together (shortest pass; the rule of HOOMD-blue's HPMC, a fixed number of trials per cell);
+                                      particles of sparse cells are moved more often than those of dense ones;
+                                      1: a cell performs n_sub * (its population) trials -- every particle is picked once per sweep on
+                                      average, the reference's per-particle rates (Updater::simulate draws uniformly among N,
+                                      updater.cpp:206-230), at the price of every pass lasting as long as its fullest cell.
+                                      Both rules leave the Boltzmann distribution invariant (the count is fixed before the pass and no
+                                      particle leaves its cell within one); fractional counts are stochastically rounded */
+    int reserved;
 } scgpu_moveparams;
 
 typedef struct scgpu_sweepstats {

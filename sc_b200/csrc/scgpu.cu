@@ -2194,7 +2194,6 @@ struct scgpu_ctx {
     int n = 0, cap = 0;
     double box[3] = {0, 0, 0};
     double shift[3] = {0, 0, 0};
-    std::vector<double> h_api;       // unused host mirror (kept for ABI stability of the struct layout in debuggers)
     std::vector<int> h_cell_of;
     double* d_api = nullptr;
     double* d_compact = nullptr;     // staging of 9-double records (scgpu_set_particles_compact)
@@ -2255,6 +2254,7 @@ struct scgpu_ctx {
     unsigned long long* d_counters = nullptr;   // 8
     void* d_sweep_acc = nullptr;
     int sweep_acc_cap = 0;
+    bool sweep_one_cell = getenv("SCGPU_SWEEP_ONE_CELL") != nullptr;      // diagnostic: sweeps without the cell decomposition
     double* d_flush = nullptr;
     size_t flush_n = 0;
     char* h_small = nullptr;         // 1 KB pinned: single-call inputs [0..255], results [256..511], update staging [512..751]
@@ -2582,7 +2582,6 @@ static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const 
         c->launches++;
         CK(cudaGetLastError());
     }
-    c->h_api.clear();
     CK(cudaStreamSynchronize(c->stream));
     // specialisation switch: only rod-rod functors and no bonded molecule among the particles present
     if (!same_types) {
@@ -2661,6 +2660,7 @@ static int build_cells_impl(scgpu_ctx* c, const double shift[3], int sweep_k) {
             nc = (int)floor(c->box[d] * sweep_k / c->maxcut);
             nc -= nc % (sweep_k + 1);
             if (nc < 2 * (sweep_k + 1)) nc = 1;
+            if (c->sweep_one_cell) nc = 1;      // diagnostic (SCGPU_SWEEP_ONE_CELL): no decomposition, one warp walks the whole system
         }
         c->nc[d] = nc;
         c->shift[d] = shift[d];
@@ -3106,7 +3106,6 @@ extern "C" int scgpu_submit_everyone(scgpu_ctx* c, const double* state9, double*
     k_particle_init<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->n, c->ntypes, c->d_compact, c->d_type, c->d_ia, c->d_api);
     c->launches++;
     CK(cudaGetLastError());
-    c->h_api.clear();
     c->cells_valid = false;
     c->api_stale = false;
     if (int r = scgpu_build_cells(c)) return r;
@@ -3216,6 +3215,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     if (chains) for (int t = 0; t < c->nmol; t++) ARG(c->h_mol[t].mol_size <= CH_MAX, "scgpu_sweep_checkerboard_chains: a molecule is longer than MAXCHL = 20");
     ARG(mp->temper > 0 && mp->n_sub >= 1, "scgpu_sweep_checkerboard: temperature and n_sub must be positive");
     ARG(mp->grid_k >= 0 && mp->grid_k <= 3, "scgpu_sweep_checkerboard: grid_k must be 0 (automatic), 1, 2 or 3");
+    ARG(mp->trial_rule == 0 || mp->trial_rule == 1, "scgpu_sweep_checkerboard: trial_rule must be 0 (per cell) or 1 (per particle)");
     ARG(c->n > 0 && c->ntypes > 0 && c->ntypes <= 40, "scgpu_sweep_checkerboard: set topology (<= 40 types) and particles first");
     CK(cudaSetDevice(c->device));
     // random grid shift and colour order for this sweep: a pure function of (seed, sweep)
@@ -3254,6 +3254,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     SweepParams sp;
     sp.temper = mp->temper;
     sp.n_sub = mp->n_sub;
+    sp.trial_rule = mp->trial_rule;
     sp.trial_scale = chains ? 1.0 - cm->chainprob : 1.0;
     ChainParams cp;
     memset(&cp, 0, sizeof cp);

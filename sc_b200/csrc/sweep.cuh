@@ -20,6 +20,7 @@ struct SweepParams {
     double trans_mx[40];
     double rot_angle[40];
     int n_sub;
+    int trial_rule;                 // 0: the same number of trials in every non-empty cell; 1: trials of a cell = n_sub x its population
     int geotype_of_type[40];
     double trial_scale;             // share of the sweep's trials that are single-particle moves (1 - chainprob)
 };
@@ -229,12 +230,14 @@ k_sweep_cells(DevSys s, SweepParams sp, unsigned long long seed, unsigned long l
     // the active cell is the centre of its own neighbourhood: where its particles sit in the staged tile
     const int centre_seg = 2 * (g.k[2] * wy + g.k[1]);
     const int centre_off = sh_off[centre_seg] + (tb - sh_b[centre_seg]);
-    // every non-empty cell performs the same number of trials (n_sub * N / non-empty cells, stochastically rounded): the count
-    // does not depend on anything a trial can change (particles never leave their cell within a pass), so detailed balance
-    // holds, and all cells of a pass finish together instead of waiting for the fullest one
+    // trials of this cell: the same number in every non-empty cell (rule 0: n_sub * N / non-empty cells; all cells of a pass finish
+    // together instead of waiting for the fullest one) or n_sub x its population (rule 1: every particle is picked once per sweep on
+    // average, the reference's rates). Either count does not depend on anything a trial can change (particles never leave their
+    // cell within a pass), so detailed balance holds. Fractional counts are stochastically rounded.
     int ntrial;
     {
-        const double avg = sp.trial_scale * (double)sp.n_sub * (double)s.n / (double)s.cell_start[s.ncells + 1];
+        const double avg = sp.trial_rule == 1 ? sp.trial_scale * (double)sp.n_sub * (double)npart
+                                              : sp.trial_scale * (double)sp.n_sub * (double)s.n / (double)s.cell_start[s.ncells + 1];
         const uint4 r = philox4x32((uint32_t)sweep, (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 24), (uint32_t)c0, 0xffffffffu, (uint32_t)seed, (uint32_t)(seed >> 32));
         const double fl = floor(avg);
         ntrial = (int)fl + (u01(r.x, r.y) < avg - fl ? 1 : 0);

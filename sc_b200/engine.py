@@ -24,7 +24,7 @@ class ScgpuError(RuntimeError):
 
 class MoveParams(C.Structure):
     _fields_ = [("temper", C.c_double), ("trans_mx", C.c_double * 40), ("rot_angle", C.c_double * 40),
-                ("n_sub", C.c_int), ("grid_k", C.c_int)]
+                ("n_sub", C.c_int), ("grid_k", C.c_int), ("trial_rule", C.c_int), ("reserved", C.c_int)]
 
 
 class SweepStats(C.Structure):

@@ -74,6 +74,32 @@ def test_energy_bookkeeping_and_invariants(kind):
     eng.close()
 
 
+def test_trial_rule_per_particle_gives_exactly_n_trials_and_keeps_the_books():
+    """scgpu_moveparams::trial_rule = 1: a cell performs (its population) trials per sweep -- N in total, exactly (no rounding), on
+    every grid fineness; energies stay exact"""
+    top, cfg = synth.small_case("psc_lattice")
+    hs = HostSystem(top, cfg)
+    for gk in (0, 1, 2):
+        eng = Engine(0, "fast").load(hs)
+        mp = move_params(0.25, 0.05, 8.0)
+        mp.trial_rule, mp.grid_k = 1, gk
+        e0 = eng.all_to_all()
+        de = 0.0
+        for sw in range(6):
+            st = eng.sweep(mp, 31, sw)
+            assert st.trans_acc + st.trans_rej + st.rot_acc + st.rot_rej == hs.n
+            de += st.energy_delta
+        e1 = eng.all_to_all()
+        assert abs((e1 - e0) - de) <= 1e-9 * max(abs(e0), abs(e1), 1.0)
+        eng.close()
+    mp.trial_rule = 2
+    eng = Engine(0, "fast").load(hs)
+    with pytest.raises(Exception):
+        eng.sweep(mp, 31, 0)
+    eng.close()
+    hs.close()
+
+
 def test_reproducible_trajectory():
     top, cfg = synth.small_case("psc_lattice")
     hs = HostSystem(top, cfg)
@@ -115,25 +141,29 @@ def test_average_energy_matches_reference_sequential_sweeps():
         ref_errs.append(_block_stderr(w))
     ref_mean = float(np.mean(ref_means))
     ref_err = max(float(np.std(ref_means, ddof=1) / math.sqrt(len(ref_means))), float(np.mean(ref_errs)) / math.sqrt(len(ref_means)))
-    gpu_means, gpu_errs = [], []
-    acc_t = acc_r = tot_t = tot_r = 0
-    for seed in (101, 202, 303, 404):
+    def one_seed(seed):          # the seeds run side by side (one context and stream each): a 1 280-particle sweep leaves the GPU almost idle
         eng = Engine(0, "fast").load(hs)
         mp = move_params(P["temper"], P["transmx"], P["rotmx"])
         e = eng.all_to_all()
         series = []
+        a_t = a_r = n_t = n_r = 0
         for sw in range(1, P["nsweeps"] + 1):
             st = eng.sweep(mp, seed, sw)
             e += st.energy_delta
-            acc_t += st.trans_acc; tot_t += st.trans_acc + st.trans_rej
-            acc_r += st.rot_acc; tot_r += st.rot_acc + st.rot_rej
+            a_t += st.trans_acc; n_t += st.trans_acc + st.trans_rej
+            a_r += st.rot_acc; n_r += st.rot_acc + st.rot_rej
             if sw > skip and sw % P["report"] == 0:
                 series.append(e)
         e_check = eng.all_to_all()
         assert abs(e_check - e) <= 1e-7 * abs(e_check)                   # running sum of dE == recomputed total
-        gpu_means.append(np.mean(series))
-        gpu_errs.append(_block_stderr(series))
         eng.close()
+        return np.mean(series), _block_stderr(series), a_t, n_t, a_r, n_r
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(4) as ex:
+        res = list(ex.map(one_seed, (101, 202, 303, 404)))
+    gpu_means, gpu_errs = [r[0] for r in res], [r[1] for r in res]
+    acc_t, tot_t, acc_r, tot_r = (sum(r[k] for r in res) for k in (2, 3, 4, 5))
     gpu_mean = float(np.mean(gpu_means))
     gpu_err = max(float(np.std(gpu_means, ddof=1) / math.sqrt(len(gpu_means))), float(np.mean(gpu_errs)) / math.sqrt(len(gpu_means)))
     sigma = math.sqrt(ref_err ** 2 + gpu_err ** 2)
@@ -284,8 +314,7 @@ def test_average_energy_with_chain_moves_matches_reference_sequential_sweeps():
         ref_errs.append(_block_stderr(w))
     ref_mean = float(np.mean(ref_means))
     ref_err = max(float(np.std(ref_means, ddof=1) / math.sqrt(len(ref_means))), float(np.mean(ref_errs)) / math.sqrt(len(ref_means)))
-    gpu_means, gpu_errs = [], []
-    for seed in (101, 202, 303, 404):
+    def one_seed(seed):
         eng = Engine(0, "fast").load(hs)
         mp = move_params(P["temper"], P["transmx"], P["rotmx"])
         cm = chain_moves(P["chainprob"], P["chainmmx"], P["chainrmx"])
@@ -298,9 +327,13 @@ def test_average_energy_with_chain_moves_matches_reference_sequential_sweeps():
                 series.append(e)
         e_check = eng.all_to_all()
         assert abs(e_check - e) <= 1e-7 * max(abs(e_check), 1.0)
-        gpu_means.append(np.mean(series))
-        gpu_errs.append(_block_stderr(series))
         eng.close()
+        return np.mean(series), _block_stderr(series)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(4) as ex:
+        res = list(ex.map(one_seed, (101, 202, 303, 404)))
+    gpu_means, gpu_errs = [r[0] for r in res], [r[1] for r in res]
     gpu_mean = float(np.mean(gpu_means))
     gpu_err = max(float(np.std(gpu_means, ddof=1) / math.sqrt(len(gpu_means))), float(np.mean(gpu_errs)) / math.sqrt(len(gpu_means)))
     sigma = math.sqrt(ref_err ** 2 + gpu_err ** 2)
@@ -407,8 +440,7 @@ def test_npt_average_volume_matches_reference_sequential_sweeps():
         ref_v.append(v[sw > skip].mean())
         se, e = np.array(run["energy_sweep"]), np.array(run["energy"])
         ref_e.append(e[se > skip].mean())
-    gpu_v, gpu_e = [], []
-    for seed in (101, 202, 303, 404, 505, 606, 707, 808):
+    def one_seed(seed):
         eng = Engine(0, "fast").load(hs)
         mp = move_params(P["temper"], P["transmx"], P["rotmx"])
         vs, es = [], []
@@ -426,9 +458,13 @@ def test_npt_average_volume_matches_reference_sequential_sweeps():
                 es.append(e)
         assert abs(eng.all_to_all() - e) <= 1e-7 * max(1.0, abs(e))
         assert 0.2 < n_acc / P["nsweeps"] < 0.9
-        gpu_v.append(np.mean(vs))
-        gpu_e.append(np.mean(es))
         eng.close()
+        return np.mean(vs), np.mean(es)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(8) as ex:
+        res = list(ex.map(one_seed, (101, 202, 303, 404, 505, 606, 707, 808)))
+    gpu_v, gpu_e = [r[0] for r in res], [r[1] for r in res]
     rv, gv = float(np.mean(ref_v)), float(np.mean(gpu_v))
     sv = math.sqrt(np.var(ref_v, ddof=1) / len(ref_v) + np.var(gpu_v, ddof=1) / len(gpu_v))
     re_, ge = float(np.mean(ref_e)), float(np.mean(gpu_e))
@@ -455,19 +491,20 @@ def test_cpsc_system_averages_three_temperatures(system):
     (8 seeds each; tests/golden/make_sweep_cpsc_golden.py). cpsc100 is the input as shipped (one cell: the proposal / acceptance logic
     alone); cpsc800 is the same configuration tiled 2 x 2 x 2 (4 cells per axis: the checkerboard decomposition, where a bias would
     show first at the lowest temperature). Both sides start from the same configuration and are compared over the same window of
-    sweeps, (W/3, W], W = 20 000: low-temperature runs are still relaxing, equal windows compare equal stages."""
+    sweeps, (W/3, W], W = 5 000, and from the configuration the reference itself starts from at that temperature (every T_x directory
+    ships its own equilibrated config.init)."""
     from concurrent.futures import ThreadPoolExecutor
     gold = _cpsc_golden()
-    W = 20000
+    W = 5000
     top = gold["top"][system]
-    cfg = next(r["config"] for r in gold["runs"] if r["system"] == system and r["config"])
+    cfgs = {round(r["temper"], 3): r["config"] for r in gold["runs"] if r["system"] == system and r["config"]}
     temps = [0.1, 0.16, 0.22]
     seeds = [5, 6, 7, 8, 9, 10, 11, 12]       # as many as the reference: a run is a single warp (cpsc100) or a few (cpsc800), they overlap on the GPU
     chunk = 50
 
     def run(job):
         temper, seed = job
-        hs = HostSystem(top, cfg)
+        hs = HostSystem(top, cfgs[round(temper, 3)])
         eng = Engine(0, "fast").load(hs)
         mp = move_params(temper, 0.03, 15.0, n_sub=chunk)
         sw, en = [], []
