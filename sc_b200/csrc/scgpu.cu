@@ -1007,7 +1007,11 @@ k_gate_rows(DevSys s, FlatList fl) {
         const int last = sh_cx[2];
         const int count = last - first + 1;
         const int C = sh_soff[18];
+#ifndef GATE_NO_MASKS
+        const int Cpad = (C + 63) / 64 * 64;          // the scan below takes the tile in half-words of 64 candidates (16 per warp)
+#else
         const int Cpad = (C + 4 * GR_SL - 1) / (4 * GR_SL) * (4 * GR_SL);
+#endif
         // unit centre in box fractions (the staged FP32 positions are wrapped into [0, 1): the difference is folded once)
         const float cen[3] = {(float)(0.5 * (sh_cx[0] + sh_cx[1] + 1) / nx - s.shift[0]), (float)((cy + 0.5) / ny - s.shift[1]), (float)((cz + 0.5) / s.nc[2] - s.shift[2])};
         auto staged = [&](const float4& f) {
@@ -1058,6 +1062,38 @@ k_gate_rows(DevSys s, FlatList fl) {
         unsigned short* buf = sh_hit[wid];
         int cur = lane;
         const int cur_max = lane + (GR_CAP - 4) * GR_STRIDE;
+#ifndef GATE_NO_MASKS
+        // Pass A: the centre-distance test of 32 candidates of this warp's slice leaves one BIT each in a register word (a broadcast
+        // LDS.128, three FMAs, a compare and a predicated OR per test -- no store, no cursor arithmetic, no branch); word j, bit b <->
+        // candidate 128 j + 16 (b >> 2) + 4 wid + (b & 3). The bits of a word are then expanded into the per-lane hit buffer
+        // (only hits cost instructions there; self-exclusion / the j < i rule of allToAll rows is applied at this point).
+        for (int j = 0; 128 * j < Cpad; j++) {
+            unsigned m = 0u;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (128 * j + 64 * h < Cpad) {          // warp-uniform
+                    const float4* tq = t_pf + 128 * j + 64 * h + 4 * wid;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const float4 q = tq[16 * t + u];
+                            const float sq = fmaf(m2z, q.z, fmaf(m2y, q.y, fmaf(m2x, q.x, q.w)));
+                            m |= sq <= thr ? 1u << (16 * h + 4 * t + u) : 0u;
+                        }
+                    }
+                }
+            }
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1u;
+                const int c = 128 * j + 16 * (b >> 2) + 4 * wid + (b & 3);
+                buf[cur] = (unsigned short)c;
+                const bool take = MODE == 2 ? t_orig[c] < target : c != c_self;
+                cur = min(cur + (take ? GR_STRIDE : 0), cur_max);
+            }
+        }
+#else
         // warp w takes the candidates 16 i + 4 w .. 16 i + 4 w + 3: four float4 reads (and, for allToAll rows, ONE int4 read of the
         // original indices), fetched one trip ahead so that the shared-memory latency hides behind the arithmetic of the current trip
         float4 qn[4];
@@ -1091,6 +1127,7 @@ k_gate_rows(DevSys s, FlatList fl) {
                 cur = min(cur, cur_max);
             }
         }
+#endif
         if (__any_sync(0xffffffffu, cur == cur_max) && lane == 0) atomicOr(fl.overflow, 4);
         // ---- segment lower bound (lb_beyond_one, pair_energy.cuh): of the candidates within the centre-distance reach only those whose
         // rods can come within the surface cutoff interact at all -- a sixth of them in a dense rod fluid. Every lane filters its own
@@ -1807,19 +1844,17 @@ k_cheap_flat(DevSys s, FlatList fl, unsigned long long* counters, const __grid_c
     }
 }
 
-// Patch terms in three dense phases per block of 128 listed pairs: most pairs drop out after the FIRST patch_intersect()
-// (the partner is simply not inside the patch wedge), so running intersect #1, intersect #2 and atr_e() as separate phases
-// with a block-level compaction of the survivors in between keeps the lanes of the expensive later phases full instead of
-// leaving a few lanes per warp on the long path.
+// Patch terms in three dense phases: most pairs drop out after the FIRST patch_intersect() (the partner is simply not inside the
+// patch wedge), so intersect #1, intersect #2 and atr_e() run as separate phases with a compaction of the survivors in between,
+// which keeps the lanes of the expensive later phases full instead of leaving a few lanes per warp on the long path.
+// The compaction is per WARP: every warp owns two ring buffers in shared memory (survivors of phase 1, survivors of phase 2) and
+// runs a later phase as soon as 32 entries wait for it -- no block barrier anywhere (the block-wide version of this kernel spent
+// 45 % of its stall cycles at its four __syncthreads per batch), warps drift apart and hide each other's gather latency.
 #ifndef PF_THREADS_N
 #define PF_THREADS_N 128
 #endif
 constexpr int PF_THREADS = PF_THREADS_N;
-
-struct PatchItem {          // everything a phase needs to re-derive the geometry of a (pair, patch combination)
-    int p;                  // index into FlatList::pair / e
-    double T1, T2, S1, S2;
-};
+constexpr int PF_Q = 64;              // ring capacity per warp: at most 31 waiting + 32 new entries
 
 // the four vectors of one patch out of a cell-sorted record (layout: dir | pd0 | s0 | s1 | pd1 | s2 | s3 | ch0 | ch1 | pos) in
 // three or four 32-byte requests instead of a dozen narrower ones: the gathers of this kernel are bound by L1 requests
@@ -1836,135 +1871,45 @@ __device__ __forceinline__ void load_patch_args(const double* rec, int pn, bool 
     }
 }
 
-__device__ __forceinline__ void patch_setup(const DevSys& s, const FlatList& fl, int p, int combo, const scgpu_iaparam*& ia, v3& r_cm,
-                                            PatchArgs& P1, PatchArgs& P2, bool& first_psc, bool& second_psc, bool& applicable,
-                                            const scgpu_iaparam* ia_one = nullptr) {
-    int2 pr = fl.pair[p];
-    double4 pi = ldg256(s.posw + pr.x), pj = ldg256(s.posw + pr.y);
-    r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
-    ia = ia_one ? ia_one : &s.ia[w_type(pi.w) * s.ntypes + w_type(pj.w)];
-    const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
-    const bool firstCH = is_chiral(g0), secondCH = is_chiral(g1), firstT = is_two_patch(g0), secondT = is_two_patch(g1);
-    first_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && is_psc_family(g0));
-    second_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && !is_psc_family(g0));
-    const int pn1 = combo & 1, pn2 = combo >> 1;
-    applicable = (combo == 0) || (combo == 1 && firstT) || (combo == 2 && secondT) || (combo == 3 && firstT && secondT);
-    const double* s1 = s.rec + (size_t)pr.x * REC;
-    const double* s2 = s.rec + (size_t)pr.y * REC;
-    load_patch_args(s1, pn1, firstCH, P1);
-    load_patch_args(s2, pn2, secondCH, P2);
-}
-
-// block-wide stable compaction: returns this thread's rank among the threads with flag set, total in *count (shared)
-__device__ __forceinline__ int block_rank(bool flag, int* sh_warp, int* count) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned m = __ballot_sync(0xffffffffu, flag);
-    if (lane == 0) sh_warp[wid] = __popc(m);
-    __syncthreads();
-    int off = 0, tot = 0;
-    for (int w = 0; w < PF_THREADS / 32; w++) { int c = sh_warp[w]; if (w < wid) off += c; tot += c; }
-    if (threadIdx.x == 0) *count = tot;
-    __syncthreads();
-    return off + __popc(m & ((1u << lane) - 1u));
-}
-
 #ifndef PATCH_MINB
-#define PATCH_MINB 7
+#define PATCH_MINB 4
 #endif
+// an item carries the slots and the separation vector, so that the later phases do not re-load the pair, both positions and
+// re-image them
+struct PfItem1 { int p, si, sj, tb; double rx, ry, rz, T1, T2; };
+struct PfItem2 { int p, si, sj, tb; double rx, ry, rz, T1, T2, S1, S2; };
+
 template <bool ONE>
 __global__ void __launch_bounds__(PF_THREADS, PATCH_MINB)
 k_patch_flat(DevSys s, FlatList fl, int any_two_patch, int mirror, const __grid_constant__ scgpu_iaparam ia1) {
     const scgpu_iaparam* ia_one = ONE ? &ia1 : nullptr;
     if (*fl.overflow) return;
-    // survivors of a phase are appended with one shared-memory atomic per warp: their order inside the block's list is arbitrary, but
-    // nothing depends on it (every item is a pair of its own, its result goes to that pair's slot) -- ONE barrier per phase instead
-    // of the three a ranked compaction needs. An item carries the slots and the separation vector, so that the later phases do not
-    // re-load the pair, both positions and re-image them.
-    struct Item { int p, si, sj, pad; double rx, ry, rz, T1, T2, S1, S2; };
-    __shared__ Item sh_a[PF_THREADS], sh_b[PF_THREADS];
-    __shared__ int sh_n[2];
-    const int lane = threadIdx.x & 31;
+    __shared__ PfItem1 sh_q1[PF_THREADS / 32][PF_Q];
+    __shared__ PfItem2 sh_q2[PF_THREADS / 32][PF_Q];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
+    PfItem1* q1 = sh_q1[wid];
+    PfItem2* q2 = sh_q2[wid];
     const int total = *fl.ptotal;
     const int ncombo = any_two_patch ? 4 : 1;
-    auto append = [&](Item* list, int* counter, bool keep, const Item& it) {
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(counter, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) list[base + __popc(m & lt_mask)] = it;
-    };
-    for (int base = blockIdx.x * PF_THREADS; base < total; base += gridDim.x * PF_THREADS) {       // block-uniform trip count
-        const int q = base + threadIdx.x;
-        const int p = q < total ? fl.plist[q] : -1;
-        int2 pr = make_int2(0, 0);
-        v3 r_cm = mk(0.0, 0.0, 0.0);
-        int tbits = 0;
-        if (p >= 0) {
-            pr = fl.pair[p];
-            const double4 pi = ldg256(s.posw + pr.x), pj = ldg256(s.posw + pr.y);
-            r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
-            tbits = w_type(pi.w) * s.ntypes + w_type(pj.w);
-        }
-        for (int combo = 0; combo < ncombo; combo++) {
-            const int pn1 = combo & 1, pn2 = combo >> 1;
-            if (threadIdx.x < 2) sh_n[threadIdx.x] = 0;
-            __syncthreads();
-            // ---- phase 1: rod 2 against the patch of rod 1 (T1, T2)
-            {
-                bool keep = false;
-                Item it;
-                it.p = p; it.si = pr.x; it.sj = pr.y; it.pad = tbits; it.rx = r_cm.x; it.ry = r_cm.y; it.rz = r_cm.z; it.T1 = it.T2 = it.S1 = it.S2 = 0.0;
-                if (p >= 0) {
-                    const scgpu_iaparam* ia = ia_one ? ia_one : &s.ia[tbits];
-                    const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
-                    const bool firstT = is_two_patch(g0), secondT = is_two_patch(g1);
-                    const bool ok = (combo == 0) || (combo == 1 && firstT) || (combo == 2 && secondT) || (combo == 3 && firstT && secondT);
-                    if (ok) {
-                        const bool first_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && is_psc_family(g0));
-                        PatchArgs P1, P2;
-                        load_patch_args(s.rec + (size_t)pr.x * REC, pn1, is_chiral(g0), P1);
-                        load_patch_args(s.rec + (size_t)pr.y * REC, pn2, is_chiral(g1), P2);
-                        const int nn = first_psc ? patch_intersect<false>(P1.dir, P2.dir, P1, r_cm, it.T1, it.T2, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1])
-                                                 : patch_intersect<true>(P1.dir, P2.dir, P1, r_cm, it.T1, it.T2, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1]);
-                        keep = nn >= 2;
-                    }
-                }
-                append(sh_a, &sh_n[0], keep, it);
-            }
-            __syncthreads();
-            const int n1 = sh_n[0];
-            // ---- phase 2: rod 1 against the patch of rod 2 (S1, S2), survivors only
-            {
-                bool keep = false;
-                Item it;
-                if ((int)threadIdx.x < n1) {
-                    it = sh_a[threadIdx.x];
-                    const scgpu_iaparam* ia = ia_one ? ia_one : &s.ia[it.pad];
-                    const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
-                    const bool second_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && !is_psc_family(g0));
-                    PatchArgs P1, P2;
-                    load_patch_args(s.rec + (size_t)it.si * REC, pn1, is_chiral(g0), P1);
-                    load_patch_args(s.rec + (size_t)it.sj * REC, pn2, is_chiral(g1), P2);
-                    const v3 vec1 = neg(mk(it.rx, it.ry, it.rz));
-                    const int nn = second_psc ? patch_intersect<false>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0])
-                                              : patch_intersect<true>(P2.dir, P1.dir, P2, vec1, it.S1, it.S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0]);
-                    keep = nn >= 2;
-                }
-                append(sh_b, &sh_n[1], keep, it);
-            }
-            __syncthreads();
-            const int n2 = sh_n[1];
-            // ---- phase 3: attraction of the survivors
-            if ((int)threadIdx.x < n2) {
-                const Item it = sh_b[threadIdx.x];
-                const scgpu_iaparam* ia = ia_one ? ia_one : &s.ia[it.pad];
+    const int gw = blockIdx.x * (PF_THREADS / 32) + wid, nwarps = gridDim.x * (PF_THREADS / 32);
+    // The patch combinations of two-patch types run one after another, each drained completely before the next starts: a pair is
+    // handled by the same warp in every combination (the batch -> warp map is fixed), so its slot of fl.e has one writer and the
+    // additions happen in program order -- bit-reproducible.
+    for (int combo = 0; combo < ncombo; combo++) {
+        const int pn1 = combo & 1, pn2 = combo >> 1;
+        int h1 = 0, n1 = 0, h2 = 0, n2 = 0;              // ring heads and fill counts (warp-uniform)
+        // ---- phase 3: attraction of the pairs both of whose rods reach into the other's patch
+        auto phase3 = [&](int cnt) {
+            if (lane < cnt) {
+                const PfItem2 it = q2[(h2 + lane) & (PF_Q - 1)];
+                const scgpu_iaparam* ia = ia_one ? ia_one : &s.ia[it.tb];
                 const int g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
                 PatchArgs P1, P2;
                 load_patch_args(s.rec + (size_t)it.si * REC, pn1, is_chiral(g0), P1);
                 load_patch_args(s.rec + (size_t)it.sj * REC, pn2, is_chiral(g1), P2);
                 const double e = atr_e(*ia, P1.dir, P2.dir, P1.pdir, P2.pdir, mk(it.rx, it.ry, it.rz), pn1, pn2, it.S1, it.S2, it.T1, it.T2);
-                fl.e[it.p].y += e;        // one writer per pair and phase; the combinations run one after another
+                fl.e[it.p].y += e;
                 if (mirror && e != 0.0) {      // every-particle pass: the partner lists this pair too -- find it in the partner's span (a few entries)
                     const int4 cj = fl.chunks[w_orig(s.posw[it.sj].w)];
                     bool found = false;
@@ -1972,7 +1917,80 @@ k_patch_flat(DevSys s, FlatList fl, int any_two_patch, int mirror, const __grid_
                     if (!found) atomicOr(fl.overflow, 8);      // cannot happen: a pair inside the patch range is listed by both sides
                 }
             }
-            __syncthreads();
+            __syncwarp();
+            h2 = (h2 + cnt) & (PF_Q - 1);
+            n2 -= cnt;
+        };
+        // ---- phase 2: rod 1 against the patch of rod 2 (S1, S2), survivors of phase 1 only
+        auto phase2 = [&](int cnt) {
+            bool keep = false;
+            PfItem2 out;
+            if (lane < cnt) {
+                const PfItem1 it = q1[(h1 + lane) & (PF_Q - 1)];
+                const scgpu_iaparam* ia = ia_one ? ia_one : &s.ia[it.tb];
+                const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
+                const bool second_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && !is_psc_family(g0));
+                PatchArgs P1, P2;
+                load_patch_args(s.rec + (size_t)it.si * REC, pn1, is_chiral(g0), P1);
+                load_patch_args(s.rec + (size_t)it.sj * REC, pn2, is_chiral(g1), P2);
+                const v3 vec1 = neg(mk(it.rx, it.ry, it.rz));
+                double S1 = 0.0, S2 = 0.0;
+                const int nn = second_psc ? patch_intersect<false>(P2.dir, P1.dir, P2, vec1, S1, S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0])
+                                          : patch_intersect<true>(P2.dir, P1.dir, P2, vec1, S1, S2, ia->pcanglsw[2 * pn2 + 1], ia->rcutSq, ia->half_len[1], ia->half_len[0]);
+                keep = nn >= 2;
+                out.p = it.p; out.si = it.si; out.sj = it.sj; out.tb = it.tb; out.rx = it.rx; out.ry = it.ry; out.rz = it.rz;
+                out.T1 = it.T1; out.T2 = it.T2; out.S1 = S1; out.S2 = S2;
+            }
+            __syncwarp();
+            h1 = (h1 + cnt) & (PF_Q - 1);
+            n1 -= cnt;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) q2[(h2 + n2 + __popc(m & lt_mask)) & (PF_Q - 1)] = out;
+            n2 += __popc(m);
+            __syncwarp();
+        };
+        // ---- phase 1: rod 2 against the patch of rod 1 (T1, T2), every listed pair, 32 at a time
+        auto phase1 = [&](int base) {
+            const int q = base + lane;
+            bool keep = false;
+            PfItem1 it;
+            if (q < total) {
+                const int p = fl.plist[q];
+                const int2 pr = fl.pair[p];
+                const double4 pi = ldg256(s.posw + pr.x), pj = ldg256(s.posw + pr.y);
+                const v3 r_cm = image(s.box, mk(pi.x, pi.y, pi.z), mk(pj.x, pj.y, pj.z));
+                const int tb = w_type(pi.w) * s.ntypes + w_type(pj.w);
+                const scgpu_iaparam* ia = ia_one ? ia_one : &s.ia[tb];
+                const int kind = (int)ia->reserved[0], g0 = (int)ia->geotype[0], g1 = (int)ia->geotype[1];
+                const bool firstT = is_two_patch(g0), secondT = is_two_patch(g1);
+                const bool ok = (combo == 0) || (combo == 1 && firstT) || (combo == 2 && secondT) || (combo == 3 && firstT && secondT);
+                if (ok) {
+                    const bool first_psc = (kind == K_SC_PSC) || (kind == K_SC_PSCCPSC && is_psc_family(g0));
+                    PatchArgs P1, P2;
+                    load_patch_args(s.rec + (size_t)pr.x * REC, pn1, is_chiral(g0), P1);
+                    load_patch_args(s.rec + (size_t)pr.y * REC, pn2, is_chiral(g1), P2);
+                    double T1 = 0.0, T2 = 0.0;
+                    const int nn = first_psc ? patch_intersect<false>(P1.dir, P2.dir, P1, r_cm, T1, T2, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1])
+                                             : patch_intersect<true>(P1.dir, P2.dir, P1, r_cm, T1, T2, ia->pcanglsw[2 * pn1], ia->rcutSq, ia->half_len[0], ia->half_len[1]);
+                    keep = nn >= 2;
+                    it.p = p; it.si = pr.x; it.sj = pr.y; it.tb = tb; it.rx = r_cm.x; it.ry = r_cm.y; it.rz = r_cm.z; it.T1 = T1; it.T2 = T2;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) q1[(h1 + n1 + __popc(m & lt_mask)) & (PF_Q - 1)] = it;
+            n1 += __popc(m);
+            __syncwarp();
+        };
+        // every phase appears ONCE in the code (the three bodies are large; duplicates would thrash the instruction cache): a small
+        // warp-uniform scheduler runs the latest phase that has a full warp of work, and drains the rings at the end
+        int base = gw * 32;
+        bool draining = false;
+        for (;;) {
+            if (n2 >= 32 || (draining && n1 == 0 && n2 > 0)) { phase3(min(n2, 32)); continue; }
+            if (n1 >= 32 || (draining && n1 > 0)) { phase2(min(n1, 32)); continue; }
+            if (base < total) { phase1(base); base += nwarps * 32; continue; }
+            if (!draining) { draining = true; continue; }
+            break;
         }
     }
 }
@@ -2938,7 +2956,7 @@ static int launch_energy(scgpu_ctx* c, int mode, int m, int gw, const int* d_tar
             if (mode == 1) k_cheap_flat<false, false, true><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1); else k_cheap_flat<false, false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, fl, d_counters, ia1);
         }
         mark(2);
-        if (one) k_patch_flat<true><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, mode == 1 ? 1 : 0, ia1); else k_patch_flat<false><<<c->sm_count * PATCH_MINB * 2, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, mode == 1 ? 1 : 0, ia1);
+        if (one) k_patch_flat<true><<<c->sm_count * PATCH_MINB, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, mode == 1 ? 1 : 0, ia1); else k_patch_flat<false><<<c->sm_count * PATCH_MINB, PF_THREADS, 0, c->stream>>>(s, fl, c->any_two_patch ? 1 : 0, mode == 1 ? 1 : 0, ia1);
         mark(3);
         k_combine_flat<<<(c->n + 31) / 32, 256, 0, c->stream>>>(c->n, fl, c->d_posw, d_out);
         mark(4);
