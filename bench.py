@@ -420,19 +420,25 @@ def run_ours(args):
         mp.trans_mx[k] = 2.0 * 0.0212
         mp.rot_angle[k] = 7.5 / 180.0 * 1.5707963267948966 * 0.5
     mp.n_sub = 1
-    eng.set_particles(hs.state, hs.type, hs.moltype)
     nsw = max(3, min(args.steps, 10))
-    for k in range(2):
-        eng.sweep(mp, 12345 + rank, k)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    acc = tot = 0
-    for k in range(nsw):
-        st = eng.sweep(mp, 12345 + rank, 2 + k)
-        acc += st.trans_acc + st.rot_acc
-        tot += st.trans_acc + st.rot_acc + st.trans_rej + st.rot_rej
-    sweep_s = time.perf_counter() - t0
+
+    def time_sweeps(rule):
+        mp.trial_rule = rule
+        eng.set_particles(hs.state, hs.type, hs.moltype)
+        for k in range(2):
+            eng.sweep(mp, 12345 + rank, k)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        a = t = 0
+        for k in range(nsw):
+            st = eng.sweep(mp, 12345 + rank, 2 + k)
+            a += st.trans_acc + st.rot_acc
+            t += st.trans_acc + st.rot_acc + st.trans_rej + st.rot_rej
+        return time.perf_counter() - t0, a, t
+
+    rule0_s, _, _ = time_sweeps(0)           # equal number of trials per non-empty cell, drawn with replacement
+    sweep_s, acc, tot = time_sweeps(2)       # the headline: every particle exactly once per sweep, random order inside its cell
     if world > 1:
         t = torch.tensor([sweep_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -440,7 +446,10 @@ def run_ours(args):
     sweeps = {"metric": "mc_sweeps_per_s", "value": nsw * world / sweep_s, "unit": "sweeps/s (1 sweep = N = 65536 trial moves per replica)",
               "ms_per_sweep": sweep_s / nsw * 1e3, "trial_moves_per_s": tot * world / sweep_s, "acceptance": acc / max(1, tot),
               "temper": 0.1, "transmx": 0.0212, "rotmx_deg": 7.5, "sweeps_timed": nsw,
-              "note": "whole scgpu_sweep_checkerboard call: shifted cell build + 8 colour passes + statistics read-back"}
+              "trial_rule": 2, "ms_per_sweep_trial_rule_0": rule0_s / nsw * 1e3,
+              "note": "whole scgpu_sweep_checkerboard call: shifted cell build + 8 colour passes of the round kernel (k_sweep_rounds: a block per active cell, "
+                      "up to 16 trials evaluated at once and resolved in sequence) + statistics read-back; trial_rule 2 = every particle exactly once per sweep "
+                      "in a fresh random order inside its cell, rule 0 = the same number of trials in every non-empty cell, with replacement"}
 
     # ---- BASELINE configs[4]: parallel tempering, 8 replicas x 65 536 PSC on `world` GPUs (8 / world replicas per GPU, each on its
     # own stream), one scgpu_replica_exchange every nrepchange = 10 sweeps: allToAll() of every replica, records packed on the device,

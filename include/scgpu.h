@@ -87,7 +87,10 @@ typedef struct scgpu_moveparams {
                                       1: a cell performs n_sub * (its population) trials -- every particle is picked once per sweep on
                                       average, the reference's per-particle rates (Updater::simulate draws uniformly among N,
                                       updater.cpp:206-230), at the price of every pass lasting as long as its fullest cell.
-                                      Both rules leave the Boltzmann distribution invariant (the count is fixed before the pass and no
+                                      2: every particle is tried exactly once per sweep: the particles of a cell are walked in a fresh
+                                      random order (a random-order sequential sweep; balance holds, the order is independent of the
+                                      configuration). Kernels that draw with replacement (bonded systems, chain sweeps) treat 2 as 1.
+                                      All rules leave the Boltzmann distribution invariant (the count is fixed before the pass and no
                                       particle leaves its cell within one); fractional counts are stochastically rounded */
     int reserved;
 } scgpu_moveparams;

@@ -2019,6 +2019,7 @@ __device__ __noinline__ double wall_energy_rec(const DevSys& s, const double* r,
 }
 
 #include "sweep.cuh"
+#include "sweep_rounds.cuh"
 
 // one thread per listed pair; grid-stride because the list length lives on the device
 __global__ void __launch_bounds__(128, 4)
@@ -3233,7 +3234,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     if (chains) for (int t = 0; t < c->nmol; t++) ARG(c->h_mol[t].mol_size <= CH_MAX, "scgpu_sweep_checkerboard_chains: a molecule is longer than MAXCHL = 20");
     ARG(mp->temper > 0 && mp->n_sub >= 1, "scgpu_sweep_checkerboard: temperature and n_sub must be positive");
     ARG(mp->grid_k >= 0 && mp->grid_k <= 3, "scgpu_sweep_checkerboard: grid_k must be 0 (automatic), 1, 2 or 3");
-    ARG(mp->trial_rule == 0 || mp->trial_rule == 1, "scgpu_sweep_checkerboard: trial_rule must be 0 (per cell) or 1 (per particle)");
+    ARG(mp->trial_rule >= 0 && mp->trial_rule <= 2, "scgpu_sweep_checkerboard: trial_rule must be 0 (per cell), 1 (per particle) or 2 (every particle once)");
     ARG(c->n > 0 && c->ntypes > 0 && c->ntypes <= 40, "scgpu_sweep_checkerboard: set topology (<= 40 types) and particles first");
     CK(cudaSetDevice(c->device));
     // random grid shift and colour order for this sweep: a pure function of (seed, sweep)
@@ -3243,8 +3244,14 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     // Fineness of the checkerboard: the serial chain of trials inside a cell is what a sweep costs, (K+1)^3 N / cells(K) trials long;
     // the largest K <= 3 that still leaves about two particles per cell. Chain moves need every member of a molecule in one cell and
     // the 27-cell neighbourhood of their kernel: sweeps with chain moves stay on the coarse grid.
+    // Systems without bonded molecules take the round kernel (sweep_rounds.cuh): the trials of a cell are evaluated several at a time,
+    // so the coarse grid (more trials per cell and pass, fewer passes) is the fast one. SCGPU_SWEEP_KERNEL=cells|rounds forces one.
+    bool bonded_any = false;
+    for (int t = 0; t < c->nmol; t++) bonded_any = bonded_any || c->h_mol[t].mol_size > 1.0;
+    bool rounds = !chains && !bonded_any;
+    if (const char* e = getenv("SCGPU_SWEEP_KERNEL")) { if (!strcmp(e, "cells")) rounds = false; else if (!strcmp(e, "rounds") && !chains && !bonded_any) rounds = true; }
     int K = 1;
-    if (!chains) {
+    if (!chains && !rounds) {
         for (int k = 3; k >= 2; k--) {
             double cells = 1.0;
             bool fits = true;
@@ -3298,7 +3305,23 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     int nactive = (c->nc[0] / ncol.x) * (c->nc[1] / ncol.y) * (c->nc[2] / ncol.z);
     const bool one = c->one_type >= 0 && c->rods_only;
     const scgpu_iaparam& ia1 = c->h_ia[one ? (size_t)c->one_type * c->ntypes + c->one_type : 0];
+    if (rounds) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            CK(cudaFuncSetAttribute(k_sweep_rounds<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrShared)));
+            CK(cudaFuncSetAttribute(k_sweep_rounds<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrShared)));
+            CK(cudaFuncSetAttribute(k_sweep_rounds<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrShared)));
+            attr_done = true;
+        }
+    }
     for (int k = 0; k < ncolours; k++) {
+        if (rounds) {
+            if (c->rods_only && one) k_sweep_rounds<true, true><<<nactive, SR_THREADS, sizeof(SrShared), c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
+            else if (c->rods_only) k_sweep_rounds<true, false><<<nactive, SR_THREADS, sizeof(SrShared), c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
+            else k_sweep_rounds<false, false><<<nactive, SR_THREADS, sizeof(SrShared), c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
+            c->launches++;
+            continue;
+        }
         if (c->rods_only && one) k_sweep_cells<true, true><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
         else if (c->rods_only) k_sweep_cells<true, false><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
         else k_sweep_cells<false, false><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
@@ -3325,6 +3348,11 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
             cstats->chainr_acc += cacc[i].rot_acc; cstats->chainr_rej += cacc[i].rot_rej;
             cstats->cell_rej += cacc[i].cell_rej; cstats->energy_delta += cacc[i].de; cstats->noop += cacc[i].pad;
         }
+    }
+    if (rounds) {
+        long long lost = 0;
+        for (int i = 0; i < c->ncells; i++) lost += acc[i].pad;
+        if (lost) { g_err = "scgpu_sweep_checkerboard: " + std::to_string(lost) + " trial(s) had more partners than the round kernel's work list holds (rejected); use SCGPU_SWEEP_KERNEL=cells for this system"; return SCGPU_ERR_STATE; }
     }
     if (stats) {
         memset(stats, 0, sizeof *stats);

@@ -236,7 +236,7 @@ k_sweep_cells(DevSys s, SweepParams sp, unsigned long long seed, unsigned long l
     // cell within a pass), so detailed balance holds. Fractional counts are stochastically rounded.
     int ntrial;
     {
-        const double avg = sp.trial_rule == 1 ? sp.trial_scale * (double)sp.n_sub * (double)npart
+        const double avg = sp.trial_rule >= 1 ? sp.trial_scale * (double)sp.n_sub * (double)npart
                                               : sp.trial_scale * (double)sp.n_sub * (double)s.n / (double)s.cell_start[s.ncells + 1];
         const uint4 r = philox4x32((uint32_t)sweep, (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 24), (uint32_t)c0, 0xffffffffu, (uint32_t)seed, (uint32_t)(seed >> 32));
         const double fl = floor(avg);

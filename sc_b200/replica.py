@@ -153,7 +153,7 @@ class ParallelTempering:
     replica (each on its own stream); every `nrepchange` sweeps one scgpu_replica_exchange. The step sizes travel with the
     temperature in the payload (the reference swaps its Statistics block): payload[0:20] = trans_mx, [20:40] = rot_angle per type."""
 
-    def __init__(self, comm, engines, temper, paraltemper, transmx, rotmx_deg, nrepchange=10, seed=145658, press=0.0, paralpress=0.0, grid_k=0):
+    def __init__(self, comm, engines, temper, paraltemper, transmx, rotmx_deg, nrepchange=10, seed=145658, press=0.0, paralpress=0.0, grid_k=0, trial_rule=2):
         from .engine import ExchangeParams, MoveParams, ReplicaState
         self.comm, self.engines = comm, engines
         self.nlocal = len(engines)
@@ -173,6 +173,7 @@ class ParallelTempering:
         self.params.nrepchange, self.params.dtemp, self.params.dpress, self.params.seed = self.nrepchange, self.dtemp, self.dpress, self.seed
         self.mp = [MoveParams() for _ in range(self.nlocal)]
         self.grid_k = int(grid_k)
+        self.trial_rule = int(trial_rule)        # scgpu_moveparams::trial_rule (2: every particle once per sweep)
         self.acc = [0] * self.nlocal
         self.rej = [0] * self.nlocal
         self.exchanges = 0
@@ -182,7 +183,7 @@ class ParallelTempering:
     def _refresh(self):
         for k in range(self.nlocal):
             s, mp = self.states[k], self.mp[k]
-            mp.temper, mp.n_sub, mp.grid_k = s.temper, 1, self.grid_k
+            mp.temper, mp.n_sub, mp.grid_k, mp.trial_rule = s.temper, 1, self.grid_k, self.trial_rule
             for t in range(40):
                 mp.trans_mx[t] = s.payload[min(t, 19)]
                 mp.rot_angle[t] = s.payload[20 + min(t, 19)]

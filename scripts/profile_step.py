@@ -50,6 +50,8 @@ for _ in range(reps):
             mp.trans_mx[k] = 0.0424
             mp.rot_angle[k] = 7.5 / 180.0 * 1.5707963267948966 * 0.5
         mp.n_sub = 1
+        mp.grid_k = int(os.environ.get("SWEEP_GRID_K", "0"))
+        mp.trial_rule = int(os.environ.get("SWEEP_TRIAL_RULE", "0"))
         eng.sweep(mp, 12345, _)
     elif what == "membrane_chainsweep":               # configs[2] with the reference's move mix for lipids: chain moves of whole 3-bead molecules
         from sc_b200.engine import MoveParams, ChainMoves

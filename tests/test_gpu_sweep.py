@@ -75,14 +75,14 @@ def test_energy_bookkeeping_and_invariants(kind):
 
 
 def test_trial_rule_per_particle_gives_exactly_n_trials_and_keeps_the_books():
-    """scgpu_moveparams::trial_rule = 1: a cell performs (its population) trials per sweep -- N in total, exactly (no rounding), on
-    every grid fineness; energies stay exact"""
+    """scgpu_moveparams::trial_rule = 1, 2: a cell performs (its population) trials per sweep -- N in total, exactly (no rounding), on
+    every grid fineness; with rule 2 every particle exactly once; energies stay exact"""
     top, cfg = synth.small_case("psc_lattice")
     hs = HostSystem(top, cfg)
-    for gk in (0, 1, 2):
+    for gk, rule in ((0, 1), (1, 1), (2, 1), (0, 2), (1, 2), (2, 2)):
         eng = Engine(0, "fast").load(hs)
         mp = move_params(0.25, 0.05, 8.0)
-        mp.trial_rule, mp.grid_k = 1, gk
+        mp.trial_rule, mp.grid_k = rule, gk
         e0 = eng.all_to_all()
         de = 0.0
         for sw in range(6):
@@ -92,10 +92,32 @@ def test_trial_rule_per_particle_gives_exactly_n_trials_and_keeps_the_books():
         e1 = eng.all_to_all()
         assert abs((e1 - e0) - de) <= 1e-9 * max(abs(e0), abs(e1), 1.0)
         eng.close()
-    mp.trial_rule = 2
+    mp.trial_rule = 3
     eng = Engine(0, "fast").load(hs)
     with pytest.raises(Exception):
         eng.sweep(mp, 31, 0)
+    eng.close()
+    hs.close()
+
+
+@pytest.mark.parametrize("kind", ["psc_lattice", "mix"])
+def test_cell_walk_kernel_on_unbonded_systems(kind, monkeypatch):
+    """systems without bonds take the round kernel by default; the one-warp-per-cell walk (k_sweep_cells, what bonded systems use)
+    must keep the same exact books on them (SCGPU_SWEEP_KERNEL=cells)"""
+    monkeypatch.setenv("SCGPU_SWEEP_KERNEL", "cells")
+    top, cfg = synth.small_case(kind)
+    hs = HostSystem(top, cfg)
+    eng = Engine(0, "fast").load(hs)
+    mp = move_params(0.5 if kind != "psc_lattice" else 0.25, 0.05, 8.0)
+    e0 = eng.all_to_all()
+    de, acc = 0.0, 0
+    for sw in range(8):
+        st = eng.sweep(mp, 778, sw)
+        de += st.energy_delta
+        acc += st.trans_acc + st.rot_acc
+    e1 = eng.all_to_all()
+    assert acc > 0
+    assert abs((e1 - e0) - de) <= 1e-9 * max(abs(e0), abs(e1), 1.0)
     eng.close()
     hs.close()
 
@@ -127,7 +149,10 @@ def _block_stderr(x, nblocks=8):
     return float(np.std(means, ddof=1) / math.sqrt(nblocks))
 
 
-def test_average_energy_matches_reference_sequential_sweeps():
+@pytest.mark.parametrize("rule", [0, 2])
+def test_average_energy_matches_reference_sequential_sweeps(rule):
+    """rule 0: the same number of trials in every cell, with replacement; rule 2: every particle once per sweep in random order
+    (scgpu_moveparams::trial_rule) -- both through the round kernel (k_sweep_rounds), this system has no bonds"""
     gold = json.load(open(os.path.join(G, "sweep_psc1280.json")))
     P = gold["params"]
     top, cfg = synth.small_case("psc_lattice")
@@ -144,6 +169,7 @@ def test_average_energy_matches_reference_sequential_sweeps():
     def one_seed(seed):          # the seeds run side by side (one context and stream each): a 1 280-particle sweep leaves the GPU almost idle
         eng = Engine(0, "fast").load(hs)
         mp = move_params(P["temper"], P["transmx"], P["rotmx"])
+        mp.trial_rule = rule
         e = eng.all_to_all()
         series = []
         a_t = a_r = n_t = n_r = 0
@@ -507,6 +533,7 @@ def test_cpsc_system_averages_three_temperatures(system):
         hs = HostSystem(top, cfgs[round(temper, 3)])
         eng = Engine(0, "fast").load(hs)
         mp = move_params(temper, 0.03, 15.0, n_sub=chunk)
+        mp.trial_rule = 1 if system == "cpsc100" else 2          # per-particle rates with replacement / every particle once per sweep
         sw, en = [], []
         ta = tr = ra = rr = 0
         for k in range(W // chunk):
