@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small driver for compute-sanitizer (memcheck / racecheck): the thread-per-target gate on the rods_wide system (one-to-all of
-everyone + allToAll), the forced fallback, and a few chain-move sweeps on the chain fluid.
+everyone + allToAll), the forced fallback, sweeps of the round kernel and the cell walk, and a few chain-move sweeps on the chain fluid.
     compute-sanitizer --tool memcheck python scripts/sanitize_small.py"""
 import os
 import sys
@@ -20,6 +20,27 @@ if what in ("all", "rows"):
     tot = eng.all_to_all()
     print("rows: sum", float(ev.sum()), "2*total", 2 * tot)
     eng.close()
+if what in ("all", "rounds"):          # the round kernel (systems without bonds), all three trial rules, and the cell walk on the same system
+    for kind in ("psc_lattice", "mix"):
+        top, cfg = synth.small_case(kind)
+        hs = HostSystem(top, cfg)
+        eng = Engine(0, "fast").load(hs)
+        mp = MoveParams()
+        mp.temper = 0.5
+        mp.n_sub = 1
+        for k in range(40):
+            mp.trans_mx[k] = 0.1
+            mp.rot_angle[k] = 0.1
+        e0 = eng.all_to_all()
+        tot = 0.0
+        for sw, rule in enumerate((0, 1, 2)):
+            mp.trial_rule = rule
+            tot += eng.sweep(mp, 9, sw).energy_delta
+        os.environ["SCGPU_SWEEP_KERNEL"] = "cells"
+        tot += eng.sweep(mp, 9, 3).energy_delta
+        del os.environ["SCGPU_SWEEP_KERNEL"]
+        print("rounds", kind, ": drift", eng.all_to_all() - e0 - tot)
+        eng.close()
 if what in ("all", "chains"):
     top, cfg = synth.small_case("chain_fluid")
     hs = HostSystem(top, cfg)
