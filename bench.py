@@ -382,7 +382,7 @@ def run_ours(args):
     peaks, peak_kind = measured_peaks()
     cell_build = {"bound": "hbm", "ms": float(np.mean(cb_ms)), "achieved": cb_bytes / (np.mean(cb_ms) * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                   "unit": "GB/s", "frac": cb_bytes / (np.mean(cb_ms) * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
-                  "bytes_per_build": cb_bytes, "kernels": "k_cell_count + k_cell_scan + k_cell_fill + k_cell_place (4 launches; launch latency is a large share at 65k particles)"}
+                  "bytes_per_build": cb_bytes, "kernels": "k_cell_count (histogram + scan through a last-block ticket) + k_cell_fill + k_cell_place (3 launches; launch latency is a large share at 65k particles)"}
 
     # ---- full-system energy (allToAll: what every NPT volume move and every replica exchange needs): every pair once
     fe_ms = []

@@ -227,6 +227,7 @@ k_sweep_cells(DevSys s, SweepParams sp, unsigned long long seed, unsigned long l
             if (pb < C) { t_pf[pb] = staged_pos(wb); t_df[pb] = db; }
         }
     }
+    __syncwarp();          // the staged tile is read by other lanes from here on (racecheck: the partner lists below)
     // the active cell is the centre of its own neighbourhood: where its particles sit in the staged tile
     const int centre_seg = 2 * (g.k[2] * wy + g.k[1]);
     const int centre_off = sh_off[centre_seg] + (tb - sh_b[centre_seg]);

@@ -23,6 +23,8 @@ import subprocess
 import sys
 import tempfile
 
+import re
+
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -390,7 +392,32 @@ def do_wall():
         print("wall:", name)
 
 
+def do_wanglandau():
+    """Tests/test_mempore (wlm = 2: hole in the xy plane of a lipid membrane, NPT ptype 2, chain moves) and Tests/test_pscthrough
+    (wlm = 1: z position of a PSC crossing the membrane), 300 sweeps of the unmodified reference program: config.last and the
+    Wang-Landau weights it writes (wl-new.dat). The order parameters stay the reference's host code above the calculator seam;
+    through oracle/_ref/SC_scgpu every energy of these runs comes from the device (tests/test_gpu_dropin.py)."""
+    for name in ("test_mempore", "test_pscthrough"):
+        src = os.path.join(REF, "Tests", name, "new")
+        inp = {fn: open(os.path.join(src, fn)).read() for fn in ("options", "top.init", "config.init", "wl.dat")}
+        inp["options"] = re.sub(r"(?m)^nsweeps\s*=\s*\d+", "nsweeps = 300", inp["options"])
+        inp["options"] = re.sub(r"(?m)^movie\s*=\s*\d+", "movie = 0", inp["options"])
+        tmp = tempfile.mkdtemp(prefix="wl_")
+        for fn, txt in inp.items():
+            with open(os.path.join(tmp, fn), "w") as f:
+                f.write(txt)
+        run([SC], tmp)
+        with gzip.GzipFile(os.path.join(HERE, name + ".inputs.json.gz"), "wb", mtime=0) as g:
+            g.write(json.dumps(inp).encode())
+        gz_copy(os.path.join(tmp, "config.last"), os.path.join(HERE, name + ".short300.config.last.gz"))
+        gz_copy(os.path.join(tmp, "wl-new.dat"), os.path.join(HERE, name + ".short300.wl-new.dat.gz"))
+        shutil.rmtree(tmp)
+        print("wanglandau:", name)
+
+
 def main():
+    if "wanglandau" in sys.argv[1:]:
+        return do_wanglandau()
     if "wall" in sys.argv[1:]:
         return do_wall()
     if "ptype45" in sys.argv[1:]:

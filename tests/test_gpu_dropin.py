@@ -59,3 +59,26 @@ def test_reference_main_full_length_test_01():
     """Tests/test_01_normal_PSC exactly as Tests/test runs it (BASELINE configs[0])"""
     got, out = run_reference_program("test_01_normal_PSC", 0)
     assert got == open(os.path.join(G, "test_01_normal_PSC.config.last")).read(), out[-800:]
+
+
+@pytest.mark.parametrize("name", ["test_mempore", "test_pscthrough"])
+def test_reference_main_wang_landau_runs(name):
+    """Tests/test_mempore (Wang-Landau on the hole in the xy plane of a 500-lipid membrane, NPT ptype 2, chain moves) and
+    Tests/test_pscthrough (Wang-Landau on the z position of a PSC crossing the membrane): the order parameters, the mesh hole search
+    and the histogram are the reference's own host code above the calculator seam (mc/wanglandau.h, mc/mesh.cpp); every energy --
+    single-particle trials, chain moves (mol2others), volume moves (allToAll) -- comes from the device. config.last AND the
+    Wang-Landau weights written at the end (wl-new.dat) must equal the unmodified reference's byte for byte."""
+    import gzip
+    if not os.path.exists(SC):
+        pytest.skip("oracle/_ref/SC_scgpu was not built (make -C oracle scgpu_ref needs /root/reference)")
+    inputs = json.loads(gzip.open(os.path.join(G, name + ".inputs.json.gz")).read().decode())
+    with tempfile.TemporaryDirectory(prefix="dropin_wl_") as tmp:
+        for fn in ("options", "top.init", "config.init", "wl.dat"):
+            with open(os.path.join(tmp, fn), "w") as f:
+                f.write(inputs[fn])
+        r = subprocess.run([SC], cwd=tmp, capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        got_cfg = open(os.path.join(tmp, "config.last")).read()
+        got_wl = open(os.path.join(tmp, "wl-new.dat")).read()
+    assert got_cfg == gzip.open(os.path.join(G, name + ".short300.config.last.gz"), "rt").read(), r.stdout[-800:]
+    assert got_wl == gzip.open(os.path.join(G, name + ".short300.wl-new.dat.gz"), "rt").read()
