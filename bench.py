@@ -110,6 +110,42 @@ def cpu_reference(ntargets, reps, nproc):
             "seconds": tmax, "gated_pairs": gated}
 
 
+def cpu_reference_membrane(mtop, mcfg, ntargets=512):
+    """The reference's per-particle energy loop on the 265 041-particle membrane (configs[2]), one process, bounded sample: `ntargets`
+    evenly spaced particles over the reference's neighbour lists. The reference's allToAll() visits all N^2/2 pairs without lists
+    (totalenergycalculator.h:502-521) -- hours at this size; N/2 x the measured per-particle time is a LOWER bound of it."""
+    import re as _re
+    drv = os.path.join(ROOT, "oracle", "_ref", "sc_ref_fast")
+    if not os.path.exists(drv):
+        return None
+    m = _re.search(r"\[System\]\s*\n\s*(\w+)\s+(\d+)\s*\n\s*(\w+)\s+(\d+)", mtop)
+    if not m:
+        return None
+    counts = [int(m.group(2)), int(m.group(4))]
+    top1 = mtop[:m.start()] + "[System]\n%s 1\n%s 1\n" % (m.group(1), m.group(3))      # one molecule of each type; the driver replicates (MAXN bypass)
+    tmp = tempfile.mkdtemp(prefix="scref_mem_")
+    try:
+        for fn, txt in (("top.init", top1), ("config.init", mcfg), ("options", options_text())):
+            with open(os.path.join(tmp, fn), "w") as f:
+                f.write(txt)
+        out = subprocess.run([drv, "time", str(ntargets), "1"] + [str(c) for c in counts], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600).stdout
+    except Exception:
+        return None
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    rec = None
+    for line in out.splitlines():
+        if line.startswith("REFJSON "):
+            rec = json.loads(line[8:])
+    if not rec:
+        return None
+    per = rec["one_to_all_s"] / max(1, rec["targets"])
+    return {"kind": "reference", "cores": 1, "us_per_particle_one_to_all": per * 1e6, "all_to_all_ms_lower_bound": per * rec["n"] / 2 * 1e3,
+            "sample": "%d evenly spaced particles, TotalEFull<PairE>::oneToAll over the reference's neighbour lists, -Ofast; list construction "
+                      "(%.1f s for the sample) not charged; the reference's own allToAll() loops over all N^2/2 = 3.5e10 pairs without lists, "
+                      "N/2 x the per-particle time is a lower bound" % (rec["targets"], rec["list_build_s"])}
+
+
 def cpu_reference_sweeps(ntargets, ntrials, nproc):
     """Measured sequential sweeps of the reference's own move code (MoveCreator::partDisplace / partRotate over TotalEFull<PairE> and the
     reference's neighbour lists; oracle/_ref/sc_ref_full, see oracle/ref_driver.cpp do_sweep): `nproc` independent processes (the
@@ -312,21 +348,24 @@ def run_ours(args):
     eng.sync()
     e2e_serial_s = time.perf_counter() - t0
     e_serial = e_host.copy()
-    # (b) the headline: the same per-step work through scgpu_submit_everyone on TWO contexts used alternately (a second replica
+    # (b) the headline: the same per-step work through scgpu_submit_everyone on FOUR contexts used in turn (further replicas
     # of the system on the same GPU), so the host<->device copies of one configuration overlap the kernels of the other.
     # Every step still uploads its configuration from page-locked memory and reads its energies back inside the timed region.
-    eng2 = Engine(local, "fast")
-    eng2.load(hs)
-    eng2.set_particles_compact(state_host, hs.type, hs.moltype)
-    engs = [eng, eng2]
-    ins = [pinned, _t.empty((n, 9), dtype=_t.float64).pin_memory()]
-    ins[1].numpy()[:] = state_host
-    outs = [e_pinned, _t.empty((n,), dtype=_t.float64).pin_memory()]
+    nctx = int(os.environ.get("BENCH_E2E_CONTEXTS", "4"))
+    engs, ins, outs = [eng], [pinned], [e_pinned]
+    for _ in range(nctx - 1):
+        e2 = Engine(local, "fast")
+        e2.load(hs)
+        e2.set_particles_compact(state_host, hs.type, hs.moltype)
+        engs.append(e2)
+        ins.append(_t.empty((n, 9), dtype=_t.float64).pin_memory())
+        ins[-1].numpy()[:] = state_host
+        outs.append(_t.empty((n,), dtype=_t.float64).pin_memory())
 
     def submit(k):
         engs[k].submit_everyone(ins[k].numpy(), outs[k].numpy())
 
-    for k in (0, 1, 0, 1):                   # warm-up; a list that had to grow is reported by sync(): submit again
+    for k in list(range(nctx)) * 2:          # warm-up; a list that had to grow is reported by sync(): submit again
         for attempt in range(4):
             submit(k)
             try:
@@ -338,15 +377,16 @@ def run_ours(args):
         dist.barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        k = i & 1
-        if i >= 2:
-            engs[k].sync()                   # step i-2 of this context is complete: its energies are in outs[k]
+        k = i % nctx
+        if i >= nctx:
+            engs[k].sync()                   # the previous step of this context is complete: its energies are in outs[k]
         submit(k)
-    engs[0].sync()
-    engs[1].sync()
+    for e_ in engs:
+        e_.sync()
     e2e_s = time.perf_counter() - t0
-    assert np.array_equal(outs[0].numpy(), e_serial) and np.array_equal(outs[1].numpy(), e_serial), "pipelined e2e differs from the serial call"
-    eng2.close()
+    assert all(np.array_equal(o.numpy(), e_serial) for o in outs), "pipelined e2e differs from the serial call"
+    for e_ in engs[1:]:
+        e_.close()
     if world > 1:
         t = torch.tensor([e2e_s, e2e_serial_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -409,6 +449,10 @@ def run_ours(args):
             mm.append(meng.timer_stop())
         full_energy["membrane_265041"] = {"workload": "BASELINE configs[2]: CPSC + SPN-SPA-SPA lipid membrane tiled 21x21 (265 041 particles), one allToAll = one NPT trial energy",
                                           "ms": float(np.mean(mm))}
+        if not args.no_cpu:
+            mref = cpu_reference_membrane(mtop, mcfg)
+            if mref:
+                full_energy["membrane_265041"]["cpu_reference"] = mref
         meng.close()
         mhs.close()
 
@@ -589,7 +633,7 @@ def run_ours(args):
            "roofline": roof, "cpu_baseline": cpu,
            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
-                   "mode": "scgpu_submit_everyone, two contexts alternating (copies of one configuration overlap the kernels of the other)",
+                   "mode": "scgpu_submit_everyone, %d contexts used in turn (copies of one configuration overlap the kernels of the others)" % nctx,
                    "one_at_a_time": {"value": float(ngate) * e2e_steps * world / e2e_serial_s, "ms_per_step": e2e_serial_s / e2e_steps * 1e3}},
            "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall, "secondary": sweeps, "cell_build": cell_build, "full_energy": full_energy, "single_call": single_call}
     if world == 1 and not args.no_cpu:

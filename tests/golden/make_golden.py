@@ -415,7 +415,39 @@ def do_wanglandau():
         print("wanglandau:", name)
 
 
+def do_othermoves():
+    """Moves that stay the reference's host code above the calculator seam, on Tests/test_01_normal_PSC: geometric cluster moves
+    (nClustMove = 10; MoveCreator::clusterMoveGeom, movecreator.cpp:54-172: allToAll + p2p) and grand-canonical insertion / deletion
+    (nGrandCanon = 5 with an activity in top.init; movecreator.cpp:797-924: the particle count changes, update(EMResize)).
+    300 sweeps of the unmodified reference program; through oracle/_ref/SC_scgpu every energy comes from the device."""
+    src = os.path.join(REF, "Tests", "test_01_normal_PSC", "new")
+    base = {fn: open(os.path.join(src, fn)).read() for fn in ("options", "top.init", "config.init")}
+    base["options"] = re.sub(r"(?m)^nsweeps\s*=\s*\d+", "nsweeps = 300", base["options"])
+    cases = {}
+    c = dict(base)
+    c["options"] = re.sub(r"(?m)^nClustMove\s*=\s*\d+", "nClustMove = 10", c["options"])
+    cases["test_01_clustermoves"] = c
+    c = dict(base)
+    c["options"] = re.sub(r"(?m)^nGrandCanon\s*=\s*\d+", "nGrandCanon = 5", c["options"])
+    c["top.init"] = c["top.init"].replace("particles:   1\n}", "particles:   1\nactivity: 0.05\n}")
+    assert "activity" in c["top.init"]
+    cases["test_01_grandcanonical"] = c
+    for name, inp in cases.items():
+        tmp = tempfile.mkdtemp(prefix="moves_")
+        for fn, txt in inp.items():
+            with open(os.path.join(tmp, fn), "w") as f:
+                f.write(txt)
+        run([SC], tmp)
+        with open(os.path.join(HERE, name + ".inputs.json"), "w") as f:
+            json.dump(inp, f)
+        shutil.copy(os.path.join(tmp, "config.last"), os.path.join(HERE, name + ".short300.config.last"))
+        shutil.rmtree(tmp)
+        print("othermoves:", name)
+
+
 def main():
+    if "othermoves" in sys.argv[1:]:
+        return do_othermoves()
     if "wanglandau" in sys.argv[1:]:
         return do_wanglandau()
     if "wall" in sys.argv[1:]:

@@ -82,3 +82,13 @@ def test_reference_main_wang_landau_runs(name):
         got_wl = open(os.path.join(tmp, "wl-new.dat")).read()
     assert got_cfg == gzip.open(os.path.join(G, name + ".short300.config.last.gz"), "rt").read(), r.stdout[-800:]
     assert got_wl == gzip.open(os.path.join(G, name + ".short300.wl-new.dat.gz"), "rt").read()
+
+
+@pytest.mark.parametrize("name", ["test_01_clustermoves", "test_01_grandcanonical"])
+def test_reference_main_cluster_and_grand_canonical_moves(name):
+    """the moves SURVEY.md section 8(f) rank 4 lists stay the reference's own host code (MoveCreator::clusterMoveGeom,
+    movecreator.cpp:54-172; muVTMove, :797-924) and run unchanged on the GPU calculator: allToAll / p2p for the cluster moves,
+    update(EMResize) -> initEM() when an insertion or deletion changes the particle count. Byte-identical config.last after 300 sweeps
+    of Tests/test_01_normal_PSC with nClustMove = 10, resp. nGrandCanon = 5 and an activity (tests/golden/make_golden.py othermoves)."""
+    got, out = run_reference_program(name, 0)
+    assert got == open(os.path.join(G, name + ".short300.config.last")).read(), out[-800:]
