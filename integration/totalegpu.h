@@ -88,11 +88,23 @@ public:
     }
     void update() override { pushBox(); }                       // accepted volume move
     void update(EMResize) override { initEM(); }                // muVT changed the particle count
-    void update(int t) override { double s[30]; pack(conf->pvec[t], s); if (scgpu_update_particle(ctx, t, s)) fail("update"); }
+    void update(int t) override { double* s = &st[(size_t)t * 30]; pack(conf->pvec[t], s); if (scgpu_update_particle(ctx, t, s)) fail("update"); }
     void update(Molecule m) override { for (unsigned k = 0; k < m.size(); k++) update(m[k]); }
 
-    double allToAll() override { double e; pushBox(); if (scgpu_all_to_all(ctx, &e, NULL)) fail("all_to_all"); return e; }
-    double allToAllTrial() override { return allToAll(); }      // the caller has already changed conf->geo.box
+    // Some callers write conf->pvec WITHOUT telling the calculator: the geometric cluster move reflects a whole cluster in place and then
+    // asks for allToAll() (movecreator.cpp:164, 172). TotalEFull recomputes from conf->pvec and is right; the default TotalEMatrix sums its
+    // (now stale) matrix. allToAll() here re-reads the host configuration and sends what changed -- the TotalEFull semantics.
+    void resync() {
+        size_t n = conf->pvec.size();
+        if (n * 30 != st.size()) { initEM(); return; }
+        double s[30];
+        for (size_t i = 0; i < n; i++) {
+            pack(conf->pvec[i], s);
+            if (memcmp(s, &st[i * 30], sizeof s)) { memcpy(&st[i * 30], s, sizeof s); if (scgpu_update_particle(ctx, (int)i, s)) fail("update"); }
+        }
+    }
+    double allToAll() override { double e; resync(); pushBox(); if (scgpu_all_to_all(ctx, &e, NULL)) fail("all_to_all"); return e; }
+    double allToAllTrial() override { double e; pushBox(); if (scgpu_all_to_all(ctx, &e, NULL)) fail("all_to_all"); return e; }      // the caller has already changed conf->geo.box
     // NB the reference restores conf->geo.box behind the calculator's back on a rejected volume move: the box is re-sent on every call
     double oneToAll(int t) override { double e; pushBox(); if (scgpu_one_to_all(ctx, t, NULL, &e, NULL)) fail("one_to_all"); return e; }
     double oneToAllTrial(int t) override {                      // the caller has already mutated conf->pvec[t]

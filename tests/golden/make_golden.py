@@ -419,7 +419,11 @@ def do_othermoves():
     """Moves that stay the reference's host code above the calculator seam, on Tests/test_01_normal_PSC: geometric cluster moves
     (nClustMove = 10; MoveCreator::clusterMoveGeom, movecreator.cpp:54-172: allToAll + p2p) and grand-canonical insertion / deletion
     (nGrandCanon = 5 with an activity in top.init; movecreator.cpp:797-924: the particle count changes, update(EMResize)).
-    300 sweeps of the unmodified reference program; through oracle/_ref/SC_scgpu every energy comes from the device."""
+    300 sweeps of the unmodified reference program; through oracle/_ref/SC_scgpu every energy comes from the device.
+    Cluster moves: the golden comes from the reference built with ITS OWN alternative calculator TotalEFull<PairE> (oracle/_ref/SC_full,
+    totalenergycalculator.h:1228). clusterMoveGeom writes conf->pvec without calling update() (movecreator.cpp:164), so the default
+    TotalEMatrix goes on with a STALE energy matrix after every cluster move (its trajectory differs from TotalEFull's from the first
+    cluster move on; without cluster moves the two calculators give byte-identical runs). TotalEFull recomputes from conf->pvec."""
     src = os.path.join(REF, "Tests", "test_01_normal_PSC", "new")
     base = {fn: open(os.path.join(src, fn)).read() for fn in ("options", "top.init", "config.init")}
     base["options"] = re.sub(r"(?m)^nsweeps\s*=\s*\d+", "nsweeps = 300", base["options"])
@@ -437,7 +441,7 @@ def do_othermoves():
         for fn, txt in inp.items():
             with open(os.path.join(tmp, fn), "w") as f:
                 f.write(txt)
-        run([SC], tmp)
+        run([os.path.join(ROOT, "oracle", "_ref", "SC_full") if name == "test_01_clustermoves" else SC], tmp)
         with open(os.path.join(HERE, name + ".inputs.json"), "w") as f:
             json.dump(inp, f)
         shutil.copy(os.path.join(tmp, "config.last"), os.path.join(HERE, name + ".short300.config.last"))

@@ -89,6 +89,9 @@ def test_reference_main_cluster_and_grand_canonical_moves(name):
     """the moves SURVEY.md section 8(f) rank 4 lists stay the reference's own host code (MoveCreator::clusterMoveGeom,
     movecreator.cpp:54-172; muVTMove, :797-924) and run unchanged on the GPU calculator: allToAll / p2p for the cluster moves,
     update(EMResize) -> initEM() when an insertion or deletion changes the particle count. Byte-identical config.last after 300 sweeps
-    of Tests/test_01_normal_PSC with nClustMove = 10, resp. nGrandCanon = 5 and an activity (tests/golden/make_golden.py othermoves)."""
+    of Tests/test_01_normal_PSC with nClustMove = 10, resp. nGrandCanon = 5 and an activity (tests/golden/make_golden.py othermoves).
+    The cluster-move golden is written by the reference built with its own TotalEFull<PairE> calculator (oracle/_ref/SC_full): the cluster
+    move writes conf->pvec behind the calculator's back (movecreator.cpp:164) and the default TotalEMatrix carries on with a stale
+    matrix; TotalEGpu::allToAll() re-reads the host configuration, as TotalEFull does."""
     got, out = run_reference_program(name, 0)
     assert got == open(os.path.join(G, name + ".short300.config.last")).read(), out[-800:]
