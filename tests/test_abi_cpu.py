@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported(variant):
 def test_record_sizes_match_header():
     txt = open(os.path.join(ROOT, "include", "scgpu.h")).read()
     assert "#define SCGPU_STATE_DOUBLES 30" in txt and "#define SCGPU_IAPARAM_DOUBLES 48" in txt
-    assert ctypes.sizeof(engine.MoveParams) == 8 + 40 * 8 * 2 + 8
+    assert ctypes.sizeof(engine.MoveParams) == 8 + 40 * 8 * 2 + 16      # temper, trans_mx, rot_angle, {n_sub, grid_k, trial_rule, reserved}
     assert ctypes.sizeof(engine.SweepStats) == 6 * 8
     assert ctypes.sizeof(engine.ChainMoves) == 8 + 32 * 8 * 2 and ctypes.sizeof(engine.ChainStats) == 7 * 8
     assert ctypes.sizeof(engine.PressureParams) == 3 * 8 + 8 and ctypes.sizeof(engine.PressureStats) == 8 + 6 * 8
