@@ -2020,6 +2020,7 @@ __device__ __noinline__ double wall_energy_rec(const DevSys& s, const double* r,
 
 #include "sweep.cuh"
 #include "sweep_rounds.cuh"
+#include "sweep_phased.cuh"
 
 // one thread per listed pair; grid-stride because the list length lives on the device
 __global__ void __launch_bounds__(128, 4)
@@ -2273,6 +2274,9 @@ struct scgpu_ctx {
     unsigned long long* d_counters = nullptr;   // 8
     void* d_sweep_acc = nullptr;
     int sweep_acc_cap = 0;
+    SwTrial* d_sw_trials = nullptr; int sw_trial_cap = 0;      // phased sweeps: per-trial records, per-cell records, per-pair flags
+    SwCell* d_sw_cells = nullptr; int sw_cell_cap = 0;
+    unsigned short* d_sw_meta = nullptr; int sw_meta_cap = 0;
     bool sweep_one_cell = getenv("SCGPU_SWEEP_ONE_CELL") != nullptr;      // diagnostic: sweeps without the cell decomposition
     double* d_flush = nullptr;
     size_t flush_n = 0;
@@ -2366,6 +2370,7 @@ extern "C" int scgpu_destroy(scgpu_ctx* c) {
     free_particles(c);
     cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_reach2); cudaFree(c->d_counts); cudaFree(c->d_cell_start); cudaFree(c->d_cursor);
     cudaFree(c->d_ticket); cudaFree(c->d_fine_of); cudaFree(c->d_fine_start); cudaFree(c->d_heavy); cudaFree(c->d_nheavy); cudaFree(c->d_wall);
+    cudaFree(c->d_sw_trials); cudaFree(c->d_sw_cells); cudaFree(c->d_sw_meta);
     cudaFree(c->d_sweep_acc);
     cudaFree(c->d_trial); cudaFree(c->d_trial_rec); cudaFree(c->d_pl_total); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_reduce); cudaFree(c->d_counters); cudaFree(c->d_flush);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -2536,10 +2541,10 @@ static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const 
         size_t N = (size_t)n;
         CK(cudaMalloc(&c->d_api, N * 30 * sizeof(double)));
         CK(cudaMalloc(&c->d_compact, N * 9 * sizeof(double)));
-        CK(cudaMalloc(&c->d_posw, N * sizeof(double4)));
+        CK(cudaMalloc(&c->d_posw, (2 * N + 64) * sizeof(double4)));      // [N, 2N): spare slots for the trial states of a sweep pass (sweep_phased.cuh)
         CK(cudaMalloc(&c->d_p32, N * sizeof(float4)));
         CK(cudaMalloc(&c->d_d32, N * sizeof(float4)));
-        CK(cudaMalloc(&c->d_rec, N * REC * sizeof(double)));
+        CK(cudaMalloc(&c->d_rec, (2 * N + 64) * REC * sizeof(double)));
         CK(cudaMalloc(&c->d_type, N * sizeof(int)));
         CK(cudaMalloc(&c->d_moltype, N * sizeof(int)));
         CK(cudaMalloc(&c->d_cell_of, N * sizeof(int)));
@@ -2997,6 +3002,13 @@ static int overflow_then_grow(scgpu_ctx* c, bool* repeat) {
         g_err = "internal error: a patch pair was listed by one side of an every-particle pass only";
         return SCGPU_ERR_STATE;
     }
+    if (which & (16 | 32 | 64)) {      // raised by the phased sweep (sweep_phased.cuh): its passes stop at the first cell or trial they cannot hold
+        CK(cudaMemsetAsync(c->d_pl_total, 0, 8 * sizeof(int), c->stream));
+        g_err = "a batched sweep could not be completed by the phased sweep kernels (a cell above " + std::to_string(SP_TR) + " particles, a neighbourhood above " +
+                std::to_string(SP_TILE) + " candidates or a trial with more than " + std::to_string(SP_EB) + " pair terms; flags " + std::to_string(which) +
+                "): the remaining passes were not performed; set SCGPU_SWEEP_KERNEL=rounds for this system";
+        return SCGPU_ERR_STATE;
+    }
     if (which & 4) {
         const unsigned heavy = (unsigned)hflag[5];       // d_pl_total[6]
         unsigned present = 0;
@@ -3249,7 +3261,11 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     bool bonded_any = false;
     for (int t = 0; t < c->nmol; t++) bonded_any = bonded_any || c->h_mol[t].mol_size > 1.0;
     bool rounds = !chains && !bonded_any;
-    if (const char* e = getenv("SCGPU_SWEEP_KERNEL")) { if (!strcmp(e, "cells")) rounds = false; else if (!strcmp(e, "rounds") && !chains && !bonded_any) rounds = true; }
+    bool phased_wanted = rounds && mp->trial_rule == 2 && mp->n_sub == 1;      // sweep_phased.cuh: a pass as four dense launches
+    if (const char* e = getenv("SCGPU_SWEEP_KERNEL")) {
+        if (!strcmp(e, "cells")) { rounds = false; phased_wanted = false; }
+        else if (!strcmp(e, "rounds")) phased_wanted = false;
+    }
     int K = 1;
     if (!chains && !rounds) {
         for (int k = 3; k >= 2; k--) {
@@ -3305,7 +3321,20 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     int nactive = (c->nc[0] / ncol.x) * (c->nc[1] / ncol.y) * (c->nc[2] / ncol.z);
     const bool one = c->one_type >= 0 && c->rods_only;
     const scgpu_iaparam& ia1 = c->h_ia[one ? (size_t)c->one_type * c->ntypes + c->one_type : 0];
-    if (rounds) {
+    const bool phased = phased_wanted && K == 1 && (double)c->n / (double)c->ncells <= 24.0;      // cells of at most SP_TR particles, neighbourhoods inside the tile
+    if (phased) {
+        static bool pattr_done = false;
+        if (!pattr_done) {
+            CK(cudaFuncSetAttribute(k_sweep_propose<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpShared)));
+            CK(cudaFuncSetAttribute(k_sweep_propose<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpShared)));
+            CK(cudaFuncSetAttribute(k_sweep_propose<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpShared)));
+            pattr_done = true;
+        }
+        if (c->sw_trial_cap < c->n + 64) { cudaFree(c->d_sw_trials); c->d_sw_trials = nullptr; CK(cudaMalloc(&c->d_sw_trials, (size_t)(c->n + 64) * sizeof(SwTrial))); c->sw_trial_cap = c->n + 64; }
+        if (c->sw_cell_cap < c->ncells) { cudaFree(c->d_sw_cells); c->d_sw_cells = nullptr; CK(cudaMalloc(&c->d_sw_cells, (size_t)c->ncells * sizeof(SwCell))); c->sw_cell_cap = c->ncells; }
+        if (c->sw_meta_cap < c->fl_cap) { cudaFree(c->d_sw_meta); c->d_sw_meta = nullptr; CK(cudaMalloc(&c->d_sw_meta, (size_t)c->fl_cap * sizeof(unsigned short))); c->sw_meta_cap = c->fl_cap; }
+    }
+    if (rounds && !phased) {
         static bool attr_done = false;
         if (!attr_done) {
             CK(cudaFuncSetAttribute(k_sweep_rounds<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrShared)));
@@ -3314,7 +3343,34 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
             attr_done = true;
         }
     }
+    FlatList sfl;
+    SweepAux sax;
+    memset(&sfl, 0, sizeof sfl);
+    memset(&sax, 0, sizeof sax);
+    if (phased) {
+        sfl.pair = c->d_fl_pair; sfl.e = c->d_fl_e; sfl.total = c->d_pl_total + 3; sfl.cap = c->fl_cap; sfl.head = c->d_fl_head;
+        sfl.chunks = c->d_fl_chunks; sfl.chunk_count = c->d_pl_total + 4; sfl.chunk_cap = c->fl_chunk_cap;
+        sfl.plist = c->d_fl_plist; sfl.ptotal = c->d_pl_total + 5; sfl.overflow = c->d_pl_overflow;
+        sfl.heavy = c->d_pl_total + 6; sfl.heavy_types = 0;
+        sax.trials = c->d_sw_trials; sax.trial_total = c->d_pl_total + 7; sax.trial_cap = c->n; sax.cells = c->d_sw_cells; sax.meta = c->d_sw_meta;
+    }
     for (int k = 0; k < ncolours; k++) {
+        if (phased) {
+            SweepAcc* ao = (SweepAcc*)c->d_sweep_acc;
+            if (c->rods_only && one) k_sweep_propose<true, true><<<nactive, SP_THREADS, sizeof(SpShared), c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, sfl, sax, ao, ia1);
+            else if (c->rods_only) k_sweep_propose<true, false><<<nactive, SP_THREADS, sizeof(SpShared), c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, sfl, sax, ao, ia1);
+            else k_sweep_propose<false, false><<<nactive, SP_THREADS, sizeof(SpShared), c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, sfl, sax, ao, ia1);
+            if (c->rods_only) {
+                const int nb = c->sm_count * CHEAP_MINB * 2;
+                if (one) k_cheap_flat<true, true, false><<<nb, 256, 0, c->stream>>>(s, sfl, nullptr, ia1);
+                else k_cheap_flat<true, false, false><<<nb, 256, 0, c->stream>>>(s, sfl, nullptr, ia1);
+            } else k_cheap_flat<false, false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, sfl, nullptr, ia1);
+            if (one) k_patch_flat<true><<<c->sm_count * PATCH_MINB, PF_THREADS, 0, c->stream>>>(s, sfl, c->any_two_patch ? 1 : 0, 0, ia1);
+            else k_patch_flat<false><<<c->sm_count * PATCH_MINB, PF_THREADS, 0, c->stream>>>(s, sfl, c->any_two_patch ? 1 : 0, 0, ia1);
+            k_sweep_resolve<<<nactive, SP_RTHREADS, 0, c->stream>>>(s, sp, order[k], grid, c->d_posw, c->d_rec, sfl, sax, ao);
+            c->launches += 4;
+            continue;
+        }
         if (rounds) {
             if (c->rods_only && one) k_sweep_rounds<true, true><<<nactive, SR_THREADS, sizeof(SrShared), c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
             else if (c->rods_only) k_sweep_rounds<true, false><<<nactive, SR_THREADS, sizeof(SrShared), c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
@@ -3349,10 +3405,21 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
             cstats->cell_rej += cacc[i].cell_rej; cstats->energy_delta += cacc[i].de; cstats->noop += cacc[i].pad;
         }
     }
+    if (phased) {
+        int* hflag = (int*)(c->h_small + 256 + 64);
+        CK(cudaMemcpyAsync(hflag, c->d_pl_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (*hflag) {
+            const int which = *hflag;
+            CK(cudaMemsetAsync(c->d_pl_total, 0, 8 * sizeof(int), c->stream));
+            g_err = "scgpu_sweep_checkerboard: a pass of the phased sweep could not list its pair terms (flags " + std::to_string(which) + "): its trials were not performed; use SCGPU_SWEEP_KERNEL=rounds for this system";
+            return SCGPU_ERR_STATE;
+        }
+    }
     if (rounds) {
         long long lost = 0;
         for (int i = 0; i < c->ncells; i++) lost += acc[i].pad;
-        if (lost) { g_err = "scgpu_sweep_checkerboard: " + std::to_string(lost) + " trial(s) had more partners than the round kernel's work list holds (rejected); use SCGPU_SWEEP_KERNEL=cells for this system"; return SCGPU_ERR_STATE; }
+        if (lost) { g_err = "scgpu_sweep_checkerboard: " + std::to_string(lost) + " trial(s) could not be evaluated by this sweep kernel (more partners than its work list holds, or a cell too dense); use SCGPU_SWEEP_KERNEL=cells (or rounds) for this system [grid " + std::to_string(c->nc[0]) + "x" + std::to_string(c->nc[1]) + "x" + std::to_string(c->nc[2]) + ", K " + std::to_string(K) + "]"; return SCGPU_ERR_STATE; }
     }
     if (stats) {
         memset(stats, 0, sizeof *stats);

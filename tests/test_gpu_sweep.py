@@ -122,6 +122,38 @@ def test_cell_walk_kernel_on_unbonded_systems(kind, monkeypatch):
     hs.close()
 
 
+@pytest.mark.parametrize("kind", ["psc_lattice", "mix"])
+def test_phased_sweep_walks_the_same_chain_as_the_round_kernel(kind, monkeypatch):
+    """trial_rule 2 on the coarse grid runs as four dense launches per colour pass (sweep_phased.cuh: k_sweep_propose, the energy
+    pipeline's k_cheap_flat / k_patch_flat, k_sweep_resolve); SCGPU_SWEEP_KERNEL=rounds forces the one-kernel form. Both draw the same
+    permutation and the same proposals and take the decisions of the same sequential walk, so the configurations after a few sweeps
+    are THE SAME (the sums are taken in different orders: a decision could only flip on a 1e-16 tie)."""
+    top, cfg = synth.small_case(kind)
+    hs = HostSystem(top, cfg)
+    finals, books = [], []
+    for kern in ("phased", "rounds"):
+        monkeypatch.setenv("SCGPU_SWEEP_KERNEL", kern)
+        eng = Engine(0, "fast").load(hs)
+        mp = move_params(0.5 if kind != "psc_lattice" else 0.25, 0.05, 8.0)
+        mp.trial_rule, mp.grid_k = 2, 1
+        e0 = eng.all_to_all()
+        de = 0.0
+        nacc = 0
+        for sw in range(4):
+            st = eng.sweep(mp, 4711, sw)
+            assert st.trans_acc + st.trans_rej + st.rot_acc + st.rot_rej == hs.n
+            de += st.energy_delta
+            nacc += st.trans_acc + st.rot_acc
+        e1 = eng.all_to_all()
+        assert abs((e1 - e0) - de) <= 1e-9 * max(abs(e0), abs(e1), 1.0), kern
+        finals.append(eng.download_particles())
+        books.append((nacc, e1))
+        eng.close()
+    assert books[0][0] == books[1][0] and books[0][0] > 0
+    assert np.array_equal(finals[0], finals[1])
+    hs.close()
+
+
 def test_reproducible_trajectory():
     top, cfg = synth.small_case("psc_lattice")
     hs = HostSystem(top, cfg)
