@@ -67,11 +67,14 @@ def test_wall_terms_against_reference_dumps(name, variant):
     hs.close()
 
 
-def test_sweeps_with_wall_keep_the_energy_books():
+@pytest.mark.parametrize("rule", [0, 2])
+def test_sweeps_with_wall_keep_the_energy_books(rule):
+    """rule 0: the round kernel; rule 2: the phased sweep (the wall term enters in k_sweep_resolve)"""
     inp = _inputs("wall_fibril")
     hs = HostSystem(inp["top.init"], inp["config.init"])
     eng = Engine(0, "fast").load(hs)
     mp = MoveParams()
+    mp.trial_rule = rule
     mp.temper = 1.0
     for k in range(40):
         mp.trans_mx[k] = 0.1
