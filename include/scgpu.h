@@ -90,7 +90,7 @@ typedef struct scgpu_moveparams {
                                       2: every particle is tried exactly once per sweep: the particles of a cell are walked in a fresh
                                       random order (a random-order sequential sweep; balance holds, the order is independent of the
                                       configuration). Kernels that draw with replacement (bonded systems, chain sweeps) treat 2 as 1.
-                                      With n_sub = 1 on a system without bonds this rule runs as four dense launches per colour pass
+                                      On a system without bonds this rule runs as four dense launches per colour pass
                                       (sweep_phased.cuh) -- the fastest form.
                                       All rules leave the Boltzmann distribution invariant (the count is fixed before the pass and no
                                       particle leaves its cell within one); fractional counts are stochastically rounded */

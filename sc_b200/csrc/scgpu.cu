@@ -3261,7 +3261,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     bool bonded_any = false;
     for (int t = 0; t < c->nmol; t++) bonded_any = bonded_any || c->h_mol[t].mol_size > 1.0;
     bool rounds = !chains && !bonded_any;
-    bool phased_wanted = rounds && mp->trial_rule == 2 && mp->n_sub == 1;      // sweep_phased.cuh: a pass as four dense launches
+    bool phased_wanted = rounds && mp->trial_rule == 2;      // sweep_phased.cuh: a pass as four dense launches
     if (const char* e = getenv("SCGPU_SWEEP_KERNEL")) {
         if (!strcmp(e, "cells")) { rounds = false; phased_wanted = false; }
         else if (!strcmp(e, "rounds")) phased_wanted = false;
@@ -3354,12 +3354,14 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
         sfl.heavy = c->d_pl_total + 6; sfl.heavy_types = 0;
         sax.trials = c->d_sw_trials; sax.trial_total = c->d_pl_total + 7; sax.trial_cap = c->n; sax.cells = c->d_sw_cells; sax.meta = c->d_sw_meta;
     }
+    const int nwalks = phased ? mp->n_sub : 1;          // the phased form walks the system n_sub times on the same grid, colour by colour
+    for (int sub = 0; sub < nwalks; sub++)
     for (int k = 0; k < ncolours; k++) {
         if (phased) {
             SweepAcc* ao = (SweepAcc*)c->d_sweep_acc;
-            if (c->rods_only && one) k_sweep_propose<true, true><<<nactive, SP_THREADS, sizeof(SpShared), c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, sfl, sax, ao, ia1);
-            else if (c->rods_only) k_sweep_propose<true, false><<<nactive, SP_THREADS, sizeof(SpShared), c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, sfl, sax, ao, ia1);
-            else k_sweep_propose<false, false><<<nactive, SP_THREADS, sizeof(SpShared), c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, sfl, sax, ao, ia1);
+            if (c->rods_only && one) k_sweep_propose<true, true><<<nactive, SP_THREADS, sizeof(SpShared), c->stream>>>(s, sp, seed, sweep, order[k], sub, grid, c->d_posw, c->d_rec, sfl, sax, ao, ia1);
+            else if (c->rods_only) k_sweep_propose<true, false><<<nactive, SP_THREADS, sizeof(SpShared), c->stream>>>(s, sp, seed, sweep, order[k], sub, grid, c->d_posw, c->d_rec, sfl, sax, ao, ia1);
+            else k_sweep_propose<false, false><<<nactive, SP_THREADS, sizeof(SpShared), c->stream>>>(s, sp, seed, sweep, order[k], sub, grid, c->d_posw, c->d_rec, sfl, sax, ao, ia1);
             if (c->rods_only) {
                 const int nb = c->sm_count * CHEAP_MINB * 2;
                 if (one) k_cheap_flat<true, true, false><<<nb, 256, 0, c->stream>>>(s, sfl, nullptr, ia1);
@@ -3367,7 +3369,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
             } else k_cheap_flat<false, false, false><<<c->sm_count * 4, 256, 0, c->stream>>>(s, sfl, nullptr, ia1);
             if (one) k_patch_flat<true><<<c->sm_count * PATCH_MINB, PF_THREADS, 0, c->stream>>>(s, sfl, c->any_two_patch ? 1 : 0, 0, ia1);
             else k_patch_flat<false><<<c->sm_count * PATCH_MINB, PF_THREADS, 0, c->stream>>>(s, sfl, c->any_two_patch ? 1 : 0, 0, ia1);
-            k_sweep_resolve<<<nactive, SP_RTHREADS, 0, c->stream>>>(s, sp, order[k], grid, c->d_posw, c->d_rec, sfl, sax, ao);
+            k_sweep_resolve<<<nactive, SP_RTHREADS, 0, c->stream>>>(s, sp, order[k], sub, grid, c->d_posw, c->d_rec, sfl, sax, ao);
             c->launches += 4;
             continue;
         }

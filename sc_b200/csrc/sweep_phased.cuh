@@ -13,7 +13,8 @@
 // The decisions are those of the sequential walk through the cell, as in k_sweep_rounds (sweep_rounds.cuh) -- but there the terms of a
 // cell were evaluated by the 128 threads of its block between barriers, here all terms of all cells of the pass (a few hundred
 // thousand) feed kernels that run at the throughput of the energy pipeline.
-// Eligible: no bonded molecules, trial_rule 2, n_sub 1, cells of at most SP_TR particles whose neighbourhood fits the staged tile
+// Eligible: no bonded molecules, trial_rule 2 (n_sub walks = n_sub times the colour passes on the same grid), coarse grid, cells of at
+// most SP_TR particles whose neighbourhood fits the staged tile
 // (anything else takes k_sweep_rounds).
 #pragma once
 
@@ -66,7 +67,7 @@ struct SpShared {
 
 template <bool RODS, bool ONE>
 __global__ void __launch_bounds__(SP_THREADS, SP_MINB)
-k_sweep_propose(DevSys s, SweepParams sp, unsigned long long seed, unsigned long long sweep, int colour, SweepGrid g,
+k_sweep_propose(DevSys s, SweepParams sp, unsigned long long seed, unsigned long long sweep, int colour, int sub, SweepGrid g,
                 double4* posw, double* rec, FlatList fl, SweepAux ax, SweepAcc* acc_out, const __grid_constant__ scgpu_iaparam ia1) {
     extern __shared__ __align__(16) unsigned char sp_raw[];
     SpShared& S = *reinterpret_cast<SpShared*>(sp_raw);
@@ -139,7 +140,8 @@ k_sweep_propose(DevSys s, SweepParams sp, unsigned long long seed, unsigned long
     }
     const int centre_seg = 2 * (g.k[2] * wy + g.k[1]);
     const int centre_off = S.seg_off[centre_seg] + (tb - S.seg_b[centre_seg]);
-    const uint32_t ctr1 = (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 24);
+    // (sub: which of the n_sub walks through the system this pass belongs to -- its own permutation and proposals)
+    const uint32_t ctr1 = (uint32_t)(sweep >> 32) ^ ((uint32_t)colour << 24) ^ ((uint32_t)sub << 8);
     const int nt = npart;
     // ---- a fresh random order of the cell's particles
     if (tid < nt) {
@@ -334,7 +336,7 @@ struct SpResolveShared {
 };
 
 __global__ void __launch_bounds__(SP_RTHREADS)
-k_sweep_resolve(DevSys s, SweepParams sp, int colour, SweepGrid g, double4* posw, double* rec, FlatList fl, SweepAux ax, SweepAcc* acc_out) {
+k_sweep_resolve(DevSys s, SweepParams sp, int colour, int sub, SweepGrid g, double4* posw, double* rec, FlatList fl, SweepAux ax, SweepAcc* acc_out) {
     __shared__ SpResolveShared S;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = SP_RTHREADS / 32;
@@ -347,6 +349,7 @@ k_sweep_resolve(DevSys s, SweepParams sp, int colour, SweepGrid g, double4* posw
     const int nt = cell.nt;
     if (nt < 0) return;                // k_sweep_propose reported the cell (SweepAcc::pad)
     SweepAcc acc = {0, 0, 0, 0, 0, 0, 0.0};
+    if (sub > 0 && tid == 0) acc = acc_out[c0];        // the statistics of a cell add up over the walks of one call
     if (nt == 0 || *fl.overflow) { if (tid == 0) acc_out[c0] = acc; return; }
     const SwTrial* tr = ax.trials + cell.trial_base;
     if (tid < nt) {
