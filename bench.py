@@ -491,9 +491,10 @@ def run_ours(args):
               "ms_per_sweep": sweep_s / nsw * 1e3, "trial_moves_per_s": tot * world / sweep_s, "acceptance": acc / max(1, tot),
               "temper": 0.1, "transmx": 0.0212, "rotmx_deg": 7.5, "sweeps_timed": nsw,
               "trial_rule": 2, "ms_per_sweep_trial_rule_0": rule0_s / nsw * 1e3,
-              "note": "whole scgpu_sweep_checkerboard call: shifted cell build + 8 colour passes of the round kernel (k_sweep_rounds: a block per active cell, "
-                      "up to 16 trials evaluated at once and resolved in sequence) + statistics read-back; trial_rule 2 = every particle exactly once per sweep "
-                      "in a fresh random order inside its cell, rule 0 = the same number of trials in every non-empty cell, with replacement"}
+              "note": "whole scgpu_sweep_checkerboard call: shifted cell build + 8 colour passes + statistics read-back. trial_rule 2 (every particle exactly "
+                      "once per sweep in a fresh random order inside its cell) runs every pass as four dense launches (sweep_phased.cuh: k_sweep_propose -> "
+                      "k_cheap_flat -> k_patch_flat -> k_sweep_resolve); rule 0 (the same number of trials in every non-empty cell, with replacement) runs "
+                      "the round kernel (k_sweep_rounds: a block per active cell, up to 16 trials evaluated at once and resolved in sequence)"}
 
     # ---- BASELINE configs[4]: parallel tempering, 8 replicas x 65 536 PSC on `world` GPUs (8 / world replicas per GPU, each on its
     # own stream), one scgpu_replica_exchange every nrepchange = 10 sweeps: allToAll() of every replica, records packed on the device,
