@@ -484,7 +484,8 @@ def test_pressure_move_mechanics():
     eng.close()
 
 
-def test_npt_average_volume_matches_reference_sequential_sweeps():
+@pytest.mark.parametrize("rule", [0, 2])
+def test_npt_average_volume_matches_reference_sequential_sweeps(rule):
     """checkerboard sweeps + one volume move per sweep (the reference draws a volume move with probability shave/N per step, i.e.
     `shave` per sweep on average) against the reference's own NPT run: <V> and <E> over the second half"""
     gold = json.load(open(os.path.join(G, "sweep_npt_psc1280.json")))
@@ -501,6 +502,7 @@ def test_npt_average_volume_matches_reference_sequential_sweeps():
     def one_seed(seed):
         eng = Engine(0, "fast").load(hs)
         mp = move_params(P["temper"], P["transmx"], P["rotmx"])
+        mp.trial_rule = rule                # 0: round kernel, 2: phased sweep (the box changes between the sweeps)
         vs, es = [], []
         n_acc = 0
         e = eng.all_to_all()
