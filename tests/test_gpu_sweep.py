@@ -122,15 +122,18 @@ def test_cell_walk_kernel_on_unbonded_systems(kind, monkeypatch):
     hs.close()
 
 
-@pytest.mark.parametrize("kind", ["psc_lattice", "mix"])
+@pytest.mark.parametrize("kind", ["psc_lattice", "mix", "psc_8192"])
 def test_phased_sweep_walks_the_same_chain_as_the_round_kernel(kind, monkeypatch):
     """trial_rule 2 on the coarse grid runs as four dense launches per colour pass (sweep_phased.cuh: k_sweep_propose, the energy
     pipeline's k_cheap_flat / k_patch_flat, k_sweep_resolve); SCGPU_SWEEP_KERNEL=rounds forces the one-kernel form. Both draw the same
     permutation and the same proposals and take the decisions of the same sequential walk, so the configurations after a few sweeps
     are THE SAME (the sums are taken in different orders: a decision could only flip on a 1e-16 tie)."""
-    top, cfg = synth.small_case(kind)
+    if kind == "psc_8192":         # 8 x 8 x 6 cells: no axis can wrap, the gate of k_sweep_propose works in length units without the fold
+        top, cfg, _ = synth.psc_bulk(32, 32, 8, seed=7, tilt=0.1)
+    else:                          # 4 x 4 x 4 cells: the fold path
+        top, cfg = synth.small_case(kind)
     hs = HostSystem(top, cfg)
-    finals, books = [], []
+    finals, books, launches = [], [], []
     for kern in ("phased", "rounds"):
         monkeypatch.setenv("SCGPU_SWEEP_KERNEL", kern)
         eng = Engine(0, "fast").load(hs)
@@ -144,11 +147,15 @@ def test_phased_sweep_walks_the_same_chain_as_the_round_kernel(kind, monkeypatch
             assert st.trans_acc + st.trans_rej + st.rot_acc + st.rot_rej == hs.n
             de += st.energy_delta
             nacc += st.trans_acc + st.rot_acc
+        l0 = eng.launches()
+        de += eng.sweep(mp, 4711, 4).energy_delta
+        launches.append(eng.launches() - l0)
         e1 = eng.all_to_all()
         assert abs((e1 - e0) - de) <= 1e-9 * max(abs(e0), abs(e1), 1.0), kern
         finals.append(eng.download_particles())
         books.append((nacc, e1))
         eng.close()
+    assert launches[0] - launches[1] == 3 * 8, launches           # four launches per colour pass against one: the two forms really ran
     assert books[0][0] == books[1][0] and books[0][0] > 0
     assert np.array_equal(finals[0], finals[1])
     hs.close()
