@@ -3229,17 +3229,28 @@ static inline unsigned long long splitmix64(unsigned long long& x) {
 }
 
 static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chainmoves* cm, uint64_t seed, uint64_t sweep, scgpu_sweepstats* stats,
-                      scgpu_chainstats* cstats);
+                      scgpu_chainstats* cstats, double single_scale = -1.0, bool chains_only = false);
 extern "C" int scgpu_sweep_checkerboard(scgpu_ctx* c, const scgpu_moveparams* mp, uint64_t seed, uint64_t sweep, scgpu_sweepstats* stats) {
     return sweep_impl(c, mp, nullptr, seed, sweep, stats, nullptr);
 }
 extern "C" int scgpu_sweep_checkerboard_chains(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chainmoves* cm, uint64_t seed, uint64_t sweep,
                                                scgpu_sweepstats* stats, scgpu_chainstats* cstats) {
-    return sweep_impl(c, mp, cm, seed, sweep, stats, cstats);
+    // Single-particle trials and chain trials of a sweep run as two series of colour passes, each on the grid that suits it: the chain
+    // kernel needs whole molecules inside a cell of the COARSE grid, the single-particle walk is several times faster on the fine one
+    // (lipid membrane, 265 041 particles: 160 ms against 380 ms per sweep). A composition of moves that each leave the Boltzmann
+    // distribution invariant; SCGPU_SWEEP_INTERLEAVED=1 restores the colour-by-colour interleaving on the coarse grid.
+    const bool chains = cm && cm->chainprob > 0.0;
+    if (!chains || getenv("SCGPU_SWEEP_INTERLEAVED") != nullptr) return sweep_impl(c, mp, cm, seed, sweep, stats, cstats);
+    ARG(c && mp, "scgpu_sweep_checkerboard: NULL argument");
+    ARG(cm->chainprob <= 1.0, "scgpu_sweep_checkerboard_chains: chainprob must be in [0, 1]");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (cm->chainprob < 1.0)
+        if (int r = sweep_impl(c, mp, nullptr, seed, sweep, stats, nullptr, 1.0 - cm->chainprob, false)) return r;
+    return sweep_impl(c, mp, cm, seed, sweep, nullptr, cstats, 0.0, true);
 }
 
 static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chainmoves* cm, uint64_t seed, uint64_t sweep, scgpu_sweepstats* stats,
-                      scgpu_chainstats* cstats) {
+                      scgpu_chainstats* cstats, double single_scale, bool chains_only) {
     ARG(c && mp, "scgpu_sweep_checkerboard: NULL argument");
     const bool chains = cm && cm->chainprob > 0.0;
     ARG(!chains || (cm->chainprob <= 1.0 && c->nmol <= CH_MAXMT), "scgpu_sweep_checkerboard_chains: chainprob must be in [0, 1] and at most 32 molecule types");
@@ -3296,7 +3307,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
     sp.temper = mp->temper;
     sp.n_sub = mp->n_sub;
     sp.trial_rule = mp->trial_rule;
-    sp.trial_scale = chains ? 1.0 - cm->chainprob : 1.0;
+    sp.trial_scale = single_scale >= 0.0 ? single_scale : (chains ? 1.0 - cm->chainprob : 1.0);
     ChainParams cp;
     memset(&cp, 0, sizeof cp);
     if (chains) {
@@ -3380,10 +3391,12 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
             c->launches++;
             continue;
         }
-        if (c->rods_only && one) k_sweep_cells<true, true><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
-        else if (c->rods_only) k_sweep_cells<true, false><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
-        else k_sweep_cells<false, false><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
-        c->launches++;
+        if (!chains_only) {
+            if (c->rods_only && one) k_sweep_cells<true, true><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
+            else if (c->rods_only) k_sweep_cells<true, false><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
+            else k_sweep_cells<false, false><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
+            c->launches++;
+        }
         if (chains) {
             k_sweep_chain_colour<<<nactive, CH_THREADS, 0, c->stream>>>(s, cp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, d_chain_acc);
             c->launches++;

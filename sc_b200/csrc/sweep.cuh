@@ -198,9 +198,9 @@ k_sweep_cells(DevSys s, SweepParams sp, unsigned long long seed, unsigned long l
     const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
     const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
     auto slot_of_p = [&](int p) {
-        int k = 0;
-        while (k + 1 < nseg && sh_off[k + 1] <= p) k++;
-        return sh_b[k] + (p - sh_off[k]);
+        int lo = 0, hi = nseg - 1;             // the last segment whose offset is <= p (offsets are non-decreasing; empty segments repeat them)
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sh_off[mid] <= p) lo = mid; else hi = mid - 1; }
+        return sh_b[lo] + (p - sh_off[lo]);
     };
     auto staged_pos = [&](const double4& pw) {
         return make_float4((float)rel_frac(pw.x + s.shift[0], ccen[0]), (float)rel_frac(pw.y + s.shift[1], ccen[1]),

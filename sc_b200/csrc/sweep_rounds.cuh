@@ -102,9 +102,9 @@ k_sweep_rounds(DevSys s, SweepParams sp, unsigned long long seed, unsigned long 
     const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
     const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
     auto slot_of_p = [&](int p) {
-        int k = 0;
-        while (k + 1 < nseg && S.seg_off[k + 1] <= p) k++;
-        return S.seg_b[k] + (p - S.seg_off[k]);
+        int lo = 0, hi = nseg - 1;             // the last segment whose offset is <= p (offsets are non-decreasing; empty segments repeat them)
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (S.seg_off[mid] <= p) lo = mid; else hi = mid - 1; }
+        return S.seg_b[lo] + (p - S.seg_off[lo]);
     };
     auto staged_xyz = [&](double x, double y, double z, int wbits) {
         return make_float4((float)rel_frac(x + s.shift[0], ccen[0]), (float)rel_frac(y + s.shift[1], ccen[1]),
