@@ -682,12 +682,16 @@ k_sweep_chain_colour(DevSys s, ChainParams cp, unsigned long long seed, unsigned
                     const v3 pc = mk(pw.x, pw.y, pw.z);
                     const int type2 = w_type(pw.w);
                     for (int k = 0; k < m; k++) {
+                        // beyond the reach of the type pair every term is exactly 0 (the connectivity list is empty here): the cutoff the
+                        // reference applies (sqmaxcut, set by the LONGEST interaction of the system) lets a lipid bead call the functor for
+                        // every bead within 10 sigma; the exact reach of a bead pair is 2.7
+                        const double reach = (double)s.reach2[sh_mtype[k] * s.ntypes + type2];
                         v3 r = image(s.box, ld3(&sh_old[k][R_POS]), pc);
                         double d = dot(r, r);
-                        if (d <= s.sqmaxcut) eo += pair_energy_gated(s.box, s.ia, s.ntypes, s.mol, r, d, sh_old[k], sh_mtype[k], moltype, rec + (size_t)slot * REC, type2, orig, cl);
+                        if (d <= s.sqmaxcut && d <= reach) eo += pair_energy_gated(s.box, s.ia, s.ntypes, s.mol, r, d, sh_old[k], sh_mtype[k], moltype, rec + (size_t)slot * REC, type2, orig, cl);
                         r = image(s.box, ld3(&sh_new[k][R_POS]), pc);
                         d = dot(r, r);
-                        if (d <= s.sqmaxcut) en += pair_energy_gated(s.box, s.ia, s.ntypes, s.mol, r, d, sh_new[k], sh_mtype[k], moltype, rec + (size_t)slot * REC, type2, orig, cl);
+                        if (d <= s.sqmaxcut && d <= reach) en += pair_energy_gated(s.box, s.ia, s.ntypes, s.mol, r, d, sh_new[k], sh_mtype[k], moltype, rec + (size_t)slot * REC, type2, orig, cl);
                     }
                 }
             }
