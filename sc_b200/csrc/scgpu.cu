@@ -2274,6 +2274,7 @@ struct scgpu_ctx {
     unsigned long long* d_counters = nullptr;   // 8
     void* d_sweep_acc = nullptr;
     int sweep_acc_cap = 0;
+    int* d_sw_maxc = nullptr; int* h_sw_maxc = nullptr;      // largest staged neighbourhood the cell walk met in the last sweep (device, pinned host copy)
     SwTrial* d_sw_trials = nullptr; int sw_trial_cap = 0;      // phased sweeps: per-trial records, per-cell records, per-pair flags
     SwCell* d_sw_cells = nullptr; int sw_cell_cap = 0;
     unsigned short* d_sw_meta = nullptr; int sw_meta_cap = 0;
@@ -2370,6 +2371,7 @@ extern "C" int scgpu_destroy(scgpu_ctx* c) {
     free_particles(c);
     cudaFree(c->d_ia); cudaFree(c->d_mol); cudaFree(c->d_reach2); cudaFree(c->d_counts); cudaFree(c->d_cell_start); cudaFree(c->d_cursor);
     cudaFree(c->d_ticket); cudaFree(c->d_fine_of); cudaFree(c->d_fine_start); cudaFree(c->d_heavy); cudaFree(c->d_nheavy); cudaFree(c->d_wall);
+    cudaFree(c->d_sw_maxc); if (c->h_sw_maxc) cudaFreeHost(c->h_sw_maxc);
     cudaFree(c->d_sw_trials); cudaFree(c->d_sw_cells); cudaFree(c->d_sw_meta);
     cudaFree(c->d_sweep_acc);
     cudaFree(c->d_trial); cudaFree(c->d_trial_rec); cudaFree(c->d_pl_total); cudaFree(c->d_targets); cudaFree(c->d_scalar); cudaFree(c->d_reduce); cudaFree(c->d_counters); cudaFree(c->d_flush);
@@ -3354,6 +3356,29 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
             attr_done = true;
         }
     }
+    // staged tile of the cell walk: the default, or as much as the mean neighbourhood needs (with head room), up to 96 KB
+    int sw_tile = SW_TILE;
+    if (!rounds && !chains_only) {
+        double meanC = (double)c->n / (double)c->ncells;
+        for (int d = 0; d < 3; d++) meanC *= (double)(2 * grid.k[d] + 1);
+        int want = (int)(meanC * 1.5) + 64;
+        if (!c->d_sw_maxc) { CK(cudaMalloc(&c->d_sw_maxc, sizeof(int))); CK(cudaMallocHost(&c->h_sw_maxc, sizeof(int))); *c->h_sw_maxc = 0; }
+        // (the mean counts empty cells too -- a membrane in water: what the previous sweep met on the device is the better guide; the copy
+        // is asynchronous, a value one sweep old is as good)
+        if (*c->h_sw_maxc > 0) want = *c->h_sw_maxc + *c->h_sw_maxc / 16 + 32;
+        CK(cudaMemsetAsync(c->d_sw_maxc, 0, sizeof(int), c->stream));
+        if (const char* e = getenv("SCGPU_SWEEP_TILE")) want = atoi(e);
+        if (want > SW_TILE) {
+            sw_tile = want > SW_TILE_MAX ? SW_TILE_MAX : (want + 63) / 64 * 64;
+            static bool tattr_done = false;
+            if (!tattr_done) {
+                CK(cudaFuncSetAttribute(k_sweep_cells<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_TILE_MAX * 2 * (int)sizeof(float4)));
+                CK(cudaFuncSetAttribute(k_sweep_cells<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_TILE_MAX * 2 * (int)sizeof(float4)));
+                CK(cudaFuncSetAttribute(k_sweep_cells<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_TILE_MAX * 2 * (int)sizeof(float4)));
+                tattr_done = true;
+            }
+        }
+    }
     FlatList sfl;
     SweepAux sax;
     memset(&sfl, 0, sizeof sfl);
@@ -3392,9 +3417,10 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
             continue;
         }
         if (!chains_only) {
-            if (c->rods_only && one) k_sweep_cells<true, true><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
-            else if (c->rods_only) k_sweep_cells<true, false><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
-            else k_sweep_cells<false, false><<<nactive, 32, 0, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, ia1);
+            const size_t dyn = (size_t)sw_tile * 2 * sizeof(float4);
+            if (c->rods_only && one) k_sweep_cells<true, true><<<nactive, 32, dyn, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, sw_tile, c->d_sw_maxc, ia1);
+            else if (c->rods_only) k_sweep_cells<true, false><<<nactive, 32, dyn, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, sw_tile, c->d_sw_maxc, ia1);
+            else k_sweep_cells<false, false><<<nactive, 32, dyn, c->stream>>>(s, sp, seed, sweep, order[k], grid, c->d_posw, c->d_rec, (SweepAcc*)c->d_sweep_acc, sw_tile, c->d_sw_maxc, ia1);
             c->launches++;
         }
         if (chains) {
@@ -3402,6 +3428,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
             c->launches++;
         }
     }
+    if (!rounds && !chains_only && c->d_sw_maxc) CK(cudaMemcpyAsync(c->h_sw_maxc, c->d_sw_maxc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaGetLastError());
     c->api_stale = true;           // the cell-sorted arrays are now the newest copy of the configuration
     c->f32_valid = false;          // ... and their FP32 copies are out of date

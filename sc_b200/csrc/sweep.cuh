@@ -86,6 +86,7 @@ constexpr int SW_WARPS = 1;       // one warp per active cell: no block barrier 
 #ifndef SW_TILE_N
 #define SW_TILE_N 576
 #endif
+constexpr int SW_TILE_MAX = 6144;   // largest staged tile the host may ask for (192 KB of dynamic shared memory: one block per SM)
 constexpr int SW_TILE = SW_TILE_N;      // staged neighbourhood: FP32 position + direction + slot, 32 B per candidate = 18 KB (8 warps per SM resident)
 constexpr int SW_BATCH = 32;      // trials whose random numbers and proposal geometry are prepared together, one lane each
 constexpr int SW_MAXROWS = 49;    // (2K+1)^2 rows of neighbour cells, K <= 3
@@ -129,9 +130,13 @@ __device__ __noinline__ double pair_energy_patch_outofline(const scgpu_iaparam& 
 template <bool RODS, bool ONE>
 __global__ void __launch_bounds__(32, SW_MINBLOCKS)
 k_sweep_cells(DevSys s, SweepParams sp, unsigned long long seed, unsigned long long sweep, int colour, SweepGrid g,
-              double4* posw, double* rec, SweepAcc* acc_out, const __grid_constant__ scgpu_iaparam ia1) {
-    __shared__ float4 t_pf[SW_TILE];          // x, y, z: box-fractional position relative to the cell centre; w: original index | type << 24
-    __shared__ float4 t_df[SW_TILE];          // direction; w: slot
+              double4* posw, double* rec, SweepAcc* acc_out, int tile_cap, int* max_c, const __grid_constant__ scgpu_iaparam ia1) {
+    // the staged neighbourhood lives in dynamic shared memory: tile_cap candidates (SW_TILE by default; the host asks for more where
+    // the neighbourhoods are large -- a lipid membrane on a grid set by a few long rods -- so that those cells keep the staged path
+    // and its per-particle partner lists instead of scanning global memory in every trial)
+    extern __shared__ __align__(16) unsigned char sw_dyn[];
+    float4* t_pf = reinterpret_cast<float4*>(sw_dyn);          // x, y, z: box-fractional position relative to the cell centre; w: original index | type << 24
+    float4* t_df = t_pf + tile_cap;                            // direction; w: slot
     __shared__ double sh_old[REC], sh_new[REC];
     __shared__ int sh_queue[128];
     __shared__ int sh_pl[32];                 // (tile entry, state) pairs that owe a patch evaluation
@@ -194,7 +199,8 @@ k_sweep_cells(DevSys s, SweepParams sp, unsigned long long seed, unsigned long l
     if (tabs) for (int k = lane; k < 2 * T * T + T; k += 32) sh_tab[k] = k < T * T ? s.reach2[k] : s.reach2[k + T];
     __syncwarp();
     const int nseg = 2 * nrows;
-    const bool tiled = C <= SW_TILE;        // denser neighbourhoods are scanned from global memory (slower, same results)
+    const bool tiled = C <= tile_cap;       // denser neighbourhoods are scanned from global memory (slower, same results)
+    if (lane == 0) atomicMax(max_c, C);     // the host sizes the tile of the NEXT sweep by what this one met
     const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
     const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
     auto slot_of_p = [&](int p) {
