@@ -3251,6 +3251,15 @@ extern "C" int scgpu_sweep_checkerboard_chains(scgpu_ctx* c, const scgpu_movepar
     return sweep_impl(c, mp, cm, seed, sweep, nullptr, cstats, 0.0, true);
 }
 
+static int ensure_sw_maxc(scgpu_ctx* c) {       // [0]: cell walk, [1]: chain kernel -- largest neighbourhood met in the last sweep
+    if (c->d_sw_maxc) return 0;
+    CK(cudaMalloc(&c->d_sw_maxc, 2 * sizeof(int)));
+    CK(cudaMemset(c->d_sw_maxc, 0, 2 * sizeof(int)));
+    CK(cudaMallocHost(&c->h_sw_maxc, 2 * sizeof(int)));
+    c->h_sw_maxc[0] = c->h_sw_maxc[1] = 0;
+    return 0;
+}
+
 static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chainmoves* cm, uint64_t seed, uint64_t sweep, scgpu_sweepstats* stats,
                       scgpu_chainstats* cstats, double single_scale, bool chains_only) {
     ARG(c && mp, "scgpu_sweep_checkerboard: NULL argument");
@@ -3362,7 +3371,7 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
         double meanC = (double)c->n / (double)c->ncells;
         for (int d = 0; d < 3; d++) meanC *= (double)(2 * grid.k[d] + 1);
         int want = (int)(meanC * 1.5) + 64;
-        if (!c->d_sw_maxc) { CK(cudaMalloc(&c->d_sw_maxc, sizeof(int))); CK(cudaMallocHost(&c->h_sw_maxc, sizeof(int))); *c->h_sw_maxc = 0; }
+        if (int r = ensure_sw_maxc(c)) return r;
         // (the mean counts empty cells too -- a membrane in water: what the previous sweep met on the device is the better guide; the copy
         // is asynchronous, a value one sweep old is as good)
         if (*c->h_sw_maxc > 0) want = *c->h_sw_maxc + *c->h_sw_maxc / 16 + 32;
@@ -3378,6 +3387,18 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
                 tattr_done = true;
             }
         }
+    }
+    // staged tile of the chain kernel (16 B per candidate of the 27-cell neighbourhood), sized the same way
+    int ch_tile = 1024;
+    if (chains) {
+        if (int r = ensure_sw_maxc(c)) return r;
+        int want = (int)(27.0 * (double)c->n / (double)c->ncells * 1.5) + 64;
+        if (c->h_sw_maxc[1] > 0) want = c->h_sw_maxc[1] + c->h_sw_maxc[1] / 16 + 32;
+        if (const char* e = getenv("SCGPU_CHAIN_TILE")) want = atoi(e);
+        ch_tile = want < 1024 ? 1024 : (want > CH_TILE_MAX ? CH_TILE_MAX : (want + 63) / 64 * 64);
+        static bool cattr_done = false;
+        if (!cattr_done) { CK(cudaFuncSetAttribute(k_sweep_chain_colour, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_TILE_MAX * (int)sizeof(float4))); cattr_done = true; }
+        CK(cudaMemsetAsync(c->d_sw_maxc + 1, 0, sizeof(int), c->stream));
     }
     FlatList sfl;
     SweepAux sax;
@@ -3424,11 +3445,12 @@ static int sweep_impl(scgpu_ctx* c, const scgpu_moveparams* mp, const scgpu_chai
             c->launches++;
         }
         if (chains) {
-            k_sweep_chain_colour<<<nactive, CH_THREADS, 0, c->stream>>>(s, cp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, d_chain_acc);
+            k_sweep_chain_colour<<<nactive, CH_THREADS, (size_t)ch_tile * sizeof(float4), c->stream>>>(s, cp, seed, sweep, order[k], ncol, c->d_posw, c->d_rec, d_chain_acc, ch_tile, c->d_sw_maxc + 1);
             c->launches++;
         }
     }
     if (!rounds && !chains_only && c->d_sw_maxc) CK(cudaMemcpyAsync(c->h_sw_maxc, c->d_sw_maxc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (chains && c->d_sw_maxc) CK(cudaMemcpyAsync(c->h_sw_maxc + 1, c->d_sw_maxc + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaGetLastError());
     c->api_stale = true;           // the cell-sorted arrays are now the newest copy of the configuration
     c->f32_valid = false;          // ... and their FP32 copies are out of date

@@ -546,6 +546,7 @@ k_sweep_cells(DevSys s, SweepParams sp, unsigned long long seed, unsigned long l
 // ------------------------------------------------------------------------------------------------
 constexpr int CH_MAX = 20;          // MAXCHL (scOOP/structures/macros.h:62)
 constexpr int CH_THREADS = 128;
+constexpr int CH_TILE_MAX = 12288;  // largest staged neighbourhood of the chain kernel (192 KB of dynamic shared memory)
 constexpr int CH_MAXMT = 32;        // molecule types with their own chain step sizes
 
 struct ChainParams {
@@ -557,7 +558,15 @@ struct ChainParams {
 
 __global__ void __launch_bounds__(CH_THREADS)
 k_sweep_chain_colour(DevSys s, ChainParams cp, unsigned long long seed, unsigned long long sweep, int colour, int3 ncol,
-                     double4* posw, double* rec, SweepAcc* acc_out) {
+                     double4* posw, double* rec, SweepAcc* acc_out, int tile_cap, int* max_c) {
+    // the 27-cell neighbourhood staged once per pass in dynamic shared memory: FP32 position relative to the cell centre (box fractions)
+    // and slot | type << 24. A trial tests the staged candidates against the exact reach of the type pairs (+ 1 % and the FP32 slack)
+    // for every member in both states and goes to global memory and FP64 only for those that pass -- a lipid bead among 6 000
+    // candidates of a grid set by a few long rods has a few dozen partners. Neighbourhoods above tile_cap: the scan of global memory.
+    extern __shared__ __align__(16) unsigned char ch_dyn[];
+    float4* tile = reinterpret_cast<float4*>(ch_dyn);
+    __shared__ float4 sh_fo[CH_MAX], sh_fn[CH_MAX];
+    __shared__ int sh_toff[29];
     __shared__ double sh_old[CH_MAX][REC], sh_new[CH_MAX][REC];
     __shared__ int sh_mslot[CH_MAX], sh_mtype[CH_MAX];
     __shared__ double sh_red[2][CH_THREADS / 32];
@@ -588,6 +597,28 @@ k_sweep_chain_colour(DevSys s, ChainParams cp, unsigned long long seed, unsigned
             len = s.cell_start[c + 1] - b;
         }
         if (lane < 28) { sh_b[lane] = b; sh_off[lane] = len; }
+        int x = len;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane < 28) sh_toff[lane] = x - len;
+        if (lane == 27) sh_toff[28] = x;
+    }
+    __syncthreads();
+    const int Ctot = sh_toff[28];
+    const bool staged = Ctot <= tile_cap;
+    if (threadIdx.x == 0) atomicMax(max_c, Ctot);      // the host sizes the tile of the next sweep by what this one met
+    const double ccen[3] = {(cx + 0.5) / s.nc[0], (cy + 0.5) / s.nc[1], (cz + 0.5) / s.nc[2]};
+    const float boxf[3] = {(float)s.box[0], (float)s.box[1], (float)s.box[2]};
+    auto stage_entry = [&](const double4& pw, int slot) {
+        return make_float4((float)rel_frac(pw.x + s.shift[0], ccen[0]), (float)rel_frac(pw.y + s.shift[1], ccen[1]),
+                           (float)rel_frac(pw.z + s.shift[2], ccen[2]), __int_as_float(slot | (w_type(pw.w) << 24)));
+    };
+    int centre_toff = 0;
+    for (int seg = 0; seg < ncell_nb; seg++) if (sh_b[seg] == tb && sh_off[seg] == npart) centre_toff = sh_toff[seg];
+    if (staged) {
+        for (int seg = 0; seg < ncell_nb; seg++) {
+            const int b = sh_b[seg], len = sh_off[seg], off = sh_toff[seg];
+            for (int i = threadIdx.x; i < len; i += blockDim.x) tile[off + i] = stage_entry(posw[b + i], b + i);
+        }
     }
     __syncthreads();
     int ntrial;
@@ -673,11 +704,47 @@ k_sweep_chain_colour(DevSys s, ChainParams cp, unsigned long long seed, unsigned
         if (threadIdx.x < 2 * m) {      // every member inside the active cell, before and after
             const double* r = (threadIdx.x < m) ? sh_old[threadIdx.x] : sh_new[threadIdx.x - m];
             if (cell_index(r + R_POS, s.shift, s.nc) != c0) sh_ok = 0;
+            const float4 f = make_float4((float)rel_frac(r[R_POS] + s.shift[0], ccen[0]), (float)rel_frac(r[R_POS + 1] + s.shift[1], ccen[1]),
+                                         (float)rel_frac(r[R_POS + 2] + s.shift[2], ccen[2]), 0.f);
+            if (threadIdx.x < m) sh_fo[threadIdx.x] = f; else sh_fn[threadIdx.x - m] = f;
         }
         __syncthreads();
         const bool in_cell = sh_ok != 0;
         double eo = 0.0, en = 0.0;
-        if (in_cell) {
+        auto evaluate = [&](int slot) {       // one candidate against every member, old and new state, exact
+            const double4 pw = posw[slot];
+            const int orig = w_orig(pw.w);
+            if (orig >= mfirst && orig < mfirst + m) return;
+            const v3 pc = mk(pw.x, pw.y, pw.z);
+            const int type2 = w_type(pw.w);
+            for (int k = 0; k < m; k++) {
+                const double reach = (double)s.reach2[sh_mtype[k] * s.ntypes + type2];
+                v3 r = image(s.box, ld3(&sh_old[k][R_POS]), pc);
+                double d = dot(r, r);
+                if (d <= s.sqmaxcut && d <= reach) eo += pair_energy_gated(s.box, s.ia, s.ntypes, s.mol, r, d, sh_old[k], sh_mtype[k], moltype, rec + (size_t)slot * REC, type2, orig, cl);
+                r = image(s.box, ld3(&sh_new[k][R_POS]), pc);
+                d = dot(r, r);
+                if (d <= s.sqmaxcut && d <= reach) en += pair_energy_gated(s.box, s.ia, s.ntypes, s.mol, r, d, sh_new[k], sh_mtype[k], moltype, rec + (size_t)slot * REC, type2, orig, cl);
+            }
+        };
+        if (in_cell && staged) {
+            for (int p = threadIdx.x; p < Ctot; p += blockDim.x) {
+                const float4 q = tile[p];
+                const int sbits = __float_as_int(q.w);
+                const int type2 = sbits >> 24;
+                bool any = false;
+                for (int k = 0; k < m; k++) {
+                    const float lim = s.reach2[sh_mtype[k] * s.ntypes + type2] * 1.01f + 1e-3f;
+                    float dx = sh_fo[k].x - q.x, dy = sh_fo[k].y - q.y, dz = sh_fo[k].z - q.z;
+                    dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
+                    any = any || dx * dx + dy * dy + dz * dz <= lim;
+                    dx = sh_fn[k].x - q.x; dy = sh_fn[k].y - q.y; dz = sh_fn[k].z - q.z;
+                    dx = (dx - rintf(dx)) * boxf[0]; dy = (dy - rintf(dy)) * boxf[1]; dz = (dz - rintf(dz)) * boxf[2];
+                    any = any || dx * dx + dy * dy + dz * dz <= lim;
+                }
+                if (any) evaluate(sbits & 0xffffff);
+            }
+        } else if (in_cell) {
             for (int seg = 0; seg < ncell_nb; seg++) {
                 const int b = sh_b[seg], len = sh_off[seg];
                 for (int i = threadIdx.x; i < len; i += blockDim.x) {
@@ -730,7 +797,9 @@ k_sweep_chain_colour(DevSys s, ChainParams cp, unsigned long long seed, unsigned
             if (threadIdx.x < m) {
                 const int sl = sh_mslot[threadIdx.x];
                 const double w = posw[sl].w;
-                posw[sl] = make_double4(sh_new[threadIdx.x][R_POS], sh_new[threadIdx.x][R_POS + 1], sh_new[threadIdx.x][R_POS + 2], w);
+                const double4 npw = make_double4(sh_new[threadIdx.x][R_POS], sh_new[threadIdx.x][R_POS + 1], sh_new[threadIdx.x][R_POS + 2], w);
+                posw[sl] = npw;
+                if (staged) tile[centre_toff + (sl - tb)] = stage_entry(npw, sl);      // the members sit in the active cell
             }
         }
     }
