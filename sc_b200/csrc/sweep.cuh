@@ -545,7 +545,10 @@ k_sweep_cells(DevSys s, SweepParams sp, unsigned long long seed, unsigned long l
 // reference's sequential sweeps with chainprob > 0.
 // ------------------------------------------------------------------------------------------------
 constexpr int CH_MAX = 20;          // MAXCHL (scOOP/structures/macros.h:62)
-constexpr int CH_THREADS = 128;
+#ifndef CH_THREADS_N
+#define CH_THREADS_N 512
+#endif
+constexpr int CH_THREADS = CH_THREADS_N;
 constexpr int CH_TILE_MAX = 12288;  // largest staged neighbourhood of the chain kernel (192 KB of dynamic shared memory)
 constexpr int CH_MAXMT = 32;        // molecule types with their own chain step sizes
 
