@@ -449,6 +449,29 @@ def run_ours(args):
             mm.append(meng.timer_stop())
         full_energy["membrane_265041"] = {"workload": "BASELINE configs[2]: CPSC + SPN-SPA-SPA lipid membrane tiled 21x21 (265 041 particles), one allToAll = one NPT trial energy",
                                           "ms": float(np.mean(mm))}
+        # sweeps of the membrane with the reference's move mix for lipids: single-bead moves + rigid moves of whole SPN-SPA-SPA molecules
+        from sc_b200.engine import MoveParams as _MP, ChainMoves as _CM
+        mmp, mcm = _MP(), _CM()
+        mmp.temper, mmp.n_sub, mcm.chainprob = 1.0, 1, 0.5
+        for k in range(40):
+            mmp.trans_mx[k] = 0.1
+            mmp.rot_angle[k] = 10.0 / 180.0 * 1.5707963267948966 * 0.5
+        for k in range(32):
+            mcm.chainm_mx[k] = 0.2
+            mcm.chainr_angle[k] = 10.0 / 180.0 * 1.5707963267948966
+        for k in range(2):
+            meng.sweep_chains(mmp, mcm, 4242, k)
+        t0m = time.perf_counter()
+        nacc = ntot = 0
+        for k in range(3):
+            st_, cst_ = meng.sweep_chains(mmp, mcm, 4242, 2 + k)
+            nacc += st_.trans_acc + st_.rot_acc + cst_.chainm_acc + cst_.chainr_acc
+            ntot += st_.trans_acc + st_.rot_acc + st_.trans_rej + st_.rot_rej + cst_.chainm_acc + cst_.chainr_acc + cst_.chainm_rej + cst_.chainr_rej
+        msw = (time.perf_counter() - t0m) / 3
+        full_energy["membrane_265041"]["sweep_with_chain_moves"] = {
+            "ms_per_sweep": msw * 1e3, "sweeps_per_s": 1.0 / msw, "trial_moves_per_s": ntot / 3 / msw, "acceptance": nacc / max(1, ntot),
+            "chainprob": 0.5, "temper": 1.0,
+            "note": "scgpu_sweep_checkerboard_chains: single-bead passes (k_sweep_cells, fine grid) + rigid moves of whole lipids (k_sweep_chain_colour, coarse grid)"}
         if not args.no_cpu:
             mref = cpu_reference_membrane(mtop, mcfg)
             if mref:
