@@ -538,7 +538,7 @@ def run_ours(args):
         comm = Comm(local, 1, 0)
     ptr = _rep.ParallelTempering(comm, engines, 0.1, 0.13, 0.0212, 7.5, nrepchange=10, seed=145658)
     nsw_pt = 20 if args.steps >= 10 else 10
-    for k in range(1, 11):                   # warm-up: 10 sweeps and one exchange (also creates the NCCL channels)
+    for k in range(1, 31):                   # warm-up: 30 sweeps and three exchanges (NCCL sets its channels up lazily over the first collectives)
         ptr.sweep(k)
     for e in engines:
         e.sync()
@@ -551,7 +551,7 @@ def run_ours(args):
         e.timer_start()
     t0 = time.perf_counter()
     t_exch = 0.0
-    for k in range(11, 11 + nsw_pt):
+    for k in range(31, 31 + nsw_pt):
         if k % 10 == 0:
             te = time.perf_counter()
             ptr.sweep(k)
