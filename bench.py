@@ -269,6 +269,17 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # one process per GPU on a multi-socket host: run on the CPUs next to the GPU, so that the page-locked buffers of the end-to-end leg
+    # are first touched on its NUMA node (NVML knows the topology). The CPU legs below lift the restriction again.
+    full_affinity = None
+    if world > 1:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            full_affinity = os.sched_getaffinity(0)
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        except Exception:
+            full_affinity = None
     from sc_b200 import Engine
     from sc_b200.host import HostSystem
     top, cfg, n = workload_texts()
@@ -609,6 +620,11 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    if full_affinity is not None:
+        try:
+            os.sched_setaffinity(0, full_affinity)       # the CPU reference legs use every host core
+        except Exception:
+            pass
     # ---- roofline of the dominant kernel (k_one_to_all): FP64 pipe. Algorithmic flops counted by the op-counting oracle
     roof = {"bound": "fp64", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None, "traffic": None}
     try:
