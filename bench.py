@@ -483,6 +483,32 @@ def run_ours(args):
             "ms_per_sweep": msw * 1e3, "sweeps_per_s": 1.0 / msw, "trial_moves_per_s": ntot / 3 / msw, "acceptance": nacc / max(1, ntot),
             "chainprob": 0.5, "temper": 1.0,
             "note": "scgpu_sweep_checkerboard_chains: single-bead passes (k_sweep_cells, fine grid) + rigid moves of whole lipids (k_sweep_chain_colour, coarse grid)"}
+        # Wang-Landau order parameters of that configuration on the device (row (f)3): the membrane hole (wlm 2, mesh of sigma / 3) + the
+        # z distance of particle 0 from the centre of mass (wlm 1) in one call; after the sweeps the newest configuration is device-resident
+        try:
+            tail_t = int(mhs.type[-1])
+            msz = float(mhs.ia[tail_t, tail_t, 3]) / 3.0
+            wl0 = meng.wl_order((2, 1), wlmtype=tail_t, minorder=(0.0, -30.0), dorder=(1.0, 0.01), meshsize=msz)
+            t0w = time.perf_counter()
+            for _ in range(20):
+                wl0 = meng.wl_order((2, 1), wlmtype=tail_t, minorder=(0.0, -30.0), dorder=(1.0, 0.01), meshsize=msz)
+            wl_us = (time.perf_counter() - t0w) / 20 * 1e6
+            wlo = {"us_per_call": wl_us, "mesh": [int(wl0.mesh_dim[0]), int(wl0.mesh_dim[1])], "largest_hole_mesh_points": int(wl0.raw[0]),
+                   "what": "scgpu_wl_order, wlm = (2, 1): mass centre + mesh fill + union-find hole search (7 launches) + one 88-byte read-back, synchronous call through ctypes"}
+            if not args.no_cpu:
+                from oracle import oracle as _O
+                st_now = meng.download_particles()
+                osys = _O.System(st_now, mhs.type, mhs.moltype, mhs.ia, mhs.mol, mhs.box, mhs.sqmaxcut, mhs.maxcut)
+                t0w = time.perf_counter()
+                for _ in range(5):
+                    href = _O.wl_raw(osys, 2, wlmtype=tail_t, meshsize=msz)
+                    zref = _O.wl_raw(osys, 1)
+                wlo["cpu_port_us_per_call"] = (time.perf_counter() - t0w) / 5 * 1e6
+                wlo["cpu_note"] = "oracle/wl_order.c (Mesh::meshInit + Conf::massCenter restated, one core, -O2); the configuration is already on the host for it"
+                wlo["matches_cpu"] = bool(int(href[0]) == int(wl0.raw[0]) and abs(zref - wl0.raw[1]) < 1e-9)
+            full_energy["membrane_265041"]["wl_order"] = wlo
+        except Exception as e:                       # a secondary leg must not take the headline down with it
+            full_energy["membrane_265041"]["wl_order"] = {"error": repr(e)[:200]}
         if not args.no_cpu:
             mref = cpu_reference_membrane(mtop, mcfg)
             if mref:

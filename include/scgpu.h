@@ -286,6 +286,35 @@ typedef struct scgpu_wlstate {
 int scgpu_wl_merge(scgpu_comm* comm, int len, double* weights, int64_t* hist, double* weights_base, int64_t* hist_base,
                    double temper, scgpu_wlstate* st);
 
+/* ---- Wang-Landau order parameters of the whole configuration, evaluated on the device -----------------------------------------
+ * The from-scratch forms the reference computes in WangLandau::init (scOOP/mc/wanglandau.cpp:56-125) and after every volume or
+ * type-switch move (WangLandau::runPress / runSwitch, scOOP/mc/wanglandau.h:168-196, 220-238), for callers whose configuration
+ * lives on the device (scgpu_sweep_checkerboard*, scgpu_pressure_move): no download of the particles, one small read-back.
+ *   wlm 1  z of particle 0 from the system centre of mass: Conf::massCenter (scOOP/structures/Conf.cpp:78-95) + zOrder (wanglandau.h:551-554)
+ *   wlm 2  largest hole of the membrane in the xy plane: Mesh::meshInit = meshFill + findHoles (scOOP/mc/mesh.cpp:11-185), holeXYPlane(wli) (wanglandau.h:313-317)
+ *   wlm 3  z component of particle 0's axis: zOrient (wanglandau.h:321-324)
+ *   wlm 4  xy distance of particles 0 and 1: twoPartDist (wanglandau.h:395-398)
+ *   wlm 7  particles of type wlmtype within sqrt(WL_CONTACTS) of particle 0: contParticlesAll (wanglandau.h:603-615, 652-678)
+ *   wlm 8, 9  box edge x / y: boxSize_x / boxSize_y (wanglandau.h:375-382)
+ * wlm 5 and 6 (pore radius, radiusholeAll, wanglandau.cpp:306-338) are refused: the reference never allocates the array they fill.
+ * order[] is binned exactly as the reference bins (ceil for 1, 4, 7, 8, 9; floor for 3; truncation for 2); the caller compares it
+ * with wl.length[] and looks up its weights. The incremental forms used by single-particle moves (meshOrderMoveMolecule,
+ * contParticlesMoveMolecule) remain host logic of the reference: they update this state trial by trial. */
+typedef struct scgpu_wlorder {
+    int wlm[2];                                 /* in: Sim::wlm[] (0 = dimension not used) */
+    int wlmtype;                                /* in: Sim::wlmtype, the particle type wlm 2 and 7 look at */
+    int reserved;
+    double minorder[2], dorder[2];              /* in: wl.minorder[], wl.dorder[] (wl.dat) */
+    double meshsize;                            /* in: wl.wl_meshsize (wlm 2; the reference uses sigma(wlmtype) / 3, wanglandau.cpp:79) */
+    int64_t order[2];                           /* out: wl.neworder[] */
+    double raw[2];                              /* out: the quantity before binning (z distance, hole size in mesh points, dir.z, distance, contacts, edge) */
+    double syscm[3], sysvolume;                 /* out: conf->syscm and conf->sysvolume of the current configuration */
+    int mesh_dim[2];                            /* out: Mesh::dim (wlm 2) */
+    int64_t mesh_occupied, mesh_skipped;        /* out: occupied mesh points; particles whose INBOX() coordinate was exactly 1 (the reference
+                                                   writes one past its mesh row for them: undefined there, skipped here) */
+} scgpu_wlorder;
+int scgpu_wl_order(scgpu_ctx* ctx, scgpu_wlorder* io);
+
 /* measurement helpers (CUDA events on the context's stream; FP64 FMA-chain peak microbenchmark) */
 int scgpu_timer_start(scgpu_ctx* ctx);
 int scgpu_timer_stop(scgpu_ctx* ctx, float* ms);

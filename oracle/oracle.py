@@ -4,6 +4,7 @@ legs (cpu_baseline / --impl reference) and __graft_entry__.smoke() may import th
 """
 import ctypes as C
 import gzip
+import math
 import os
 import subprocess
 
@@ -73,6 +74,18 @@ def lib():
         L.sco_psc_rotate.argtypes = [_dp, C.c_int, C.c_double, _dp, C.c_int]
         L.sco_min_dist_segments.argtypes = [_dp, _dp, C.c_double, C.c_double, _dp, _dp]
         L.sco_image.argtypes = [_dp, _dp, _dp, _dp]
+        # Wang-Landau order parameters (oracle/wl_order.c)
+        L.sco_wl_mass_center.argtypes = [C.c_int, _dp, _ip, _dp, _dp]
+        L.sco_wl_z.restype = C.c_double
+        L.sco_wl_z.argtypes = [_dp, _dp, _dp]
+        L.sco_wl_two_part_dist.restype = C.c_double
+        L.sco_wl_two_part_dist.argtypes = [_dp, _dp]
+        L.sco_wl_contacts.restype = C.c_long
+        L.sco_wl_contacts.argtypes = [C.c_int, _dp, _ip, C.c_int, _dp]
+        L.sco_wl_bin.restype = C.c_long
+        L.sco_wl_bin.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+        L.sco_wl_mesh_hole.restype = C.c_int
+        L.sco_wl_mesh_hole.argtypes = [C.c_int, _dp, _ip, C.c_int, _dp, C.c_double, _ip, _ip, C.POINTER(C.c_long), C.POINTER(C.c_long)]
         _lib = L
     return _lib
 
@@ -256,6 +269,86 @@ def psc_rotate(state, geotype, angle, axis, positive):
     ax = np.ascontiguousarray(axis, dtype=np.float64)
     lib().sco_psc_rotate(_d(st), int(geotype), float(angle), _d(ax), int(positive))
     return st
+
+
+# ------------------------------------------------------------------------------------------------
+# Wang-Landau order parameters of a whole configuration (oracle/wl_order.c)
+# ------------------------------------------------------------------------------------------------
+def type_volumes(system):
+    """Ia_param::volume per particle type (scOOP/structures/topo.cpp:388-392): sphere + cylinder for the spherocylinder geotypes"""
+    v = np.zeros(system.ntypes)
+    for t in range(system.ntypes):
+        sig, g, ln = system.ia[t, t, 3], int(system.ia[t, t, 0]), system.ia[t, t, 41]
+        v[t] = 4.0 / 3.0 * math.pi * math.pow(sig / 2.0, 3.0)
+        if 0 < g < 30:
+            v[t] = 4.0 / 3.0 * math.pi * math.pow(sig / 2.0, 3.0) + math.pi / 2.0 * ln * math.pow(sig / 2.0, 2.0)
+    return v
+
+
+def wl_mass_center(system, volumes=None):
+    """-> (syscm[3], sysvolume), Conf::massCenter"""
+    v = np.ascontiguousarray(type_volumes(system) if volumes is None else volumes, dtype=np.float64)
+    out = np.zeros(4)
+    lib().sco_wl_mass_center(system.n, _d(system.state), _i(system.type), _d(v), _d(out))
+    return out[:3].copy(), float(out[3])
+
+
+def wl_raw(system, wlm, wlmtype=0, meshsize=0.0, volumes=None):
+    """the quantity before binning of order parameter wlm (1, 2, 3, 4, 7, 8, 9); wlm 2 -> (maxsize, dim, occupied, skipped)"""
+    L = lib()
+    if wlm == 1:
+        cm, _ = wl_mass_center(system, volumes)
+        return L.sco_wl_z(_d(system.state), _d(np.ascontiguousarray(cm)), _d(system.box))
+    if wlm == 2:
+        dim = np.zeros(2, dtype=np.int32)
+        occ, skip = C.c_long(0), C.c_long(0)
+        m = L.sco_wl_mesh_hole(system.n, _d(system.state), _i(system.type), int(wlmtype), _d(system.box), float(meshsize), _i(dim), None,
+                               C.byref(occ), C.byref(skip))
+        return m, (int(dim[0]), int(dim[1])), occ.value, skip.value
+    if wlm == 3:
+        return float(system.state[0, 5])
+    if wlm == 4:
+        return L.sco_wl_two_part_dist(_d(system.state), _d(system.box))
+    if wlm == 7:
+        return L.sco_wl_contacts(system.n, _d(system.state), _i(system.type), int(wlmtype), _d(system.box))
+    if wlm in (8, 9):
+        return float(system.box[wlm - 8])
+    raise ValueError("wlm %d" % wlm)
+
+
+def wl_bin(wlm, raw, minorder, dorder):
+    return lib().sco_wl_bin(int(wlm), float(raw), float(minorder), float(dorder))
+
+
+def load_wlorder_dump(path):
+    """oracle/ref_driver.cpp `wlorder` dump -> dict: n, box, syscm, sysvolume, vol{type}, bins[(min, dorder)] -> {W1, W3, W4, W8, W9: order,
+    W7: {type: (contacts, order)}}, mesh: list of (type, meshsize, dim0, dim1, maxsize, occupied, order at min 1 / dorder 4)"""
+    op = gzip.open if path.endswith(".gz") else open
+    out = {"vol": {}, "bins": {}, "mesh": []}
+    cur = None
+    with op(path, "rt") as f:
+        for line in f:
+            t = line.split()
+            if not t:
+                continue
+            if t[0] == "N":
+                out["n"] = int(t[1])
+            elif t[0] == "BOX":
+                out["box"] = np.array([_hx(x) for x in t[1:4]])
+            elif t[0] == "SYSCM":
+                out["syscm"] = np.array([_hx(x) for x in t[1:4]])
+                out["sysvolume"] = _hx(t[4])
+            elif t[0] == "VOL":
+                out["vol"][int(t[1])] = _hx(t[2])
+            elif t[0] == "BIN":
+                cur = out["bins"].setdefault((_hx(t[1]), _hx(t[2])), {"W7": {}})
+            elif t[0] in ("W1", "W3", "W4", "W8", "W9"):
+                cur[t[0]] = int(t[1])
+            elif t[0] == "W7":
+                cur["W7"][int(t[1])] = (int(t[2]), int(t[3]))
+            elif t[0] == "W2":
+                out["mesh"].append((int(t[1]), _hx(t[2]), int(t[3]), int(t[4]), int(t[5]), int(t[6]), int(t[7])))
+    return out
 
 
 def system_from_text(top_text, config_text, counts=None):

@@ -19,6 +19,7 @@
 // No reference source text is copied here; this file only *calls* the reference API.
 //
 // usage:  cd <dir with options,top.init,config.init> && sc_ref_driver dump|dump0 [out]   (dump0: pairs with particle 0 only)
+//         sc_ref_driver wlorder [out]   Wang-Landau order parameters of the configuration, from-scratch forms (wanglandau.h:125-290, 516-660, mesh.cpp:10-187)
 //         sc_ref_driver time <ntargets> <reps> [count_per_moltype ...]  -> "REFJSON {...}" line: oneToAll timing
 #include <cstdio>
 #include <cstring>
@@ -30,6 +31,12 @@
 #include "mc/inicializer.h"
 #include "mc/totalenergycalculator.h"
 #include "mc/randomGenerator.h"
+// the `wlorder` mode calls the reference's own order-parameter members (WangLandau::zOrder, zOrient, twoPartDist, contParticlesAll,
+// boxSize_x/y: private inline members of mc/wanglandau.h): the class is opened for this one header (access only; everything the
+// header includes has been included above or has no private part)
+#define private public
+#include "mc/wanglandau.h"
+#undef private
 #ifdef REF_FULL      // sc_ref_full: built from a scratch copy whose calculator typedef is TotalEFull (oracle/Makefile); the sweep mode calls the
 #include <iomanip>   // reference's own MoveCreator::partDisplace / partRotate on chosen targets (private members: opened for this one header,
 #include "mc/wanglandau.h"   // everything it includes has been included above)
@@ -352,6 +359,65 @@ static int do_sweep(int argc, char** argv) {
 }
 #endif
 
+// Wang-Landau order parameters of the whole configuration in the current directory, as the reference computes them from scratch
+// (WangLandau::init, wanglandau.cpp:56-125, and the runPress forms, wanglandau.h:170-196): Conf::massCenter + zOrder (wlm 1),
+// Mesh::meshInit = meshFill + findHoles (wlm 2, mesh.cpp:10-187), zOrient (3), twoPartDist (4), contParticlesAll (7), boxSize_x/y (8, 9).
+// wlm 5 / 6 (radiusholeAll, wanglandau.cpp:306-338) are not dumped: a local variable shadows the member radiusholemax, the array is never
+// allocated and the first call writes through a null pointer.
+static int do_wlorder(const char* outname) {
+    FileNames files(0);
+    Conf conf;
+    Sim* sim = nullptr;
+    load(conf, sim, files, 0, nullptr);
+    FILE* f = fopen(outname, "w");
+    const long n = (long)conf.pvec.size();
+    fprintf(f, "N %ld\n", n);
+    fprintf(f, "BOX %a %a %a\n", conf.geo.box.x, conf.geo.box.y, conf.geo.box.z);
+    conf.massCenter();                                         // Conf.cpp:78-95
+    fprintf(f, "SYSCM %a %a %a %a\n", conf.syscm.x, conf.syscm.y, conf.syscm.z, conf.sysvolume);
+    bool used[MAXT] = {false};
+    for (long i = 0; i < n; i++) used[conf.pvec[i].type] = true;
+    for (int t = 0; t < MAXT; t++) if (used[t]) fprintf(f, "VOL %d %a\n", t, topo.ia_params[t][t].volume);
+    WangLandau wl(&conf, sim);
+    wl.currorder[0] = wl.currorder[1] = 0;
+    wl.neworder[0] = wl.neworder[1] = 0;
+    wl.mesh.data = NULL; wl.mesh.tmp = NULL;
+    const double bins[3][2] = {{-3.0, 0.25}, {0.0, 1.0}, {-1.0, 0.0078125}};      // (minorder, dorder) pairs
+    for (int b = 0; b < 3; b++) {
+        wl.minorder[0] = bins[b][0]; wl.dorder[0] = bins[b][1];
+        fprintf(f, "BIN %a %a\n", wl.minorder[0], wl.dorder[0]);
+        fprintf(f, "W1 %ld\n", wl.zOrder(0));
+        wl.zOrient(0, 0);
+        fprintf(f, "W3 %ld\n", wl.neworder[0]);
+        if (n > 1) fprintf(f, "W4 %ld\n", wl.twoPartDist(0));
+        wl.boxSize_x(0);
+        fprintf(f, "W8 %ld\n", wl.neworder[0]);
+        wl.boxSize_y(0);
+        fprintf(f, "W9 %ld\n", wl.neworder[0]);
+        for (int t = 0; t < MAXT; t++) if (used[t]) {
+            wl.wlmtype = t;
+            long o = wl.contParticlesAll(0);
+            fprintf(f, "W7 %d %ld %ld\n", t, wl.partincontact, o);
+        }
+    }
+    // hole in the xy plane: the mesh of every particle type present, at the reference's own mesh size sigma / 3 (wanglandau.cpp:79)
+    // and at finer ones (more and larger holes); order = (long)((maxsize - minorder) / dorder) as wanglandau.cpp:84-88
+    for (int t = 0; t < MAXT; t++) if (used[t]) {
+        const double sig = topo.ia_params[t][t].sigma;
+        const double sizes[4] = {sig / 3.0, sig / 5.0, sig / 8.0, sig / 12.0};
+        for (int k = 0; k < 4; k++) {
+            if ((int)(conf.geo.box.x / sizes[k]) < 1 || (int)(conf.geo.box.y / sizes[k]) < 1) continue;
+            int maxsize = wl.mesh.meshInit(sizes[k], n, t, conf.geo.box, &conf.pvec);
+            long occupied = 0;
+            for (int i = 0; i < wl.mesh.dim[0] * wl.mesh.dim[1]; i++) if (wl.mesh.data[i] < 0) occupied++;
+            fprintf(f, "W2 %d %a %d %d %d %ld %ld\n", t, sizes[k], wl.mesh.dim[0], wl.mesh.dim[1], maxsize, occupied,
+                    (long)((maxsize - 1.0) / 4.0));
+        }
+    }
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char** argv) {
 #ifdef REF_FULL
     if (argc >= 2 && !strcmp(argv[1], "sweep")) return do_sweep(argc, argv);
@@ -359,6 +425,7 @@ int main(int argc, char** argv) {
     if (argc >= 2 && !strcmp(argv[1], "dump")) return do_dump(argc > 2 ? argv[2] : "ref_dump.txt", false);
     if (argc >= 2 && !strcmp(argv[1], "dump0")) return do_dump(argc > 2 ? argv[2] : "ref_dump.txt", true);
     if (argc >= 2 && !strcmp(argv[1], "exter")) return do_exter(argc > 2 ? argv[2] : "ref_exter.txt");
+    if (argc >= 2 && !strcmp(argv[1], "wlorder")) return do_wlorder(argc > 2 ? argv[2] : "ref_wlorder.txt");
     if (argc >= 2 && !strcmp(argv[1], "time")) return do_time(argc, argv);
     fprintf(stderr, "usage: sc_ref_driver dump|dump0 [out] | time <ntargets> <reps> [count_per_moltype ...]\n");
     return 2;

@@ -9,7 +9,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "scgpu.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "pair_energy.cuh"), os.path.join(HERE, "csrc", "sweep.cuh"), os.path.join(HERE, "csrc", "comm.cuh"), os.path.join(HERE, "csrc", "wall.cuh"), os.path.join(HERE, "csrc", "sweep_rounds.cuh"), os.path.join(HERE, "csrc", "sweep_phased.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "pair_energy.cuh"), os.path.join(HERE, "csrc", "sweep.cuh"), os.path.join(HERE, "csrc", "comm.cuh"), os.path.join(HERE, "csrc", "wall.cuh"), os.path.join(HERE, "csrc", "sweep_rounds.cuh"), os.path.join(HERE, "csrc", "sweep_phased.cuh"), os.path.join(HERE, "csrc", "wl_order.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "scgpu.h")]
 VARIANTS = {"fast": ("libscgpu.so", ["-fmad=true", "-DSCG_FAST_DIV"]), "strict": ("libscgpu_strict.so", ["-fmad=false"])}
 

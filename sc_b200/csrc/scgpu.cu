@@ -27,6 +27,7 @@
 
 #include "pair_energy.cuh"
 #include "wall.cuh"
+#include "wl_order.cuh"
 
 using namespace scg;
 
@@ -2283,6 +2284,9 @@ struct scgpu_ctx {
     size_t flush_n = 0;
     char* h_small = nullptr;         // 1 KB pinned: single-call inputs [0..255], results [256..511], update staging [512..751]
     char* d_single = nullptr;        // 256 B device staging of a single call: trial record [0..239], target index [240..243]
+    char* d_wl = nullptr;            // scgpu_wl_order: block partials, results, counters (WL_BYTES)
+    int *d_wl_mesh = nullptr, *d_wl_parent = nullptr, *d_wl_size = nullptr;      // the hole mesh of wlm 2 and its union-find arrays
+    int wl_mesh_cap = 0;
     void* h_pinned = nullptr;        // pinned staging, grown on demand
     size_t pinned_bytes = 0;
     int64_t launches = 0;
@@ -2378,6 +2382,7 @@ extern "C" int scgpu_destroy(scgpu_ctx* c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_small) cudaFreeHost(c->h_small);
     cudaFree(c->d_single);
+    cudaFree(c->d_wl); cudaFree(c->d_wl_mesh); cudaFree(c->d_wl_parent); cudaFree(c->d_wl_size);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -3627,6 +3632,107 @@ extern "C" int scgpu_flush_l2(scgpu_ctx* c) {
     k_flush<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_flush, c->flush_n);
     c->launches++;
     CK(cudaGetLastError());
+    return SCGPU_OK;
+}
+
+// ---- Wang-Landau order parameters of the whole configuration (wl_order.cuh) ------------------------------------------------------
+#define WL_OFF_PARTIAL 0
+#define WL_OFF_PARTIAL_C (WL_OFF_PARTIAL + WL_MAX_BLOCKS * 4 * sizeof(double))
+#define WL_OFF_OUT (WL_OFF_PARTIAL_C + WL_MAX_BLOCKS * sizeof(long long))
+#define WL_OFF_OUT_C (WL_OFF_OUT + 8 * sizeof(double))
+#define WL_OFF_COUNTERS (WL_OFF_OUT_C + sizeof(long long))
+#define WL_BYTES (WL_OFF_COUNTERS + 4 * sizeof(int))
+#define WL_RESULT_BYTES (WL_BYTES - WL_OFF_OUT)
+
+extern "C" int scgpu_wl_order(scgpu_ctx* c, scgpu_wlorder* io) {
+    ARG(c && io, "scgpu_wl_order: NULL argument");
+    ARG(c->n > 0 && c->ntypes > 0 && c->types_valid && c->box[0] > 0, "scgpu_wl_order: topology, particles (with types) and box must be set first");
+    bool need_mesh = false;
+    for (int w = 0; w < 2; w++) {
+        const int m = io->wlm[w];
+        ARG(m >= 0 && m <= 9, "scgpu_wl_order: wlm must be 0 .. 9");
+        ARG(m != 5 && m != 6, "scgpu_wl_order: wlm 5 / 6 (pore radius) have no defined behaviour in the reference: WangLandau::radiusholeAll "
+                              "(scOOP/mc/wanglandau.cpp:306-338) never allocates its array (a local shadows radiusholemax) and writes through a null pointer");
+        if (m == 0) continue;
+        ARG(io->dorder[w] > 0, "scgpu_wl_order: dorder must be positive");
+        if (m == 2) need_mesh = true;
+        if (m == 4) ARG(c->n >= 2, "scgpu_wl_order: wlm 4 needs two particles");
+    }
+    if (need_mesh || io->wlm[0] == 7 || io->wlm[1] == 7) ARG(io->wlmtype >= 0 && io->wlmtype < c->ntypes, "scgpu_wl_order: wlmtype is not a particle type of the topology");
+    CK(cudaSetDevice(c->device));
+    if (int r = sync_api_from_sorted(c)) return r;      // after device sweeps the cell-sorted arrays hold the newest configuration
+    if (!c->d_wl) CK(cudaMalloc(&c->d_wl, WL_BYTES));
+    if (int r = ensure_pinned(c, WL_RESULT_BYTES)) return r;
+    double* d_partial = (double*)(c->d_wl + WL_OFF_PARTIAL);
+    long long* d_partial_c = (long long*)(c->d_wl + WL_OFF_PARTIAL_C);
+    double* d_out = (double*)(c->d_wl + WL_OFF_OUT);
+    long long* d_out_c = (long long*)(c->d_wl + WL_OFF_OUT_C);
+    int* d_counters = (int*)(c->d_wl + WL_OFF_COUNTERS);
+    CK(cudaMemsetAsync(c->d_wl + WL_OFF_OUT, 0, WL_RESULT_BYTES, c->stream));
+    int d0 = 0, d1 = 0;
+    {   // the centre of mass and the system volume are always returned: O(N), one pass
+        int nb = (c->n + WL_BLOCK * 4 - 1) / (WL_BLOCK * 4);
+        if (nb > WL_MAX_BLOCKS) nb = WL_MAX_BLOCKS;
+        if (nb < 1) nb = 1;
+        k_wl_partial<<<nb, WL_BLOCK, 0, c->stream>>>(c->d_api, c->d_type, c->n, c->d_ia, c->ntypes, c->box[0], c->box[1], c->box[2],
+                                                     io->wlmtype, d_partial, d_partial_c);
+        k_wl_final<<<1, 32, 0, c->stream>>>(c->d_api, c->n, nb, c->box[0], c->box[1], c->box[2], d_partial, d_partial_c, d_out, d_out_c);
+        c->launches += 2;
+        CK(cudaGetLastError());
+    }
+    if (need_mesh) {
+        ARG(io->meshsize > 0, "scgpu_wl_order: meshsize must be positive (wlm 2)");
+        const double f0 = c->box[0] / io->meshsize, f1 = c->box[1] / io->meshsize;      // Mesh::meshInit, mesh.cpp:15-16
+        ARG(f0 >= 1 && f1 >= 1 && f0 * f1 < 1.0e9, "scgpu_wl_order: the mesh must have 1 .. 1e9 points");
+        d0 = (int)f0; d1 = (int)f1;
+        const int len = d0 * d1;
+        if (len > c->wl_mesh_cap) {
+            cudaFree(c->d_wl_mesh); cudaFree(c->d_wl_parent); cudaFree(c->d_wl_size);
+            c->d_wl_mesh = c->d_wl_parent = c->d_wl_size = nullptr; c->wl_mesh_cap = 0;
+            const int cap = len + len / 4;
+            CK(cudaMalloc(&c->d_wl_mesh, sizeof(int) * (size_t)cap));
+            CK(cudaMalloc(&c->d_wl_parent, sizeof(int) * (size_t)cap));
+            CK(cudaMalloc(&c->d_wl_size, sizeof(int) * (size_t)cap));
+            c->wl_mesh_cap = cap;
+        }
+        CK(cudaMemsetAsync(c->d_wl_mesh, 0, sizeof(int) * (size_t)len, c->stream));
+        const int gm = (len + WL_BLOCK - 1) / WL_BLOCK;
+        k_mesh_fill<<<(c->n + WL_BLOCK - 1) / WL_BLOCK, WL_BLOCK, 0, c->stream>>>(c->d_api, c->d_type, c->n, io->wlmtype, d0, d1, c->d_wl_mesh, d_counters);
+        k_mesh_init<<<gm, WL_BLOCK, 0, c->stream>>>(c->d_wl_mesh, len, c->d_wl_parent, c->d_wl_size, d_counters);
+        k_mesh_union<<<gm, WL_BLOCK, 0, c->stream>>>(d0, d1, c->d_wl_parent);
+        k_mesh_count<<<gm, WL_BLOCK, 0, c->stream>>>(len, c->d_wl_parent, c->d_wl_size);
+        k_mesh_max<<<gm, WL_BLOCK, 0, c->stream>>>(len, c->d_wl_size, d_counters);
+        c->launches += 5;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_wl + WL_OFF_OUT, WL_RESULT_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const char* h = (const char*)c->h_pinned;
+    const double* out = (const double*)h;
+    const long long contacts = *(const long long*)(h + (WL_OFF_OUT_C - WL_OFF_OUT));
+    const int* counters = (const int*)(h + (WL_OFF_COUNTERS - WL_OFF_OUT));
+    for (int k = 0; k < 3; k++) io->syscm[k] = out[k];
+    io->sysvolume = out[3];
+    io->mesh_dim[0] = d0; io->mesh_dim[1] = d1;
+    io->mesh_occupied = need_mesh ? counters[1] : 0;
+    io->mesh_skipped = need_mesh ? counters[2] : 0;
+    for (int w = 0; w < 2; w++) {
+        double raw = 0;
+        int64_t o = 0;
+        const double mn = io->minorder[w], dd = io->dorder[w];
+        switch (io->wlm[w]) {
+            case 1: raw = out[4]; o = (int64_t)ceil((raw - mn) / dd); break;                 // zOrder, wanglandau.h:551-554
+            case 2: raw = (double)counters[0]; o = (int64_t)((raw - mn) / dd); break;        // holeXYPlane(wli), wanglandau.h:313-317
+            case 3: raw = out[5]; o = (int64_t)floor((raw - mn) / dd); break;                // zOrient, wanglandau.h:321-324
+            case 4: raw = out[6]; o = (int64_t)ceil((raw - mn) / dd); break;                 // twoPartDist, wanglandau.h:395-398
+            case 7: raw = (double)contacts; o = (int64_t)ceil((raw - mn) / dd); break;       // contParticlesOrder, wanglandau.h:652-654
+            case 8: raw = c->box[0]; o = (int64_t)ceil((raw - mn) / dd); break;              // boxSize_x, wanglandau.h:375-377
+            case 9: raw = c->box[1]; o = (int64_t)ceil((raw - mn) / dd); break;              // boxSize_y, wanglandau.h:380-382
+            default: break;
+        }
+        io->raw[w] = raw;
+        io->order[w] = o;
+    }
     return SCGPU_OK;
 }
 

@@ -50,6 +50,13 @@ class PressureStats(C.Structure):
                 ("enthalpy_delta", C.c_double), ("box", C.c_double * 3)]
 
 
+class WlOrder(C.Structure):
+    """scgpu_wlorder (include/scgpu.h): Wang-Landau order parameters of the whole configuration, in / out"""
+    _fields_ = [("wlm", C.c_int * 2), ("wlmtype", C.c_int), ("reserved", C.c_int), ("minorder", C.c_double * 2), ("dorder", C.c_double * 2),
+                ("meshsize", C.c_double), ("order", C.c_int64 * 2), ("raw", C.c_double * 2), ("syscm", C.c_double * 3), ("sysvolume", C.c_double),
+                ("mesh_dim", C.c_int * 2), ("mesh_occupied", C.c_int64), ("mesh_skipped", C.c_int64)]
+
+
 class ReplicaState(C.Structure):
     """scgpu_replica_state (include/scgpu.h): what a replica owns and what travels on an accepted exchange"""
     _fields_ = [("temper", C.c_double), ("press", C.c_double), ("pseudo_rank", C.c_int), ("replica", C.c_int),
@@ -74,7 +81,7 @@ SYMBOLS = ["scgpu_last_error", "scgpu_device_count", "scgpu_create", "scgpu_dest
            "scgpu_one_to_all_batch", "scgpu_one_to_all_everyone", "scgpu_submit_everyone", "scgpu_mol_to_others", "scgpu_all_to_all",
            "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_sweep_checkerboard_chains", "scgpu_pressure_move",
            "scgpu_comm_unique_id", "scgpu_comm_create", "scgpu_comm_attach", "scgpu_comm_destroy", "scgpu_replica_exchange",
-           "scgpu_comm_last_exchange_us", "scgpu_wl_merge",
+           "scgpu_comm_last_exchange_us", "scgpu_wl_merge", "scgpu_wl_order",
            "scgpu_timer_start", "scgpu_timer_stop", "scgpu_sync", "scgpu_fp64_peak", "scgpu_profile_everyone", "scgpu_flush_l2",
            "scgpu_kernel_launches"]
 
@@ -113,6 +120,7 @@ def load_library(variant="fast"):
     L.scgpu_overlap_all.argtypes = [vp, C.c_int, _ip]
     L.scgpu_sweep_checkerboard.argtypes = [vp, C.POINTER(MoveParams), C.c_uint64, C.c_uint64, C.POINTER(SweepStats)]
     L.scgpu_pressure_move.argtypes = [vp, C.POINTER(PressureParams), C.c_uint64, C.c_uint64, C.POINTER(PressureStats)]
+    L.scgpu_wl_order.argtypes = [vp, C.POINTER(WlOrder)]
     L.scgpu_sweep_checkerboard_chains.argtypes = [vp, C.POINTER(MoveParams), C.POINTER(ChainMoves), C.c_uint64, C.c_uint64,
                                                   C.POINTER(SweepStats), C.POINTER(ChainStats)]
     L.scgpu_comm_unique_id.argtypes = [C.c_char_p]
@@ -320,6 +328,20 @@ class Engine:
         st = PressureStats()
         self._ck(self.L.scgpu_pressure_move(self.h, C.byref(pp), int(seed), int(step), C.byref(st)))
         return st
+
+    def wl_order(self, wlm, wlmtype=0, minorder=(0.0, 0.0), dorder=(1.0, 1.0), meshsize=0.0):
+        """Wang-Landau order parameters of the configuration on the device (WangLandau::init / runPress forms, scOOP/mc/wanglandau.h:168-196,
+        wanglandau.cpp:56-125); wlm = one method or a pair (second 0 = unused) -> WlOrder (order, raw, syscm, mesh_dim, ...)"""
+        w = WlOrder()
+        wl = (int(wlm), 0) if np.isscalar(wlm) else tuple(int(x) for x in wlm)
+        mn = (float(minorder), 0.0) if np.isscalar(minorder) else tuple(float(x) for x in minorder)
+        dd = (float(dorder), 1.0) if np.isscalar(dorder) else tuple(float(x) for x in dorder)
+        w.wlm[0], w.wlm[1] = wl
+        w.minorder[0], w.minorder[1] = mn
+        w.dorder[0], w.dorder[1] = dd
+        w.wlmtype, w.meshsize = int(wlmtype), float(meshsize)
+        self._ck(self.L.scgpu_wl_order(self.h, C.byref(w)))
+        return w
 
     # ---- measurement
     def timer_start(self):

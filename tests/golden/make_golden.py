@@ -449,7 +449,29 @@ def do_othermoves():
         print("othermoves:", name)
 
 
+def do_wlorder():
+    """Wang-Landau order parameters of whole configurations, from the reference's own members (oracle/ref_driver.cpp `wlorder`):
+    Tests/test_mempore (the membrane whose hole wlm 2 measures), Tests/test_pscthrough (wlm 1: a PSC through the membrane), the
+    multi-type mixture extra_mix, and test_mempore's end state after 300 sweeps of the reference (a configuration off the lattice)."""
+    for name in ("test_mempore", "test_pscthrough", "extra_mix", "test_mempore.short300"):
+        base = name.split(".")[0]
+        inp = json.loads(gzip.open(os.path.join(HERE, base + ".inputs.json.gz")).read().decode())
+        tmp = tempfile.mkdtemp(prefix="wlo_")
+        for fn in ("options", "top.init", "config.init"):
+            with open(os.path.join(tmp, fn), "w") as f:
+                f.write(inp[fn])
+        if name.endswith(".short300"):
+            with open(os.path.join(tmp, "config.init"), "wb") as f:
+                f.write(gzip.open(os.path.join(HERE, name + ".config.last.gz")).read())
+        run([DRIVER, "wlorder", "ref_wlorder.txt"], tmp)
+        gz_copy(os.path.join(tmp, "ref_wlorder.txt"), os.path.join(HERE, name + ".wlorder.gz"))
+        shutil.rmtree(tmp)
+        print("wlorder:", name)
+
+
 def main():
+    if "wlorder" in sys.argv[1:]:
+        return do_wlorder()
     if "othermoves" in sys.argv[1:]:
         return do_othermoves()
     if "wanglandau" in sys.argv[1:]:

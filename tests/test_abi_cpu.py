@@ -35,6 +35,7 @@ def test_record_sizes_match_header():
     assert ctypes.sizeof(engine.SweepStats) == 6 * 8
     assert ctypes.sizeof(engine.ChainMoves) == 8 + 32 * 8 * 2 and ctypes.sizeof(engine.ChainStats) == 7 * 8
     assert ctypes.sizeof(engine.PressureParams) == 3 * 8 + 8 and ctypes.sizeof(engine.PressureStats) == 8 + 6 * 8
+    assert ctypes.sizeof(engine.WlOrder) == 16 + 4 * 8 + 8 + 2 * 8 + 2 * 8 + 4 * 8 + 8 + 2 * 8      # scgpu_wlorder
 
 
 def test_host_library_loads():
