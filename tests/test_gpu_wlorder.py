@@ -145,7 +145,7 @@ def test_membrane_265k_hole_and_centre_of_mass():
         m, dim, occ, skip = O.wl_raw(s, 2, wlmtype=tail, meshsize=meshsize)
         assert (w.raw[0], tuple(w.mesh_dim[:]), w.mesh_occupied, w.mesh_skipped) == (m, dim, occ, skip)
         cm, vol = O.wl_mass_center(s)
-        assert np.allclose(np.array(w.syscm[:]), cm, rtol=0, atol=1e-12) and abs(w.sysvolume - vol) <= 1e-12 * vol
+        assert np.allclose(np.array(w.syscm[:]), cm, rtol=0, atol=1e-12) and abs(w.sysvolume - vol) <= 1e-10 * vol      # 265 041 terms: the sequential sum carries ~3e-12
         assert abs(w.raw[1] - O.wl_raw(s, 1)) <= 1e-10
     w = eng.wl_order(7, wlmtype=tail)
     assert w.raw[0] == O.wl_raw(s, 7, wlmtype=tail) and w.raw[0] > 0
