@@ -314,6 +314,12 @@ typedef struct scgpu_wlorder {
                                                    writes one past its mesh row for them: undefined there, skipped here) */
 } scgpu_wlorder;
 int scgpu_wl_order(scgpu_ctx* ctx, scgpu_wlorder* io);
+/* Mesh::data as Mesh::meshInit leaves it (scOOP/mc/mesh.cpp:11-35, 135-185) for the mesh of the last scgpu_wl_order call with wlm 2:
+ * occupied points hold minus the number of particles covering them, every free point the number of its hole (1, 2, ... in the order
+ * the reference's scan meets the holes). len = mesh_dim[0] * mesh_dim[1]. The reference's incremental updates of single-particle and
+ * chain moves (Mesh::addPart / removePart, WangLandau::meshOrderMoveMolecule, scOOP/mc/wanglandau.cpp:7-52) carry on from this array:
+ * a caller that lets the device do the from-scratch search after a volume move hands it to its host-side Mesh (integration/wl_gpu_hook.h). */
+int scgpu_wl_mesh(scgpu_ctx* ctx, int* data, int len);
 
 /* measurement helpers (CUDA events on the context's stream; FP64 FMA-chain peak microbenchmark) */
 int scgpu_timer_start(scgpu_ctx* ctx);

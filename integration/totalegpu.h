@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "scgpu.h"
+#include "wl_gpu_hook.h"      // scgpu_dropin_ctx(): lets the optional Wang-Landau hook (Mesh::meshInit on the device) find this calculator's context
 
 template<typename pairEFce>
 class TotalEGpu : public TotalE<pairEFce> {
@@ -75,8 +76,8 @@ public:
     using TotalE<pairEFce>::mol2others;
     using TotalE<pairEFce>::oneToAll;
 
-    TotalEGpu(Sim* sim, Conf* conf) : TotalE<pairEFce>(sim, conf), ctx(NULL) { if (scgpu_create(&ctx, sim->mpirank)) fail("create"); }   // one replica per GPU
-    ~TotalEGpu() { scgpu_destroy(ctx); }
+    TotalEGpu(Sim* sim, Conf* conf) : TotalE<pairEFce>(sim, conf), ctx(NULL) { if (scgpu_create(&ctx, sim->mpirank)) fail("create"); scgpu_dropin_ctx() = ctx; }   // one replica per GPU
+    ~TotalEGpu() { if (scgpu_dropin_ctx() == ctx) scgpu_dropin_ctx() = NULL; scgpu_destroy(ctx); }
 
     void initEM() override {                                   // replaces allToAll(eMat.energyMatrix)
         size_t n = conf->pvec.size();

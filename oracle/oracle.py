@@ -86,6 +86,8 @@ def lib():
         L.sco_wl_bin.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
         L.sco_wl_mesh_hole.restype = C.c_int
         L.sco_wl_mesh_hole.argtypes = [C.c_int, _dp, _ip, C.c_int, _dp, C.c_double, _ip, _ip, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+        L.sco_wl_mesh_labels.restype = C.c_int
+        L.sco_wl_mesh_labels.argtypes = [C.c_int, _dp, _ip, C.c_int, _dp, C.c_double, _ip, _ip]
         _lib = L
     return _lib
 
@@ -316,6 +318,23 @@ def wl_raw(system, wlm, wlmtype=0, meshsize=0.0, volumes=None):
     raise ValueError("wlm %d" % wlm)
 
 
+def wl_mesh_labels(system, wlmtype, meshsize):
+    """Mesh::data after Mesh::meshInit: int32 [dim1][dim0], occupied < 0, free = hole number"""
+    dim = np.zeros(2, dtype=np.int32)
+    cap = int(system.box[0] / meshsize) * int(system.box[1] / meshsize)
+    out = np.zeros(max(cap, 1), dtype=np.int32)
+    lib().sco_wl_mesh_labels(system.n, _d(system.state), _i(system.type), int(wlmtype), _d(system.box), float(meshsize), _i(dim), _i(out))
+    return out[:dim[0] * dim[1]].reshape(int(dim[1]), int(dim[0]))
+
+
+def mesh_hash(a):
+    """FNV-1a over the int32 values of a mesh (the hash oracle/ref_driver.cpp `wlorder` prints for Mesh::data)"""
+    h = 0xcbf29ce484222325
+    for v in np.asarray(a, dtype=np.int32).ravel().view(np.uint32).tolist():
+        h = ((h ^ v) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
 def wl_bin(wlm, raw, minorder, dorder):
     return lib().sco_wl_bin(int(wlm), float(raw), float(minorder), float(dorder))
 
@@ -348,6 +367,7 @@ def load_wlorder_dump(path):
                 cur["W7"][int(t[1])] = (int(t[2]), int(t[3]))
             elif t[0] == "W2":
                 out["mesh"].append((int(t[1]), _hx(t[2]), int(t[3]), int(t[4]), int(t[5]), int(t[6]), int(t[7])))
+                out.setdefault("mesh_labels", []).append((int(t[8]), int(t[9], 16)))       # number of holes, FNV-1a of Mesh::data
     return out
 
 

@@ -410,8 +410,15 @@ static int do_wlorder(const char* outname) {
             int maxsize = wl.mesh.meshInit(sizes[k], n, t, conf.geo.box, &conf.pvec);
             long occupied = 0;
             for (int i = 0; i < wl.mesh.dim[0] * wl.mesh.dim[1]; i++) if (wl.mesh.data[i] < 0) occupied++;
-            fprintf(f, "W2 %d %a %d %d %d %ld %ld\n", t, sizes[k], wl.mesh.dim[0], wl.mesh.dim[1], maxsize, occupied,
-                    (long)((maxsize - 1.0) / 4.0));
+            // Mesh::data as findHoles left it (occupied < 0, free = hole number): number of holes and an FNV-1a hash of the array
+            int nholes = 0;
+            unsigned long long h = 0xcbf29ce484222325ull;
+            for (int i = 0; i < wl.mesh.dim[0] * wl.mesh.dim[1]; i++) {
+                if (wl.mesh.data[i] > nholes) nholes = wl.mesh.data[i];
+                h = (h ^ (unsigned long long)(unsigned int)wl.mesh.data[i]) * 0x100000001b3ull;
+            }
+            fprintf(f, "W2 %d %a %d %d %d %ld %ld %d %llx\n", t, sizes[k], wl.mesh.dim[0], wl.mesh.dim[1], maxsize, occupied,
+                    (long)((maxsize - 1.0) / 4.0), nholes, h);
         }
     }
     fclose(f);

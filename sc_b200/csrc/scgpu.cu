@@ -2287,6 +2287,8 @@ struct scgpu_ctx {
     char* d_wl = nullptr;            // scgpu_wl_order: block partials, results, counters (WL_BYTES)
     int *d_wl_mesh = nullptr, *d_wl_parent = nullptr, *d_wl_size = nullptr;      // the hole mesh of wlm 2 and its union-find arrays
     int wl_mesh_cap = 0;
+    int wl_mesh_len = 0;             // mesh points of the last wlm-2 call (0: none); wl_mesh_labelled: d_wl_mesh already holds Mesh::data
+    bool wl_mesh_labelled = false;
     void* h_pinned = nullptr;        // pinned staging, grown on demand
     size_t pinned_bytes = 0;
     int64_t launches = 0;
@@ -3704,6 +3706,7 @@ extern "C" int scgpu_wl_order(scgpu_ctx* c, scgpu_wlorder* io) {
         k_mesh_max<<<gm, WL_BLOCK, 0, c->stream>>>(len, c->d_wl_size, d_counters);
         c->launches += 5;
         CK(cudaGetLastError());
+        c->wl_mesh_len = len; c->wl_mesh_labelled = false;
     }
     CK(cudaMemcpyAsync(c->h_pinned, c->d_wl + WL_OFF_OUT, WL_RESULT_BYTES, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -3733,6 +3736,23 @@ extern "C" int scgpu_wl_order(scgpu_ctx* c, scgpu_wlorder* io) {
         io->raw[w] = raw;
         io->order[w] = o;
     }
+    return SCGPU_OK;
+}
+
+extern "C" int scgpu_wl_mesh(scgpu_ctx* c, int* data, int len) {
+    ARG(c && data, "scgpu_wl_mesh: NULL argument");
+    ARG(c->wl_mesh_len > 0, "scgpu_wl_mesh: no mesh yet (call scgpu_wl_order with wlm 2 first)");
+    ARG(len == c->wl_mesh_len, "scgpu_wl_mesh: len must be mesh_dim[0] * mesh_dim[1] of the last scgpu_wl_order call");
+    CK(cudaSetDevice(c->device));
+    if (!c->wl_mesh_labelled) {
+        k_mesh_label<<<1, 1024, 0, c->stream>>>(len, c->d_wl_parent, c->d_wl_size);        // the hole sizes are not needed any more: d_wl_size takes the labels
+        k_mesh_export<<<(len + WL_BLOCK - 1) / WL_BLOCK, WL_BLOCK, 0, c->stream>>>(len, c->d_wl_mesh, c->d_wl_parent, c->d_wl_size);
+        c->launches += 2;
+        CK(cudaGetLastError());
+        c->wl_mesh_labelled = true;
+    }
+    CK(cudaMemcpyAsync(data, c->d_wl_mesh, sizeof(int) * (size_t)len, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return SCGPU_OK;
 }
 

@@ -179,3 +179,33 @@ __global__ void __launch_bounds__(WL_BLOCK) k_mesh_max(int len, const int* __res
         if (m > 0) atomicMax(&counters[0], m);
     }
 }
+
+// The mesh as Mesh::findHoles leaves it in Mesh::data (mesh.cpp:135-185): occupied points keep their (negative) count, every free point carries
+// the number of its hole, holes numbered 1, 2, ... in the order the reference's scan meets them = by their smallest mesh index -- which is
+// the root of the union-find (the larger root is always hooked under the smaller). The reference's INCREMENTAL updates
+// (Mesh::addPart / removePart, meshOrderMoveMolecule) go on from exactly this array, so a caller that lets the device do the from-scratch
+// search and the host the incremental steps needs it bit for bit (scgpu_wl_mesh).
+__global__ void __launch_bounds__(1024) k_mesh_label(int len, const int* __restrict__ parent, int* __restrict__ label) {
+    __shared__ int sh[1024];
+    const int tid = threadIdx.x;
+    const int per = (len + 1023) / 1024;
+    const int lo = min(len, tid * per), hi = min(len, lo + per);
+    int cnt = 0;
+    for (int i = lo; i < hi; i++) cnt += parent[i] == i;
+    sh[tid] = cnt;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {          // inclusive scan of the per-thread root counts
+        const int v = tid >= off ? sh[tid - off] : 0;
+        __syncthreads();
+        sh[tid] += v;
+        __syncthreads();
+    }
+    int run = sh[tid] - cnt;
+    for (int i = lo; i < hi; i++) if (parent[i] == i) label[i] = ++run;
+}
+
+__global__ void __launch_bounds__(WL_BLOCK) k_mesh_export(int len, int* mesh, int* parent, const int* __restrict__ label) {
+    const int i = blockIdx.x * WL_BLOCK + threadIdx.x;
+    if (i >= len || parent[i] < 0) return;
+    mesh[i] = label[uf_find(parent, i)];
+}

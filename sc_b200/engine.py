@@ -81,7 +81,7 @@ SYMBOLS = ["scgpu_last_error", "scgpu_device_count", "scgpu_create", "scgpu_dest
            "scgpu_one_to_all_batch", "scgpu_one_to_all_everyone", "scgpu_submit_everyone", "scgpu_mol_to_others", "scgpu_all_to_all",
            "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_sweep_checkerboard_chains", "scgpu_pressure_move",
            "scgpu_comm_unique_id", "scgpu_comm_create", "scgpu_comm_attach", "scgpu_comm_destroy", "scgpu_replica_exchange",
-           "scgpu_comm_last_exchange_us", "scgpu_wl_merge", "scgpu_wl_order",
+           "scgpu_comm_last_exchange_us", "scgpu_wl_merge", "scgpu_wl_order", "scgpu_wl_mesh",
            "scgpu_timer_start", "scgpu_timer_stop", "scgpu_sync", "scgpu_fp64_peak", "scgpu_profile_everyone", "scgpu_flush_l2",
            "scgpu_kernel_launches"]
 
@@ -121,6 +121,7 @@ def load_library(variant="fast"):
     L.scgpu_sweep_checkerboard.argtypes = [vp, C.POINTER(MoveParams), C.c_uint64, C.c_uint64, C.POINTER(SweepStats)]
     L.scgpu_pressure_move.argtypes = [vp, C.POINTER(PressureParams), C.c_uint64, C.c_uint64, C.POINTER(PressureStats)]
     L.scgpu_wl_order.argtypes = [vp, C.POINTER(WlOrder)]
+    L.scgpu_wl_mesh.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
     L.scgpu_sweep_checkerboard_chains.argtypes = [vp, C.POINTER(MoveParams), C.POINTER(ChainMoves), C.c_uint64, C.c_uint64,
                                                   C.POINTER(SweepStats), C.POINTER(ChainStats)]
     L.scgpu_comm_unique_id.argtypes = [C.c_char_p]
@@ -342,6 +343,12 @@ class Engine:
         w.wlmtype, w.meshsize = int(wlmtype), float(meshsize)
         self._ck(self.L.scgpu_wl_order(self.h, C.byref(w)))
         return w
+
+    def wl_mesh(self, dim):
+        """Mesh::data of the last wl_order call with wlm 2 (occupied: -count, free: hole number) as an int32 array [dim1][dim0]"""
+        out = np.zeros(int(dim[0]) * int(dim[1]), dtype=np.int32)
+        self._ck(self.L.scgpu_wl_mesh(self.h, out.ctypes.data_as(C.POINTER(C.c_int)), out.size))
+        return out.reshape(int(dim[1]), int(dim[0]))
 
     # ---- measurement
     def timer_start(self):

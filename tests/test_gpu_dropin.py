@@ -84,6 +84,32 @@ def test_reference_main_wang_landau_runs(name):
     assert got_wl == gzip.open(os.path.join(G, name + ".short300.wl-new.dat.gz"), "rt").read()
 
 
+def test_reference_main_with_the_hole_search_on_the_device():
+    """oracle/_ref/SC_scgpu_wl = SC_scgpu with ONE more call of the reference redirected (integration/wl_gpu_hook.h; oracle/Makefile
+    scgpu_wl_ref): WangLandau::holeXYPlane(wli) -- the from-scratch membrane-hole order parameter WangLandau::runPress evaluates after every
+    volume move (mc/wanglandau.h:168-196, 313-317) -- calls scgpu_mesh_init instead of Mesh::meshInit: mesh fill + hole search on the device
+    (scgpu_wl_order), Mesh::data handed back (scgpu_wl_mesh) for the incremental updates of the following single-particle and chain moves,
+    which stay the reference's host code. Tests/test_mempore (wlm 2, NPT ptype 2, ~1 volume move per sweep): config.last AND wl-new.dat
+    byte-identical to the unmodified reference."""
+    import gzip
+    sc_wl = os.path.join(ROOT, "oracle", "_ref", "SC_scgpu_wl")
+    if not os.path.exists(sc_wl):
+        pytest.skip("oracle/_ref/SC_scgpu_wl was not built (make -C oracle scgpu_wl_ref needs /root/reference)")
+    name = "test_mempore"
+    inputs = json.loads(gzip.open(os.path.join(G, name + ".inputs.json.gz")).read().decode())
+    with tempfile.TemporaryDirectory(prefix="dropin_wlgpu_") as tmp:
+        for fn in ("options", "top.init", "config.init", "wl.dat"):
+            with open(os.path.join(tmp, fn), "w") as f:
+                f.write(inputs[fn])
+        r = subprocess.run([sc_wl], cwd=tmp, capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        got_cfg = open(os.path.join(tmp, "config.last")).read()
+        got_wl = open(os.path.join(tmp, "wl-new.dat")).read()
+    assert "Mesh::meshInit runs on the device" in r.stderr            # the hook was really taken
+    assert got_cfg == gzip.open(os.path.join(G, name + ".short300.config.last.gz"), "rt").read(), r.stdout[-800:]
+    assert got_wl == gzip.open(os.path.join(G, name + ".short300.wl-new.dat.gz"), "rt").read()
+
+
 @pytest.mark.parametrize("name", ["test_01_clustermoves", "test_01_grandcanonical"])
 def test_reference_main_cluster_and_grand_canonical_moves(name):
     """the moves SURVEY.md section 8(f) rank 4 lists stay the reference's own host code (MoveCreator::clusterMoveGeom,

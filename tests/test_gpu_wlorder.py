@@ -49,6 +49,11 @@ def test_order_parameters_against_reference_dumps(name, variant):
         assert tuple(w.mesh_dim[:]) == (d0, d1) and w.mesh_skipped == 0
         assert w.mesh_occupied == occupied, (t, meshsize)                   # Mesh::meshFill
         assert w.raw[0] == maxsize and w.order[0] == order, (t, meshsize)   # Mesh::findHoles
+    for (t, meshsize, d0, d1, maxsize, occupied, order), (nholes, fnv) in zip(d["mesh"], d["mesh_labels"]):
+        eng.wl_order(2, wlmtype=t, meshsize=meshsize)
+        lab = eng.wl_mesh((d0, d1))                                          # Mesh::data as findHoles leaves it, bit for bit
+        assert max(int(lab.max()), 0) == nholes and O.mesh_hash(lab) == fnv, (t, meshsize)
+        assert np.array_equal(lab, eng.wl_mesh((d0, d1)))                    # a second read returns the same array
     # two dimensions at once, as `wlm = 2 1` of an options file
     t, meshsize, _, _, maxsize, _, _ = d["mesh"][1]
     (mn, dd), ref = next(iter(d["bins"].items()))
@@ -73,6 +78,11 @@ def test_refused_methods_and_arguments():
         eng.wl_order(2, wlmtype=99, meshsize=0.3)
     with pytest.raises(ScgpuError):
         eng.wl_order(1, dorder=0.0)
+    with pytest.raises(ScgpuError):
+        eng.wl_mesh((10, 10))                                                # no mesh yet
+    w = eng.wl_order(2, wlmtype=1, meshsize=0.5)
+    with pytest.raises(ScgpuError):
+        eng.wl_mesh((w.mesh_dim[0] + 1, w.mesh_dim[1]))                      # wrong size
     eng.close()
 
 
@@ -128,6 +138,7 @@ def test_hole_search_on_random_sparse_meshes():
             m, dim, occ, skip = O.wl_raw(sys2, 2, wlmtype=t, meshsize=meshsize)
             assert (w.raw[0], tuple(w.mesh_dim[:]), w.mesh_occupied, w.mesh_skipped) == (m, dim, occ, skip), (n, box, t)
             assert m < dim[0] * dim[1]
+            assert np.array_equal(eng.wl_mesh(dim), O.wl_mesh_labels(sys2, t, meshsize)), (n, box, t)
     eng.close()
 
 
@@ -147,6 +158,7 @@ def test_membrane_265k_hole_and_centre_of_mass():
         cm, vol = O.wl_mass_center(s)
         assert np.allclose(np.array(w.syscm[:]), cm, rtol=0, atol=1e-12) and abs(w.sysvolume - vol) <= 1e-10 * vol      # 265 041 terms: the sequential sum carries ~3e-12
         assert abs(w.raw[1] - O.wl_raw(s, 1)) <= 1e-10
+        assert np.array_equal(eng.wl_mesh(dim), O.wl_mesh_labels(s, tail, meshsize))
     w = eng.wl_order(7, wlmtype=tail)
     assert w.raw[0] == O.wl_raw(s, 7, wlmtype=tail) and w.raw[0] > 0
     eng.close()

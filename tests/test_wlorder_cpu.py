@@ -47,7 +47,10 @@ def test_wl_order_oracle_is_bit_exact_against_the_reference(name):
             assert c == cnt and O.wl_bin(7, c, mn, dd) == order, t
     assert len(d["mesh"]) >= 8
     holes = set()
-    for t, meshsize, d0, d1, maxsize, occupied, order in d["mesh"]:
+    for (t, meshsize, d0, d1, maxsize, occupied, order), (nholes, fnv) in zip(d["mesh"], d["mesh_labels"]):
+        lab = O.wl_mesh_labels(s, t, meshsize)                            # Mesh::data after findHoles: hole numbers in scan order
+        assert lab.shape == (d1, d0) and max(int(lab.max()), 0) == nholes and O.mesh_hash(lab) == fnv, (t, meshsize)
+        assert np.count_nonzero(lab < 0) == occupied and (nholes == 0 or np.bincount(lab[lab > 0]).max() == maxsize)
         m, dim, occ, skip = O.wl_raw(s, 2, wlmtype=t, meshsize=meshsize)
         assert dim == (d0, d1) and skip == 0
         assert occ == occupied, (t, meshsize)                             # Mesh::meshFill
