@@ -162,6 +162,10 @@ int scgpu_set_particles_compact(scgpu_ctx* ctx, int n, const double* state9, con
 int scgpu_set_box(scgpu_ctx* ctx, const double box[3]);
 /* update(int target) after an accepted single-particle move (totalenergycalculator.h:326-328) */
 int scgpu_update_particle(scgpu_ctx* ctx, int idx, const double* state30);
+/* MoveCreator::switchTypeMove (scOOP/mc/movecreator.cpp:233-303) changes conf->pvec[target].type in place before oneToAllTrial(target) and keeps
+ * the new type on acceptance: the type of ONE particle changes on the device (the state record travels as usual, through the trial state /
+ * scgpu_update_particle). The kernels' specialisations follow the census of types present; the next energy call re-sorts the cells. */
+int scgpu_set_particle_type(scgpu_ctx* ctx, int idx, int type);
 int scgpu_download_particles(scgpu_ctx* ctx, double* state30);
 
 /* Replaces Updater::genSimplePairList (scOOP/mc/updater.cpp:484-552): counting sort by cell. Called implicitly by

@@ -39,10 +39,23 @@ class TotalEGpu : public TotalE<pairEFce> {
                                &p.patchsides[2], &p.patchsides[3], &p.chdir[0], &p.chdir[1]};
         for (int k = 0; k < 10; k++) { o[3 * k] = v[k]->x; o[3 * k + 1] = v[k]->y; o[3 * k + 2] = v[k]->z; }
     }
-    void pushBox() { double b[3] = {conf->geo.box.x, conf->geo.box.y, conf->geo.box.z}; if (scgpu_set_box(ctx, b)) fail("set_box"); }
+    // Type-switch moves (MoveCreator::switchTypeMove, mc/movecreator.cpp:233-303) change conf->pvec[t].type in place before oneToAllTrial(t)
+    // and, when the move is rejected, change it back WITHOUT telling the calculator. The device holds each particle's type: it follows the host
+    // at the trial (syncType) and the particle is remembered, so that whichever entry point is called next settles a rejected switch first.
+    int switched;
+    void syncType(int t) {
+        if (conf->pvec[t].type != type[t]) { type[t] = conf->pvec[t].type; if (scgpu_set_particle_type(ctx, t, type[t])) fail("set_particle_type"); }
+    }
+    void settle() { if (switched >= 0) { int t = switched; switched = -1; syncType(t); } }
+    void pushBox() { settle(); double b[3] = {conf->geo.box.x, conf->geo.box.y, conf->geo.box.z}; if (scgpu_set_box(ctx, b)) fail("set_box"); }
     void pushTopology() {
         int T = 0, M = conf->pvec.molTypeCount;
         for (unsigned i = 0; i < conf->pvec.size(); i++) if (conf->pvec[i].type + 1 > T) T = conf->pvec[i].type + 1;
+        for (int m = 0; m < M; m++) {                         // types a switch move may turn a particle into (moleculeparams.h:36-38)
+            MoleculeParams& q = topo.moleculeParam[m];
+            for (unsigned k = 0; k < q.switchTypes.size(); k++) if (q.switchTypes[k] + 1 > T) T = q.switchTypes[k] + 1;
+            for (unsigned k = 0; k < q.particleTypes.size(); k++) if (q.particleTypes[k] + 1 > T) T = q.particleTypes[k] + 1;
+        }
         std::vector<scgpu_iaparam> tab((size_t)T * T);
         for (int a = 0; a < T; a++) for (int b = 0; b < T; b++) {
             const Ia_param& q = topo.ia_params[a][b];
@@ -76,20 +89,25 @@ public:
     using TotalE<pairEFce>::mol2others;
     using TotalE<pairEFce>::oneToAll;
 
-    TotalEGpu(Sim* sim, Conf* conf) : TotalE<pairEFce>(sim, conf), ctx(NULL) { if (scgpu_create(&ctx, sim->mpirank)) fail("create"); scgpu_dropin_ctx() = ctx; }   // one replica per GPU
+    TotalEGpu(Sim* sim, Conf* conf) : TotalE<pairEFce>(sim, conf), ctx(NULL), switched(-1) { if (scgpu_create(&ctx, sim->mpirank)) fail("create"); scgpu_dropin_ctx() = ctx; }   // one replica per GPU
     ~TotalEGpu() { if (scgpu_dropin_ctx() == ctx) scgpu_dropin_ctx() = NULL; scgpu_destroy(ctx); }
 
     void initEM() override {                                   // replaces allToAll(eMat.energyMatrix)
         size_t n = conf->pvec.size();
         st.resize(n * 30); type.resize(n); moltype.resize(n);
         for (size_t i = 0; i < n; i++) { pack(conf->pvec[i], &st[i * 30]); type[i] = conf->pvec[i].type; moltype[i] = conf->pvec[i].molType; }
+        switched = -1;
         pushTopology();
         pushBox();
         if (scgpu_set_particles(ctx, (int)n, st.data(), type.data(), moltype.data())) fail("set_particles");
     }
     void update() override { pushBox(); }                       // accepted volume move
     void update(EMResize) override { initEM(); }                // muVT changed the particle count
-    void update(int t) override { double* s = &st[(size_t)t * 30]; pack(conf->pvec[t], s); if (scgpu_update_particle(ctx, t, s)) fail("update"); }
+    void update(int t) override {
+        settle();
+        syncType(t);                                            // an accepted type switch keeps the new type
+        double* s = &st[(size_t)t * 30]; pack(conf->pvec[t], s); if (scgpu_update_particle(ctx, t, s)) fail("update");
+    }
     void update(Molecule m) override { for (unsigned k = 0; k < m.size(); k++) update(m[k]); }
 
     // Some callers write conf->pvec WITHOUT telling the calculator: the geometric cluster move reflects a whole cluster in place and then
@@ -101,6 +119,7 @@ public:
         double s[30];
         for (size_t i = 0; i < n; i++) {
             pack(conf->pvec[i], s);
+            syncType((int)i);
             if (memcmp(s, &st[i * 30], sizeof s)) { memcpy(&st[i * 30], s, sizeof s); if (scgpu_update_particle(ctx, (int)i, s)) fail("update"); }
         }
     }
@@ -112,6 +131,7 @@ public:
         double s[30], e;
         pack(conf->pvec[t], s);
         pushBox();
+        if (conf->pvec[t].type != type[t]) { syncType(t); switched = t; }      // switchTypeMove: the trial carries a new type
         if (scgpu_one_to_all(ctx, t, s, &e, NULL)) fail("one_to_all");
         return e;
     }

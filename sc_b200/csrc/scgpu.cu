@@ -2231,6 +2231,7 @@ struct scgpu_ctx {
     int sub = 1;                     // sub-cells per cell and axis of the current cell list
     unsigned present_mask = 0;       // particle types present (bit per type, types < 32)
     long long type_count[40] = {0};
+    std::vector<char> mol_used;      // molecule types present
     unsigned fine_heavy = 0;         // types whose reach exceeds a sub-cell: their pairs stay on the coarse grid
     int *d_heavy = nullptr, *d_nheavy = nullptr;             // sorted slots of the heavy-type particles
     int heavy_cap = 0;
@@ -2293,6 +2294,34 @@ struct scgpu_ctx {
     size_t pinned_bytes = 0;
     int64_t launches = 0;
 };
+
+// what the kernels' specialisations depend on, from the census of particle types (type_count) and molecule types (mol_used) present
+static void derive_type_flags(scgpu_ctx* c) {
+    c->use_rows = true;
+    c->heavy_types = 0;
+    std::vector<char> tu(c->ntypes, 0);
+    for (int t = 0; t < c->ntypes; t++) tu[t] = c->type_count[t] > 0;
+    c->present_mask = 0;
+    for (int t = 0; t < c->ntypes && t < 32; t++) if (tu[t]) c->present_mask |= 1u << t;
+    bool rods = true;
+    for (int a = 0; a < c->ntypes && rods; a++) for (int b = 0; b < c->ntypes && rods; b++) {
+        if (!tu[a] || !tu[b]) continue;
+        int k = (int)c->h_ia[(size_t)a * c->ntypes + b].reserved[0];
+        if (!(k == K_SC_PSCCPSC || k == K_SC_CPSC || k == K_SC_PSC || k == K_SC_SCN)) rods = false;
+    }
+    for (int mm = 0; mm < c->nmol && rods; mm++) if (c->mol_used[mm] && c->h_mol[mm].mol_size != 1.0) rods = false;
+    c->rods_only = rods;
+    {
+        int nt = 0, last = -1;
+        for (int a = 0; a < c->ntypes; a++) if (tu[a]) { nt++; last = a; }
+        c->one_type = nt == 1 ? last : -1;
+    }
+    c->any_two_patch = false;
+    for (int a = 0; a < c->ntypes; a++) if (tu[a]) {
+        int g = (int)c->h_ia[(size_t)a * c->ntypes + a].geotype[0];
+        if (g == SCGPU_TPSC || g == SCGPU_TCPSC || g == SCGPU_TCHPSC || g == SCGPU_TCHCPSC) c->any_two_patch = true;
+    }
+}
 
 static int ensure_pinned(scgpu_ctx* c, size_t bytes) {
     if (bytes <= c->pinned_bytes) return 0;
@@ -2619,32 +2648,11 @@ static int set_particles_impl(scgpu_ctx* c, int n, const double* state30, const 
     // specialisation switch: only rod-rod functors and no bonded molecule among the particles present
     if (!same_types) {
         c->types_valid = true;
-        c->use_rows = true;
-        c->heavy_types = 0;
-        std::vector<char> tu(c->ntypes, 0), mu(c->nmol, 0);
-        for (int i = 0; i < n; i++) { tu[type[i]] = 1; mu[moltype[i]] = 1; }
-        c->present_mask = 0;
         for (int t = 0; t < 40; t++) c->type_count[t] = 0;
         for (int i = 0; i < n; i++) c->type_count[type[i]]++;
-        for (int t = 0; t < c->ntypes && t < 32; t++) if (tu[t]) c->present_mask |= 1u << t;
-        bool rods = true;
-        for (int a = 0; a < c->ntypes && rods; a++) for (int b = 0; b < c->ntypes && rods; b++) {
-            if (!tu[a] || !tu[b]) continue;
-            int k = (int)c->h_ia[(size_t)a * c->ntypes + b].reserved[0];
-            if (!(k == K_SC_PSCCPSC || k == K_SC_CPSC || k == K_SC_PSC || k == K_SC_SCN)) rods = false;
-        }
-        for (int mm = 0; mm < c->nmol && rods; mm++) if (mu[mm] && c->h_mol[mm].mol_size != 1.0) rods = false;
-        c->rods_only = rods;
-        {
-            int nt = 0, last = -1;
-            for (int a = 0; a < c->ntypes; a++) if (tu[a]) { nt++; last = a; }
-            c->one_type = nt == 1 ? last : -1;
-        }
-        c->any_two_patch = false;
-        for (int a = 0; a < c->ntypes; a++) if (tu[a]) {
-            int g = (int)c->h_ia[(size_t)a * c->ntypes + a].geotype[0];
-            if (g == SCGPU_TPSC || g == SCGPU_TCPSC || g == SCGPU_TCHPSC || g == SCGPU_TCHCPSC) c->any_two_patch = true;
-        }
+        c->mol_used.assign(c->nmol, 0);
+        for (int i = 0; i < n; i++) c->mol_used[moltype[i]] = 1;
+        derive_type_flags(c);
     }
     c->cells_valid = false;
     c->api_stale = false;
@@ -2841,6 +2849,34 @@ extern "C" int scgpu_update_particle(scgpu_ctx* c, int idx, const double* state3
             CK(cudaGetLastError());
         }
     }
+    return SCGPU_OK;
+}
+
+// MoveCreator::switchTypeMove (scOOP/mc/movecreator.cpp:233-303) changes conf->pvec[target].type in place (and re-derives the patch
+// vectors with Particle::init for the new type) before it asks for oneToAllTrial(target), and keeps the new type when the move is
+// accepted. The type of a particle lives on the device (uploaded by scgpu_set_particles): this call changes it for ONE particle.
+// The cell-sorted arrays carry the type of every partner, and the kernels' specialisations depend on which types are present: both
+// are refreshed (the next energy call re-sorts). Type switches are rare (switchprob per sweep), the re-sort is not on a hot path.
+extern "C" int scgpu_set_particle_type(scgpu_ctx* c, int idx, int type) {
+    ARG(c, "scgpu_set_particle_type: NULL context");
+    ARG(c->types_valid && idx >= 0 && idx < c->n, "scgpu_set_particle_type: index out of range (or no particles with types uploaded)");
+    ARG(type >= 0 && type < c->ntypes, "scgpu_set_particle_type: not a particle type of the topology");
+    CK(cudaSetDevice(c->device));
+    if (sync_api_from_sorted(c)) return SCGPU_ERR_CUDA;
+    CK(cudaStreamSynchronize(c->stream));        // the staging slot is reused
+    int* h = (int*)(c->h_small + 768);
+    CK(cudaMemcpyAsync(h, c->d_type + idx, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int old = h[0];
+    if (old == type) return SCGPU_OK;
+    h[1] = type;
+    CK(cudaMemcpyAsync(c->d_type + idx, h + 1, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->type_count[old]--;
+    c->type_count[type]++;
+    derive_type_flags(c);
+    c->cells_valid = false;
+    c->f32_valid = false;
     return SCGPU_OK;
 }
 

@@ -76,7 +76,7 @@ class WLState(C.Structure):
 
 
 SYMBOLS = ["scgpu_last_error", "scgpu_device_count", "scgpu_create", "scgpu_destroy", "scgpu_set_topology",
-           "scgpu_set_particles", "scgpu_set_particles_compact", "scgpu_set_exter", "scgpu_set_box", "scgpu_update_particle", "scgpu_download_particles",
+           "scgpu_set_particles", "scgpu_set_particles_compact", "scgpu_set_exter", "scgpu_set_box", "scgpu_update_particle", "scgpu_set_particle_type", "scgpu_download_particles",
            "scgpu_build_cells", "scgpu_cell_assignment", "scgpu_cell_order", "scgpu_one_to_all",
            "scgpu_one_to_all_batch", "scgpu_one_to_all_everyone", "scgpu_submit_everyone", "scgpu_mol_to_others", "scgpu_all_to_all",
            "scgpu_overlap_one", "scgpu_overlap_all", "scgpu_sweep_checkerboard", "scgpu_sweep_checkerboard_chains", "scgpu_pressure_move",
@@ -106,6 +106,7 @@ def load_library(variant="fast"):
     L.scgpu_set_box.argtypes = [vp, _dp]
     L.scgpu_set_exter.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double]
     L.scgpu_update_particle.argtypes = [vp, C.c_int, _dp]
+    L.scgpu_set_particle_type.argtypes = [vp, C.c_int, C.c_int]
     L.scgpu_download_particles.argtypes = [vp, _dp]
     L.scgpu_build_cells.argtypes = [vp]
     L.scgpu_cell_assignment.argtypes = [vp, _ip, _ip]
@@ -223,6 +224,10 @@ class Engine:
     def update_particle(self, idx, state):
         st = np.ascontiguousarray(state, dtype=np.float64)
         self._ck(self.L.scgpu_update_particle(self.h, int(idx), _d(st)))
+
+    def set_particle_type(self, idx, ptype):
+        """switchTypeMove: the type of one particle changes on the device"""
+        self._ck(self.L.scgpu_set_particle_type(self.h, int(idx), int(ptype)))
 
     def download_particles(self):
         out = np.zeros((self.n, STATE))

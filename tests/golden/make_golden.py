@@ -449,6 +449,35 @@ def do_othermoves():
         print("othermoves:", name)
 
 
+def do_switchmoves():
+    """Type-switch moves (MoveCreator::switchTypeMove, movecreator.cpp:233-303) on Tests/test_wallfibril: every CPSC (type 1) may switch to
+    the chiral CHCPSC (type 2) with delta_mu = 5 -- the line the shipped top.init carries as a comment (`#particles: 1 2 5`) and
+    Tests/test_wallfibril/old/options enables with switchprob -- at switchprob = 0.02 per step (~2400 attempts in 300 sweeps), external
+    wall present. 300 sweeps of the unmodified reference program; config.last records every particle's `switched` flag."""
+    src = os.path.join(REF, "Tests", "test_wallfibril", "new")
+    inp = {fn: open(os.path.join(src, fn)).read() for fn in ("options", "top.init", "config.init")}
+    inp["options"] = re.sub(r"(?m)^nsweeps\s*=\s*\d+", "nsweeps = 300", inp["options"])
+    inp["options"] = re.sub(r"(?m)^switchprob\s*=\s*[0-9.]+", "switchprob = 0.02", inp["options"])
+    assert "switchprob = 0.02" in inp["options"]
+    lines = inp["top.init"].split("\n")
+    k = [i for i, l in enumerate(lines) if l.strip().startswith("particles:")]
+    assert len(k) == 1
+    lines[k[0]] = "particles:   1        2           5"
+    inp["top.init"] = "\n".join(lines)
+    name = "test_wallfibril_switchmoves"
+    tmp = tempfile.mkdtemp(prefix="switch_")
+    for fn, txt in inp.items():
+        with open(os.path.join(tmp, fn), "w") as f:
+            f.write(txt)
+    run([SC], tmp)
+    with open(os.path.join(HERE, name + ".inputs.json"), "w") as f:
+        json.dump(inp, f)
+    shutil.copy(os.path.join(tmp, "config.last"), os.path.join(HERE, name + ".short300.config.last"))
+    last = open(os.path.join(tmp, "config.last")).read().split("\n")[1:]
+    print("switchmoves:", name, "particles switched at the end:", sum(1 for l in last if l.split() and l.split()[-1] == "1"))
+    shutil.rmtree(tmp)
+
+
 def do_wlorder():
     """Wang-Landau order parameters of whole configurations, from the reference's own members (oracle/ref_driver.cpp `wlorder`):
     Tests/test_mempore (the membrane whose hole wlm 2 measures), Tests/test_pscthrough (wlm 1: a PSC through the membrane), the
@@ -472,6 +501,8 @@ def do_wlorder():
 def main():
     if "wlorder" in sys.argv[1:]:
         return do_wlorder()
+    if "switchmoves" in sys.argv[1:]:
+        return do_switchmoves()
     if "othermoves" in sys.argv[1:]:
         return do_othermoves()
     if "wanglandau" in sys.argv[1:]:

@@ -84,6 +84,18 @@ def test_reference_main_wang_landau_runs(name):
     assert got_wl == gzip.open(os.path.join(G, name + ".short300.wl-new.dat.gz"), "rt").read()
 
 
+def test_reference_main_type_switch_moves():
+    """MoveCreator::switchTypeMove (movecreator.cpp:233-303): the reference changes conf->pvec[target].type in place before oneToAllTrial and
+    restores it behind the calculator's back on rejection; TotalEGpu follows through scgpu_set_particle_type. Tests/test_wallfibril with
+    the switch line of its top.init enabled (CPSC <-> CHCPSC, delta_mu 5, ~2400 attempts, external wall): config.last -- which records
+    every particle's `switched` flag, 143 particles end up switched -- byte-identical to the unmodified reference
+    (tests/golden/make_golden.py switchmoves)."""
+    got, out = run_reference_program("test_wallfibril_switchmoves", 0)
+    want = open(os.path.join(G, "test_wallfibril_switchmoves.short300.config.last")).read()
+    assert sum(1 for l in want.split("\n")[1:] if l.split() and l.split()[-1] == "1") > 100
+    assert got == want, out[-800:]
+
+
 def test_reference_main_with_the_hole_search_on_the_device():
     """oracle/_ref/SC_scgpu_wl = SC_scgpu with ONE more call of the reference redirected (integration/wl_gpu_hook.h; oracle/Makefile
     scgpu_wl_ref): WangLandau::holeXYPlane(wli) -- the from-scratch membrane-hole order parameter WangLandau::runPress evaluates after every
