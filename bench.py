@@ -272,7 +272,7 @@ def run_ours(args):
     # one process per GPU on a multi-socket host: run on the CPUs next to the GPU, so that the page-locked buffers of the end-to-end leg
     # are first touched on its NUMA node (NVML knows the topology). The CPU legs below lift the restriction again.
     full_affinity = None
-    if world > 1:
+    if world > 1 or os.environ.get("BENCH_AFFINITY") == "1":
         try:
             import pynvml
             pynvml.nvmlInit()
