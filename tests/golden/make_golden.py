@@ -478,6 +478,40 @@ def do_switchmoves():
     shutil.rmtree(tmp)
 
 
+def do_verify_grids():
+    """The pose grids of tests/golden/grid_config_*.txt.gz are written by the Python generator above; this check builds the REFERENCE's own
+    generator (Tests/Interactions_tests/main.cpp -> Spc_config_generator) and replays Tests/Interactions_tests/test.sh's loops
+    (Grid_energy_test_Spherocylinder.sh "..." 10 1.0 3.0; Grid_energy_test_Spherocylinder_Sphere.sh "..." 0.77) on it: the concatenated
+    config.init texts must be byte-identical to ours. Writes tests/golden/grid_config.sha256 (checked by tests/test_oracle_golden.py)."""
+    import hashlib
+    tmp = tempfile.mkdtemp(prefix="grids_")
+    gen = os.path.join(tmp, "Spc_config_generator")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-w", os.path.join(REF, "Tests", "Interactions_tests", "main.cpp"), "-o", gen])
+    pre = open(os.path.join(REF, "Tests", "Interactions_tests", "config.init_prescript")).read()
+    sc = pre
+    for x in (1, 4, 7):                                   # seq 1.0 3.0 9.0
+        for y in (1, 4, 7):
+            for z in (1, 4, 7):
+                out = subprocess.run([gen, str(x), str(y), str(z), "10", "1.0"], capture_output=True, text=True, check=True).stdout
+                sc += "\n".join(out.split("\n")[:-2]) + "\n"       # head -n -1: the last line is the particle count
+    seq = lambda hi: subprocess.run(["seq", "1.0", "0.77", hi], capture_output=True, text=True, check=True).stdout.split()
+    scsp = pre
+    for x in seq("9.0"):
+        for y in seq("9.0"):
+            for z in seq("5.0"):
+                scsp += "%s %s %s %s\n" % (x, y, z, " 1 0 0  0 1 0  0 0")
+    res = {}
+    for kind, ref_text in (("sc", sc), ("scsp", scsp)):
+        ours = gzip.open(os.path.join(HERE, "grid_config_%s.txt.gz" % kind), "rt").read()
+        assert ours == ref_text, "pose grid %s differs from the reference generator's output" % kind
+        res[kind] = hashlib.sha256(ref_text.encode()).hexdigest()
+    with open(os.path.join(HERE, "grid_config.sha256"), "w") as f:
+        json.dump({"what": "sha256 of the config.init text the reference's own Tests/Interactions_tests generator + test.sh loops produce "
+                           "(tests/golden/make_golden.py verify_grids); grid_config_<kind>.txt.gz must hash to the same value", **res}, f, indent=1)
+    shutil.rmtree(tmp)
+    print("verify_grids: sc and scsp pose grids byte-identical to the reference generator's output", res)
+
+
 def do_wlorder():
     """Wang-Landau order parameters of whole configurations, from the reference's own members (oracle/ref_driver.cpp `wlorder`):
     Tests/test_mempore (the membrane whose hole wlm 2 measures), Tests/test_pscthrough (wlm 1: a PSC through the membrane), the
@@ -499,6 +533,8 @@ def do_wlorder():
 
 
 def main():
+    if "verify_grids" in sys.argv[1:]:
+        return do_verify_grids()
     if "wlorder" in sys.argv[1:]:
         return do_wlorder()
     if "switchmoves" in sys.argv[1:]:

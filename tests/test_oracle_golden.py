@@ -100,6 +100,17 @@ def test_pose_grid_bitexact(name):
     assert np.array_equal(ov0j, z["ov0j"]) and np.array_equal(ovj0, z["ovj0"])
 
 
+def test_pose_grids_are_the_reference_generators_own():
+    """the spherocylinder and spherocylinder-sphere pose sets are byte-identical to what the reference's own generator
+    (Tests/Interactions_tests/main.cpp) and test.sh loops write (tests/golden/make_golden.py verify_grids recorded the hashes)"""
+    import hashlib
+    import json
+    want = json.load(open(os.path.join(G, "grid_config.sha256")))
+    for kind in ("sc", "scsp"):
+        txt = gzip.open(os.path.join(G, "grid_config_%s.txt.gz" % kind)).read()
+        assert hashlib.sha256(txt).hexdigest() == want[kind], kind
+
+
 def test_known_answers_test01():
     """two full-precision known answers from test_01's initial configuration"""
     r = O.load_ref_dump(os.path.join(G, "test_01_normal_PSC_init.ref.gz"))
