@@ -689,7 +689,7 @@ def run_ours(args):
         roof["error"] = repr(ex)
     cpu = None
     if world == 1 and not args.no_cpu:
-        cpu = cpu_reference(2048, 24, os.cpu_count() or 1) or cpu_port_fallback(256)
+        cpu = cpu_reference(2048, 96, os.cpu_count() or 1) or cpu_port_fallback(256)      # ~0.7 s per process: ~10 core-seconds on the 16-core box
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
@@ -717,7 +717,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    ntargets, reps = 2048, 8
+    ntargets, reps = 2048, 32      # ~0.2 s per process and step
     vals, secs = [], []
     r = None
     for k in range(args.warmup + args.steps):
